@@ -1,0 +1,456 @@
+"""spark_rapids_b200 — Python host binding over the C ABI of libb200sql.so.
+
+The product is the CUDA library; this module is (a) the ctypes binding used by tests/bench and
+(b) the host-side mirror of the reference's operator interface (see execs.py).  There is no CPU
+implementation here: every operation goes to the library, which fails loudly without a GPU."""
+import ctypes
+import numpy as np
+
+from ._lib import lib, check, B2Error, B2ColumnInfo, B2AggSpec, B2OrderByArg, parse_header, LIB_PATH  # noqa: F401
+
+# b2_dtype
+BOOL8, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, DATE32, TIMESTAMP_US, DECIMAL32, DECIMAL64, DECIMAL128, STRING = range(13)
+DTYPE_NAMES = ["bool8", "int8", "int16", "int32", "int64", "float32", "float64", "date32", "timestamp_us",
+               "decimal32", "decimal64", "decimal128", "string"]
+_NP = {BOOL8: np.int8, INT8: np.int8, INT16: np.int16, INT32: np.int32, INT64: np.int64, FLOAT32: np.float32,
+       FLOAT64: np.float64, DATE32: np.int32, TIMESTAMP_US: np.int64, DECIMAL32: np.int32, DECIMAL64: np.int64}
+
+# b2_expr_op
+OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_MOD, OP_PMOD, OP_NEG, OP_ABS = 1, 2, 3, 4, 5, 6, 7, 8
+OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_EQ_NULLSAFE = 10, 11, 12, 13, 14, 15, 16
+OP_AND, OP_OR, OP_NOT = 20, 21, 22
+OP_IS_NULL, OP_IS_NOT_NULL, OP_COALESCE, OP_IF = 30, 31, 32, 33
+OP_NORMALIZE_NAN_ZERO, OP_YEAR = 41, 42
+# b2_agg_kind
+AGG_SUM, AGG_COUNT, AGG_MIN, AGG_MAX, AGG_COUNT_ALL = 1, 2, 3, 4, 5
+# b2_join_kind
+JOIN_INNER, JOIN_LEFT_OUTER, JOIN_LEFT_SEMI, JOIN_LEFT_ANTI, JOIN_FULL_OUTER = 0, 1, 2, 3, 4
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def is_decimal(dt):
+    return dt in (DECIMAL32, DECIMAL64, DECIMAL128)
+
+
+def pack_bits(valid):
+    """bool array -> Arrow LSB-first bitmask bytes"""
+    return np.packbits(np.asarray(valid, dtype=bool), bitorder="little")
+
+
+def unpack_bits(buf, n):
+    return np.unpackbits(buf, bitorder="little")[:n].astype(bool)
+
+
+def ints_to_i128(vals):
+    """python ints -> (n, 2) uint64 little-endian two's complement"""
+    out = np.zeros((len(vals), 2), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        v = int(v) & ((1 << 128) - 1)
+        out[i, 0] = v & 0xFFFFFFFFFFFFFFFF
+        out[i, 1] = v >> 64
+    return out
+
+
+def i128_to_ints(arr):
+    out = []
+    for lo, hi in arr.reshape(-1, 2):
+        v = (int(hi) << 64) | int(lo)
+        if v >= 1 << 127:
+            v -= 1 << 128
+        out.append(v)
+    return out
+
+
+class Column:
+    """ai.rapids.cudf.ColumnVector analogue: owns one reference on a native column."""
+
+    def __init__(self, handle):
+        self.h = ctypes.c_int64(handle)
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_column_close(self.h)
+            self.h = ctypes.c_int64(0)
+
+    # ---- construction
+    @staticmethod
+    def from_numpy(values, dtype=None, valid=None, scale=0):
+        values = np.asarray(values)
+        if dtype is None:
+            dtype = {np.dtype(np.bool_): BOOL8, np.dtype(np.int8): INT8, np.dtype(np.int16): INT16, np.dtype(np.int32): INT32,
+                     np.dtype(np.int64): INT64, np.dtype(np.float32): FLOAT32, np.dtype(np.float64): FLOAT64}[values.dtype]
+        n = len(values)
+        if dtype == DECIMAL128:
+            data = ints_to_i128(values) if values.ndim == 1 else np.ascontiguousarray(values, dtype=np.uint64)
+        else:
+            data = np.ascontiguousarray(values.astype(_NP[dtype], copy=False))
+        vb = None if valid is None else np.ascontiguousarray(pack_bits(valid))
+        out = ctypes.c_int64()
+        check(lib.b2_column_from_host(dtype, scale, n, _ptr(data), _ptr(vb), None, ctypes.byref(out)))
+        return Column(out.value)
+
+    @staticmethod
+    def from_strings(strings):
+        """list of str/bytes/None"""
+        valid = np.array([s is not None for s in strings], dtype=bool)
+        enc = [(s.encode() if isinstance(s, str) else (s or b"")) for s in strings]
+        offsets = np.zeros(len(enc) + 1, dtype=np.int32)
+        if enc:
+            offsets[1:] = np.cumsum([len(e) for e in enc])
+        chars = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, np.uint8)
+        vb = None if valid.all() else np.ascontiguousarray(pack_bits(valid))
+        out = ctypes.c_int64()
+        check(lib.b2_column_from_host(STRING, 0, len(enc), _ptr(chars) if len(chars) else None, _ptr(vb), _ptr(offsets), ctypes.byref(out)))
+        return Column(out.value)
+
+    # ---- inspection
+    def info(self):
+        ci = B2ColumnInfo()
+        check(lib.b2_column_info_get(self.h, ctypes.byref(ci)))
+        return ci
+
+    @property
+    def dtype(self):
+        return self.info().dtype
+
+    @property
+    def scale(self):
+        return self.info().scale
+
+    def __len__(self):
+        return self.info().size
+
+    @property
+    def null_count(self):
+        return self.info().null_count
+
+    def to_numpy(self):
+        """-> (values, valid).  DECIMAL128 -> object array of python ints; STRING -> object array of bytes."""
+        ci = self.info()
+        n = ci.size
+        vb = np.zeros((n + 7) // 8, dtype=np.uint8)
+        if ci.dtype == STRING:
+            offsets = np.zeros(n + 1, dtype=np.int32)
+            chars = np.zeros(max(ci.data_bytes, 1), dtype=np.uint8)
+            check(lib.b2_column_to_host(self.h, _ptr(chars), _ptr(vb), _ptr(offsets)))
+            raw = chars.tobytes()
+            vals = np.array([raw[offsets[i]:offsets[i + 1]] for i in range(n)], dtype=object)
+        elif ci.dtype == DECIMAL128:
+            data = np.zeros((n, 2), dtype=np.uint64)
+            check(lib.b2_column_to_host(self.h, _ptr(data), _ptr(vb), None))
+            vals = np.array(i128_to_ints(data), dtype=object)
+        else:
+            data = np.zeros(n, dtype=_NP[ci.dtype])
+            check(lib.b2_column_to_host(self.h, _ptr(data), _ptr(vb), None))
+            vals = data
+        return vals, unpack_bits(vb, n)
+
+    def to_pylist(self):
+        vals, valid = self.to_numpy()
+        dt = self.dtype
+        out = []
+        for v, ok in zip(vals, valid):
+            if not ok:
+                out.append(None)
+            elif dt == BOOL8:
+                out.append(bool(v))
+            elif dt == STRING:
+                out.append(v.decode("utf-8", "replace"))
+            elif dt in (FLOAT32, FLOAT64):
+                out.append(float(v))
+            else:
+                out.append(int(v))
+        return out
+
+
+class Table:
+    """ai.rapids.cudf.Table analogue."""
+
+    def __init__(self, handle):
+        self.h = ctypes.c_int64(handle)
+
+    @staticmethod
+    def from_columns(cols):
+        arr = (ctypes.c_int64 * len(cols))(*[c.h.value for c in cols])
+        out = ctypes.c_int64()
+        check(lib.b2_table_create(arr, len(cols), ctypes.byref(out)))
+        return Table(out.value)
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_table_close(self.h)
+            self.h = ctypes.c_int64(0)
+
+    @property
+    def num_rows(self):
+        out = ctypes.c_int64()
+        check(lib.b2_table_num_rows(self.h, ctypes.byref(out)))
+        return out.value
+
+    @property
+    def num_columns(self):
+        out = ctypes.c_int32()
+        check(lib.b2_table_num_columns(self.h, ctypes.byref(out)))
+        return out.value
+
+    def column(self, i):
+        out = ctypes.c_int64()
+        check(lib.b2_table_column(self.h, i, ctypes.byref(out)))
+        return Column(out.value)
+
+    def columns(self):
+        return [self.column(i) for i in range(self.num_columns)]
+
+    def to_pylists(self):
+        return [c.to_pylist() for c in self.columns()]
+
+    def to_rows(self):
+        cols = self.to_pylists()
+        return list(zip(*cols)) if cols else []
+
+
+# ------------------------------------------------------------------------------------------------
+# expressions (GpuExpression trees; each node also has a neutral s-expression form used by the
+# test oracle so that the same tree drives both sides)
+class Expr:
+    def __init__(self, handle, sexpr):
+        self.h = ctypes.c_int64(handle)
+        self.sexpr = sexpr
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_expr_close(self.h)
+            self.h = ctypes.c_int64(0)
+
+    def type(self):
+        dt, p, s, nl = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        check(lib.b2_expr_type(self.h, ctypes.byref(dt), ctypes.byref(p), ctypes.byref(s), ctypes.byref(nl)))
+        return dt.value, p.value, s.value, bool(nl.value)
+
+    def _bin(self, op, name, other):
+        other = other if isinstance(other, Expr) else lit(other)
+        out = ctypes.c_int64()
+        check(lib.b2_expr_binary(op, self.h, other.h, ctypes.byref(out)))
+        return Expr(out.value, (name, self.sexpr, other.sexpr))
+
+    def _un(self, op, name):
+        out = ctypes.c_int64()
+        check(lib.b2_expr_unary(op, self.h, ctypes.byref(out)))
+        return Expr(out.value, (name, self.sexpr))
+
+    def __add__(self, o): return self._bin(OP_ADD, "add", o)
+    def __sub__(self, o): return self._bin(OP_SUB, "sub", o)
+    def __mul__(self, o): return self._bin(OP_MUL, "mul", o)
+    def __truediv__(self, o): return self._bin(OP_DIV, "div", o)
+    def __mod__(self, o): return self._bin(OP_MOD, "mod", o)
+    def pmod(self, o): return self._bin(OP_PMOD, "pmod", o)
+    def __eq__(self, o): return self._bin(OP_EQ, "eq", o)
+    def __ne__(self, o): return self._bin(OP_NE, "ne", o)
+    def __lt__(self, o): return self._bin(OP_LT, "lt", o)
+    def __le__(self, o): return self._bin(OP_LE, "le", o)
+    def __gt__(self, o): return self._bin(OP_GT, "gt", o)
+    def __ge__(self, o): return self._bin(OP_GE, "ge", o)
+    def eq_null_safe(self, o): return self._bin(OP_EQ_NULLSAFE, "eqns", o)
+    def __and__(self, o): return self._bin(OP_AND, "and", o)
+    def __or__(self, o): return self._bin(OP_OR, "or", o)
+    def __invert__(self): return self._un(OP_NOT, "not")
+    def __neg__(self): return self._un(OP_NEG, "neg")
+    def abs(self): return self._un(OP_ABS, "abs")
+    def is_null(self): return self._un(OP_IS_NULL, "isnull")
+    def is_not_null(self): return self._un(OP_IS_NOT_NULL, "isnotnull")
+    def normalize_nan_zero(self): return self._un(OP_NORMALIZE_NAN_ZERO, "normnz")
+    def year(self): return self._un(OP_YEAR, "year")
+    def coalesce(self, o): return self._bin(OP_COALESCE, "coalesce", o)
+    __hash__ = None
+
+    def cast(self, dtype, precision=0, scale=0):
+        out = ctypes.c_int64()
+        check(lib.b2_expr_cast(self.h, dtype, precision, scale, ctypes.byref(out)))
+        return Expr(out.value, ("cast", self.sexpr, (dtype, precision, scale)))
+
+
+def col(index, dtype, precision=0, scale=0, nullable=True):
+    out = ctypes.c_int64()
+    check(lib.b2_expr_column(index, dtype, precision, scale, int(nullable), ctypes.byref(out)))
+    return Expr(out.value, ("col", index, (dtype, precision, scale)))
+
+
+def lit(value, dtype=None, precision=0, scale=0):
+    """GpuLiteral.  For decimals `value` is the UNSCALED integer."""
+    if dtype is None:
+        if isinstance(value, bool):
+            dtype = BOOL8
+        elif isinstance(value, int):
+            dtype = INT32 if -2**31 <= value < 2**31 else INT64
+        elif isinstance(value, float):
+            dtype = FLOAT64
+        else:
+            raise TypeError("cannot infer literal type of %r" % (value,))
+    buf = np.zeros(2, dtype=np.uint64)
+    is_null = value is None
+    if not is_null:
+        if dtype == FLOAT64:
+            buf[0] = np.array([value], dtype=np.float64).view(np.uint64)[0]
+        elif dtype == FLOAT32:
+            buf[0] = int(np.array([value], dtype=np.float32).view(np.uint32)[0])
+        else:
+            v = int(value) & ((1 << 128) - 1)
+            buf[0] = v & 0xFFFFFFFFFFFFFFFF
+            buf[1] = v >> 64
+    out = ctypes.c_int64()
+    check(lib.b2_expr_literal(dtype, precision, scale, _ptr(buf), int(is_null), ctypes.byref(out)))
+    return Expr(out.value, ("lit", value, (dtype, precision, scale)))
+
+
+def if_else(pred, a, b):
+    out = ctypes.c_int64()
+    check(lib.b2_expr_ternary(OP_IF, pred.h, a.h, b.h, ctypes.byref(out)))
+    return Expr(out.value, ("if", pred.sexpr, a.sexpr, b.sexpr))
+
+
+class Program:
+    """ast.CompiledExpression analogue: N bound expressions compiled into one fused kernel program."""
+
+    def __init__(self, exprs):
+        self.exprs = list(exprs)
+        arr = (ctypes.c_int64 * len(self.exprs))(*[e.h.value for e in self.exprs])
+        out = ctypes.c_int64()
+        check(lib.b2_program_compile(arr, len(self.exprs), ctypes.byref(out)))
+        self.h = ctypes.c_int64(out.value)
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_program_close(self.h)
+            self.h = ctypes.c_int64(0)
+
+
+def _agg_specs(aggs):
+    """aggs: list of (kind, column, out_dtype, out_scale, out_precision)"""
+    arr = (B2AggSpec * max(len(aggs), 1))()
+    for i, a in enumerate(aggs):
+        a = tuple(a) + (0,) * (5 - len(a))
+        arr[i].kind, arr[i].column, arr[i].out_dtype, arr[i].out_scale, arr[i].out_precision = a
+    return arr
+
+
+def _i32s(xs):
+    return (ctypes.c_int32 * max(len(xs), 1))(*xs)
+
+
+def _order_args(keys):
+    arr = (B2OrderByArg * max(len(keys), 1))()
+    for i, k in enumerate(keys):
+        arr[i].column, arr[i].ascending, arr[i].nulls_first = int(k[0]), int(k[1]), int(k[2])
+    return arr
+
+
+def init(device=0, pool_bytes=0):
+    check(lib.b2_init(device, pool_bytes))
+
+
+def sync():
+    check(lib.b2_stream_sync())
+
+
+def project(program, table):
+    out = ctypes.c_int64()
+    check(lib.b2_project(program.h, table.h, ctypes.byref(out)))
+    return Table(out.value)
+
+
+def filter(program, table):  # noqa: A001 - mirrors Table.filter
+    out = ctypes.c_int64()
+    check(lib.b2_filter(program.h, table.h, ctypes.byref(out)))
+    return Table(out.value)
+
+
+def filter_mask(table, mask):
+    out = ctypes.c_int64()
+    check(lib.b2_filter_mask(table.h, mask.h, ctypes.byref(out)))
+    return Table(out.value)
+
+
+def filter_count(program, table):
+    out = ctypes.c_int64()
+    check(lib.b2_filter_count(program.h, table.h, ctypes.byref(out)))
+    return out.value
+
+
+def reduce(table, aggs):  # noqa: A001
+    out = ctypes.c_int64()
+    check(lib.b2_reduce(table.h, _agg_specs(aggs), len(aggs), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def groupby(table, keys, aggs):
+    out = ctypes.c_int64()
+    check(lib.b2_groupby(table.h, _i32s(keys), len(keys), _agg_specs(aggs), len(aggs), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def scan_aggregate(program, has_predicate, table, keys, aggs):
+    out = ctypes.c_int64()
+    check(lib.b2_scan_aggregate(program.h, int(has_predicate), table.h, _i32s(keys), len(keys), _agg_specs(aggs), len(aggs),
+                                ctypes.byref(out)))
+    return Table(out.value)
+
+
+def distinct_count(table, keys):
+    out = ctypes.c_int64()
+    check(lib.b2_distinct_count(table.h, _i32s(keys), len(keys), ctypes.byref(out)))
+    return out.value
+
+
+def gather(table, gather_map, nullify_oob=False):
+    out = ctypes.c_int64()
+    check(lib.b2_gather(table.h, gather_map.h, int(nullify_oob), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def concat(tables):
+    arr = (ctypes.c_int64 * len(tables))(*[t.h.value for t in tables])
+    out = ctypes.c_int64()
+    check(lib.b2_concat(arr, len(tables), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def slice_table(table, start, end):
+    out = ctypes.c_int64()
+    check(lib.b2_slice(table.h, start, end, ctypes.byref(out)))
+    return Table(out.value)
+
+
+def kernel_launch_count():
+    out = ctypes.c_int64()
+    check(lib.b2_kernel_launch_count(ctypes.byref(out)))
+    return out.value
+
+
+class Event:
+    def __init__(self):
+        out = ctypes.c_int64()
+        check(lib.b2_event_create(ctypes.byref(out)))
+        self.h = ctypes.c_int64(out.value)
+
+    def record(self):
+        check(lib.b2_event_record(self.h))
+        return self
+
+    def elapsed_ms(self, stop):
+        ms = ctypes.c_float()
+        check(lib.b2_event_elapsed_ms(self.h, stop.h, ctypes.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_event_close(self.h)
+            self.h = ctypes.c_int64(0)

@@ -1,0 +1,616 @@
+// agg.cu — a3/a4/a5: reductions and hash group-by, fused with the child filter and the pre-step
+// projection (one kernel: predicate -> project -> aggregate).
+//
+// Reference: AggHelper.performReduction / performGroupByAggregation (GpuAggregateExec.scala:540-585),
+// GpuAggFirstPassIterator (:730-742), CudfSum/Count/Min/Max (aggregateFunctions.scala:38-68),
+// GpuDecimalSum / GpuDecimal128Sum / GpuExtractChunk32 / GpuAssembleSumChunks (:607-700, 1106-1290).
+//
+// The reference expands a DECIMAL128 sum into four 32-bit chunk sums plus isEmpty/overflow columns
+// (~30 cudf aggregations for TPC-H q1) because cudf cannot sum 128-bit values with overflow
+// detection.  Here every decimal sum is accumulated exactly in a 128- or 192-bit two's-complement
+// accumulator (64-bit limbs + carry), which is observably identical: the exact sum, NULL when it
+// does not fit the result precision, NULL for an empty / all-null group.
+//
+// Two regimes, one accumulate routine:
+//   * shared-memory table per CTA (<= SMEM_SLOTS groups): rows of a warp that hit the same group
+//     are combined with __match_any_sync + REDUX (__reduce_add_sync on 16-bit pieces) so only one
+//     lane per group per warp touches the accumulator; CTAs merge into the global table once.
+//   * global open-addressing table (any cardinality): insert by CAS on a representative row index,
+//     key equality against that row, RED/ATOM on per-slot accumulators.
+#include "prim.cuh"
+#include "rowops.cuh"
+#include "vm.cuh"
+
+namespace b2 {
+
+constexpr int AG_MAX_AGGS = 24;
+constexpr int SMEM_SLOTS = 128;  // groups per CTA table (power of two)
+constexpr int32_t SLOT_EMPTY = -1;
+
+struct AggD {
+  int32_t kind;      // b2_agg_kind
+  int32_t out_idx;   // program output feeding this aggregate (-1: none)
+  int32_t in_mt;     // machine type of the input
+  int32_t nlimbs;    // 64-bit limbs of the accumulator
+  int32_t limb_off;  // first limb inside the slot's accumulator block
+  int32_t track_valid;  // count valid inputs (nullable input or keyless reduction)
+  int32_t valid_off;
+  int32_t is_float;
+};
+struct AggPlan {
+  int32_t nkeys, naggs, limbs, nvalids, has_pred;
+  KeyCols keys;
+  AggD aggs[AG_MAX_AGGS];
+};
+struct GTable {
+  int32_t* slots;     // representative row per slot, SLOT_EMPTY when free
+  uint64_t* acc;      // [cap][limbs]
+  uint32_t* nvalid;   // [cap][nvalids]
+  uint32_t mask;      // cap - 1
+  int32_t* overflow;  // set when a shared-memory table filled up
+};
+
+// order-preserving maps to u64 for MIN/MAX (Spark float order: NaN greatest, aggregateFunctions.scala:368-465)
+__device__ __forceinline__ uint64_t ord_i64(int64_t v) { return (uint64_t)v ^ 0x8000000000000000ull; }
+__device__ __forceinline__ uint64_t ord_f64(double d) {
+  if (d != d) return 0xffffffffffffffffull;
+  if (d == 0.0) d = 0.0;
+  uint64_t b = (uint64_t)__double_as_longlong(d);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double unord_f64(uint64_t k) {
+  if (k == 0xffffffffffffffffull) { uint64_t n = 0x7ff8000000000000ull; double d; memcpy(&d, &n, 8); return d; }
+  uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  double d; memcpy(&d, &b, 8); return d;
+}
+
+__device__ __forceinline__ uint64_t init_limb(const AggD& a) {
+  return a.kind == B2_AGG_MIN ? 0xffffffffffffffffull : 0ull;
+}
+
+// multi-limb two's-complement add with carry via 64-bit atomics (exact mod 2^(64*n), order free)
+__device__ __forceinline__ void acc_add_limbs(uint64_t* acc, int nlimbs, uint64_t l0, uint64_t l1, uint64_t l2) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(acc);
+  if (nlimbs == 1) { if (l0) atomicAdd(&a[0], (unsigned long long)l0); return; }
+  if (l0 == 0 && l1 == 0 && l2 == 0) return;
+  uint64_t old0 = atomicAdd(&a[0], (unsigned long long)l0);
+  uint64_t c0 = (old0 + l0) < old0 ? 1 : 0;
+  uint64_t s1 = l1 + c0;
+  uint64_t c1a = s1 < l1 ? 1 : 0;
+  if (nlimbs == 2) { if (s1) atomicAdd(&a[1], (unsigned long long)s1); return; }
+  uint64_t old1 = atomicAdd(&a[1], (unsigned long long)s1);
+  uint64_t c1 = c1a + ((old1 + s1) < old1 ? 1 : 0);
+  uint64_t s2 = l2 + c1;
+  if (s2) atomicAdd(&a[2], (unsigned long long)s2);
+}
+
+// sum over the lanes in `m` of a 64-bit piece, as a 128-bit unsigned value (4 REDUX on 16-bit pieces)
+__device__ __forceinline__ u128 group_sum_u64(uint32_t m, uint64_t x) {
+  uint32_t s0 = __reduce_add_sync(m, (uint32_t)(x & 0xffff));
+  uint32_t s1 = __reduce_add_sync(m, (uint32_t)((x >> 16) & 0xffff));
+  uint32_t s2 = __reduce_add_sync(m, (uint32_t)((x >> 32) & 0xffff));
+  uint32_t s3 = __reduce_add_sync(m, (uint32_t)((x >> 48) & 0xffff));
+  return (u128)s0 + ((u128)s1 << 16) + ((u128)s2 << 32) + ((u128)s3 << 48);
+}
+
+// Accumulate one warp-slice (32 rows) into per-slot accumulators.  `m` = lanes sharing my slot,
+// leader = lowest lane of m.  acc/nvalid point at MY slot's blocks (only dereferenced by leaders,
+// or by every active lane for float / min / max).
+__device__ __forceinline__ void accumulate_slice(const AggPlan& plan, const VMCtx& cx, const Opnd* ops, int i, int64_t g,
+                                                 bool active, uint32_t m, bool leader, uint64_t* acc, uint32_t* nvalid) {
+  for (int k = 0; k < plan.naggs; k++) {
+    const AggD& a = plan.aggs[k];
+    bool valid = active;
+    if (a.out_idx >= 0 && active) valid = opnd_valid(ops[k], i, g);
+    const uint32_t vcount = __popc(__ballot_sync(0xffffffffu, valid) & m);
+    if (a.track_valid && leader && active && vcount) atomicAdd(&nvalid[a.valid_off], vcount);
+    switch (a.kind) {
+      case B2_AGG_COUNT: case B2_AGG_COUNT_ALL:
+        if (leader && active && vcount) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[a.limb_off]), (unsigned long long)vcount);
+        break;
+      case B2_AGG_SUM: {
+        if (a.is_float) {
+          double v = 0.0;
+          if (valid) v = a.in_mt == MT_F32 ? (double)opnd_ld<float>(ops[k], i) : opnd_ld<double>(ops[k], i);
+          if (valid) atomicAdd(reinterpret_cast<double*>(&acc[a.limb_off]), v);
+          break;
+        }
+        // integer / decimal: sign-extended value as (lo, hi)
+        uint64_t lo = 0, hi = 0;
+        if (valid) {
+          switch (a.in_mt) {
+            case MT_I8: lo = (uint64_t)(int64_t)opnd_ld<int8_t>(ops[k], i); break;
+            case MT_I16: lo = (uint64_t)(int64_t)opnd_ld<int16_t>(ops[k], i); break;
+            case MT_I32: lo = (uint64_t)(int64_t)opnd_ld<int32_t>(ops[k], i); break;
+            case MT_I64: lo = (uint64_t)opnd_ld<int64_t>(ops[k], i); break;
+            default: { i128 v = opnd_ld<i128>(ops[k], i); lo = (uint64_t)v; hi = (uint64_t)(v >> 64); } break;
+          }
+          if (a.in_mt != MT_I128) hi = ((int64_t)lo < 0) ? ~0ull : 0ull;
+        }
+        const bool neg = (int64_t)hi < 0;
+        const uint32_t nneg = __popc(__ballot_sync(0xffffffffu, neg) & m);
+        u128 slo = group_sum_u64(m, lo);
+        if (a.in_mt == MT_I128) {
+          // 192-bit: sum = slo + (shi << 64) - (nneg << 128)
+          u128 shi = group_sum_u64(m, hi);
+          if (leader && active) {
+            uint64_t l0 = (uint64_t)slo;
+            u128 mid = (slo >> 64) + (u128)(uint64_t)shi;
+            uint64_t l1 = (uint64_t)mid;
+            uint64_t l2 = (uint64_t)(mid >> 64) + (uint64_t)(shi >> 64) - (uint64_t)nneg;
+            acc_add_limbs(&acc[a.limb_off], 3, l0, l1, l2);
+          }
+        } else if (leader && active) {
+          uint64_t l0 = (uint64_t)slo;
+          uint64_t l1 = (uint64_t)(slo >> 64) - (uint64_t)nneg;  // each negative contributes -2^64
+          acc_add_limbs(&acc[a.limb_off], a.nlimbs, l0, l1, 0);
+        }
+      } break;
+      case B2_AGG_MIN: case B2_AGG_MAX: {
+        if (!valid) break;
+        uint64_t key;
+        switch (a.in_mt) {
+          case MT_I8: key = ord_i64(opnd_ld<int8_t>(ops[k], i)); break;
+          case MT_I16: key = ord_i64(opnd_ld<int16_t>(ops[k], i)); break;
+          case MT_I32: key = ord_i64(opnd_ld<int32_t>(ops[k], i)); break;
+          case MT_I64: key = ord_i64(opnd_ld<int64_t>(ops[k], i)); break;
+          case MT_F32: key = ord_f64((double)opnd_ld<float>(ops[k], i)); break;
+          default: key = ord_f64(opnd_ld<double>(ops[k], i)); break;
+        }
+        unsigned long long* p = reinterpret_cast<unsigned long long*>(&acc[a.limb_off]);
+        if (a.kind == B2_AGG_MIN) atomicMin(p, (unsigned long long)key); else atomicMax(p, (unsigned long long)key);
+      } break;
+      default: break;
+    }
+  }
+}
+
+// find-or-insert row `row` in the global table; returns the slot
+__device__ __forceinline__ uint32_t global_insert(const GTable& gt, const KeyCols& keys, int64_t row) {
+  if (keys.n == 0) { gt.slots[0] = 0; return 0; }
+  uint32_t idx = row_hash(keys, row) & gt.mask;
+  while (true) {
+    int32_t cur = gt.slots[idx];
+    if (cur == SLOT_EMPTY) {
+      int32_t old = atomicCAS(&gt.slots[idx], SLOT_EMPTY, (int32_t)row);
+      if (old == SLOT_EMPTY) return idx;
+      cur = old;
+    }
+    if (cur == (int32_t)row || rows_equal(keys, row, keys, cur, true)) return idx;
+    idx = (idx + 1) & gt.mask;
+  }
+}
+
+__global__ void init_table_kernel(GTable gt, const __grid_constant__ AggPlan plan, int64_t cap) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < cap; s += (int64_t)gridDim.x * blockDim.x) {
+    gt.slots[s] = SLOT_EMPTY;
+    for (int k = 0; k < plan.naggs; k++)
+      for (int l = 0; l < plan.aggs[k].nlimbs; l++) gt.acc[s * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
+    for (int v = 0; v < plan.nvalids; v++) gt.nvalid[s * plan.nvalids + v] = 0;
+  }
+}
+
+// SMEM = true: per-CTA shared table + merge; false: straight to the global table
+template <bool SMEM>
+__global__ void __launch_bounds__(VM_NT) aggregate_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
+                                                          const __grid_constant__ VMInputs in, const __grid_constant__ AggPlan plan,
+                                                          GTable gt, int64_t nrows, int smem_regs_bytes) {
+  __shared__ VMShared sh;
+  extern __shared__ __align__(16) char dyn[];
+  char* regs = dyn;
+  // shared table lives after the VM registers
+  int32_t* s_slots = reinterpret_cast<int32_t*>(dyn + smem_regs_bytes);
+  uint64_t* s_acc = reinterpret_cast<uint64_t*>(dyn + smem_regs_bytes + SMEM_SLOTS * 4);
+  uint32_t* s_nvalid = reinterpret_cast<uint32_t*>(s_acc + (SMEM ? SMEM_SLOTS * plan.limbs : 0));
+  const VMInstr* code = vm_load_program(sh, g_hdr, g_code);
+  const int lane = threadIdx.x & 31;
+  // a keyless reduction always has its single group, even over zero rows (GpuAggregateExec.scala:1107-1126)
+  if (plan.nkeys == 0 && blockIdx.x == 0 && threadIdx.x == 0) gt.slots[0] = 0;
+  if (SMEM) {
+    for (int s = threadIdx.x; s < SMEM_SLOTS; s += VM_NT) {
+      s_slots[s] = SLOT_EMPTY;
+      for (int k = 0; k < plan.naggs; k++)
+        for (int l = 0; l < plan.aggs[k].nlimbs; l++) s_acc[s * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
+      for (int v = 0; v < plan.nvalids; v++) s_nvalid[s * plan.nvalids + v] = 0;
+    }
+    __syncthreads();
+  }
+  const int64_t ntiles = (nrows + VM_TILE - 1) / VM_TILE;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (SMEM && *reinterpret_cast<volatile int32_t*>(gt.overflow)) break;  // someone overflowed: the launch is void
+    VMCtx cx; cx.hdr = &sh.hdr; cx.in = &in; cx.smem = regs; cx.tile_base = tile * VM_TILE; cx.nrows = nrows;
+    vm_run(cx, code);
+    Opnd pred;
+    if (plan.has_pred) pred = resolve(cx, sh.hdr.outs[0], 1);
+    Opnd ops[AG_MAX_AGGS];
+    for (int k = 0; k < plan.naggs; k++)
+      if (plan.aggs[k].out_idx >= 0) ops[k] = resolve(cx, sh.hdr.outs[plan.aggs[k].out_idx], mt_width(plan.aggs[k].in_mt));
+#pragma unroll 1
+    for (int j = 0; j < VM_K; j++) {
+      const int i = threadIdx.x + j * VM_NT;
+      const int64_t g = cx.tile_base + i;
+      bool active = g < nrows;
+      if (active && plan.has_pred) active = opnd_valid(pred, i, g) && opnd_ld<int8_t>(pred, i) != 0;
+      int32_t slot = -1;
+      if (active) {
+        if (SMEM) {
+          if (plan.nkeys == 0) { slot = 0; s_slots[0] = 0; }
+          else {
+            uint32_t idx = row_hash(plan.keys, g) & (SMEM_SLOTS - 1);
+            int probes = 0;
+            while (true) {
+              int32_t cur = s_slots[idx];
+              if (cur == SLOT_EMPTY) {
+                int32_t old = atomicCAS(&s_slots[idx], SLOT_EMPTY, (int32_t)g);
+                if (old == SLOT_EMPTY) { slot = idx; break; }
+                cur = old;
+              }
+              if (cur == (int32_t)g || rows_equal(plan.keys, g, plan.keys, cur, true)) { slot = idx; break; }
+              idx = (idx + 1) & (SMEM_SLOTS - 1);
+              if (++probes >= SMEM_SLOTS * 3 / 4) { atomicExch(gt.overflow, 1); active = false; break; }
+            }
+          }
+        } else {
+          slot = (int32_t)global_insert(gt, plan.keys, g);
+        }
+      }
+      const uint32_t m = __match_any_sync(0xffffffffu, slot);
+      const bool leader = lane == (__ffs(m) - 1);
+      uint64_t* acc = nullptr; uint32_t* nv = nullptr;
+      if (slot >= 0) {
+        acc = SMEM ? &s_acc[slot * plan.limbs] : &gt.acc[(int64_t)slot * plan.limbs];
+        nv = SMEM ? &s_nvalid[slot * plan.nvalids] : &gt.nvalid[(int64_t)slot * plan.nvalids];
+      }
+      accumulate_slice(plan, cx, ops, i, g, active && slot >= 0, m, leader, acc, nv);
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    if (*reinterpret_cast<volatile int32_t*>(gt.overflow)) return;
+    for (int s = threadIdx.x; s < SMEM_SLOTS; s += VM_NT) {
+      const int32_t row = s_slots[s];
+      if (row == SLOT_EMPTY) continue;
+      const uint32_t gs = global_insert(gt, plan.keys, row);
+      uint64_t* ga = &gt.acc[(int64_t)gs * plan.limbs];
+      const uint64_t* sa = &s_acc[s * plan.limbs];
+      for (int k = 0; k < plan.naggs; k++) {
+        const AggD& a = plan.aggs[k];
+        unsigned long long* p = reinterpret_cast<unsigned long long*>(&ga[a.limb_off]);
+        if (a.kind == B2_AGG_MIN) atomicMin(p, (unsigned long long)sa[a.limb_off]);
+        else if (a.kind == B2_AGG_MAX) atomicMax(p, (unsigned long long)sa[a.limb_off]);
+        else if (a.is_float) atomicAdd(reinterpret_cast<double*>(p), __longlong_as_double((long long)sa[a.limb_off]));
+        else acc_add_limbs(&ga[a.limb_off], a.nlimbs, sa[a.limb_off], a.nlimbs > 1 ? sa[a.limb_off + 1] : 0, a.nlimbs > 2 ? sa[a.limb_off + 2] : 0);
+      }
+      for (int v = 0; v < plan.nvalids; v++)
+        if (s_nvalid[s * plan.nvalids + v]) atomicAdd(&gt.nvalid[(int64_t)gs * plan.nvalids + v], s_nvalid[s * plan.nvalids + v]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void occupied_flags_kernel(const int32_t* __restrict__ slots, int64_t cap, int32_t* __restrict__ flags) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < cap; s += (int64_t)gridDim.x * blockDim.x)
+    flags[s] = slots[s] != SLOT_EMPTY;
+}
+
+struct AggOut {
+  void* data[AG_MAX_AGGS];
+  uint32_t* valid[AG_MAX_AGGS];  // zero-initialised
+  int32_t out_dtype[AG_MAX_AGGS];
+  int32_t out_precision[AG_MAX_AGGS];
+};
+
+__device__ __forceinline__ i128 pow10_128(int e) {
+  i128 r = 1;
+  for (int i = 0; i < e; i++) r *= 10;
+  return r;
+}
+
+__global__ void finalize_kernel(GTable gt, const __grid_constant__ AggPlan plan, int64_t cap, const int32_t* __restrict__ pos,
+                                const __grid_constant__ AggOut out, int32_t* __restrict__ rep_rows) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < cap; s += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t row = gt.slots[s];
+    if (row == SLOT_EMPTY) continue;
+    const int32_t o = pos[s];
+    rep_rows[o] = row;
+    for (int k = 0; k < plan.naggs; k++) {
+      const AggD& a = plan.aggs[k];
+      const uint64_t* acc = &gt.acc[s * plan.limbs + a.limb_off];
+      bool valid = true;
+      if (a.track_valid) valid = gt.nvalid[s * plan.nvalids + a.valid_off] > 0;
+      switch (a.kind) {
+        case B2_AGG_COUNT: case B2_AGG_COUNT_ALL:
+          reinterpret_cast<int64_t*>(out.data[k])[o] = (int64_t)acc[0]; valid = true; break;
+        case B2_AGG_SUM:
+          if (a.is_float) {
+            double d = __longlong_as_double((long long)acc[0]);
+            if (out.out_dtype[k] == B2_FLOAT32) reinterpret_cast<float*>(out.data[k])[o] = (float)d;
+            else reinterpret_cast<double*>(out.data[k])[o] = d;
+          } else if (a.nlimbs == 1) {
+            reinterpret_cast<int64_t*>(out.data[k])[o] = (int64_t)acc[0];  // long sum wraps (aggregateFunctions.scala:1041-1104)
+          } else {
+            // exact 128/192-bit sum -> decimal; NULL when it needs more than out_precision digits
+            i128 v = (i128)(((u128)acc[1] << 64) | acc[0]);
+            bool fits = true;
+            if (a.nlimbs == 3) {
+              const int64_t ext = (int64_t)acc[2];
+              fits = (ext == 0 && (int64_t)acc[1] >= 0) || (ext == -1 && (int64_t)acc[1] < 0);
+            }
+            const i128 lim = pow10_128(out.out_precision[k]);
+            if (!fits || v >= lim || v <= -lim) valid = false;
+            if (out.out_dtype[k] == B2_DECIMAL128) reinterpret_cast<i128*>(out.data[k])[o] = valid ? v : (i128)0;
+            else reinterpret_cast<int64_t*>(out.data[k])[o] = valid ? (int64_t)v : 0;
+          }
+          break;
+        case B2_AGG_MIN: case B2_AGG_MAX: {
+          const uint64_t key = acc[0];
+          if (a.in_mt == MT_F32) reinterpret_cast<float*>(out.data[k])[o] = (float)unord_f64(key);
+          else if (a.in_mt == MT_F64) reinterpret_cast<double*>(out.data[k])[o] = unord_f64(key);
+          else {
+            const int64_t v = (int64_t)(key ^ 0x8000000000000000ull);
+            switch (a.in_mt) {
+              case MT_I8: reinterpret_cast<int8_t*>(out.data[k])[o] = (int8_t)v; break;
+              case MT_I16: reinterpret_cast<int16_t*>(out.data[k])[o] = (int16_t)v; break;
+              case MT_I32: reinterpret_cast<int32_t*>(out.data[k])[o] = (int32_t)v; break;
+              default: reinterpret_cast<int64_t*>(out.data[k])[o] = v; break;
+            }
+          }
+        } break;
+        default: break;
+      }
+      if (valid && out.valid[k]) atomicOr(&out.valid[k][o >> 5], 1u << (o & 31));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+void check_program_inputs(const Program* p, const Table* t);
+void fill_inputs(VMInputs& in, const Table* t);
+int vm_grid(int64_t nrows, int smem_bytes);
+Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullify_oob, const std::vector<int>* only_cols);
+Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
+
+static int mt_of_dtype(int dtype) {
+  switch (dtype) {
+    case B2_BOOL8: case B2_INT8: return MT_I8;
+    case B2_INT16: return MT_I16;
+    case B2_INT32: case B2_DATE32: case B2_DECIMAL32: return MT_I32;
+    case B2_INT64: case B2_TIMESTAMP_US: case B2_DECIMAL64: return MT_I64;
+    case B2_DECIMAL128: return MT_I128;
+    case B2_FLOAT32: return MT_F32;
+    case B2_FLOAT64: return MT_F64;
+  }
+  throw Error(B2_ERR_UNSUPPORTED, "aggregation over dtype " + std::to_string(dtype));
+}
+
+// core: program outputs -> (keys, aggregates).  Key outputs must be plain input columns.
+Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const int* key_outs, int nkeys,
+                      const b2_agg_spec* specs, int naggs) {
+  check_program_inputs(prog, t);
+  B2_CHECK(naggs <= AG_MAX_AGGS, "too many aggregates");
+  B2_CHECK(nkeys <= MAX_KEYS, "too many group-by keys");
+  if (has_pred) B2_CHECK(prog->hdr.nouts >= 1 && prog->out_dtype[0] == B2_BOOL8, "fused predicate must be output 0 and BOOL8");
+  const int base = has_pred ? 1 : 0;
+  const int64_t n = t->rows;
+  AggPlan plan; memset(&plan, 0, sizeof(plan));
+  plan.nkeys = nkeys; plan.naggs = naggs; plan.has_pred = has_pred;
+  std::vector<int> key_table_cols;
+  for (int k = 0; k < nkeys; k++) {
+    int o = key_outs[k] + base;
+    B2_CHECK(o >= 0 && o < prog->hdr.nouts, "key output index out of range");
+    const VMOperand& op = prog->hdr.outs[o];
+    if (op.kind != OK_COL) throw Error(B2_ERR_UNSUPPORTED, "group-by keys must be plain columns of the input (project computed keys first)");
+    key_table_cols.push_back(op.idx);
+  }
+  plan.keys = key_cols_of(t, key_table_cols.data(), nkeys);
+  int limbs = 0, nvalids = 0;
+  for (int k = 0; k < naggs; k++) {
+    AggD& a = plan.aggs[k];
+    a.kind = specs[k].kind;
+    a.out_idx = -1; a.in_mt = MT_I64; a.is_float = 0;
+    bool in_nullable = false;
+    int in_dtype = B2_INT64;
+    if (a.kind != B2_AGG_COUNT_ALL) {
+      int o = specs[k].column + base;
+      B2_CHECK(o >= 0 && o < prog->hdr.nouts, "aggregate input index out of range");
+      a.out_idx = o; a.in_mt = prog->hdr.out_mt[o]; in_nullable = prog->out_nullable[o]; in_dtype = prog->out_dtype[o];
+      if (in_dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "aggregates over strings");
+    }
+    a.is_float = (a.in_mt == MT_F32 || a.in_mt == MT_F64);
+    switch (a.kind) {
+      case B2_AGG_SUM:
+        if (a.is_float) a.nlimbs = 1;
+        else if (is_decimal(in_dtype)) {
+          a.nlimbs = a.in_mt == MT_I128 ? 3 : 2;
+          B2_CHECK(specs[k].out_dtype == B2_DECIMAL128 || specs[k].out_dtype == B2_DECIMAL64, "decimal sum needs a decimal result type");
+          B2_CHECK(specs[k].out_precision >= 1 && specs[k].out_precision <= 38, "decimal sum needs out_precision");
+        } else {
+          B2_CHECK(specs[k].out_dtype == B2_INT64, "integral sum result type is INT64");
+          a.nlimbs = 1;
+        }
+        break;
+      case B2_AGG_COUNT: case B2_AGG_COUNT_ALL: a.nlimbs = 1; break;
+      case B2_AGG_MIN: case B2_AGG_MAX:
+        if (a.in_mt == MT_I128) throw Error(B2_ERR_UNSUPPORTED, "min/max over DECIMAL128");
+        a.nlimbs = 1; break;
+      default: throw Error(B2_ERR_UNSUPPORTED, "aggregate kind " + std::to_string(a.kind));
+    }
+    a.limb_off = limbs; limbs += a.nlimbs;
+    a.track_valid = (a.kind == B2_AGG_SUM || a.kind == B2_AGG_MIN || a.kind == B2_AGG_MAX) && (in_nullable || nkeys == 0 || has_pred);
+    if (a.track_valid) a.valid_off = nvalids++;
+  }
+  plan.limbs = std::max(limbs, 1); plan.nvalids = std::max(nvalids, 1);
+  VMInputs in; fill_inputs(in, t);
+  const int vm_smem = prog->hdr.smem_bytes;
+
+  auto alloc_table = [&](int64_t cap, DevBuf& slots, DevBuf& acc, DevBuf& nv, DevBuf& ovf, GTable& gt) {
+    slots = DevBuf((size_t)cap * 4); acc = DevBuf((size_t)cap * plan.limbs * 8); nv = DevBuf((size_t)cap * plan.nvalids * 4);
+    ovf = DevBuf(4);
+    gt.slots = slots.as<int32_t>(); gt.acc = acc.as<uint64_t>(); gt.nvalid = nv.as<uint32_t>(); gt.mask = (uint32_t)(cap - 1);
+    gt.overflow = ovf.as<int32_t>();
+    CUDA_CHECK(cudaMemsetAsync(ovf.p, 0, 4, stream()));
+    init_table_kernel<<<grid_for(cap, 256), 256, 0, stream()>>>(gt, plan, cap);
+    count_launch();
+  };
+
+  DevBuf slots, acc, nv, ovf;
+  GTable gt;
+  int64_t cap = 0;
+  bool done = false;
+  // regime 1: shared-memory tables (always right for reductions; optimistic for group-by)
+  {
+    int table_bytes = SMEM_SLOTS * 4 + SMEM_SLOTS * plan.limbs * 8 + SMEM_SLOTS * plan.nvalids * 4;
+    int smem = ((vm_smem + 15) & ~15) + table_bytes;
+    if (smem <= 160 * 1024) {
+      int grid = n > 0 ? vm_grid(n, smem) : 1;
+      cap = 1;
+      while (cap < (int64_t)grid * SMEM_SLOTS * 2) cap <<= 1;
+      if (nkeys == 0) cap = 1;
+      alloc_table(cap, slots, acc, nv, ovf, gt);
+      if (n > 0 || nkeys == 0) {
+        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        aggregate_kernel<true><<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, plan, gt, n,
+                                                                  (vm_smem + 15) & ~15);
+        CUDA_CHECK(cudaGetLastError());
+        count_launch();
+      }
+      int32_t h_ovf = 0;
+      if (nkeys > 0) { d2h(&h_ovf, ovf.p, 1); sync(); }
+      done = h_ovf == 0;
+    }
+  }
+  if (!done) {  // regime 2: global table sized for the worst case (every row its own group)
+    cap = 1024;
+    while (cap < n * 2) cap <<= 1;
+    alloc_table(cap, slots, acc, nv, ovf, gt);
+    if (vm_smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem));
+    aggregate_kernel<false><<<vm_grid(n, vm_smem), VM_NT, vm_smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in,
+                                                                                plan, gt, n, (vm_smem + 15) & ~15);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  // compact occupied slots
+  DevBuf pos((size_t)(cap + 1) * 4);
+  occupied_flags_kernel<<<grid_for(cap, 256), 256, 0, stream()>>>(gt.slots, cap, pos.as<int32_t>());
+  count_launch();
+  DevBuf sums = exclusive_scan<int32_t, int32_t>(pos.as<int32_t>(), pos.as<int32_t>(), cap, true);
+  int32_t ngroups = 0;
+  d2h(&ngroups, pos.as<int32_t>() + cap, 1);
+  sync();
+  ColsGuard outs;
+  AggOut ao; memset(&ao, 0, sizeof(ao));
+  for (int k = 0; k < naggs; k++) {
+    int odt = specs[k].out_dtype;
+    if (plan.aggs[k].kind == B2_AGG_COUNT || plan.aggs[k].kind == B2_AGG_COUNT_ALL) odt = B2_INT64;
+    if (plan.aggs[k].kind == B2_AGG_MIN || plan.aggs[k].kind == B2_AGG_MAX) odt = prog->out_dtype[plan.aggs[k].out_idx];
+    bool nullable = plan.aggs[k].track_valid || (plan.aggs[k].kind == B2_AGG_SUM && plan.aggs[k].nlimbs >= 2);
+    int oscale = (plan.aggs[k].kind == B2_AGG_MIN || plan.aggs[k].kind == B2_AGG_MAX) ? prog->out_scale[plan.aggs[k].out_idx] : specs[k].out_scale;
+    Column* c = new_column(odt, oscale, ngroups, nullable);
+    outs.v.push_back(c);
+    ao.data[k] = c->data.p; ao.valid[k] = c->valid.as<uint32_t>();
+    ao.out_dtype[k] = odt; ao.out_precision[k] = specs[k].out_precision;
+    if (c->valid.p) CUDA_CHECK(cudaMemsetAsync(c->valid.p, 0, c->valid.bytes, stream()));
+  }
+  DevBuf rep((size_t)std::max(ngroups, 1) * 4);
+  finalize_kernel<<<grid_for(cap, 256), 256, 0, stream()>>>(gt, plan, cap, pos.as<int32_t>(), ao, rep.as<int32_t>());
+  CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  std::vector<Column*> result;
+  if (nkeys > 0) {
+    Table* kt = gather_table(t, rep.as<int32_t>(), ngroups, false, &key_table_cols);
+    for (auto*& c : kt->cols) { result.push_back(c); c = nullptr; }
+    kt->cols.clear();
+    delete kt;
+  }
+  for (auto* c : outs.release()) result.push_back(c);
+  return new_table(std::move(result));
+}
+
+// identity program over selected columns of a table (used by the unfused b2_reduce / b2_groupby)
+Program* make_passthrough_program(const Table* t, const std::vector<int>& cols) {
+  std::unique_ptr<Program> p(new Program());
+  memset(&p->hdr, 0, sizeof(p->hdr));
+  B2_CHECK((int)cols.size() <= VM_MAX_OUTS, "too many columns");
+  p->hdr.nouts = (int)cols.size();
+  p->col_dtype.assign(t->cols.size() > VM_MAX_COLS ? VM_MAX_COLS : t->cols.size(), -1);
+  int maxc = 0;
+  for (size_t i = 0; i < cols.size(); i++) {
+    int c = cols[i];
+    B2_CHECK(c >= 0 && c < (int)t->cols.size() && c < VM_MAX_COLS, "column index out of range");
+    const Column* col = t->cols[c];
+    VMOperand& o = p->hdr.outs[i];
+    memset(&o, 0, sizeof(o));
+    o.kind = OK_COL; o.idx = c; o.nullable = col->nullable();
+    p->hdr.out_mt[i] = col->dtype == B2_STRING ? MT_I8 : (uint8_t)mt_of_dtype(col->dtype);
+    p->out_dtype.push_back(col->dtype); p->out_scale.push_back(col->scale); p->out_precision.push_back(0);
+    p->out_nullable.push_back(col->nullable());
+    p->col_dtype[c] = col->dtype;
+    maxc = std::max(maxc, c + 1);
+  }
+  p->hdr.ncols = maxc;
+  p->col_dtype.resize(maxc);
+  p->d_hdr = DevBuf(sizeof(VMProgramHeader));
+  h2d(p->d_hdr.p, &p->hdr, 1);
+  p->d_code = DevBuf(sizeof(VMInstr));
+  sync();
+  return p.release();
+}
+
+}  // namespace b2
+
+using namespace b2;
+extern "C" {
+
+int b2_scan_aggregate(b2_handle program, int32_t has_predicate, b2_handle table, const int32_t* key_cols, int32_t nkeys,
+                      const b2_agg_spec* aggs, int32_t naggs, b2_handle* out_table) {
+  B2_TRY
+  *out_table = to_handle(scan_aggregate(program_from(program), has_predicate != 0, table_from(table), key_cols, nkeys, aggs, naggs));
+  B2_CATCH
+}
+
+static Table* unfused(const Table* t, const int32_t* key_cols, int nkeys, const b2_agg_spec* aggs, int naggs) {
+  std::vector<int> cols;
+  std::vector<int> key_outs;
+  for (int k = 0; k < nkeys; k++) { key_outs.push_back((int)cols.size()); cols.push_back(key_cols[k]); }
+  std::vector<b2_agg_spec> specs(aggs, aggs + naggs);
+  for (auto& s : specs) {
+    if (s.kind == B2_AGG_COUNT_ALL) continue;
+    int c = s.column;
+    s.column = (int)cols.size();
+    cols.push_back(c);
+  }
+  if (cols.empty()) cols.push_back(0);
+  std::unique_ptr<Program> p(make_passthrough_program(t, cols));
+  return scan_aggregate(p.get(), false, t, key_outs.data(), nkeys, specs.data(), naggs);
+}
+
+int b2_reduce(b2_handle table, const b2_agg_spec* aggs, int32_t naggs, b2_handle* out_table) {
+  B2_TRY
+  *out_table = to_handle(unfused(table_from(table), nullptr, 0, aggs, naggs));
+  B2_CATCH
+}
+
+int b2_groupby(b2_handle table, const int32_t* key_cols, int32_t nkeys, const b2_agg_spec* aggs, int32_t naggs, b2_handle* out_table) {
+  B2_TRY
+  *out_table = to_handle(unfused(table_from(table), key_cols, nkeys, aggs, naggs));
+  B2_CATCH
+}
+
+__global__ void count_occupied_kernel(const int32_t* slots, int64_t cap, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < cap; s += (int64_t)gridDim.x * blockDim.x) acc += slots[s] != SLOT_EMPTY;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+int b2_distinct_count(b2_handle table, const int32_t* key_cols, int32_t nkeys, int64_t* out) {
+  B2_TRY
+  // Table.distinctCount: group-by with no aggregates; the row count of the result
+  Table* t = table_from(table);
+  std::unique_ptr<Table, void (*)(Table*)> r(unfused(t, key_cols, nkeys, nullptr, 0), table_release);
+  // a key-only group-by yields exactly the distinct rows; with zero keys every row is one group
+  *out = nkeys == 0 ? (t->rows > 0 ? 1 : 0) : r->rows;
+  B2_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,442 @@
+// core.cu — runtime (device init, stream-ordered pool, per-thread stream), column/table handles,
+// host<->device transfer, events.  Reference counterparts: GpuDeviceManager.scala:349-445
+// (Rmm.initialize, ASYNC allocator mode), GpuColumnVector.java:621-660, HostColumnarToGpu.scala,
+// GpuColumnarToRowExec.scala:337-384 (copyToHost).
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+
+namespace b2 {
+
+static thread_local std::string g_err;
+void set_last_error(const std::string& m) { g_err = m; }
+
+int translate_exception() {
+  try {
+    throw;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::bad_alloc& e) {
+    g_err = "host allocation failed";
+    return B2_ERR_INVALID;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return B2_ERR_INVALID;
+  } catch (...) {
+    g_err = "unknown error";
+    return B2_ERR_FATAL;
+  }
+}
+
+void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+  if (e == cudaSuccess) return;
+  std::string m = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + file +
+                  ":" + std::to_string(line) + " (" + what + ")";
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    throw Error(B2_ERR_OOM, m);
+  }
+  // sticky errors poison the context: the reference exits the executor (Plugin.scala:823-848)
+  bool fatal = (e == cudaErrorIllegalAddress || e == cudaErrorLaunchFailure ||
+                e == cudaErrorHardwareStackError || e == cudaErrorIllegalInstruction ||
+                e == cudaErrorMisalignedAddress || e == cudaErrorECCUncorrectable);
+  throw Error(fatal ? B2_ERR_FATAL : B2_ERR_CUDA, m);
+}
+
+// ---------------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static bool g_inited = false;
+static int g_device = 0;
+static int g_sms = 148;
+static std::atomic<int64_t> g_in_use{0};
+static std::atomic<int64_t> g_limit{0};
+static std::atomic<int64_t> g_launches{0};
+static std::unordered_map<void*, size_t> g_sizes;
+static thread_local cudaStream_t t_stream = nullptr;
+static thread_local bool t_stream_owned = false;
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int sm_count() { return g_sms; }
+
+static void ensure_init() {
+  if (g_inited) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_inited) return;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(B2_ERR_CUDA, "libb200sql: no CUDA device available (this library has no CPU fallback)");
+  }
+  CUDA_CHECK(cudaGetDevice(&g_device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, g_device));
+  g_sms = prop.multiProcessorCount;
+  cudaMemPool_t pool;
+  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, g_device));
+  uint64_t thr = UINT64_MAX;  // keep freed memory in the pool: Rmm pool behaviour
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  g_inited = true;
+}
+
+cudaStream_t stream() {
+  if (!t_stream) {
+    ensure_init();
+    CUDA_CHECK(cudaSetDevice(g_device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&t_stream, cudaStreamNonBlocking));
+    t_stream_owned = true;
+  }
+  return t_stream;
+}
+
+void* dev_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 64;
+  bytes = pad64(bytes);
+  int64_t lim = g_limit.load();
+  if (lim > 0 && g_in_use.load() + (int64_t)bytes > lim)
+    throw Error(B2_ERR_OOM, "allocation of " + std::to_string(bytes) + " B exceeds the configured limit");
+  void* p = nullptr;
+  cudaStream_t s = stream();
+  cudaError_t e = cudaMallocAsync(&p, bytes, s);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    // give outstanding frees a chance to land, then retry once (DeviceMemoryEventHandler analogue)
+    cudaDeviceSynchronize();
+    e = cudaMallocAsync(&p, bytes, s);
+  }
+  if (e != cudaSuccess) cuda_check(e, "cudaMallocAsync", __FILE__, __LINE__);
+  g_in_use.fetch_add((int64_t)bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_sizes[p] = bytes;
+  }
+  return p;
+}
+
+void dev_free(void* p) {
+  if (!p) return;
+  size_t bytes = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_sizes.find(p);
+    if (it != g_sizes.end()) { bytes = it->second; g_sizes.erase(it); }
+  }
+  g_in_use.fetch_sub((int64_t)bytes);
+  cudaFreeAsync(p, stream());
+}
+
+// ---------------------------------------------------------------------------------------------
+Table::~Table() {
+  for (auto* c : cols) if (c) col_release(c);
+}
+Column* col_from(b2_handle h) {
+  if (h == 0) throw Error(B2_ERR_INVALID, "null column handle");
+  return reinterpret_cast<Column*>((intptr_t)h);
+}
+Table* table_from(b2_handle h) {
+  if (h == 0) throw Error(B2_ERR_INVALID, "null table handle");
+  return reinterpret_cast<Table*>((intptr_t)h);
+}
+void col_incref(Column* c) { c->refs.fetch_add(1); }
+void col_release(Column* c) {
+  if (c->refs.fetch_sub(1) == 1) delete c;
+}
+void table_release(Table* t) {
+  if (t->refs.fetch_sub(1) == 1) delete t;
+}
+
+Column* new_column(int dtype, int scale, int64_t size, bool with_validity) {
+  if (size > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "column of " + std::to_string(size) + " rows");
+  std::unique_ptr<Column> c(new Column());
+  c->dtype = dtype; c->scale = scale; c->size = size;
+  int w = dtype_width(dtype);
+  if (w > 0) c->data = DevBuf((size_t)size * w);
+  if (with_validity) c->valid = DevBuf(validity_bytes(size));
+  c->null_count = with_validity ? -1 : 0;
+  return c.release();
+}
+
+Table* new_table(std::vector<Column*>&& cols) {
+  Table* t = new Table();
+  t->cols = std::move(cols);
+  t->rows = t->cols.empty() ? 0 : t->cols[0]->size;
+  for (auto* c : t->cols)
+    if (c->size != t->rows) { delete t; throw Error(B2_ERR_INVALID, "table columns differ in length"); }
+  return t;
+}
+
+__global__ void count_valid_kernel(const uint32_t* __restrict__ m, int64_t rows, unsigned long long* out) {
+  int64_t words = (rows + 31) >> 5;
+  unsigned long long acc = 0;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = m[w];
+    if (w == words - 1 && (rows & 31)) v &= (1u << (rows & 31)) - 1u;
+    acc += __popc(v);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+static int64_t count_nulls(Column* c) {
+  if (!c->valid.p) return 0;
+  if (c->size == 0) return 0;
+  DevBuf cnt(8);
+  CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 8, stream()));
+  int64_t words = (c->size + 31) >> 5;
+  count_valid_kernel<<<grid_for(words, 256), 256, 0, stream()>>>(c->validity(), c->size, cnt.as<unsigned long long>());
+  count_launch();
+  unsigned long long h = 0;
+  d2h(&h, cnt.p, 1);
+  sync();
+  return c->size - (int64_t)h;
+}
+
+void finalize_nulls(Column* c) {
+  if (c->null_count < 0) c->null_count = count_nulls(c);
+}
+
+__global__ void fill_kernel(uint8_t* out, int64_t n, int width, uint4 v) {
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(&v);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int b = 0; b < width; b++) out[i * width + b] = src[b];
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+const char* b2_version(void) { return "b200sql 0.1 (sm_100a)"; }
+
+int b2_init(int device, size_t pool_bytes) {
+  B2_TRY
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(B2_ERR_CUDA, "libb200sql: no CUDA device available (this library has no CPU fallback)");
+  }
+  B2_CHECK(device >= 0 && device < ndev, "bad device ordinal");
+  CUDA_CHECK(cudaSetDevice(device));
+  ensure_init();
+  g_device = device;
+  if (pool_bytes) {  // pre-warm the pool like Rmm.initialize(pool size)
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, pool_bytes, stream()) == cudaSuccess) cudaFreeAsync(p, stream());
+    else cudaGetLastError();
+    sync();
+  }
+  B2_CATCH
+}
+
+int b2_shutdown(void) {
+  B2_TRY
+  if (t_stream && t_stream_owned) { cudaStreamSynchronize(t_stream); cudaStreamDestroy(t_stream); }
+  t_stream = nullptr;
+  B2_CATCH
+}
+
+int b2_stream_sync(void) {
+  B2_TRY
+  sync();
+  B2_CATCH
+}
+
+int b2_set_stream(void* s) {
+  B2_TRY
+  ensure_init();
+  if (t_stream && t_stream_owned) { cudaStreamSynchronize(t_stream); cudaStreamDestroy(t_stream); }
+  t_stream = (cudaStream_t)s;
+  t_stream_owned = false;
+  B2_CATCH
+}
+
+void* b2_get_stream(void) {
+  try { return (void*)stream(); } catch (...) { translate_exception(); return nullptr; }
+}
+
+int b2_device_bytes_in_use(int64_t* out) { *out = g_in_use.load(); return B2_OK; }
+int b2_set_alloc_limit(int64_t bytes) { g_limit.store(bytes); return B2_OK; }
+int b2_kernel_launch_count(int64_t* out) { *out = g_launches.load(); return B2_OK; }
+
+static Column* column_build(int32_t dtype, int32_t scale, int64_t size, const void* data,
+                            const void* validity, const int32_t* offsets, cudaMemcpyKind kind) {
+  B2_CHECK(size >= 0, "negative size");
+  if (size > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "too many rows");
+  std::unique_ptr<Column> c(new Column());
+  c->dtype = dtype; c->scale = scale; c->size = size;
+  int w = dtype_width(dtype);
+  cudaStream_t s = stream();
+  if (dtype == B2_STRING) {
+    B2_CHECK(offsets != nullptr || size == 0, "string column needs offsets");
+    c->offsets = DevBuf((size_t)(size + 1) * 4);
+    int32_t nchars = 0;
+    if (size > 0) {
+      CUDA_CHECK(cudaMemcpyAsync(c->offsets.p, offsets, (size_t)(size + 1) * 4, kind, s));
+      if (kind == cudaMemcpyHostToDevice) nchars = offsets[size];
+      else { d2h(&nchars, (const char*)c->offsets.p + size * 4, 1); sync(); }
+    } else {
+      CUDA_CHECK(cudaMemsetAsync(c->offsets.p, 0, 4, s));
+    }
+    c->chars_bytes = nchars;
+    c->data = DevBuf((size_t)nchars);
+    if (nchars) CUDA_CHECK(cudaMemcpyAsync(c->data.p, data, (size_t)nchars, kind, s));
+  } else {
+    c->data = DevBuf((size_t)size * w);
+    if (size) CUDA_CHECK(cudaMemcpyAsync(c->data.p, data, (size_t)size * w, kind, s));
+  }
+  if (validity) {
+    size_t vb = validity_bytes(size);
+    c->valid = DevBuf(vb);
+    CUDA_CHECK(cudaMemsetAsync(c->valid.p, 0, vb, s));
+    CUDA_CHECK(cudaMemcpyAsync(c->valid.p, validity, (size_t)((size + 7) / 8), kind, s));
+    c->null_count = -1;
+  }
+  if (kind == cudaMemcpyHostToDevice) sync();  // the caller may free its host buffers on return
+  return c.release();
+}
+
+int b2_column_from_host(int32_t dtype, int32_t scale, int64_t size, const void* data,
+                        const uint8_t* validity_bits, const int32_t* offsets, b2_handle* out) {
+  B2_TRY
+  *out = to_handle(column_build(dtype, scale, size, data, validity_bits, offsets, cudaMemcpyHostToDevice));
+  B2_CATCH
+}
+
+int b2_column_from_device(int32_t dtype, int32_t scale, int64_t size, const void* data,
+                          const uint32_t* validity_bits, const int32_t* offsets, b2_handle* out) {
+  B2_TRY
+  *out = to_handle(column_build(dtype, scale, size, data, validity_bits, offsets, cudaMemcpyDeviceToDevice));
+  B2_CATCH
+}
+
+int b2_column_info_get(b2_handle h, b2_column_info* out) {
+  B2_TRY
+  Column* c = col_from(h);
+  finalize_nulls(c);
+  out->dtype = c->dtype; out->scale = c->scale; out->size = c->size; out->null_count = c->null_count;
+  out->data = c->data.p; out->validity = c->validity(); out->offsets = c->offsets.as<int32_t>();
+  out->data_bytes = c->dtype == B2_STRING ? c->chars_bytes : c->size * dtype_width(c->dtype);
+  B2_CATCH
+}
+
+int b2_column_to_host(b2_handle h, void* data, uint8_t* validity_bits, int32_t* offsets) {
+  B2_TRY
+  Column* c = col_from(h);
+  cudaStream_t s = stream();
+  if (c->dtype == B2_STRING) {
+    if (offsets) CUDA_CHECK(cudaMemcpyAsync(offsets, c->offsets.p, (size_t)(c->size + 1) * 4, cudaMemcpyDeviceToHost, s));
+    if (data && c->chars_bytes) CUDA_CHECK(cudaMemcpyAsync(data, c->data.p, (size_t)c->chars_bytes, cudaMemcpyDeviceToHost, s));
+  } else if (data && c->size) {
+    CUDA_CHECK(cudaMemcpyAsync(data, c->data.p, (size_t)c->size * dtype_width(c->dtype), cudaMemcpyDeviceToHost, s));
+  }
+  if (validity_bits) {
+    size_t nb = (size_t)((c->size + 7) / 8);
+    if (c->valid.p) CUDA_CHECK(cudaMemcpyAsync(validity_bits, c->valid.p, nb, cudaMemcpyDeviceToHost, s));
+    else memset(validity_bits, 0xff, nb);
+  }
+  sync();
+  B2_CATCH
+}
+
+int b2_column_incref(b2_handle h) {
+  B2_TRY
+  col_incref(col_from(h));
+  B2_CATCH
+}
+int b2_column_close(b2_handle h) {
+  B2_TRY
+  col_release(col_from(h));
+  B2_CATCH
+}
+
+int b2_column_from_scalar(int32_t dtype, int32_t scale, int64_t size, const void* value16,
+                          int32_t is_valid, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(dtype != B2_STRING, "string scalars not supported here");
+  ColGuard g(new_column(dtype, scale, size, !is_valid));
+  uint4 v = {0, 0, 0, 0};
+  if (value16) memcpy(&v, value16, 16);
+  if (size) {
+    fill_kernel<<<grid_for(size, 256), 256, 0, stream()>>>(g.c->data.as<uint8_t>(), size, dtype_width(dtype), v);
+    count_launch();
+  }
+  if (!is_valid) {
+    CUDA_CHECK(cudaMemsetAsync(g.c->valid.p, 0, g.c->valid.bytes, stream()));
+    g.c->null_count = size;
+  }
+  *out = to_handle(g.release());
+  B2_CATCH
+}
+
+int b2_table_create(const b2_handle* cols, int32_t ncols, b2_handle* out) {
+  B2_TRY
+  std::vector<Column*> v;
+  for (int i = 0; i < ncols; i++) v.push_back(col_from(cols[i]));
+  for (auto* c : v) col_incref(c);
+  *out = to_handle(new_table(std::move(v)));
+  B2_CATCH
+}
+int b2_table_num_rows(b2_handle t, int64_t* out) {
+  B2_TRY
+  *out = table_from(t)->rows;
+  B2_CATCH
+}
+int b2_table_num_columns(b2_handle t, int32_t* out) {
+  B2_TRY
+  *out = (int32_t)table_from(t)->cols.size();
+  B2_CATCH
+}
+int b2_table_column(b2_handle t, int32_t i, b2_handle* out) {
+  B2_TRY
+  Table* tb = table_from(t);
+  B2_CHECK(i >= 0 && i < (int)tb->cols.size(), "column index out of range");
+  col_incref(tb->cols[i]);
+  *out = to_handle(tb->cols[i]);
+  B2_CATCH
+}
+int b2_table_incref(b2_handle t) {
+  B2_TRY
+  table_from(t)->refs.fetch_add(1);
+  B2_CATCH
+}
+int b2_table_close(b2_handle t) {
+  B2_TRY
+  table_release(table_from(t));
+  B2_CATCH
+}
+
+struct Event { cudaEvent_t ev; };
+int b2_event_create(b2_handle* out) {
+  B2_TRY
+  stream();
+  Event* e = new Event();
+  CUDA_CHECK(cudaEventCreate(&e->ev));
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_event_record(b2_handle h) {
+  B2_TRY
+  CUDA_CHECK(cudaEventRecord(reinterpret_cast<Event*>((intptr_t)h)->ev, stream()));
+  B2_CATCH
+}
+int b2_event_elapsed_ms(b2_handle a, b2_handle b, float* ms) {
+  B2_TRY
+  Event* ea = reinterpret_cast<Event*>((intptr_t)a);
+  Event* eb = reinterpret_cast<Event*>((intptr_t)b);
+  CUDA_CHECK(cudaEventSynchronize(eb->ev));
+  CUDA_CHECK(cudaEventElapsedTime(ms, ea->ev, eb->ev));
+  B2_CATCH
+}
+int b2_event_close(b2_handle h) {
+  B2_TRY
+  Event* e = reinterpret_cast<Event*>((intptr_t)h);
+  cudaEventDestroy(e->ev);
+  delete e;
+  B2_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,463 @@
+// expr.cu — host side of a1: bound expression trees with Spark types and their compilation into a
+// VM program (vm.cuh).  Mirrors what GpuExpression.convertToAst + ast.CompiledExpression do in
+// the reference (GpuExpressions.scala:197; basicPhysicalOperators.scala:865-884), including the
+// Spark decimal result-type rules the reference applies in arithmetic.scala:411-640
+// (DecimalMultiplyChecks) and Spark's DecimalPrecision.
+#include <algorithm>
+#include <map>
+#include "vm.cuh"
+
+namespace b2 {
+
+struct Expr {
+  std::atomic<int> refs{1};
+  int op = 0;            // 0 = column, -1 = literal, -2 = cast, else b2_expr_op
+  int dtype = B2_INT64, precision = 0, scale = 0;
+  bool nullable = false;
+  int column = -1;
+  int64_t lit_lo = 0, lit_hi = 0;
+  bool lit_null = false;
+  std::vector<Expr*> kids;
+  ~Expr() {
+    for (auto* k : kids)
+      if (k->refs.fetch_sub(1) == 1) delete k;
+  }
+};
+static Expr* expr_from(b2_handle h) {
+  if (!h) throw Error(B2_ERR_INVALID, "null expression handle");
+  return reinterpret_cast<Expr*>((intptr_t)h);
+}
+Program* program_from(b2_handle h) {
+  if (!h) throw Error(B2_ERR_INVALID, "null program handle");
+  return reinterpret_cast<Program*>((intptr_t)h);
+}
+
+static int mt_of(int dtype) {
+  switch (dtype) {
+    case B2_BOOL8: case B2_INT8: return MT_I8;
+    case B2_INT16: return MT_I16;
+    case B2_INT32: case B2_DATE32: case B2_DECIMAL32: return MT_I32;
+    case B2_INT64: case B2_TIMESTAMP_US: case B2_DECIMAL64: return MT_I64;
+    case B2_DECIMAL128: return MT_I128;
+    case B2_FLOAT32: return MT_F32;
+    case B2_FLOAT64: return MT_F64;
+  }
+  throw Error(B2_ERR_UNSUPPORTED, "expression over dtype " + std::to_string(dtype) + " is not supported");
+}
+static int decimal_dtype_for(int precision) {  // DecimalUtil.scala:24-40
+  return precision <= 9 ? B2_DECIMAL32 : (precision <= 18 ? B2_DECIMAL64 : B2_DECIMAL128);
+}
+static int default_precision(int dtype) {
+  switch (dtype) {  // Spark DecimalType.forType
+    case B2_INT8: return 3; case B2_INT16: return 5; case B2_INT32: return 10; case B2_INT64: return 20;
+  }
+  return 0;
+}
+// DecimalType.adjustPrecisionScale (allowPrecisionLoss = true)
+static void adjust_precision_scale(int& p, int& s) {
+  if (p <= 38) return;
+  int int_digits = p - s;
+  int min_scale = std::min(s, 6);
+  int adj = std::max(38 - int_digits, min_scale);
+  p = 38; s = adj;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Val {  // a compiled sub-expression
+  VMOperand o;
+  int mt;
+  int dtype, precision, scale;
+  bool nullable;
+};
+
+struct Compiler {
+  Program* prog;
+  struct Slot { int off; int width; };
+  std::map<int, std::vector<int>> free_slots;  // width -> free offsets
+  int bump = 0;
+  std::vector<int> reg_width;
+  std::vector<bool> reg_pinned;
+
+  int alloc_slot(int width) {
+    auto& fl = free_slots[width];
+    if (!fl.empty()) { int o = fl.back(); fl.pop_back(); return o; }
+    int bytes = width * VM_TILE;
+    bump = (bump + 15) & ~15;
+    int o = bump; bump += bytes;
+    return o;
+  }
+  int alloc_reg(int mt, bool nullable) {
+    int r = (int)reg_width.size();
+    if (r >= VM_MAX_REGS) throw Error(B2_ERR_UNSUPPORTED, "expression needs too many registers");
+    int w = mt_width(mt);
+    reg_width.push_back(w);
+    reg_pinned.push_back(false);
+    prog->hdr.regs[r].off = alloc_slot(w);
+    prog->hdr.regs[r].voff = nullable ? alloc_slot(1) : 0;
+    reg_nullable.push_back(nullable);
+    return r;
+  }
+  std::vector<bool> reg_nullable;
+  void release(const Val& v) {
+    if (v.o.kind != OK_REG) return;
+    int r = v.o.idx;
+    if (reg_pinned[r]) return;
+    free_slots[reg_width[r]].push_back(prog->hdr.regs[r].off);
+    if (reg_nullable[r]) free_slots[1].push_back(prog->hdr.regs[r].voff);
+    reg_pinned[r] = true;  // never release twice
+  }
+
+  static VMOperand none() { VMOperand o; memset(&o, 0, sizeof(o)); return o; }
+  static VMOperand lit(int64_t lo, int64_t hi, bool is_null) {
+    VMOperand o = none(); o.kind = OK_LIT; o.lo = lo; o.hi = hi; o.lit_null = is_null; o.nullable = is_null; return o;
+  }
+
+  Val emit(int op, int mt, int mt2, int out_mt, bool out_nullable, int aux, const Val* a, const Val* b, const Val* c,
+           int dtype, int precision, int scale) {
+    VMInstr ins; memset(&ins, 0, sizeof(ins));
+    ins.op = (uint8_t)op; ins.mt = (uint8_t)mt; ins.mt2 = (uint8_t)mt2; ins.aux = aux;
+    ins.a = a ? a->o : none(); ins.b = b ? b->o : none(); ins.c = c ? c->o : none();
+    // sources may be recycled for the destination: every handler reads a row before writing it
+    if (a) release(*a);
+    if (b) release(*b);
+    if (c) release(*c);
+    int r = alloc_reg(out_mt, out_nullable);
+    ins.dst = r; ins.dst_nullable = out_nullable;
+    prog->code.push_back(ins);
+    Val v; v.o = none(); v.o.kind = OK_REG; v.o.idx = r; v.o.nullable = out_nullable;
+    v.mt = out_mt; v.dtype = dtype; v.precision = precision; v.scale = scale; v.nullable = out_nullable;
+    return v;
+  }
+
+  // literal re-typed to another machine type at compile time
+  static bool retype_literal(Val& v, int to_mt) {
+    if (v.o.kind != OK_LIT) return false;
+    if (v.mt == MT_F32 || v.mt == MT_F64 || to_mt == MT_F32 || to_mt == MT_F64) {
+      double d;
+      if (v.mt == MT_F32) { float f; memcpy(&f, &v.o.lo, 4); d = f; }
+      else if (v.mt == MT_F64) memcpy(&d, &v.o.lo, 8);
+      else d = (double)(int64_t)v.o.lo;
+      if (to_mt == MT_F32) { float f = (float)d; v.o.lo = 0; memcpy(&v.o.lo, &f, 4); v.o.hi = 0; }
+      else if (to_mt == MT_F64) { memcpy(&v.o.lo, &d, 8); v.o.hi = 0; }
+      else return false;
+    } else {
+      // integer widening/narrowing keeps the two's complement value (already sign-extended)
+    }
+    v.mt = to_mt;
+    return true;
+  }
+
+  Val widen_int(Val v, int to_mt) {  // integer machine type change (sign extending / truncating)
+    if (v.mt == to_mt) return v;
+    if (v.o.kind == OK_LIT) { retype_literal(v, to_mt); return v; }
+    return emit(V_CAST, v.mt, to_mt, to_mt, v.nullable, 0, &v, nullptr, nullptr, v.dtype, v.precision, v.scale);
+  }
+
+  // bring a decimal (or integral literal/column) to decimal(precision, scale) in machine type of that precision
+  Val to_decimal(Val v, int precision, int scale, bool check) {
+    int target_dt = decimal_dtype_for(precision);
+    int target_mt = mt_of(target_dt);
+    int from_scale = is_decimal(v.dtype) ? v.scale : 0;
+    int from_prec = is_decimal(v.dtype) ? v.precision : default_precision(v.dtype);
+    if (v.mt == MT_F32 || v.mt == MT_F64) throw Error(B2_ERR_UNSUPPORTED, "float -> decimal cast is not supported");
+    Val cur = v;
+    if (scale >= from_scale) {
+      cur = widen_int(cur, target_mt >= cur.mt ? target_mt : cur.mt);
+      int ds = scale - from_scale;
+      if (ds > 0) {
+        // 10^ds * x can only leave the machine type when its digits exceed what the type holds
+        int max_digits = cur.mt == MT_I32 ? 9 : (cur.mt == MT_I64 ? 18 : 38);
+        bool may_overflow = from_prec + ds > max_digits;
+        cur = emit(V_RESCALE_UP, cur.mt, cur.mt, cur.mt, cur.nullable || may_overflow, ds, &cur, nullptr, nullptr,
+                   target_dt, precision, scale);
+      }
+      if (cur.mt != target_mt) cur = widen_int(cur, target_mt);
+    } else {
+      int ds = from_scale - scale;
+      cur = emit(V_RESCALE_DOWN, cur.mt, cur.mt, cur.mt, cur.nullable, ds, &cur, nullptr, nullptr, target_dt, precision, scale);
+      // after rounding the value has at most from_prec - ds + 1 digits
+      if (target_mt < cur.mt) {
+        if (check && precision < from_prec - ds + 1)
+          cur = emit(V_CHECK_PREC, cur.mt, cur.mt, cur.mt, true, precision, &cur, nullptr, nullptr, target_dt, precision, scale);
+        check = false;
+      }
+      cur = widen_int(cur, target_mt);
+    }
+    if (check && (precision - scale) < (from_prec - from_scale))
+      cur = emit(V_CHECK_PREC, cur.mt, cur.mt, cur.mt, true, precision, &cur, nullptr, nullptr, target_dt, precision, scale);
+    cur.dtype = target_dt; cur.precision = precision; cur.scale = scale;
+    return cur;
+  }
+
+  Val compile(Expr* e) {
+    if (e->op == 0) {  // GpuBoundReference
+      Val v; v.o = none(); v.o.kind = OK_COL; v.o.idx = e->column; v.o.nullable = e->nullable;
+      v.mt = mt_of(e->dtype); v.dtype = e->dtype; v.precision = e->precision; v.scale = e->scale; v.nullable = e->nullable;
+      if (e->column >= VM_MAX_COLS) throw Error(B2_ERR_UNSUPPORTED, "too many input columns");
+      if ((int)prog->col_dtype.size() <= e->column) prog->col_dtype.resize(e->column + 1, -1);
+      if (prog->col_dtype[e->column] >= 0 && prog->col_dtype[e->column] != e->dtype)
+        throw Error(B2_ERR_INVALID, "column bound with two different types");
+      prog->col_dtype[e->column] = e->dtype;
+      return v;
+    }
+    if (e->op == -1) {  // GpuLiteral
+      Val v; v.o = lit(e->lit_lo, e->lit_hi, e->lit_null);
+      v.mt = mt_of(e->dtype); v.dtype = e->dtype; v.precision = e->precision; v.scale = e->scale; v.nullable = e->lit_null;
+      return v;
+    }
+    if (e->op == -2) return compile_cast(e);
+    switch (e->op) {
+      case B2_OP_ADD: case B2_OP_SUB: case B2_OP_MUL: case B2_OP_DIV: case B2_OP_MOD: case B2_OP_PMOD:
+        return compile_arith(e);
+      case B2_OP_EQ: case B2_OP_NE: case B2_OP_LT: case B2_OP_LE: case B2_OP_GT: case B2_OP_GE: case B2_OP_EQ_NULLSAFE:
+        return compile_compare(e);
+      case B2_OP_AND: case B2_OP_OR: {
+        Val a = compile(e->kids[0]), b = compile(e->kids[1]);
+        if (a.dtype != B2_BOOL8 || b.dtype != B2_BOOL8) throw Error(B2_ERR_INVALID, "AND/OR need boolean operands");
+        if (a.o.kind == OK_LIT) std::swap(a, b);
+        return emit(e->op == B2_OP_AND ? V_AND : V_OR, MT_I8, MT_I8, MT_I8, a.nullable || b.nullable, 0, &a, &b, nullptr, B2_BOOL8, 0, 0);
+      }
+      case B2_OP_NOT: {
+        Val a = compile(e->kids[0]);
+        if (a.dtype != B2_BOOL8) throw Error(B2_ERR_INVALID, "NOT needs a boolean operand");
+        return emit(V_NOT, MT_I8, MT_I8, MT_I8, a.nullable, 0, &a, nullptr, nullptr, B2_BOOL8, 0, 0);
+      }
+      case B2_OP_IS_NULL: case B2_OP_IS_NOT_NULL: {
+        Val a = compile(e->kids[0]);
+        return emit(e->op == B2_OP_IS_NULL ? V_ISNULL : V_ISNOTNULL, a.mt, MT_I8, MT_I8, false, 0, &a, nullptr, nullptr, B2_BOOL8, 0, 0);
+      }
+      case B2_OP_NEG: case B2_OP_ABS: {
+        Val a = compile(e->kids[0]);
+        return emit(e->op == B2_OP_NEG ? V_NEG : V_ABS, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, a.precision, a.scale);
+      }
+      case B2_OP_COALESCE: {
+        Val a = compile(e->kids[0]), b = compile(e->kids[1]);
+        unify(a, b);
+        return emit(V_COALESCE, a.mt, a.mt, a.mt, a.nullable && b.nullable, 0, &a, &b, nullptr, a.dtype, a.precision, a.scale);
+      }
+      case B2_OP_IF: {
+        Val p = compile(e->kids[0]), a = compile(e->kids[1]), b = compile(e->kids[2]);
+        if (p.dtype != B2_BOOL8) throw Error(B2_ERR_INVALID, "IF needs a boolean predicate");
+        unify(a, b);
+        return emit(V_IF, a.mt, a.mt, a.mt, a.nullable || b.nullable, 0, &p, &a, &b, a.dtype, a.precision, a.scale);
+      }
+      case B2_OP_NORMALIZE_NAN_ZERO: {
+        Val a = compile(e->kids[0]);
+        if (!is_float(a.dtype)) return a;
+        return emit(V_NORM_NAN_ZERO, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, 0, 0);
+      }
+      case B2_OP_YEAR: {
+        Val a = compile(e->kids[0]);
+        if (a.dtype != B2_DATE32) throw Error(B2_ERR_UNSUPPORTED, "YEAR needs a date");
+        return emit(V_YEAR, MT_I32, MT_I32, MT_I32, a.nullable, 0, &a, nullptr, nullptr, B2_INT32, 0, 0);
+      }
+    }
+    throw Error(B2_ERR_UNSUPPORTED, "expression op " + std::to_string(e->op) + " is not supported");
+  }
+
+  void unify(Val& a, Val& b) {
+    if (is_decimal(a.dtype) && is_decimal(b.dtype)) {
+      int s = std::max(a.scale, b.scale);
+      int p = std::max(a.precision - a.scale, b.precision - b.scale) + s;
+      if (p > 38) throw Error(B2_ERR_UNSUPPORTED, "decimal operands too wide to unify");
+      a = to_decimal(a, p, s, false); b = to_decimal(b, p, s, false);
+      return;
+    }
+    if (a.dtype != b.dtype) throw Error(B2_ERR_INVALID, "operand types differ: " + std::to_string(a.dtype) + " vs " + std::to_string(b.dtype));
+  }
+
+  Val compile_compare(Expr* e) {
+    Val a = compile(e->kids[0]), b = compile(e->kids[1]);
+    unify(a, b);
+    int op = V_EQ + (e->op - B2_OP_EQ);
+    if (a.o.kind == OK_LIT && b.o.kind != OK_LIT) {  // keep the literal on the right
+      std::swap(a, b);
+      switch (op) { case V_LT: op = V_GT; break; case V_LE: op = V_GE; break; case V_GT: op = V_LT; break; case V_GE: op = V_LE; break; }
+    }
+    bool nullable = (a.nullable || b.nullable) && op != V_EQNS;
+    return emit(op, a.mt, MT_I8, MT_I8, nullable, 0, &a, &b, nullptr, B2_BOOL8, 0, 0);
+  }
+
+  Val compile_arith(Expr* e) {
+    Val a = compile(e->kids[0]), b = compile(e->kids[1]);
+    int vop = V_ADD + (e->op - B2_OP_ADD);
+    if (is_decimal(a.dtype) || is_decimal(b.dtype)) {
+      if (!is_decimal(a.dtype)) a = to_decimal(a, default_precision(a.dtype), 0, false);
+      if (!is_decimal(b.dtype)) b = to_decimal(b, default_precision(b.dtype), 0, false);
+      int p1 = a.precision, s1 = a.scale, p2 = b.precision, s2 = b.scale;
+      if (e->op == B2_OP_ADD || e->op == B2_OP_SUB) {
+        int s = std::max(s1, s2);
+        int p = std::max(p1 - s1, p2 - s2) + s + 1;
+        int rp = p, rs = s;
+        adjust_precision_scale(rp, rs);
+        if (rs != s) throw Error(B2_ERR_UNSUPPORTED, "decimal add with precision loss is not supported");
+        a = to_decimal(a, rp, rs, false); b = to_decimal(b, rp, rs, false);
+        bool capped = p > 38;
+        if (a.o.kind == OK_LIT && e->op == B2_OP_ADD) std::swap(a, b);
+        if (a.o.kind == OK_LIT) a = emit(V_MOV, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, a.precision, a.scale);
+        bool nullable = a.nullable || b.nullable || (a.mt == MT_I128 && capped);
+        Val r = emit(vop, a.mt, a.mt, a.mt, nullable, 0, &a, &b, nullptr, decimal_dtype_for(rp), rp, rs);
+        if (capped) r = emit(V_CHECK_PREC, r.mt, r.mt, r.mt, true, 38, &r, nullptr, nullptr, r.dtype, rp, rs);
+        return r;
+      }
+      if (e->op == B2_OP_MUL) {
+        int p = p1 + p2 + 1, s = s1 + s2;
+        int rp = p, rs = s;
+        adjust_precision_scale(rp, rs);
+        int rdt = decimal_dtype_for(rp), rmt = mt_of(rdt);
+        if (a.o.kind == OK_LIT) std::swap(a, b);
+        if (a.o.kind == OK_LIT) a = emit(V_MOV, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, a.precision, a.scale);
+        if (p <= 38) {
+          a = widen_int(a, rmt); b = widen_int(b, rmt);
+          return emit(V_MUL, rmt, rmt, rmt, a.nullable || b.nullable, 0, &a, &b, nullptr, rdt, rp, rs);
+        }
+        a = widen_int(a, MT_I128); b = widen_int(b, MT_I128);
+        return emit(V_MULDEC, MT_I128, MT_I128, MT_I128, true, s - rs, &a, &b, nullptr, B2_DECIMAL128, rp, rs);
+      }
+      throw Error(B2_ERR_UNSUPPORTED, "decimal divide/remainder is not supported yet");
+    }
+    if (a.dtype != b.dtype) throw Error(B2_ERR_INVALID, "arithmetic operand types differ");
+    if (a.dtype == B2_BOOL8 || a.dtype == B2_STRING) throw Error(B2_ERR_INVALID, "arithmetic on non-numeric type");
+    bool commut = e->op == B2_OP_ADD || e->op == B2_OP_MUL;
+    if (a.o.kind == OK_LIT && commut) std::swap(a, b);
+    if (a.o.kind == OK_LIT) a = emit(V_MOV, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, a.precision, a.scale);
+    bool div_like = e->op == B2_OP_DIV || e->op == B2_OP_MOD || e->op == B2_OP_PMOD;
+    return emit(vop, a.mt, a.mt, a.mt, a.nullable || b.nullable || div_like, 0, &a, &b, nullptr, a.dtype, 0, 0);
+  }
+
+  Val compile_cast(Expr* e) {  // GpuCast.scala:295 doCast (numeric subset)
+    Val a = compile(e->kids[0]);
+    int to = e->dtype;
+    if (a.dtype == to && (!is_decimal(to) || (a.precision == e->precision && a.scale == e->scale))) return a;
+    if (to == B2_STRING || a.dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "string casts are not supported");
+    if (is_decimal(to)) {
+      if (a.dtype == B2_BOOL8 || a.dtype == B2_DATE32 || a.dtype == B2_TIMESTAMP_US) throw Error(B2_ERR_UNSUPPORTED, "cast to decimal from this type");
+      return to_decimal(a, e->precision, e->scale, true);
+    }
+    if (is_decimal(a.dtype)) {
+      if (to == B2_FLOAT64 || to == B2_FLOAT32) {
+        Val r = emit(V_DEC2F64, a.mt, MT_F64, MT_F64, a.nullable, a.scale, &a, nullptr, nullptr, B2_FLOAT64, 0, 0);
+        if (to == B2_FLOAT32) r = emit(V_CAST, MT_F64, MT_F32, MT_F32, r.nullable, 0, &r, nullptr, nullptr, B2_FLOAT32, 0, 0);
+        return r;
+      }
+      throw Error(B2_ERR_UNSUPPORTED, "decimal -> integral cast is not supported yet");
+    }
+    int smt = a.mt, dmt = mt_of(to);
+    if (to == B2_BOOL8) {  // x != 0
+      Val z; z.o = lit(0, 0, false); z.mt = smt; z.dtype = a.dtype; z.precision = 0; z.scale = 0; z.nullable = false;
+      return emit(V_NE, smt, MT_I8, MT_I8, a.nullable, 0, &a, &z, nullptr, B2_BOOL8, 0, 0);
+    }
+    if (smt == dmt) { a.dtype = to; return a; }
+    if (a.o.kind == OK_LIT && retype_literal(a, dmt)) { a.dtype = to; return a; }
+    return emit(V_CAST, smt, dmt, dmt, a.nullable, 0, &a, nullptr, nullptr, to, 0, 0);
+  }
+};
+
+static Program* compile_program(const b2_handle* exprs, int n) {
+  if (n <= 0 || n > VM_MAX_OUTS) throw Error(B2_ERR_INVALID, "bad number of output expressions");
+  std::unique_ptr<Program> prog(new Program());
+  memset(&prog->hdr, 0, sizeof(prog->hdr));
+  Compiler cc; cc.prog = prog.get();
+  for (int i = 0; i < n; i++) {
+    Val v = cc.compile(expr_from(exprs[i]));
+    if (v.o.kind == OK_REG) cc.reg_pinned[v.o.idx] = true;  // outputs stay live
+    prog->hdr.outs[i] = v.o;
+    prog->hdr.out_mt[i] = (uint8_t)v.mt;
+    prog->out_dtype.push_back(v.dtype); prog->out_scale.push_back(v.scale); prog->out_precision.push_back(v.precision);
+    prog->out_nullable.push_back(v.nullable);
+  }
+  prog->hdr.ninstr = (int)prog->code.size();
+  prog->hdr.nregs = (int)cc.reg_width.size();
+  prog->hdr.ncols = (int)prog->col_dtype.size();
+  prog->hdr.nouts = n;
+  prog->hdr.smem_bytes = (cc.bump + 15) & ~15;
+  if (prog->hdr.smem_bytes > 200 * 1024) throw Error(B2_ERR_UNSUPPORTED, "expression needs too much shared memory");
+  prog->d_hdr = DevBuf(sizeof(VMProgramHeader));
+  h2d(prog->d_hdr.p, &prog->hdr, 1);
+  prog->d_code = DevBuf(std::max<size_t>(1, prog->code.size()) * sizeof(VMInstr));
+  if (!prog->code.empty()) h2d(prog->d_code.p, prog->code.data(), prog->code.size());
+  sync();
+  return prog.release();
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+int b2_expr_column(int32_t index, int32_t dtype, int32_t precision, int32_t scale, int32_t nullable, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(index >= 0, "negative column index");
+  Expr* e = new Expr();
+  e->op = 0; e->column = index; e->dtype = dtype; e->precision = precision; e->scale = scale; e->nullable = nullable != 0;
+  *out = to_handle(e);
+  B2_CATCH
+}
+
+int b2_expr_literal(int32_t dtype, int32_t precision, int32_t scale, const void* value16, int32_t is_null, b2_handle* out) {
+  B2_TRY
+  Expr* e = new Expr();
+  e->op = -1; e->dtype = dtype; e->precision = precision; e->scale = scale; e->lit_null = is_null != 0; e->nullable = is_null != 0;
+  if (value16) { memcpy(&e->lit_lo, value16, 8); memcpy(&e->lit_hi, (const char*)value16 + 8, 8); }
+  *out = to_handle(e);
+  B2_CATCH
+}
+
+static Expr* make_node(int op, std::initializer_list<b2_handle> kids) {
+  std::unique_ptr<Expr> e(new Expr());
+  e->op = op;
+  for (auto h : kids) { Expr* k = expr_from(h); k->refs.fetch_add(1); e->kids.push_back(k); }
+  return e.release();
+}
+
+int b2_expr_unary(int32_t op, b2_handle child, b2_handle* out) {
+  B2_TRY
+  *out = to_handle(make_node(op, {child}));
+  B2_CATCH
+}
+int b2_expr_binary(int32_t op, b2_handle l, b2_handle r, b2_handle* out) {
+  B2_TRY
+  *out = to_handle(make_node(op, {l, r}));
+  B2_CATCH
+}
+int b2_expr_ternary(int32_t op, b2_handle a, b2_handle b, b2_handle c, b2_handle* out) {
+  B2_TRY
+  *out = to_handle(make_node(op, {a, b, c}));
+  B2_CATCH
+}
+int b2_expr_cast(b2_handle child, int32_t dtype, int32_t precision, int32_t scale, b2_handle* out) {
+  B2_TRY
+  Expr* e = make_node(-2, {child});
+  e->dtype = dtype; e->precision = precision; e->scale = scale;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_expr_close(b2_handle h) {
+  B2_TRY
+  Expr* e = expr_from(h);
+  if (e->refs.fetch_sub(1) == 1) delete e;
+  B2_CATCH
+}
+
+int b2_expr_type(b2_handle h, int32_t* dtype, int32_t* precision, int32_t* scale, int32_t* nullable) {
+  B2_TRY
+  // type inference = compile into a scratch program and read the output descriptor
+  b2_handle hs[1] = {h};
+  std::unique_ptr<Program> p(compile_program(hs, 1));
+  *dtype = p->out_dtype[0]; *precision = p->out_precision[0]; *scale = p->out_scale[0]; *nullable = p->out_nullable[0];
+  B2_CATCH
+}
+
+int b2_program_compile(const b2_handle* exprs, int32_t nexprs, b2_handle* out) {
+  B2_TRY
+  *out = to_handle(compile_program(exprs, nexprs));
+  B2_CATCH
+}
+int b2_program_close(b2_handle h) {
+  B2_TRY
+  delete program_from(h);
+  B2_CATCH
+}
+
+}  // extern "C"
