@@ -454,3 +454,127 @@ class Event:
         if getattr(self, "h", None) is not None and self.h.value:
             lib.b2_event_close(self.h)
             self.h = ctypes.c_int64(0)
+
+
+# ---- a6/a7 joins ----------------------------------------------------------------------------------
+class JoinHashTable:
+    """persistent build-side hash table (built once per build batch)"""
+
+    def __init__(self, build_keys, nulls_equal=False):
+        out = ctypes.c_int64()
+        check(lib.b2_join_build(build_keys.h, int(nulls_equal), ctypes.byref(out)))
+        self.h = ctypes.c_int64(out.value)
+
+    def probe(self, probe_keys, kind=JOIN_INNER):
+        """-> (left_map Column, right_map Column|None)"""
+        lm, rm = ctypes.c_int64(), ctypes.c_int64()
+        check(lib.b2_join_probe(self.h, probe_keys.h, kind, ctypes.byref(lm), ctypes.byref(rm)))
+        return Column(lm.value), (Column(rm.value) if rm.value else None)
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_join_hash_table_close(self.h)
+            self.h = ctypes.c_int64(0)
+
+
+# ---- a8 sort ----------------------------------------------------------------------------------------
+def sort_order(table, keys):
+    """keys: [(column, ascending, nulls_first)] -> INT32 permutation column"""
+    out = ctypes.c_int64()
+    check(lib.b2_sort_order(table.h, _order_args(keys), len(keys), ctypes.byref(out)))
+    return Column(out.value)
+
+
+def order_by(table, keys):
+    out = ctypes.c_int64()
+    check(lib.b2_order_by(table.h, _order_args(keys), len(keys), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def top_n(table, keys, n):
+    out = ctypes.c_int64()
+    check(lib.b2_top_n(table.h, _order_args(keys), len(keys), n, ctypes.byref(out)))
+    return Table(out.value)
+
+
+def merge_sorted(tables, keys):
+    arr = (ctypes.c_int64 * len(tables))(*[t.h.value for t in tables])
+    out = ctypes.c_int64()
+    check(lib.b2_merge_sorted(arr, len(tables), _order_args(keys), len(keys), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def search_bounds(sorted_table, values_table, keys, upper):
+    out = ctypes.c_int64()
+    check(lib.b2_search_bounds(sorted_table.h, values_table.h, _order_args(keys), len(keys), int(upper), ctypes.byref(out)))
+    return Column(out.value)
+
+
+# ---- a9 hash partition ------------------------------------------------------------------------------
+def murmur3(table, cols, seed=42):
+    out = ctypes.c_int64()
+    check(lib.b2_murmur3(table.h, _i32s(cols), len(cols), seed, ctypes.byref(out)))
+    return Column(out.value)
+
+
+def hash_partition(table, key_cols, num_partitions, seed=42):
+    """-> (partitioned Table, offsets list[num_partitions+1])"""
+    out = ctypes.c_int64()
+    offs = (ctypes.c_int32 * (num_partitions + 1))()
+    check(lib.b2_hash_partition(table.h, _i32s(key_cols), len(key_cols), seed, num_partitions, ctypes.byref(out), offs))
+    return Table(out.value), list(offs)
+
+
+def partition_by_ids(table, part_ids, num_partitions):
+    out = ctypes.c_int64()
+    offs = (ctypes.c_int32 * (num_partitions + 1))()
+    check(lib.b2_partition_by_ids(table.h, part_ids.h, num_partitions, ctypes.byref(out), offs))
+    return Table(out.value), list(offs)
+
+
+# ---- a11 rows ---------------------------------------------------------------------------------------
+def table_to_rows(table):
+    """-> (numpy uint8 [nrows, row_bytes])"""
+    rb = ctypes.c_int32()
+    check(lib.b2_rows_size(table.h, ctypes.byref(rb)))
+    n = table.num_rows
+    buf = np.zeros((n, rb.value), dtype=np.uint8)
+    check(lib.b2_table_to_rows(table.h, _ptr(buf), buf.nbytes))
+    return buf
+
+
+def table_from_rows(rows, dtypes, scales=None):
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    scales = scales or [0] * len(dtypes)
+    out = ctypes.c_int64()
+    check(lib.b2_table_from_rows(_ptr(rows), rows.shape[0], _i32s(dtypes), _i32s(scales), len(dtypes), ctypes.byref(out)))
+    return Table(out.value)
+
+
+# ---- (e) exchange -----------------------------------------------------------------------------------
+class Comm:
+    """NCCL communicator for the shuffle exchange; the unique id is broadcast by the caller
+    (torch.distributed / any rendezvous)."""
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        check(lib.b2_comm_unique_id(_ptr(buf)))
+        return buf
+
+    def __init__(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        out = ctypes.c_int64()
+        check(lib.b2_comm_init(_ptr(uid), rank, world, ctypes.byref(out)))
+        self.h = ctypes.c_int64(out.value)
+        self.rank, self.world = rank, world
+
+    def exchange(self, partitioned_table, offsets):
+        out = ctypes.c_int64()
+        check(lib.b2_exchange(self.h, partitioned_table.h, _i32s(offsets), ctypes.byref(out)))
+        return Table(out.value)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_comm_close(self.h)
+            self.h = ctypes.c_int64(0)

@@ -114,6 +114,8 @@ struct Compiler {
 
   Val emit(int op, int mt, int mt2, int out_mt, bool out_nullable, int aux, const Val* a, const Val* b, const Val* c,
            int dtype, int precision, int scale) {
+    for (const Val* v : {a, b, c})
+      if (v && v->dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "string expressions are not supported yet");
     VMInstr ins; memset(&ins, 0, sizeof(ins));
     ins.op = (uint8_t)op; ins.mt = (uint8_t)mt; ins.mt2 = (uint8_t)mt2; ins.aux = aux;
     ins.a = a ? a->o : none(); ins.b = b ? b->o : none(); ins.c = c ? c->o : none();
@@ -192,7 +194,9 @@ struct Compiler {
   Val compile(Expr* e) {
     if (e->op == 0) {  // GpuBoundReference
       Val v; v.o = none(); v.o.kind = OK_COL; v.o.idx = e->column; v.o.nullable = e->nullable;
-      v.mt = mt_of(e->dtype); v.dtype = e->dtype; v.precision = e->precision; v.scale = e->scale; v.nullable = e->nullable;
+      // strings can only pass through (group-by keys / filter payload); they never enter the VM
+      v.mt = e->dtype == B2_STRING ? MT_I8 : mt_of(e->dtype);
+      v.dtype = e->dtype; v.precision = e->precision; v.scale = e->scale; v.nullable = e->nullable;
       if (e->column >= VM_MAX_COLS) throw Error(B2_ERR_UNSUPPORTED, "too many input columns");
       if ((int)prog->col_dtype.size() <= e->column) prog->col_dtype.resize(e->column + 1, -1);
       if (prog->col_dtype[e->column] >= 0 && prog->col_dtype[e->column] != e->dtype)
@@ -256,6 +260,7 @@ struct Compiler {
   }
 
   void unify(Val& a, Val& b) {
+    if (a.dtype == B2_STRING || b.dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "string expressions are not supported yet");
     if (is_decimal(a.dtype) && is_decimal(b.dtype)) {
       int s = std::max(a.scale, b.scale);
       int p = std::max(a.precision - a.scale, b.precision - b.scale) + s;

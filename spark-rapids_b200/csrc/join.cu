@@ -1,0 +1,171 @@
+// join.cu — a6: hash join build / probe producing gather maps.
+// Reference: JoinImpl.innerHashJoin{BuildLeft,BuildRight} -> JoinPrimitives.hashInnerJoin
+// (GpuHashJoin.scala:309-409), leftJoin/leftSemi/leftAnti gather maps (:466-600),
+// JoinPrimitives.makeLeftOuter/makeSemi/makeAnti (:256-302), null-key rules (:602-640),
+// HashJoinIterator (:1374-1553), build-side null filtering (GpuShuffledHashJoinExec.scala:207-212).
+//
+// The reference API takes both key tables on every call, so the hash table is rebuilt for every
+// stream batch.  Here the build side is hashed ONCE into a persistent open-addressing multimap
+// (8-byte slots: 32-bit hash tag + 32-bit build row) that any number of probe calls reuse.
+// Probe is count -> scan -> write so the gather maps are exactly sized and ordered by stream row.
+#include "prim.cuh"
+#include "rowops.cuh"
+
+namespace b2 {
+
+constexpr uint64_t JSLOT_EMPTY = 0xffffffffffffffffull;
+
+struct JoinTable {
+  Table* keys;        // one reference on the build key table
+  DevBuf slots;       // uint64 [cap]
+  int64_t cap;
+  int64_t build_rows;
+  bool nulls_equal;
+  std::vector<int> key_idx;
+  ~JoinTable() { if (keys) table_release(keys); }
+};
+
+__device__ __forceinline__ bool any_null_key(const KeyCols& k, int64_t r) {
+  for (int i = 0; i < k.n; i++) if (!row_valid(k.c[i].valid, r)) return true;
+  return false;
+}
+
+__global__ void join_build_kernel(const __grid_constant__ KeyCols keys, int64_t n, uint64_t* __restrict__ slots, uint32_t mask, bool nulls_equal) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    if (!nulls_equal && any_null_key(keys, r)) continue;  // a NULL key can never match: keep it out of the table
+    const uint32_t h = row_hash(keys, r);
+    const uint64_t entry = ((uint64_t)h << 32) | (uint32_t)r;
+    uint32_t idx = h & mask;
+    while (true) {
+      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&slots[idx]), (unsigned long long)JSLOT_EMPTY, (unsigned long long)entry);
+      if (old == JSLOT_EMPTY) break;
+      idx = (idx + 1) & mask;
+    }
+  }
+}
+
+// MODE 0: count matches per probe row; MODE 1: write pairs at offsets
+template <int MODE>
+__global__ void join_probe_kernel(const __grid_constant__ KeyCols probe, const __grid_constant__ KeyCols build, int64_t n,
+                                  const uint64_t* __restrict__ slots, uint32_t mask, bool nulls_equal, int kind,
+                                  int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                  int32_t* __restrict__ left_map, int32_t* __restrict__ right_map) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int32_t matches = 0;
+    int64_t o = MODE == 1 ? offsets[r] : 0;
+    const bool semi_like = kind == B2_JOIN_LEFT_SEMI || kind == B2_JOIN_LEFT_ANTI;
+    if (nulls_equal || !any_null_key(probe, r)) {
+      const uint32_t h = row_hash(probe, r);
+      uint32_t idx = h & mask;
+      while (true) {
+        const uint64_t e = slots[idx];
+        if (e == JSLOT_EMPTY) break;
+        if ((uint32_t)(e >> 32) == h) {
+          const int32_t br = (int32_t)(uint32_t)e;
+          if (rows_equal(probe, r, build, br, nulls_equal)) {
+            if (MODE == 1 && !semi_like) { left_map[o + matches] = (int32_t)r; right_map[o + matches] = br; }
+            matches++;
+            if (semi_like) break;
+          }
+        }
+        idx = (idx + 1) & mask;
+      }
+    }
+    int32_t emit;
+    switch (kind) {
+      case B2_JOIN_INNER: emit = matches; break;
+      case B2_JOIN_LEFT_OUTER: emit = matches > 0 ? matches : 1; break;
+      case B2_JOIN_LEFT_SEMI: emit = matches > 0 ? 1 : 0; break;
+      default: emit = matches > 0 ? 0 : 1; break;  // LEFT_ANTI
+    }
+    if (MODE == 0) counts[r] = emit;
+    else {
+      if (semi_like) { if (emit) left_map[o] = (int32_t)r; }
+      else if (kind == B2_JOIN_LEFT_OUTER && matches == 0) { left_map[o] = (int32_t)r; right_map[o] = INT32_MIN; }
+    }
+  }
+}
+
+static JoinTable* jt_from(b2_handle h) {
+  if (!h) throw Error(B2_ERR_INVALID, "null hash table handle");
+  return reinterpret_cast<JoinTable*>((intptr_t)h);
+}
+
+}  // namespace b2
+
+using namespace b2;
+extern "C" {
+
+int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* out_hash_table) {
+  B2_TRY
+  Table* t = table_from(build_keys_table);
+  B2_CHECK(!t->cols.empty() && (int)t->cols.size() <= MAX_KEYS, "join needs 1..8 key columns");
+  std::unique_ptr<JoinTable> jt(new JoinTable());
+  t->refs.fetch_add(1);
+  jt->keys = t;
+  jt->build_rows = t->rows;
+  jt->nulls_equal = nulls_equal != 0;
+  for (int i = 0; i < (int)t->cols.size(); i++) jt->key_idx.push_back(i);
+  int64_t cap = 1024;
+  while (cap < t->rows * 2) cap <<= 1;
+  jt->cap = cap;
+  jt->slots = DevBuf((size_t)cap * 8);
+  CUDA_CHECK(cudaMemsetAsync(jt->slots.p, 0xff, (size_t)cap * 8, stream()));
+  if (t->rows) {
+    KeyCols keys = key_cols_of(t, jt->key_idx.data(), (int)jt->key_idx.size());
+    join_build_kernel<<<grid_for(t->rows, 256), 256, 0, stream()>>>(keys, t->rows, jt->slots.as<uint64_t>(), (uint32_t)(cap - 1), jt->nulls_equal);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  *out_hash_table = to_handle(jt.release());
+  B2_CATCH
+}
+
+int b2_join_hash_table_close(b2_handle ht) {
+  B2_TRY
+  delete jt_from(ht);
+  B2_CATCH
+}
+
+int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_handle* out_left_map, b2_handle* out_right_map) {
+  B2_TRY
+  JoinTable* jt = jt_from(ht);
+  Table* pt = table_from(probe_keys_table);
+  B2_CHECK(pt->cols.size() == jt->keys->cols.size(), "probe and build key counts differ");
+  for (size_t i = 0; i < pt->cols.size(); i++)
+    B2_CHECK(pt->cols[i]->dtype == jt->keys->cols[i]->dtype, "probe and build key dtypes differ");
+  if (kind == B2_JOIN_FULL_OUTER) throw Error(B2_ERR_UNSUPPORTED, "full outer join is not supported yet");
+  B2_CHECK(kind >= B2_JOIN_INNER && kind <= B2_JOIN_LEFT_ANTI, "bad join kind");
+  const int64_t n = pt->rows;
+  const bool semi_like = kind == B2_JOIN_LEFT_SEMI || kind == B2_JOIN_LEFT_ANTI;
+  KeyCols pk = key_cols_of(pt, jt->key_idx.data(), (int)jt->key_idx.size());
+  KeyCols bk = key_cols_of(jt->keys, jt->key_idx.data(), (int)jt->key_idx.size());
+  DevBuf counts((size_t)std::max<int64_t>(n, 1) * 4), offsets((size_t)(n + 1) * 8);
+  int64_t total = 0;
+  if (n) {
+    join_probe_kernel<0><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, kind,
+                                                                  counts.as<int32_t>(), nullptr, nullptr, nullptr);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    exclusive_scan<int32_t, int64_t>(counts.as<int32_t>(), offsets.as<int64_t>(), n, true);
+    d2h(&total, offsets.as<int64_t>() + n, 1);
+    sync();
+  }
+  // the reference splits the stream batch when the maps would pass the batch target
+  // (AbstractGpuJoinIterator.scala:235-250); the hard limit here is the int32 row index
+  if (total > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "join output exceeds 2^31-1 rows; split the stream batch");
+  ColGuard lm(new_column(B2_INT32, 0, total, false));
+  ColGuard rm(semi_like ? nullptr : new_column(B2_INT32, 0, total, false));
+  if (n && total) {
+    join_probe_kernel<1><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, kind,
+                                                                  nullptr, offsets.as<int64_t>(), lm.c->data.as<int32_t>(),
+                                                                  semi_like ? nullptr : rm.c->data.as<int32_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  *out_left_map = to_handle(lm.release());
+  if (out_right_map) *out_right_map = semi_like ? 0 : to_handle(rm.release());
+  B2_CATCH
+}
+
+}  // extern "C"
