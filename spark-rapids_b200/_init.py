@@ -578,3 +578,23 @@ class Comm:
         if getattr(self, "h", None) is not None and self.h.value:
             lib.b2_comm_close(self.h)
             self.h = ctypes.c_int64(0)
+
+
+# ---- a10 parquet ------------------------------------------------------------------------------------
+def parquet_decode(buf, columns):
+    """buf: bytes / numpy uint8 holding the reassembled mini file (PAR1 ... footer len PAR1);
+    columns: names in output order.  H2D copy happens inside the call."""
+    arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    names = (ctypes.c_char_p * len(columns))(*[c.encode() for c in columns])
+    out = ctypes.c_int64()
+    check(lib.b2_parquet_decode(_ptr(arr), arr.nbytes, names, len(columns), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def parquet_decode_device(buf, dev_ptr, columns):
+    """same, with the file bytes already resident in device memory at dev_ptr (>= 16 bytes of slack after the end)"""
+    arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    names = (ctypes.c_char_p * len(columns))(*[c.encode() for c in columns])
+    out = ctypes.c_int64()
+    check(lib.b2_parquet_decode_device(_ptr(arr), ctypes.c_void_p(dev_ptr), arr.nbytes, names, len(columns), ctypes.byref(out)))
+    return Table(out.value)

@@ -185,7 +185,8 @@ struct Compiler {
       }
       cur = widen_int(cur, target_mt);
     }
-    if (check && (precision - scale) < (from_prec - from_scale))
+    // HALF_UP rounding on a scale decrease can carry into one more integer digit
+    if (check && (precision - scale) < (from_prec - from_scale) + (scale < from_scale ? 1 : 0))
       cur = emit(V_CHECK_PREC, cur.mt, cur.mt, cur.mt, true, precision, &cur, nullptr, nullptr, target_dt, precision, scale);
     cur.dtype = target_dt; cur.precision = precision; cur.scale = scale;
     return cur;

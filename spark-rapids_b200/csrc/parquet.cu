@@ -1,0 +1,814 @@
+// parquet.cu — a10: Parquet -> device columns (Table.readParquet(ParquetOptions, HostMemoryBuffer)).
+// Reference: MakeParquetTableProducer / ParquetTableReader (GpuParquetScan.scala:3322-3503), host
+// reassembly readPartFile (:2089-2127: "PAR1" + needed column chunks + rewritten footer + len +
+// "PAR1"), getParquetOptions (:2234-2244: columns selected by name, in includeColumn order),
+// timestamps delivered as microseconds.  The file format is Apache Parquet (external spec).
+//
+// Host: parse the thrift-compact footer and walk every page header of the selected column chunks
+// (headers are tiny; payloads are never touched on the CPU).  Device: (1) snappy-decompress all
+// pages, one warp per page; (2) decode definition levels (RLE / bit-packed hybrid) per page;
+// (3) decode values per page — PLAIN, PLAIN/RLE_DICTIONARY, FIXED_LEN_BYTE_ARRAY decimals — with
+// one CTA per page: one thread parses a batch of run headers, all warps expand the runs;
+// (4) strings: lengths -> scan -> chars copy; (5) only if a column really has NULLs, scatter the
+// dense values to their rows.  Flat schemas (what Spark/TPC-H tables are); nested -> UNSUPPORTED.
+#include <map>
+#include "prim.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------
+// thrift compact protocol reader (host)
+struct TReader {
+  const uint8_t* p;
+  const uint8_t* end;
+  explicit TReader(const uint8_t* b, const uint8_t* e) : p(b), end(e) {}
+  uint8_t byte() { if (p >= end) throw Error(B2_ERR_INVALID, "parquet: truncated thrift data"); return *p++; }
+  uint64_t varint() {
+    uint64_t v = 0; int shift = 0;
+    while (true) { uint8_t b = byte(); v |= (uint64_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; if (shift > 63) throw Error(B2_ERR_INVALID, "parquet: bad varint"); }
+    return v;
+  }
+  int64_t zigzag() { uint64_t v = varint(); return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
+  std::string str() { uint64_t n = varint(); if ((uint64_t)(end - p) < n) throw Error(B2_ERR_INVALID, "parquet: truncated string"); std::string s((const char*)p, n); p += n; return s; }
+  // field header: returns false at STOP.  type: 1/2 bool true/false, 3 i8, 4 i16, 5 i32, 6 i64, 7 double, 8 binary, 9 list, 10 set, 11 map, 12 struct
+  bool field(int& id, int& type, int& last) {
+    uint8_t b = byte();
+    if (b == 0) return false;
+    type = b & 0x0f;
+    int delta = b >> 4;
+    if (delta) id = last + delta; else id = (int)zigzag();
+    last = id;
+    return true;
+  }
+  void list_header(int& n, int& etype) { uint8_t b = byte(); etype = b & 0x0f; n = b >> 4; if (n == 15) n = (int)varint(); }
+  void skip(int type) {
+    switch (type) {
+      case 1: case 2: break;
+      case 3: byte(); break;
+      case 4: case 5: case 6: zigzag(); break;
+      case 7: for (int i = 0; i < 8; i++) byte(); break;
+      case 8: str(); break;
+      case 9: case 10: { int n, et; list_header(n, et); for (int i = 0; i < n; i++) skip(et == 1 || et == 2 ? 3 : et); } break;
+      case 11: { uint64_t n = varint(); if (n) { uint8_t kv = byte(); for (uint64_t i = 0; i < n; i++) { skip(kv >> 4); skip(kv & 15); } } } break;
+      case 12: { int id, t, last = 0; while (field(id, t, last)) skip(t); } break;
+      default: throw Error(B2_ERR_INVALID, "parquet: unknown thrift type");
+    }
+  }
+};
+
+enum { PT_BOOLEAN = 0, PT_INT32 = 1, PT_INT64 = 2, PT_INT96 = 3, PT_FLOAT = 4, PT_DOUBLE = 5, PT_BYTE_ARRAY = 6, PT_FLBA = 7 };
+enum { ENC_PLAIN = 0, ENC_PLAIN_DICT = 2, ENC_RLE = 3, ENC_BIT_PACKED = 4, ENC_RLE_DICT = 8 };
+enum { PG_DATA = 0, PG_INDEX = 1, PG_DICT = 2, PG_DATA_V2 = 3 };
+enum { CODEC_NONE = 0, CODEC_SNAPPY = 1 };
+
+struct SchemaElem {
+  int type = -1, type_length = 0, repetition = 0, num_children = 0, converted = -1, scale = 0, precision = 0;
+  std::string name;
+  bool lt_decimal = false, lt_date = false, lt_timestamp = false, lt_string = false;
+  int lt_ts_unit = 0;  // 1 millis 2 micros 3 nanos
+  int lt_int_bits = 0;
+};
+struct ChunkMeta {
+  int type = -1, codec = 0;
+  int64_t num_values = 0, total_compressed = 0, data_page_offset = 0, dict_page_offset = -1;
+  std::vector<std::string> path;
+};
+struct RowGroupMeta { int64_t num_rows = 0; std::vector<ChunkMeta> chunks; };
+struct FileMeta { std::vector<SchemaElem> schema; int64_t num_rows = 0; std::vector<RowGroupMeta> row_groups; };
+
+static void parse_logical_type(TReader& r, SchemaElem& e) {
+  int id, t, last = 0;
+  while (r.field(id, t, last)) {
+    if (t != 12) { r.skip(t); continue; }
+    int id2, t2, last2 = 0;
+    switch (id) {
+      case 1: e.lt_string = true; r.skip(12); break;
+      case 5: e.lt_decimal = true; while (r.field(id2, t2, last2)) { if (id2 == 1) e.scale = (int)r.zigzag(); else if (id2 == 2) e.precision = (int)r.zigzag(); else r.skip(t2); } break;
+      case 6: e.lt_date = true; r.skip(12); break;
+      case 8:
+        e.lt_timestamp = true;
+        while (r.field(id2, t2, last2)) {
+          if (id2 == 2 && t2 == 12) { int id3, t3, last3 = 0; while (r.field(id3, t3, last3)) { e.lt_ts_unit = id3; r.skip(t3); } }
+          else r.skip(t2);
+        }
+        break;
+      case 10: while (r.field(id2, t2, last2)) { if (id2 == 1) e.lt_int_bits = (int8_t)r.byte(); else r.skip(t2); } break;
+      default: r.skip(12); break;
+    }
+  }
+}
+
+static FileMeta parse_footer(const uint8_t* buf, int64_t len) {
+  if (len < 12 || memcmp(buf, "PAR1", 4) != 0 || memcmp(buf + len - 4, "PAR1", 4) != 0) throw Error(B2_ERR_INVALID, "parquet: missing PAR1 magic");
+  uint32_t flen;
+  memcpy(&flen, buf + len - 8, 4);
+  if ((int64_t)flen + 12 > len) throw Error(B2_ERR_INVALID, "parquet: bad footer length");
+  TReader r(buf + len - 8 - flen, buf + len - 8);
+  FileMeta fm;
+  int id, t, last = 0;
+  while (r.field(id, t, last)) {
+    if (id == 2 && t == 9) {
+      int n, et; r.list_header(n, et);
+      for (int i = 0; i < n; i++) {
+        SchemaElem e; int id2, t2, last2 = 0;
+        while (r.field(id2, t2, last2)) {
+          switch (id2) {
+            case 1: e.type = (int)r.zigzag(); break;
+            case 2: e.type_length = (int)r.zigzag(); break;
+            case 3: e.repetition = (int)r.zigzag(); break;
+            case 4: e.name = r.str(); break;
+            case 5: e.num_children = (int)r.zigzag(); break;
+            case 6: e.converted = (int)r.zigzag(); break;
+            case 7: e.scale = (int)r.zigzag(); break;
+            case 8: e.precision = (int)r.zigzag(); break;
+            case 10: if (t2 == 12) parse_logical_type(r, e); else r.skip(t2); break;
+            default: r.skip(t2); break;
+          }
+        }
+        fm.schema.push_back(e);
+      }
+    } else if (id == 3) {
+      fm.num_rows = r.zigzag();
+    } else if (id == 4 && t == 9) {
+      int n, et; r.list_header(n, et);
+      for (int i = 0; i < n; i++) {
+        RowGroupMeta rg; int id2, t2, last2 = 0;
+        while (r.field(id2, t2, last2)) {
+          if (id2 == 1 && t2 == 9) {
+            int nc, ect; r.list_header(nc, ect);
+            for (int c = 0; c < nc; c++) {
+              ChunkMeta cm; int id3, t3, last3 = 0;
+              while (r.field(id3, t3, last3)) {
+                if (id3 == 3 && t3 == 12) {
+                  int id4, t4, last4 = 0;
+                  while (r.field(id4, t4, last4)) {
+                    switch (id4) {
+                      case 1: cm.type = (int)r.zigzag(); break;
+                      case 3: { int np, pt; r.list_header(np, pt); for (int k = 0; k < np; k++) cm.path.push_back(r.str()); } break;
+                      case 4: cm.codec = (int)r.zigzag(); break;
+                      case 5: cm.num_values = r.zigzag(); break;
+                      case 7: cm.total_compressed = r.zigzag(); break;
+                      case 9: cm.data_page_offset = r.zigzag(); break;
+                      case 11: cm.dict_page_offset = r.zigzag(); break;
+                      default: r.skip(t4); break;
+                    }
+                  }
+                } else r.skip(t3);
+              }
+              rg.chunks.push_back(cm);
+            }
+          } else if (id2 == 3) rg.num_rows = r.zigzag();
+          else r.skip(t2);
+        }
+        fm.row_groups.push_back(rg);
+      }
+    } else r.skip(t);
+  }
+  return fm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side descriptors
+struct PageD {
+  int64_t src_off;      // payload offset in the file buffer
+  int64_t dst_off;      // payload offset in the scratch buffer (-1: read in place from the file buffer)
+  int32_t comp_size, uncomp_size;
+  int32_t num_values;   // rows in the page (nulls included)
+  int32_t encoding;
+  int32_t kind;         // PG_*
+  int32_t chunk;        // index into ChunkD
+  int32_t lvl_bytes;    // v2: bytes of (uncompressed) rep+def levels in front of the values
+  int32_t compressed;   // payload (v2: the part after the levels) is snappy compressed
+  int64_t row_start;    // first row of this page inside the output column
+  int64_t value_base;   // first dense value of this page inside the column
+};
+struct ChunkD {
+  int32_t col;          // output column
+  int32_t phys;         // PT_*
+  int32_t type_length;
+  int32_t max_def;      // 0 REQUIRED, 1 OPTIONAL
+  int32_t dict_page;    // page index or -1
+  int32_t dict_count;
+  int64_t dict_str_off; // strings: first entry of this chunk in the dictionary offset arrays
+};
+struct ColD {
+  int32_t out_dtype, out_width;
+  int32_t phys, type_length;
+  int32_t conv;         // 0 copy, 1 *1000 (millis -> micros), 2 big-endian FLBA -> integer, 3 narrow int32, 4 boolean bits, 5 string
+  void* dense;          // fixed width: dense values
+  int64_t* str_src;     // strings: absolute source address of each value's bytes
+  int32_t* str_len;
+  uint8_t* lvl;         // per-row validity bytes (max_def > 0)
+};
+
+__device__ __forceinline__ const uint8_t* page_ptr(const PageD& pg, const uint8_t* file, const uint8_t* scratch) {
+  return pg.dst_off >= 0 ? scratch + pg.dst_off : file + pg.src_off;
+}
+
+// ---- snappy: one warp per page ------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t len, int lane) {
+  for (uint32_t k = lane; k < len; k += 32) dst[k] = src[k];
+}
+__global__ void __launch_bounds__(128) snappy_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, int ntodo,
+                                                     const uint8_t* __restrict__ file, uint8_t* __restrict__ scratch, int32_t* __restrict__ errors) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= ntodo) return;
+  const PageD pg = pages[todo[w]];
+  const uint8_t* in = file + pg.src_off;
+  uint8_t* out = scratch + pg.dst_off;
+  uint32_t in_len = (uint32_t)pg.comp_size, out_len = (uint32_t)pg.uncomp_size;
+  if (pg.lvl_bytes) {  // v2: levels are stored uncompressed in front of the compressed values
+    warp_copy(out, in, (uint32_t)pg.lvl_bytes, lane);
+    in += pg.lvl_bytes; out += pg.lvl_bytes; in_len -= pg.lvl_bytes; out_len -= pg.lvl_bytes;
+  }
+  uint32_t ip = 0, op = 0;
+  // preamble: uncompressed length varint
+  uint32_t ulen = 0;
+  { int shift = 0; while (ip < in_len) { uint8_t b = in[ip++]; ulen |= (uint32_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; } }
+  bool bad = ulen != out_len;
+  while (!bad && ip < in_len && op < out_len) {
+    // lane 0 decodes the element header, everyone copies
+    uint32_t len = 0, off = 0, hdr = 0;
+    if (lane == 0) {
+      const uint8_t tag = in[ip];
+      const uint32_t t = tag & 3;
+      if (t == 0) {
+        len = tag >> 2;
+        if (len < 60) { len += 1; hdr = 1; }
+        else { const uint32_t nb = len - 59; uint32_t v = 0; for (uint32_t k = 0; k < nb; k++) v |= (uint32_t)in[ip + 1 + k] << (8 * k); len = v + 1; hdr = 1 + nb; }
+      } else if (t == 1) { len = 4 + ((tag >> 2) & 7); off = ((uint32_t)(tag >> 5) << 8) | in[ip + 1]; hdr = 2; }
+      else if (t == 2) { len = (tag >> 2) + 1; off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8); hdr = 3; }
+      else { len = (tag >> 2) + 1; off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8) | ((uint32_t)in[ip + 3] << 16) | ((uint32_t)in[ip + 4] << 24); hdr = 5; }
+    }
+    len = __shfl_sync(0xffffffffu, len, 0); off = __shfl_sync(0xffffffffu, off, 0); hdr = __shfl_sync(0xffffffffu, hdr, 0);
+    if (off == 0) {  // literal
+      if (ip + hdr + len > in_len || op + len > out_len) { bad = true; break; }
+      warp_copy(out + op, in + ip + hdr, len, lane);
+      ip += hdr + len;
+    } else {  // copy from `off` bytes back; overlapping copies repeat with period `off`
+      if (off > op || op + len > out_len) { bad = true; break; }
+      const uint8_t* src = out + op - off;
+      for (uint32_t k = lane; k < len; k += 32) out[op + k] = src[off >= len ? k : k % off];
+      ip += hdr;
+    }
+    op += len;
+    __syncwarp();
+  }
+  if ((bad || op != out_len) && lane == 0) atomicExch(errors, 1);
+}
+
+// ---- RLE / bit-packed hybrid ---------------------------------------------------------------------
+struct RunD { int32_t start, count, packed; uint32_t value; const uint8_t* data; };
+constexpr int PQ_NT = 256;
+constexpr int PQ_RUNS = 64;
+
+__device__ __forceinline__ uint32_t extract_bits(const uint8_t* data, uint64_t bitpos, int bw) {
+  const uint8_t* a = data + (bitpos >> 3);
+  const uintptr_t base = reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)7;
+  const uint64_t w0 = *reinterpret_cast<const uint64_t*>(base), w1 = *reinterpret_cast<const uint64_t*>(base + 8);
+  const int sh = (int)((reinterpret_cast<uintptr_t>(a) & 7) * 8 + (bitpos & 7));
+  uint64_t v = w0 >> sh;
+  if (sh) v |= w1 << (64 - sh);
+  return (uint32_t)(v & ((bw >= 32) ? 0xffffffffull : ((1ull << bw) - 1)));
+}
+
+// CTA-cooperative decode of `count` values; Sink::put(k, v) is called once per value by some thread
+template <typename Sink>
+__device__ void decode_hybrid(const uint8_t* p, const uint8_t* end, int bw, int count, Sink& sink) {
+  __shared__ RunD s_runs[PQ_RUNS];
+  __shared__ int s_nruns, s_done;
+  __shared__ const uint8_t* s_pos;
+  if (threadIdx.x == 0) { s_pos = p; s_done = 0; }
+  __syncthreads();
+  const int vbytes = (bw + 7) >> 3;
+  while (true) {
+    if (threadIdx.x == 0) {
+      const uint8_t* q = s_pos;
+      int done = s_done, n = 0;
+      while (n < PQ_RUNS && done < count && q < end) {
+        uint32_t h = 0; int shift = 0;
+        while (q < end) { uint8_t b = *q++; h |= (uint32_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; }
+        RunD r; r.start = done;
+        if (h & 1) { const int groups = (int)(h >> 1); r.packed = 1; r.count = min(groups * 8, count - done); r.data = q; r.value = 0; q += (size_t)groups * bw; }
+        else { r.packed = 0; r.count = min((int)(h >> 1), count - done); uint32_t v = 0; for (int k = 0; k < vbytes && q < end; k++) v |= (uint32_t)(*q++) << (8 * k); r.value = v; r.data = nullptr; }
+        if (r.count <= 0) { if (!(h & 1) && (h >> 1) == 0) { done = count; } break; }
+        done += r.count;
+        s_runs[n++] = r;
+      }
+      if (n == 0) done = count;  // malformed / exhausted stream: stop
+      s_nruns = n; s_done = done; s_pos = q;
+    }
+    __syncthreads();
+    const int n = s_nruns;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < n; r += PQ_NT / 32) {
+      const RunD run = s_runs[r];
+      if (run.packed) for (int k = lane; k < run.count; k += 32) sink.put(run.start + k, extract_bits(run.data, (uint64_t)k * bw, bw));
+      else for (int k = lane; k < run.count; k += 32) sink.put(run.start + k, run.value);
+    }
+    __syncthreads();
+    if (s_done >= count) break;
+  }
+}
+
+// ---- pass 1: definition levels -> per-row validity bytes + per-page non-null count ---------------
+struct LevelSink {
+  uint8_t* lvl; int max_def; unsigned int* cnt;
+  __device__ __forceinline__ void put(int k, uint32_t v) { const bool ok = (int)v == max_def; lvl[k] = ok; if (ok) atomicAdd(cnt, 1u); }
+};
+__device__ __forceinline__ const uint8_t* levels_of(const PageD& pg, const uint8_t* d, const uint8_t*& lv_end, const uint8_t*& values) {
+  if (pg.kind == PG_DATA_V2) { lv_end = d + pg.lvl_bytes; values = d + pg.lvl_bytes; return d; }
+  uint32_t n; memcpy(&n, d, 4);
+  lv_end = d + 4 + n; values = d + 4 + n;
+  return d + 4;
+}
+__global__ void __launch_bounds__(PQ_NT) levels_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, const ChunkD* __restrict__ chunks,
+                                                       const ColD* __restrict__ cols, const uint8_t* __restrict__ file, const uint8_t* __restrict__ scratch,
+                                                       int32_t* __restrict__ nonnull) {
+  __shared__ unsigned int s_cnt;
+  const int pi = todo[blockIdx.x];
+  const PageD pg = pages[pi];
+  const ChunkD ch = chunks[pg.chunk];
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const uint8_t* d = page_ptr(pg, file, scratch);
+  const uint8_t *lv_end, *vals;
+  const uint8_t* lv = levels_of(pg, d, lv_end, vals);
+  LevelSink sink{cols[ch.col].lvl + pg.row_start, ch.max_def, &s_cnt};
+  decode_hybrid(lv, lv_end, 1, pg.num_values, sink);  // flat schema: max_def == 1 -> bit width 1
+  __syncthreads();
+  if (threadIdx.x == 0) nonnull[pi] = (int32_t)s_cnt;
+}
+
+// ---- pass 2: values ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t load_le(const uint8_t* p, int nbytes) {
+  uint64_t v = 0;
+  if ((reinterpret_cast<uintptr_t>(p) & (nbytes - 1)) == 0) {
+    if (nbytes == 8) return *reinterpret_cast<const uint64_t*>(p);
+    if (nbytes == 4) return *reinterpret_cast<const uint32_t*>(p);
+  }
+  for (int k = 0; k < nbytes; k++) v |= (uint64_t)p[k] << (8 * k);
+  return v;
+}
+// big-endian two's complement of `len` bytes -> sign-extended (lo, hi)
+__device__ __forceinline__ void load_be_int(const uint8_t* p, int len, uint64_t& lo, uint64_t& hi) {
+  const uint64_t sign = (p[0] & 0x80) ? ~0ull : 0ull;
+  lo = sign; hi = sign;
+  for (int k = 0; k < len; k++) {
+    hi = (hi << 8) | (lo >> 56);
+    lo = (lo << 8) | p[k];
+  }
+}
+
+struct ValueWriter {
+  ColD col; int64_t base;  // dense index of this page's first value
+  const uint8_t* dict; int dict_count; const int64_t* dict_src; const int32_t* dict_len;
+  __device__ __forceinline__ void write_fixed(int64_t k, const uint8_t* src) {
+    void* out = col.dense;
+    const int64_t o = base + k;
+    switch (col.conv) {
+      case 0:
+        if (col.out_width == 4) reinterpret_cast<uint32_t*>(out)[o] = (uint32_t)load_le(src, 4);
+        else reinterpret_cast<uint64_t*>(out)[o] = load_le(src, 8);
+        break;
+      case 1: reinterpret_cast<int64_t*>(out)[o] = (int64_t)load_le(src, 8) * 1000; break;
+      case 2: {
+        uint64_t lo, hi; load_be_int(src, col.type_length, lo, hi);
+        if (col.out_width == 4) reinterpret_cast<uint32_t*>(out)[o] = (uint32_t)lo;
+        else if (col.out_width == 8) reinterpret_cast<uint64_t*>(out)[o] = lo;
+        else { reinterpret_cast<uint64_t*>(out)[2 * o] = lo; reinterpret_cast<uint64_t*>(out)[2 * o + 1] = hi; }
+      } break;
+      case 3:
+        if (col.out_width == 1) reinterpret_cast<int8_t*>(out)[o] = (int8_t)load_le(src, 4);
+        else reinterpret_cast<int16_t*>(out)[o] = (int16_t)load_le(src, 4);
+        break;
+      default: break;
+    }
+  }
+};
+struct DictSink {
+  ValueWriter w; int src_width; int32_t* errors;
+  __device__ __forceinline__ void put(int k, uint32_t idx) {
+    if ((int)idx >= w.dict_count) { atomicExch(errors, 2); return; }
+    if (w.col.conv == 5) { w.col.str_src[w.base + k] = w.dict_src[idx]; w.col.str_len[w.base + k] = w.dict_len[idx]; }
+    else w.write_fixed(k, w.dict + (size_t)idx * src_width);
+  }
+};
+
+__global__ void __launch_bounds__(PQ_NT) values_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, const ChunkD* __restrict__ chunks,
+                                                       const ColD* __restrict__ cols, const uint8_t* __restrict__ file, const uint8_t* __restrict__ scratch,
+                                                       const int32_t* __restrict__ nonnull, const int64_t* __restrict__ dict_src,
+                                                       const int32_t* __restrict__ dict_len, int32_t* __restrict__ errors) {
+  const int pi = todo[blockIdx.x];
+  const PageD pg = pages[pi];
+  const ChunkD ch = chunks[pg.chunk];
+  const ColD col = cols[ch.col];
+  const uint8_t* d = page_ptr(pg, file, scratch);
+  const uint8_t* vals = d;
+  const uint8_t* pend = d + pg.uncomp_size;
+  if (ch.max_def > 0) { const uint8_t* lv_end; levels_of(pg, d, lv_end, vals); }
+  else if (pg.kind == PG_DATA_V2) vals = d + pg.lvl_bytes;
+  const int nvals = ch.max_def > 0 ? nonnull[pi] : pg.num_values;
+  ValueWriter w; w.col = col; w.base = pg.value_base; w.dict = nullptr; w.dict_count = 0;
+  w.dict_src = dict_src + ch.dict_str_off; w.dict_len = dict_len + ch.dict_str_off;
+  const int src_width = ch.phys == PT_INT32 || ch.phys == PT_FLOAT ? 4 : (ch.phys == PT_FLBA ? ch.type_length : 8);
+  if (pg.encoding == ENC_PLAIN_DICT || pg.encoding == ENC_RLE_DICT) {
+    if (ch.dict_page < 0) { if (threadIdx.x == 0) atomicExch(errors, 3); return; }
+    w.dict = page_ptr(pages[ch.dict_page], file, scratch);
+    w.dict_count = ch.dict_count;
+    const int bw = vals[0];
+    DictSink sink{w, src_width, errors};
+    if (bw == 0) { for (int k = threadIdx.x; k < nvals; k += PQ_NT) sink.put(k, 0); }
+    else decode_hybrid(vals + 1, pend, bw, nvals, sink);
+  } else if (pg.encoding == ENC_PLAIN) {
+    if (ch.phys == PT_BOOLEAN) {
+      for (int k = threadIdx.x; k < nvals; k += PQ_NT) reinterpret_cast<int8_t*>(col.dense)[w.base + k] = (vals[k >> 3] >> (k & 7)) & 1;
+    } else if (ch.phys == PT_BYTE_ARRAY) {
+      // length-prefixed values: a sequential walk (dictionary pages normally carry the strings)
+      if (threadIdx.x == 0) {
+        const uint8_t* q = vals;
+        for (int k = 0; k < nvals && q + 4 <= pend; k++) {
+          uint32_t n; memcpy(&n, q, 4);
+          col.str_src[w.base + k] = (int64_t)reinterpret_cast<uintptr_t>(q + 4);
+          col.str_len[w.base + k] = (int32_t)n;
+          q += 4 + n;
+        }
+      }
+    } else {
+      for (int k = threadIdx.x; k < nvals; k += PQ_NT) w.write_fixed(k, vals + (size_t)k * src_width);
+    }
+  } else {
+    if (threadIdx.x == 0) atomicExch(errors, 4);
+  }
+}
+
+// string dictionaries: walk the length-prefixed entries of each dictionary page once
+__global__ void dict_strings_kernel(const PageD* __restrict__ pages, const ChunkD* __restrict__ chunks, int nchunks, const uint8_t* __restrict__ file,
+                                    const uint8_t* __restrict__ scratch, int64_t* __restrict__ dict_src, int32_t* __restrict__ dict_len) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const ChunkD ch = chunks[c];
+  if (ch.phys != PT_BYTE_ARRAY || ch.dict_page < 0) return;
+  const PageD pg = pages[ch.dict_page];
+  const uint8_t* q = page_ptr(pg, file, scratch);
+  const uint8_t* end = q + pg.uncomp_size;
+  for (int k = 0; k < ch.dict_count && q + 4 <= end; k++) {
+    uint32_t n; memcpy(&n, q, 4);
+    dict_src[ch.dict_str_off + k] = (int64_t)reinterpret_cast<uintptr_t>(q + 4);
+    dict_len[ch.dict_str_off + k] = (int32_t)n;
+    q += 4 + n;
+  }
+}
+
+__global__ void string_chars_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ offsets, int64_t n, uint8_t* __restrict__ chars) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int32_t o = offsets[i], len = offsets[i + 1] - o;
+    const uint8_t* s = reinterpret_cast<const uint8_t*>((uintptr_t)src[i]);
+    for (int k = lane; k < len; k += 32) chars[o + k] = s[k];
+  }
+}
+
+// NULL expansion: out[row] = lvl[row] ? dense[idx[row]] : 0, validity bits by ballot
+__global__ void expand_nulls_kernel(const uint8_t* __restrict__ lvl, const int64_t* __restrict__ idx, int64_t n, int width,
+                                    const uint8_t* __restrict__ dense, uint8_t* __restrict__ out, uint32_t* __restrict__ valid) {
+  const int64_t nround = (n + 31) & ~(int64_t)31;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool v = i < n && lvl[i] != 0;
+    if (i < n) {
+      const int64_t s = idx[i];
+      for (int b = 0; b < width; b++) out[i * width + b] = v ? dense[s * width + b] : 0;
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && i < n) valid[i >> 5] = bits;
+  }
+}
+__global__ void expand_null_lengths_kernel(const uint8_t* __restrict__ lvl, const int64_t* __restrict__ idx, int64_t n, const int32_t* __restrict__ dense_len,
+                                           const int64_t* __restrict__ dense_src, int32_t* __restrict__ out_len, int64_t* __restrict__ out_src,
+                                           uint32_t* __restrict__ valid) {
+  const int64_t nround = (n + 31) & ~(int64_t)31;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool v = i < n && lvl[i] != 0;
+    if (i < n) { out_len[i] = v ? dense_len[idx[i]] : 0; out_src[i] = v ? dense_src[idx[i]] : 0; }
+    const uint32_t bits = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && i < n) valid[i >> 5] = bits;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct OutColPlan {
+  int schema_idx;
+  int out_dtype, out_scale, out_width, conv;
+  int phys, type_length, max_def;
+};
+
+static OutColPlan plan_column(const SchemaElem& e, int schema_idx) {
+  OutColPlan p; memset(&p, 0, sizeof(p));
+  p.schema_idx = schema_idx; p.phys = e.type; p.type_length = e.type_length;
+  if (e.repetition == 2) throw Error(B2_ERR_UNSUPPORTED, "parquet: repeated (nested) column '" + e.name + "'");
+  p.max_def = e.repetition == 1 ? 1 : 0;
+  const bool dec = e.converted == 5 || e.lt_decimal;
+  switch (e.type) {
+    case PT_BOOLEAN: p.out_dtype = B2_BOOL8; p.out_width = 1; p.conv = 4; break;
+    case PT_INT32:
+      p.out_width = 4; p.conv = 0;
+      if (dec) { p.out_dtype = B2_DECIMAL32; p.out_scale = e.scale; }
+      else if (e.converted == 6 || e.lt_date) p.out_dtype = B2_DATE32;
+      else if (e.converted == 15 || e.lt_int_bits == 8) { p.out_dtype = B2_INT8; p.out_width = 1; p.conv = 3; }
+      else if (e.converted == 16 || e.lt_int_bits == 16) { p.out_dtype = B2_INT16; p.out_width = 2; p.conv = 3; }
+      else p.out_dtype = B2_INT32;
+      break;
+    case PT_INT64:
+      p.out_width = 8; p.conv = 0;
+      if (dec) { p.out_dtype = B2_DECIMAL64; p.out_scale = e.scale; }
+      else if (e.converted == 10 || (e.lt_timestamp && e.lt_ts_unit == 2)) p.out_dtype = B2_TIMESTAMP_US;
+      else if (e.converted == 9 || (e.lt_timestamp && e.lt_ts_unit == 1)) { p.out_dtype = B2_TIMESTAMP_US; p.conv = 1; }
+      else if (e.lt_timestamp) throw Error(B2_ERR_UNSUPPORTED, "parquet: nanosecond timestamps");
+      else p.out_dtype = B2_INT64;
+      break;
+    case PT_FLOAT: p.out_dtype = B2_FLOAT32; p.out_width = 4; break;
+    case PT_DOUBLE: p.out_dtype = B2_FLOAT64; p.out_width = 8; break;
+    case PT_BYTE_ARRAY: p.out_dtype = B2_STRING; p.out_width = 0; p.conv = 5; break;
+    case PT_FLBA:
+      if (!dec) throw Error(B2_ERR_UNSUPPORTED, "parquet: FIXED_LEN_BYTE_ARRAY that is not a decimal");
+      if (e.type_length > 16) throw Error(B2_ERR_UNSUPPORTED, "parquet: decimal wider than 16 bytes");
+      p.conv = 2; p.out_scale = e.scale;
+      if (e.precision <= 9) { p.out_dtype = B2_DECIMAL32; p.out_width = 4; }
+      else if (e.precision <= 18) { p.out_dtype = B2_DECIMAL64; p.out_width = 8; }
+      else { p.out_dtype = B2_DECIMAL128; p.out_width = 16; }
+      break;
+    default: throw Error(B2_ERR_UNSUPPORTED, "parquet: physical type " + std::to_string(e.type) + " (INT96?) is not supported");
+  }
+  return p;
+}
+
+static std::string lower(std::string s) { for (auto& c : s) c = (char)tolower(c); return s; }
+
+Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, const char* const* names, int ncols) {
+  FileMeta fm = parse_footer(host, len);
+  if (fm.schema.empty()) throw Error(B2_ERR_INVALID, "parquet: empty schema");
+  // leaves in depth-first order = column-chunk order; only top-level (flat) leaves can be selected
+  std::vector<int> leaf_schema;     // schema index of every leaf
+  std::vector<bool> leaf_flat;
+  {
+    std::vector<int> remaining;     // children still to visit at each depth
+    remaining.push_back(fm.schema[0].num_children);
+    for (size_t i = 1; i < fm.schema.size(); i++) {
+      while (!remaining.empty() && remaining.back() == 0) remaining.pop_back();
+      if (remaining.empty()) break;
+      remaining.back()--;
+      const int depth = (int)remaining.size();
+      if (fm.schema[i].num_children > 0) remaining.push_back(fm.schema[i].num_children);
+      else { leaf_schema.push_back((int)i); leaf_flat.push_back(depth == 1); }
+    }
+  }
+  std::vector<OutColPlan> plans;
+  std::vector<int> leaf_of_col;
+  for (int c = 0; c < ncols; c++) {
+    int found = -1;
+    for (size_t l = 0; l < leaf_schema.size(); l++)
+      if (leaf_flat[l] && fm.schema[leaf_schema[l]].name == names[c]) found = (int)l;
+    if (found < 0)  // case-insensitive fallback (GpuParquetScan.scala:965-1070 isCaseSensitive=false)
+      for (size_t l = 0; l < leaf_schema.size(); l++)
+        if (lower(fm.schema[leaf_schema[l]].name) == lower(names[c])) found = (int)l;
+    if (found < 0) throw Error(B2_ERR_INVALID, std::string("parquet: column '") + names[c] + "' not in file");
+    if (!leaf_flat[found]) throw Error(B2_ERR_UNSUPPORTED, std::string("parquet: column '") + names[c] + "' is nested");
+    plans.push_back(plan_column(fm.schema[leaf_schema[found]], leaf_schema[found]));
+    leaf_of_col.push_back(found);
+  }
+  int64_t total_rows = 0;
+  for (auto& rg : fm.row_groups) total_rows += rg.num_rows;
+  if (total_rows > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "parquet: more than 2^31-1 rows in one read; use chunked reads");
+
+  // walk page headers
+  std::vector<PageD> pages;
+  std::vector<ChunkD> chunks;
+  std::vector<int64_t> col_rows(ncols, 0);
+  int64_t scratch_bytes = 0, dict_str_total = 0;
+  for (auto& rg : fm.row_groups) {
+    for (int c = 0; c < ncols; c++) {
+      if (leaf_of_col[c] >= (int)rg.chunks.size()) throw Error(B2_ERR_INVALID, "parquet: row group lacks a column chunk");
+      const ChunkMeta& cm = rg.chunks[leaf_of_col[c]];
+      if (cm.codec != CODEC_NONE && cm.codec != CODEC_SNAPPY) throw Error(B2_ERR_UNSUPPORTED, "parquet: codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED / SNAPPY)");
+      ChunkD cd; memset(&cd, 0, sizeof(cd));
+      cd.col = c; cd.phys = cm.type; cd.type_length = plans[c].type_length; cd.max_def = plans[c].max_def; cd.dict_page = -1;
+      cd.dict_str_off = dict_str_total;
+      const int chunk_idx = (int)chunks.size();
+      int64_t pos = cm.data_page_offset;
+      if (cm.dict_page_offset > 0 && cm.dict_page_offset < pos) pos = cm.dict_page_offset;
+      const int64_t chunk_end = pos + cm.total_compressed;
+      if (pos < 4 || chunk_end > len - 8) throw Error(B2_ERR_INVALID, "parquet: column chunk outside the buffer");
+      int64_t values_seen = 0;
+      while (pos < chunk_end && values_seen < cm.num_values) {
+        TReader r(host + pos, host + chunk_end);
+        int id, t, last = 0;
+        int ptype = -1, usize = 0, csize = 0, nvals = 0, enc = 0, v2_def_len = 0, v2_rep_len = 0, v2_compressed = 1;
+        while (r.field(id, t, last)) {
+          if (id == 1) ptype = (int)r.zigzag();
+          else if (id == 2) usize = (int)r.zigzag();
+          else if (id == 3) csize = (int)r.zigzag();
+          else if ((id == 5 || id == 7 || id == 8) && t == 12) {
+            int id2, t2, last2 = 0;
+            while (r.field(id2, t2, last2)) {
+              if (id2 == 1) nvals = (int)r.zigzag();
+              else if (id == 5 && id2 == 2) enc = (int)r.zigzag();
+              else if (id == 7 && id2 == 2) enc = (int)r.zigzag();
+              else if (id == 8 && id2 == 4) enc = (int)r.zigzag();
+              else if (id == 8 && id2 == 5) v2_def_len = (int)r.zigzag();
+              else if (id == 8 && id2 == 6) v2_rep_len = (int)r.zigzag();
+              else if (id == 8 && id2 == 7) v2_compressed = (t2 == 1);
+              else r.skip(t2);
+            }
+          } else r.skip(t);
+        }
+        const int64_t payload = r.p - host;
+        if (payload + csize > chunk_end) throw Error(B2_ERR_INVALID, "parquet: page runs past its chunk");
+        if (ptype == PG_INDEX) { pos = payload + csize; continue; }
+        PageD pg; memset(&pg, 0, sizeof(pg));
+        pg.src_off = payload; pg.comp_size = csize; pg.uncomp_size = usize; pg.num_values = nvals; pg.encoding = enc; pg.kind = ptype; pg.chunk = chunk_idx;
+        pg.lvl_bytes = ptype == PG_DATA_V2 ? v2_def_len + v2_rep_len : 0;
+        pg.compressed = cm.codec == CODEC_SNAPPY && (ptype != PG_DATA_V2 || v2_compressed);
+        if (ptype == PG_DATA_V2 && v2_rep_len) throw Error(B2_ERR_UNSUPPORTED, "parquet: repetition levels");
+        if (pg.compressed) { pg.dst_off = scratch_bytes; scratch_bytes += ((int64_t)usize + 15) & ~15LL; }
+        else pg.dst_off = -1;
+        if (ptype == PG_DICT) {
+          if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT) throw Error(B2_ERR_UNSUPPORTED, "parquet: dictionary page encoding " + std::to_string(enc));
+          cd.dict_page = (int)pages.size(); cd.dict_count = nvals;
+          if (cm.type == PT_BYTE_ARRAY) dict_str_total += nvals;
+        } else if (ptype == PG_DATA || ptype == PG_DATA_V2) {
+          if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT && enc != ENC_RLE_DICT)
+            throw Error(B2_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(enc) + " (DELTA_* / BYTE_STREAM_SPLIT are not supported)");
+          pg.row_start = col_rows[c];
+          col_rows[c] += nvals; values_seen += nvals;
+        } else throw Error(B2_ERR_INVALID, "parquet: unknown page type");
+        pages.push_back(pg);
+        pos = payload + csize;
+      }
+      chunks.push_back(cd);
+    }
+  }
+  for (int c = 0; c < ncols; c++)
+    if (col_rows[c] != total_rows) throw Error(B2_ERR_INVALID, "parquet: page row counts disagree with the footer");
+
+  cudaStream_t s = stream();
+  // device copy of the file bytes (H2D inside the call unless the caller already has them resident)
+  DevBuf file_buf;
+  const uint8_t* d_file = dev_in;
+  if (!d_file) {
+    file_buf = DevBuf((size_t)len + 64);
+    CUDA_CHECK(cudaMemcpyAsync(file_buf.p, host, (size_t)len, cudaMemcpyHostToDevice, s));
+    d_file = file_buf.as<uint8_t>();
+  }
+  DevBuf scratch((size_t)scratch_bytes + 64);
+  DevBuf d_pages(std::max<size_t>(1, pages.size()) * sizeof(PageD)), d_chunks(std::max<size_t>(1, chunks.size()) * sizeof(ChunkD));
+  DevBuf d_err(4), d_nonnull(std::max<size_t>(1, pages.size()) * 4);
+  CUDA_CHECK(cudaMemsetAsync(d_err.p, 0, 4, s));
+  CUDA_CHECK(cudaMemsetAsync(d_nonnull.p, 0, d_nonnull.bytes, s));
+  if (!chunks.empty()) h2d(d_chunks.p, chunks.data(), chunks.size());
+
+  // outputs
+  std::vector<ColD> cold(ncols);
+  std::vector<DevBuf> dense(ncols), str_src(ncols), str_len(ncols), lvl(ncols);
+  for (int c = 0; c < ncols; c++) {
+    ColD& cd = cold[c]; memset(&cd, 0, sizeof(cd));
+    cd.out_dtype = plans[c].out_dtype; cd.out_width = plans[c].out_width; cd.phys = plans[c].phys; cd.type_length = plans[c].type_length; cd.conv = plans[c].conv;
+    if (cd.conv == 5) {
+      str_src[c] = DevBuf((size_t)std::max<int64_t>(total_rows, 1) * 8); str_len[c] = DevBuf((size_t)(total_rows + 1) * 4);
+      cd.str_src = str_src[c].as<int64_t>(); cd.str_len = str_len[c].as<int32_t>();
+    } else {
+      dense[c] = DevBuf((size_t)std::max<int64_t>(total_rows, 1) * cd.out_width);
+      cd.dense = dense[c].p;
+    }
+    if (plans[c].max_def > 0) { lvl[c] = DevBuf((size_t)std::max<int64_t>(total_rows, 1)); cd.lvl = lvl[c].as<uint8_t>(); }
+  }
+  DevBuf d_cols((size_t)ncols * sizeof(ColD));
+  h2d(d_cols.p, cold.data(), cold.size());
+
+  std::vector<int32_t> todo_snappy, todo_levels, todo_values;
+  for (size_t i = 0; i < pages.size(); i++) {
+    if (pages[i].compressed) todo_snappy.push_back((int32_t)i);
+    if (pages[i].kind != PG_DICT) { todo_values.push_back((int32_t)i); if (chunks[pages[i].chunk].max_def > 0) todo_levels.push_back((int32_t)i); }
+  }
+  // value_base is only known after the level pass when a column has NULLs; start with rows
+  for (auto& pg : pages) pg.value_base = pg.row_start;
+  if (!pages.empty()) h2d(d_pages.p, pages.data(), pages.size());
+  auto upload = [&](const std::vector<int32_t>& v, DevBuf& b) { b = DevBuf(std::max<size_t>(1, v.size()) * 4); if (!v.empty()) h2d(b.p, v.data(), v.size()); };
+  DevBuf d_todo_s, d_todo_l, d_todo_v;
+  upload(todo_snappy, d_todo_s); upload(todo_levels, d_todo_l); upload(todo_values, d_todo_v);
+  if (!todo_snappy.empty()) {
+    snappy_kernel<<<((int)todo_snappy.size() * 32 + 127) / 128, 128, 0, s>>>(d_pages.as<PageD>(), d_todo_s.as<int32_t>(), (int)todo_snappy.size(), d_file,
+                                                                              scratch.as<uint8_t>(), d_err.as<int32_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  std::vector<int64_t> col_nonnull(ncols, 0);
+  std::vector<bool> has_nulls(ncols, false);
+  if (!todo_levels.empty()) {
+    levels_kernel<<<(int)todo_levels.size(), PQ_NT, 0, s>>>(d_pages.as<PageD>(), d_todo_l.as<int32_t>(), d_chunks.as<ChunkD>(), d_cols.as<ColD>(), d_file,
+                                                            scratch.as<uint8_t>(), d_nonnull.as<int32_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    std::vector<int32_t> nn(pages.size());
+    d2h(nn.data(), d_nonnull.p, nn.size());
+    sync();
+    std::vector<int64_t> run(ncols, 0);
+    for (size_t i = 0; i < pages.size(); i++) {
+      PageD& pg = pages[i];
+      if (pg.kind == PG_DICT) continue;
+      const int c = chunks[pg.chunk].col;
+      if (chunks[pg.chunk].max_def > 0) { pg.value_base = run[c]; run[c] += nn[i]; }
+    }
+    for (int c = 0; c < ncols; c++) if (plans[c].max_def > 0) { col_nonnull[c] = run[c]; has_nulls[c] = run[c] != total_rows; }
+    h2d(d_pages.p, pages.data(), pages.size());
+  }
+  DevBuf d_dict_src((size_t)std::max<int64_t>(dict_str_total, 1) * 8), d_dict_len((size_t)std::max<int64_t>(dict_str_total, 1) * 4);
+  if (dict_str_total) {
+    dict_strings_kernel<<<((int)chunks.size() + 63) / 64, 64, 0, s>>>(d_pages.as<PageD>(), d_chunks.as<ChunkD>(), (int)chunks.size(), d_file,
+                                                                       scratch.as<uint8_t>(), d_dict_src.as<int64_t>(), d_dict_len.as<int32_t>());
+    count_launch();
+  }
+  if (!todo_values.empty()) {
+    values_kernel<<<(int)todo_values.size(), PQ_NT, 0, s>>>(d_pages.as<PageD>(), d_todo_v.as<int32_t>(), d_chunks.as<ChunkD>(), d_cols.as<ColD>(), d_file,
+                                                            scratch.as<uint8_t>(), d_nonnull.as<int32_t>(), d_dict_src.as<int64_t>(), d_dict_len.as<int32_t>(),
+                                                            d_err.as<int32_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  // assemble output columns
+  ColsGuard outs;
+  for (int c = 0; c < ncols; c++) {
+    std::unique_ptr<Column> oc(new Column());
+    oc->dtype = plans[c].out_dtype; oc->scale = plans[c].out_scale; oc->size = total_rows;
+    DevBuf idx;
+    if (has_nulls[c]) {
+      idx = DevBuf((size_t)(total_rows + 1) * 8);
+      exclusive_scan<uint8_t, int64_t>(lvl[c].as<uint8_t>(), idx.as<int64_t>(), total_rows, false);
+      oc->valid = DevBuf(validity_bytes(total_rows)); oc->null_count = total_rows - col_nonnull[c];
+    }
+    if (plans[c].conv == 5) {
+      int32_t* lens = str_len[c].as<int32_t>();
+      int64_t* srcs = str_src[c].as<int64_t>();
+      DevBuf xl, xs;
+      if (has_nulls[c]) {
+        xl = DevBuf((size_t)(total_rows + 1) * 4); xs = DevBuf((size_t)std::max<int64_t>(total_rows, 1) * 8);
+        if (total_rows) {
+          expand_null_lengths_kernel<<<grid_for(total_rows, 256), 256, 0, s>>>(lvl[c].as<uint8_t>(), idx.as<int64_t>(), total_rows, lens, srcs, xl.as<int32_t>(),
+                                                                                xs.as<int64_t>(), oc->valid.as<uint32_t>());
+          count_launch();
+        }
+        lens = xl.as<int32_t>(); srcs = xs.as<int64_t>();
+      }
+      oc->offsets = DevBuf((size_t)(total_rows + 1) * 4);
+      DevBuf sums = exclusive_scan<int32_t, int32_t>(lens, oc->offsets.as<int32_t>(), total_rows, true);
+      int64_t chars = 0;
+      d2h(&chars, sums.as<int64_t>() + std::max<int64_t>(1, (total_rows + SCAN_TILE - 1) / SCAN_TILE), 1);
+      sync();
+      if (chars > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "parquet: string column exceeds 2^31-1 chars");
+      oc->chars_bytes = chars;
+      oc->data = DevBuf((size_t)chars);
+      if (chars) {
+        string_chars_kernel<<<grid_for(total_rows * 32, 256), 256, 0, s>>>(srcs, oc->offsets.as<int32_t>(), total_rows, oc->data.as<uint8_t>());
+        count_launch();
+        sync();  // srcs / scratch are read by the kernel; keep them alive
+      }
+    } else if (has_nulls[c]) {
+      oc->data = DevBuf((size_t)total_rows * plans[c].out_width);
+      expand_nulls_kernel<<<grid_for(total_rows, 256), 256, 0, s>>>(lvl[c].as<uint8_t>(), idx.as<int64_t>(), total_rows, plans[c].out_width,
+                                                                     dense[c].as<uint8_t>(), oc->data.as<uint8_t>(), oc->valid.as<uint32_t>());
+      count_launch();
+    } else {
+      oc->data = std::move(dense[c]);  // no NULLs: the dense decode IS the column
+    }
+    outs.v.push_back(oc.release());
+  }
+  int32_t err = 0;
+  d2h(&err, d_err.p, 1);
+  sync();
+  if (err == 1) throw Error(B2_ERR_INVALID, "parquet: corrupt snappy stream");
+  if (err) throw Error(B2_ERR_INVALID, "parquet: corrupt page data (code " + std::to_string(err) + ")");
+  return new_table(outs.release());
+}
+
+}  // namespace b2
+
+using namespace b2;
+extern "C" {
+
+int b2_parquet_decode(const uint8_t* host_buf, int64_t len, const char* const* column_names, int32_t ncols, b2_handle* out_table) {
+  B2_TRY
+  B2_CHECK(host_buf && len > 0 && ncols >= 1, "bad arguments");
+  *out_table = to_handle(parquet_decode(host_buf, nullptr, len, column_names, ncols));
+  B2_CATCH
+}
+
+int b2_parquet_decode_device(const uint8_t* host_buf, const uint8_t* dev_buf, int64_t len, const char* const* column_names, int32_t ncols,
+                             b2_handle* out_table) {
+  B2_TRY
+  B2_CHECK(host_buf && dev_buf && len > 0 && ncols >= 1, "bad arguments");
+  *out_table = to_handle(parquet_decode(host_buf, dev_buf, len, column_names, ncols));
+  B2_CATCH
+}
+
+}  // extern "C"

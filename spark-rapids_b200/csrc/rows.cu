@@ -58,7 +58,10 @@ __global__ void __launch_bounds__(256) to_rows_kernel(const __grid_constant__ Ro
           case 2: *reinterpret_cast<uint16_t*>(row + L.off[c]) = reinterpret_cast<const uint16_t*>(L.data[c])[g]; break;
           case 4: *reinterpret_cast<uint32_t*>(row + L.off[c]) = reinterpret_cast<const uint32_t*>(L.data[c])[g]; break;
           case 8: *reinterpret_cast<uint64_t*>(row + L.off[c]) = reinterpret_cast<const uint64_t*>(L.data[c])[g]; break;
-          default: *reinterpret_cast<ulonglong2*>(row + L.off[c]) = reinterpret_cast<const ulonglong2*>(L.data[c])[g]; break;
+          default: {  // rows are only 8-byte aligned in shared memory
+            const ulonglong2 v16 = reinterpret_cast<const ulonglong2*>(L.data[c])[g];
+            reinterpret_cast<uint64_t*>(row + L.off[c])[0] = v16.x; reinterpret_cast<uint64_t*>(row + L.off[c])[1] = v16.y;
+          } break;
         }
       }
     }
@@ -94,7 +97,11 @@ __global__ void __launch_bounds__(256) from_rows_kernel(const __grid_constant__ 
             case 2: reinterpret_cast<uint16_t*>(L.data[c])[g] = *reinterpret_cast<const uint16_t*>(row + L.off[c]); break;
             case 4: reinterpret_cast<uint32_t*>(L.data[c])[g] = *reinterpret_cast<const uint32_t*>(row + L.off[c]); break;
             case 8: reinterpret_cast<uint64_t*>(L.data[c])[g] = *reinterpret_cast<const uint64_t*>(row + L.off[c]); break;
-            default: reinterpret_cast<ulonglong2*>(L.data[c])[g] = *reinterpret_cast<const ulonglong2*>(row + L.off[c]); break;
+            default: {
+              ulonglong2 v16;
+              v16.x = reinterpret_cast<const uint64_t*>(row + L.off[c])[0]; v16.y = reinterpret_cast<const uint64_t*>(row + L.off[c])[1];
+              reinterpret_cast<ulonglong2*>(L.data[c])[g] = v16;
+            } break;
           }
         }
         const uint32_t bits = __ballot_sync(0xffffffffu, v);

@@ -1,0 +1,78 @@
+"""Generates tests/golden/parquet_testing.json from the Apache parquet-testing corpus that the
+reference vendors under thirdparty/parquet-testing/data (the fixtures its own
+integration_tests/src/main/python/parquet_testing_test.py reads).  Run in the build container
+(where /root/reference exists); the JSON travels to the GPU box, /root/reference does not.
+
+Each entry: file bytes (base64), the flat columns we decode, and the expected values as decoded by
+pyarrow (the independent reader), normalised to python values: decimals -> unscaled ints,
+dates -> days, timestamps -> microseconds, binary/strings -> latin-1 text.
+"""
+import base64
+import decimal
+import json
+import os
+
+import pyarrow as pa
+import pyarrow.parquet as pq
+
+SRC = "/root/reference/thirdparty/parquet-testing/data"
+FILES = {
+    "alltypes_plain.parquet": ["id", "bool_col", "tinyint_col", "smallint_col", "int_col", "bigint_col", "float_col", "double_col", "date_string_col", "string_col"],
+    "alltypes_plain.snappy.parquet": ["id", "bool_col", "int_col", "bigint_col", "float_col", "double_col", "string_col"],
+    "alltypes_dictionary.parquet": ["id", "bool_col", "tinyint_col", "int_col", "bigint_col", "float_col", "double_col", "date_string_col", "string_col"],
+    "int32_decimal.parquet": ["value"],
+    "int64_decimal.parquet": ["value"],
+    "fixed_length_decimal.parquet": ["value"],
+    "fixed_length_decimal_legacy.parquet": ["value"],
+    "datapage_v1-snappy-compressed-checksum.parquet": ["a", "b"],
+    "plain-dict-uncompressed-checksum.parquet": ["long_field", "binary_field"],
+    "rle-dict-snappy-checksum.parquet": ["long_field", "binary_field"],
+    "datapage_v2.snappy.parquet": ["a", "c"],
+    "binary.parquet": ["foo"],
+    "int32_with_null_pages.parquet": ["int32_field"],
+    "dict-page-offset-zero.parquet": ["l_partkey"],
+    "single_nan.parquet": ["mycol"],
+    "nan_in_stats.parquet": ["x"],
+}
+
+
+def norm(v, typ):
+    if v is None:
+        return None
+    if pa.types.is_decimal(typ):
+        return int(decimal.Decimal(v).scaleb(typ.scale))
+    if pa.types.is_binary(typ) or pa.types.is_string(typ) or pa.types.is_large_string(typ):
+        return (v if isinstance(v, bytes) else v.encode()).decode("latin-1")
+    if pa.types.is_floating(typ):
+        return "nan" if v != v else float(v)
+    if pa.types.is_boolean(typ):
+        return bool(v)
+    return int(v)
+
+
+def main():
+    out = {}
+    for name, cols in FILES.items():
+        path = os.path.join(SRC, name)
+        raw = open(path, "rb").read()
+        tbl = pq.read_table(path, columns=cols)
+        expect = {}
+        for c in cols:
+            col = tbl.column(c)
+            typ = col.type
+            if pa.types.is_date32(typ):
+                vals = [None if v is None else int(v) for v in col.cast(pa.int32()).to_pylist()]
+            elif pa.types.is_timestamp(typ):
+                vals = [None if v is None else int(v) for v in col.cast(pa.timestamp("us")).cast(pa.int64()).to_pylist()]
+            else:
+                vals = [norm(v, typ) for v in col.to_pylist()]
+            expect[c] = {"type": str(typ), "values": vals}
+        out[name] = {"b64": base64.b64encode(raw).decode(), "columns": cols, "expect": expect}
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "parquet_testing.json")
+    with open(dst, "w") as fh:
+        json.dump(out, fh)
+    print("wrote", dst, os.path.getsize(dst), "bytes")
+
+
+if __name__ == "__main__":
+    main()
