@@ -253,6 +253,11 @@ int b2_parquet_decode(const uint8_t* host_buf, int64_t len, const char* const* c
 int b2_parquet_decode_device(const uint8_t* host_buf, const uint8_t* dev_buf, int64_t len,
                              const char* const* column_names, int32_t ncols, b2_handle* out_table);
 
+/* byte accounting of this thread's last decode (roofline numerators of bench.py):
+ * out[0] compressed bytes fed to the decompressor, out[1] bytes it produced, out[2] uncompressed
+ * bytes of all data+dictionary pages, out[3] bytes of the output columns, out[4] pages */
+int b2_parquet_last_stats(int64_t* out5);
+
 /* ---- a11: row <-> column (GpuColumnarToRowExec.scala:44-220 RowConversion.convertToRows*;
  *           GpuRowToColumnarExec.scala:574-755) -------------------------------------------------- */
 /* JCUDF fixed-width row format: columns packed in order at natural alignment, then validity
@@ -281,6 +286,17 @@ int b2_event_record(b2_handle ev);
 int b2_event_elapsed_ms(b2_handle start, b2_handle stop, float* ms);
 int b2_event_close(b2_handle ev);
 int b2_kernel_launch_count(int64_t* out);   /* number of kernels this library launched so far */
+/* per-kernel device time (CUDA events around each launch on the library stream), for the roofline
+ * line of bench.py.  report: JSON array [{"name":..,"launches":n,"ms":total}] written to buf. */
+int b2_profile_enable(int32_t on);
+int b2_profile_report(char* buf, int64_t capacity);
+/* pin / unpin caller memory for fast H2D (HostAlloc.scala pinned pool analogue) */
+int b2_host_register(void* ptr, int64_t bytes);
+int b2_host_unregister(void* ptr);
+/* raw device buffer (bench: Parquet bytes resident in HBM) */
+int b2_device_alloc(int64_t bytes, void** out);
+int b2_device_free(void* ptr);
+int b2_memcpy_h2d(void* dst, const void* src, int64_t bytes);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -598,3 +598,44 @@ def parquet_decode_device(buf, dev_ptr, columns):
     out = ctypes.c_int64()
     check(lib.b2_parquet_decode_device(_ptr(arr), ctypes.c_void_p(dev_ptr), arr.nbytes, names, len(columns), ctypes.byref(out)))
     return Table(out.value)
+
+
+# ---- profiling / raw buffers (bench.py) ---------------------------------------------------------------
+def profile_enable(on=True):
+    check(lib.b2_profile_enable(int(on)))
+
+
+def profile_report():
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib.b2_profile_report(buf, len(buf)))
+    return json.loads(buf.value.decode())
+
+
+def host_register(arr):
+    check(lib.b2_host_register(_ptr(arr), arr.nbytes))
+
+
+def host_unregister(arr):
+    check(lib.b2_host_unregister(_ptr(arr)))
+
+
+class DeviceBuffer:
+    def __init__(self, nbytes):
+        out = ctypes.c_void_p()
+        check(lib.b2_device_alloc(nbytes, ctypes.byref(out)))
+        self.ptr, self.nbytes = out.value, nbytes
+
+    def copy_from_host(self, arr):
+        check(lib.b2_memcpy_h2d(ctypes.c_void_p(self.ptr), _ptr(arr), arr.nbytes))
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib.b2_device_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def parquet_last_stats():
+    out = (ctypes.c_int64 * 5)()
+    check(lib.b2_parquet_last_stats(out))
+    return {"compressed_in": out[0], "decompressed_out": out[1], "page_bytes": out[2], "column_bytes": out[3], "pages": out[4]}

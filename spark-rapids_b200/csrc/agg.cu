@@ -469,6 +469,7 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
       alloc_table(cap, slots, acc, nv, ovf, gt);
       if (n > 0 || nkeys == 0) {
         if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KernelTimer kt_aggregate_smem_kernel("aggregate_smem_kernel");
         aggregate_kernel<true><<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, plan, gt, n,
                                                                   (vm_smem + 15) & ~15);
         CUDA_CHECK(cudaGetLastError());
@@ -484,6 +485,7 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
     while (cap < n * 2) cap <<= 1;
     alloc_table(cap, slots, acc, nv, ovf, gt);
     if (vm_smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem));
+    KernelTimer kt_aggregate_global_kernel("aggregate_global_kernel");
     aggregate_kernel<false><<<vm_grid(n, vm_smem), VM_NT, vm_smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in,
                                                                                 plan, gt, n, (vm_smem + 15) & ~15);
     CUDA_CHECK(cudaGetLastError());

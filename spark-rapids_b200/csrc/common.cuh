@@ -44,6 +44,11 @@ cudaStream_t stream();
 void* dev_alloc(size_t bytes);            // throws Error(B2_ERR_OOM)
 void dev_free(void* p);
 void count_launch(int n = 1);
+struct KernelTimer {  // scoped CUDA-event timer around a kernel launch; no-op unless profiling is on
+  void* rec;
+  explicit KernelTimer(const char* name);
+  ~KernelTimer();
+};
 int sm_count();
 
 struct DevBuf {  // RAII stream-ordered device buffer

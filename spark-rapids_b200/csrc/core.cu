@@ -4,6 +4,7 @@
 // GpuColumnarToRowExec.scala:337-384 (copyToHost).
 #include <mutex>
 #include <unordered_map>
+#include <cstdio>
 #include "common.cuh"
 
 namespace b2 {
@@ -57,6 +58,26 @@ static thread_local cudaStream_t t_stream = nullptr;
 static thread_local bool t_stream_owned = false;
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::atomic<bool> g_prof{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec*> g_prof_recs;
+KernelTimer::KernelTimer(const char* name) : rec(nullptr) {
+  if (!g_prof.load(std::memory_order_relaxed)) return;
+  ProfRec* r = new ProfRec();
+  r->name = name;
+  cudaEventCreate(&r->a); cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, stream());
+  rec = r;
+}
+KernelTimer::~KernelTimer() {
+  if (!rec) return;
+  ProfRec* r = reinterpret_cast<ProfRec*>(rec);
+  cudaEventRecord(r->b, stream());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back(r);
+}
 int sm_count() { return g_sms; }
 
 static void ensure_init() {
@@ -406,6 +427,67 @@ int b2_table_incref(b2_handle t) {
 int b2_table_close(b2_handle t) {
   B2_TRY
   table_release(table_from(t));
+  B2_CATCH
+}
+
+int b2_profile_enable(int32_t on) {
+  B2_TRY
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto* r : g_prof_recs) { cudaEventDestroy(r->a); cudaEventDestroy(r->b); delete r; }
+  g_prof_recs.clear();
+  g_prof.store(on != 0);
+  B2_CATCH
+}
+int b2_profile_report(char* buf, int64_t capacity) {
+  B2_TRY
+  sync();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::vector<std::string> names; std::vector<double> ms; std::vector<int64_t> cnt;
+  for (auto* r : g_prof_recs) {
+    float t = 0;
+    cudaEventSynchronize(r->b);
+    cudaEventElapsedTime(&t, r->a, r->b);
+    size_t k = 0;
+    for (; k < names.size(); k++) if (names[k] == r->name) break;
+    if (k == names.size()) { names.push_back(r->name); ms.push_back(0); cnt.push_back(0); }
+    ms[k] += t; cnt[k] += 1;
+  }
+  std::string out = "[";
+  for (size_t k = 0; k < names.size(); k++) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s{\"name\":\"%s\",\"launches\":%lld,\"ms\":%.6f}", k ? "," : "", names[k].c_str(), (long long)cnt[k], ms[k]);
+    out += line;
+  }
+  out += "]";
+  B2_CHECK((int64_t)out.size() + 1 <= capacity, "profile buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  B2_CATCH
+}
+int b2_host_register(void* ptr, int64_t bytes) {
+  B2_TRY
+  stream();
+  CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  B2_CATCH
+}
+int b2_host_unregister(void* ptr) {
+  B2_TRY
+  CUDA_CHECK(cudaHostUnregister(ptr));
+  B2_CATCH
+}
+int b2_device_alloc(int64_t bytes, void** out) {
+  B2_TRY
+  *out = dev_alloc((size_t)bytes);
+  B2_CATCH
+}
+int b2_device_free(void* ptr) {
+  B2_TRY
+  dev_free(ptr);
+  B2_CATCH
+}
+int b2_memcpy_h2d(void* dst, const void* src, int64_t bytes) {
+  B2_TRY
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, stream()));
+  sync();
   B2_CATCH
 }
 

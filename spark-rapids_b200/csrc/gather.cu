@@ -129,6 +129,7 @@ Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullif
   std::vector<int> fixed_slots;
   auto flush = [&]() {
     if (gc.ncols == 0 || n == 0) { gc.ncols = 0; return; }
+    KernelTimer kt_gather_fixed_kernel("gather_fixed_kernel");
     gather_fixed_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(gc, d_map, n, t->rows);
     CUDA_CHECK(cudaGetLastError());
     count_launch();

@@ -161,6 +161,7 @@ int b2_hash_partition(b2_handle table, const int32_t* key_cols, int32_t nkeys, i
   KeyCols keys = key_cols_of(t, key_cols, nkeys);
   DevBuf pids((size_t)std::max<int64_t>(t->rows, 1) * 4);
   if (t->rows) {
+    KernelTimer kt_murmur_pmod_kernel("murmur_pmod_kernel");
     murmur_kernel<<<grid_for(t->rows, 256), 256, 0, stream()>>>(keys, t->rows, (uint32_t)seed, num_partitions, pids.as<int32_t>());
     CUDA_CHECK(cudaGetLastError());
     count_launch();

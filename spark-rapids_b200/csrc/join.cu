@@ -113,6 +113,7 @@ int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* ou
   CUDA_CHECK(cudaMemsetAsync(jt->slots.p, 0xff, (size_t)cap * 8, stream()));
   if (t->rows) {
     KeyCols keys = key_cols_of(t, jt->key_idx.data(), (int)jt->key_idx.size());
+    KernelTimer kt_join_build_kernel("join_build_kernel");
     join_build_kernel<<<grid_for(t->rows, 256), 256, 0, stream()>>>(keys, t->rows, jt->slots.as<uint64_t>(), (uint32_t)(cap - 1), jt->nulls_equal);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -143,6 +144,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
   DevBuf counts((size_t)std::max<int64_t>(n, 1) * 4), offsets((size_t)(n + 1) * 8);
   int64_t total = 0;
   if (n) {
+    KernelTimer kt_join_probe_count_kernel("join_probe_count_kernel");
     join_probe_kernel<0><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, kind,
                                                                   counts.as<int32_t>(), nullptr, nullptr, nullptr);
     CUDA_CHECK(cudaGetLastError());
@@ -157,6 +159,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
   ColGuard lm(new_column(B2_INT32, 0, total, false));
   ColGuard rm(semi_like ? nullptr : new_column(B2_INT32, 0, total, false));
   if (n && total) {
+    KernelTimer kt_join_probe_write_kernel("join_probe_write_kernel");
     join_probe_kernel<1><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, kind,
                                                                   nullptr, offsets.as<int64_t>(), lm.c->data.as<int32_t>(),
                                                                   semi_like ? nullptr : rm.c->data.as<int32_t>());

@@ -438,6 +438,11 @@ __global__ void __launch_bounds__(PQ_NT) values_kernel(const PageD* __restrict__
     } else {
       for (int k = threadIdx.x; k < nvals; k += PQ_NT) w.write_fixed(k, vals + (size_t)k * src_width);
     }
+  } else if (pg.encoding == ENC_RLE && ch.phys == PT_BOOLEAN) {
+    // RLE booleans (data page v2 writers): 4-byte length, then the hybrid stream at bit width 1
+    struct BoolSink { int8_t* out; __device__ __forceinline__ void put(int k, uint32_t v) { out[k] = (int8_t)(v & 1); } };
+    BoolSink sink{reinterpret_cast<int8_t*>(col.dense) + w.base};
+    decode_hybrid(vals + 4, pend, 1, nvals, sink);
   } else {
     if (threadIdx.x == 0) atomicExch(errors, 4);
   }
@@ -546,6 +551,8 @@ static OutColPlan plan_column(const SchemaElem& e, int schema_idx) {
 
 static std::string lower(std::string s) { for (auto& c : s) c = (char)tolower(c); return s; }
 
+static thread_local int64_t t_pq_stats[5];
+
 Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, const char* const* names, int ncols) {
   FileMeta fm = parse_footer(host, len);
   if (fm.schema.empty()) throw Error(B2_ERR_INVALID, "parquet: empty schema");
@@ -599,6 +606,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
       int64_t pos = cm.data_page_offset;
       if (cm.dict_page_offset > 0 && cm.dict_page_offset < pos) pos = cm.dict_page_offset;
       const int64_t chunk_end = pos + cm.total_compressed;
+      if (cm.num_values == 0) { chunks.push_back(cd); continue; }  // empty row group
       if (pos < 4 || chunk_end > len - 8) throw Error(B2_ERR_INVALID, "parquet: column chunk outside the buffer");
       int64_t values_seen = 0;
       while (pos < chunk_end && values_seen < cm.num_values) {
@@ -638,7 +646,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
           cd.dict_page = (int)pages.size(); cd.dict_count = nvals;
           if (cm.type == PT_BYTE_ARRAY) dict_str_total += nvals;
         } else if (ptype == PG_DATA || ptype == PG_DATA_V2) {
-          if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT && enc != ENC_RLE_DICT)
+          if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT && enc != ENC_RLE_DICT && !(enc == ENC_RLE && cm.type == PT_BOOLEAN))
             throw Error(B2_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(enc) + " (DELTA_* / BYTE_STREAM_SPLIT are not supported)");
           pg.row_start = col_rows[c];
           col_rows[c] += nvals; values_seen += nvals;
@@ -652,6 +660,14 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   for (int c = 0; c < ncols; c++)
     if (col_rows[c] != total_rows) throw Error(B2_ERR_INVALID, "parquet: page row counts disagree with the footer");
 
+  {
+    int64_t comp = 0, prod = 0, unc = 0;
+    for (auto& pg : pages) {
+      unc += pg.uncomp_size;
+      if (pg.compressed) { comp += pg.comp_size - pg.lvl_bytes; prod += pg.uncomp_size - pg.lvl_bytes; }
+    }
+    t_pq_stats[0] = comp; t_pq_stats[1] = prod; t_pq_stats[2] = unc; t_pq_stats[3] = 0; t_pq_stats[4] = (int64_t)pages.size();
+  }
   cudaStream_t s = stream();
   // device copy of the file bytes (H2D inside the call unless the caller already has them resident)
   DevBuf file_buf;
@@ -698,6 +714,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   DevBuf d_todo_s, d_todo_l, d_todo_v;
   upload(todo_snappy, d_todo_s); upload(todo_levels, d_todo_l); upload(todo_values, d_todo_v);
   if (!todo_snappy.empty()) {
+    KernelTimer kt_snappy_kernel("snappy_kernel");
     snappy_kernel<<<((int)todo_snappy.size() * 32 + 127) / 128, 128, 0, s>>>(d_pages.as<PageD>(), d_todo_s.as<int32_t>(), (int)todo_snappy.size(), d_file,
                                                                               scratch.as<uint8_t>(), d_err.as<int32_t>());
     CUDA_CHECK(cudaGetLastError());
@@ -706,6 +723,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   std::vector<int64_t> col_nonnull(ncols, 0);
   std::vector<bool> has_nulls(ncols, false);
   if (!todo_levels.empty()) {
+    KernelTimer kt_levels_kernel("levels_kernel");
     levels_kernel<<<(int)todo_levels.size(), PQ_NT, 0, s>>>(d_pages.as<PageD>(), d_todo_l.as<int32_t>(), d_chunks.as<ChunkD>(), d_cols.as<ColD>(), d_file,
                                                             scratch.as<uint8_t>(), d_nonnull.as<int32_t>());
     CUDA_CHECK(cudaGetLastError());
@@ -730,6 +748,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
     count_launch();
   }
   if (!todo_values.empty()) {
+    KernelTimer kt_values_kernel("values_kernel");
     values_kernel<<<(int)todo_values.size(), PQ_NT, 0, s>>>(d_pages.as<PageD>(), d_todo_v.as<int32_t>(), d_chunks.as<ChunkD>(), d_cols.as<ColD>(), d_file,
                                                             scratch.as<uint8_t>(), d_nonnull.as<int32_t>(), d_dict_src.as<int64_t>(), d_dict_len.as<int32_t>(),
                                                             d_err.as<int32_t>());
@@ -781,6 +800,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
     } else {
       oc->data = std::move(dense[c]);  // no NULLs: the dense decode IS the column
     }
+    t_pq_stats[3] += (int64_t)oc->data.bytes + (int64_t)oc->offsets.bytes + (int64_t)oc->valid.bytes;
     outs.v.push_back(oc.release());
   }
   int32_t err = 0;
@@ -795,6 +815,11 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
 
 using namespace b2;
 extern "C" {
+
+int b2_parquet_last_stats(int64_t* out5) {
+  for (int i = 0; i < 5; i++) out5[i] = t_pq_stats[i];
+  return B2_OK;
+}
 
 int b2_parquet_decode(const uint8_t* host_buf, int64_t len, const char* const* column_names, int32_t ncols, b2_handle* out_table) {
   B2_TRY

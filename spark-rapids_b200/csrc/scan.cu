@@ -274,10 +274,12 @@ static int64_t run_filter(const Program* prog, const VMInputs& in, FilterCols& f
   int grid = vm_grid(nrows, smem);
   if (count_only) {
     set_dyn_smem(filter_kernel<true>, smem);
+    KernelTimer kt_filter_count_kernel("filter_count_kernel");
     filter_kernel<true><<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, fc,
                                                           nrows, nullptr, work.as<FilterWork>());
   } else {
     set_dyn_smem(filter_kernel<false>, smem);
+    KernelTimer kt_filter_kernel("filter_kernel");
     filter_kernel<false><<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, fc,
                                                            nrows, status.as<uint64_t>(), work.as<FilterWork>());
   }
@@ -365,6 +367,7 @@ int b2_project(b2_handle program, b2_handle table, b2_handle* out_table) {
   if (n > 0) {
     int smem = prog->hdr.smem_bytes;
     set_dyn_smem(project_kernel, smem);
+    KernelTimer kt_project_kernel("project_kernel");
     project_kernel<<<vm_grid(n, smem), VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, oc, n);
     CUDA_CHECK(cudaGetLastError());
     count_launch();

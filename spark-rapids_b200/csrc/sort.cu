@@ -126,9 +126,11 @@ int radix_sort_pairs(uint64_t* keys_a, int32_t* vals_a, uint64_t* keys_b, int32_
     if (trivial) continue;
     uint64_t* kin = cur ? keys_b : keys_a; int32_t* vin = cur ? vals_b : vals_a;
     uint64_t* kout = cur ? keys_a : keys_b; int32_t* vout = cur ? vals_a : vals_b;
+    KernelTimer kt_radix_tile_hist_kernel("radix_tile_hist_kernel");
     tile_hist_kernel<<<(int)ntiles, RS_NT, 0, stream()>>>(kin, n, 8 * d, th.as<int32_t>(), ntiles);
     count_launch();
     exclusive_scan<int32_t, int64_t>(th.as<int32_t>(), to.as<int64_t>(), 256 * ntiles, false);
+    KernelTimer kt_radix_scatter_kernel("radix_scatter_kernel");
     scatter_kernel<<<(int)ntiles, RS_NT, 0, stream()>>>(kin, vin, kout, vout, n, 8 * d, to.as<int64_t>(), ntiles);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
