@@ -206,55 +206,131 @@ __device__ __forceinline__ const uint8_t* page_ptr(const PageD& pg, const uint8_
 }
 
 // ---- snappy: one warp per page ------------------------------------------------------------------
-__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t len, int lane) {
-  for (uint32_t k = lane; k < len; k += 32) dst[k] = src[k];
+// LZ77 streams are sequential per page; pages are independent (tens of thousands per partition).
+// Per warp: the compressed input is staged through a shared-memory ring (refilled 512 B at a time,
+// coalesced), every lane decodes the element header redundantly from shared memory (broadcast
+// reads, no shuffles), and the output goes through a second ring that serves the back-references
+// (<= 1 KB back: the common case for column data) and is flushed to HBM as aligned 16-byte stores.
+constexpr int SN_WARPS = 4;            // warps (pages) per CTA
+constexpr int SN_IN = 1024;            // input ring bytes
+constexpr int SN_OUT = 2048;           // output ring bytes
+constexpr int SN_HIST = 1024;          // back-reference distance served from the ring
+
+struct SnappyWarp {
+  uint8_t in[SN_IN];
+  uint8_t out[SN_OUT];
+};
+
+__device__ __forceinline__ void sn_refill(SnappyWarp& w, const uint8_t* __restrict__ src, uint32_t in_len, uint32_t& loaded, uint32_t ip, int lane) {
+  // keep [ip, loaded) valid; top up in 512-byte slabs while there is room
+  while (loaded < in_len && loaded - ip <= SN_IN - 512) {
+    const uint32_t n = min(512u, in_len - loaded);
+    for (uint32_t k = lane; k < n; k += 32) w.in[(loaded + k) & (SN_IN - 1)] = src[loaded + k];
+    loaded += n;
+  }
+  __syncwarp();
 }
-__global__ void __launch_bounds__(128) snappy_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, int ntodo,
-                                                     const uint8_t* __restrict__ file, uint8_t* __restrict__ scratch, int32_t* __restrict__ errors) {
+
+// flush complete 512-byte slabs of the output ring with 16-byte stores (dst is 16-byte aligned)
+__device__ __forceinline__ void sn_flush(SnappyWarp& w, uint8_t* __restrict__ dst, uint32_t& flushed, uint32_t op, int lane, bool final) {
+  while (op - flushed >= 512) {
+    const uint4 v = *reinterpret_cast<const uint4*>(&w.out[(flushed + lane * 16) & (SN_OUT - 1)]);
+    *reinterpret_cast<uint4*>(dst + flushed + lane * 16) = v;
+    flushed += 512;
+  }
+  if (final && flushed < op) {
+    for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)];
+    flushed = op;
+  }
+}
+
+__global__ void __launch_bounds__(SN_WARPS * 32) snappy_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, int ntodo,
+                                                               const uint8_t* __restrict__ file, uint8_t* __restrict__ scratch, int32_t* __restrict__ errors) {
+  __shared__ __align__(16) SnappyWarp s_w[SN_WARPS];
   const int lane = threadIdx.x & 31;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= ntodo) return;
-  const PageD pg = pages[todo[w]];
+  const int wi = threadIdx.x >> 5;
+  const int wg = blockIdx.x * SN_WARPS + wi;
+  if (wg >= ntodo) return;
+  SnappyWarp& w = s_w[wi];
+  const PageD pg = pages[todo[wg]];
   const uint8_t* in = file + pg.src_off;
   uint8_t* out = scratch + pg.dst_off;
   uint32_t in_len = (uint32_t)pg.comp_size, out_len = (uint32_t)pg.uncomp_size;
+  uint32_t lvl = 0;
   if (pg.lvl_bytes) {  // v2: levels are stored uncompressed in front of the compressed values
-    warp_copy(out, in, (uint32_t)pg.lvl_bytes, lane);
-    in += pg.lvl_bytes; out += pg.lvl_bytes; in_len -= pg.lvl_bytes; out_len -= pg.lvl_bytes;
+    lvl = (uint32_t)pg.lvl_bytes;
+    for (uint32_t k = lane; k < lvl; k += 32) out[k] = in[k];
+    in += lvl; in_len -= lvl; out_len -= lvl;
   }
-  uint32_t ip = 0, op = 0;
-  // preamble: uncompressed length varint
+  // the value part of a v2 page may start unaligned: fall back to byte stores for the flushes then
+  uint8_t* dst = out + lvl;
+  bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  uint32_t ip = 0, op = 0, loaded = 0, flushed = 0;
+  sn_refill(w, in, in_len, loaded, ip, lane);
   uint32_t ulen = 0;
-  { int shift = 0; while (ip < in_len) { uint8_t b = in[ip++]; ulen |= (uint32_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; } }
+  { int shift = 0; while (ip < in_len) { const uint8_t b = w.in[ip & (SN_IN - 1)]; ip++; ulen |= (uint32_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; } }
   bool bad = ulen != out_len;
   while (!bad && ip < in_len && op < out_len) {
-    // lane 0 decodes the element header, everyone copies
-    uint32_t len = 0, off = 0, hdr = 0;
-    if (lane == 0) {
-      const uint8_t tag = in[ip];
-      const uint32_t t = tag & 3;
-      if (t == 0) {
-        len = tag >> 2;
-        if (len < 60) { len += 1; hdr = 1; }
-        else { const uint32_t nb = len - 59; uint32_t v = 0; for (uint32_t k = 0; k < nb; k++) v |= (uint32_t)in[ip + 1 + k] << (8 * k); len = v + 1; hdr = 1 + nb; }
-      } else if (t == 1) { len = 4 + ((tag >> 2) & 7); off = ((uint32_t)(tag >> 5) << 8) | in[ip + 1]; hdr = 2; }
-      else if (t == 2) { len = (tag >> 2) + 1; off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8); hdr = 3; }
-      else { len = (tag >> 2) + 1; off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8) | ((uint32_t)in[ip + 3] << 16) | ((uint32_t)in[ip + 4] << 24); hdr = 5; }
+    if (loaded - ip < 8 && loaded < in_len) sn_refill(w, in, in_len, loaded, ip, lane);
+    // every lane decodes the same header from shared memory
+    const uint32_t tag = w.in[ip & (SN_IN - 1)];
+    const uint32_t b1 = w.in[(ip + 1) & (SN_IN - 1)], b2 = w.in[(ip + 2) & (SN_IN - 1)], b3 = w.in[(ip + 3) & (SN_IN - 1)], b4 = w.in[(ip + 4) & (SN_IN - 1)];
+    const uint32_t t = tag & 3;
+    uint32_t len, off = 0, hdr;
+    if (t == 0) {
+      len = tag >> 2;
+      if (len < 60) { len += 1; hdr = 1; }
+      else { const uint32_t nb = len - 59; const uint32_t v = b1 | (b2 << 8) | (b3 << 16) | (b4 << 24); len = (nb == 4 ? v : (v & ((1u << (8 * nb)) - 1))) + 1; hdr = 1 + nb; }
+    } else if (t == 1) { len = 4 + ((tag >> 2) & 7); off = ((tag >> 5) << 8) | b1; hdr = 2; }
+    else if (t == 2) { len = (tag >> 2) + 1; off = b1 | (b2 << 8); hdr = 3; }
+    else { len = (tag >> 2) + 1; off = b1 | (b2 << 8) | (b3 << 16) | (b4 << 24); hdr = 5; }
+    if (op + len > out_len || (t == 0 && ip + hdr + len > in_len) || (t != 0 && (off == 0 || off > op))) { bad = true; break; }
+    ip += hdr;
+    if (t == 0) {
+      // literal: stream it through the rings in <= 512-byte pieces
+      uint32_t left = len;
+      while (left) {
+        const uint32_t n = min(left, 512u);
+        if (loaded - ip < n) sn_refill(w, in, in_len, loaded, ip, lane);
+        const uint32_t have = min(n, loaded - ip);
+        for (uint32_t k = lane; k < have; k += 32) w.out[(op + k) & (SN_OUT - 1)] = w.in[(ip + k) & (SN_IN - 1)];
+        __syncwarp();
+        ip += have; op += have; left -= have;
+        if (op - flushed >= 512) {
+          if (aligned) sn_flush(w, dst, flushed, op, lane, false);
+          else { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; flushed = op; }
+          __syncwarp();
+        }
+        if (have == 0) { bad = true; break; }
+      }
+    } else {
+      if (off <= SN_HIST) {
+        // back-reference served from the ring; overlapping copies repeat with period `off`
+        uint8_t v = 0;
+        if (lane < (int)len) v = w.out[(op - off + (off >= len ? lane : lane % off)) & (SN_OUT - 1)];
+        uint8_t v2 = 0;
+        if (lane + 32 < (int)len) v2 = w.out[(op - off + (off >= len ? lane + 32 : (lane + 32) % off)) & (SN_OUT - 1)];
+        __syncwarp();
+        if (lane < (int)len) w.out[(op + lane) & (SN_OUT - 1)] = v;
+        if (lane + 32 < (int)len) w.out[(op + lane + 32) & (SN_OUT - 1)] = v2;
+      } else {
+        // far reference: the source is already in HBM except possibly its unflushed tail
+        if (flushed < op) { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; flushed = op; aligned = aligned && (flushed & 15) == 0; }
+        __syncwarp();
+        const uint8_t* src = dst + op - off;
+        for (uint32_t k = lane; k < len; k += 32) w.out[(op + k) & (SN_OUT - 1)] = src[k];  // off > len here (len <= 64 < 1024 < off)
+      }
+      __syncwarp();
+      op += len;
+      if (op - flushed >= 512) {
+        if (aligned) sn_flush(w, dst, flushed, op, lane, false);
+        else { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; flushed = op; }
+        __syncwarp();
+      }
     }
-    len = __shfl_sync(0xffffffffu, len, 0); off = __shfl_sync(0xffffffffu, off, 0); hdr = __shfl_sync(0xffffffffu, hdr, 0);
-    if (off == 0) {  // literal
-      if (ip + hdr + len > in_len || op + len > out_len) { bad = true; break; }
-      warp_copy(out + op, in + ip + hdr, len, lane);
-      ip += hdr + len;
-    } else {  // copy from `off` bytes back; overlapping copies repeat with period `off`
-      if (off > op || op + len > out_len) { bad = true; break; }
-      const uint8_t* src = out + op - off;
-      for (uint32_t k = lane; k < len; k += 32) out[op + k] = src[off >= len ? k : k % off];
-      ip += hdr;
-    }
-    op += len;
-    __syncwarp();
   }
+  __syncwarp();
+  if (flushed < op) { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; }
   if ((bad || op != out_len) && lane == 0) atomicExch(errors, 1);
 }
 
@@ -715,7 +791,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   upload(todo_snappy, d_todo_s); upload(todo_levels, d_todo_l); upload(todo_values, d_todo_v);
   if (!todo_snappy.empty()) {
     KernelTimer kt_snappy_kernel("snappy_kernel");
-    snappy_kernel<<<((int)todo_snappy.size() * 32 + 127) / 128, 128, 0, s>>>(d_pages.as<PageD>(), d_todo_s.as<int32_t>(), (int)todo_snappy.size(), d_file,
+    snappy_kernel<<<((int)todo_snappy.size() + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, 0, s>>>(d_pages.as<PageD>(), d_todo_s.as<int32_t>(), (int)todo_snappy.size(), d_file,
                                                                               scratch.as<uint8_t>(), d_err.as<int32_t>());
     CUDA_CHECK(cudaGetLastError());
     count_launch();
