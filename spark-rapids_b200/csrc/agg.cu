@@ -96,12 +96,16 @@ __device__ __forceinline__ u128 group_sum_u64(uint32_t m, uint64_t x) {
 // Accumulate one warp-slice (32 rows) into per-slot accumulators.  `m` = lanes sharing my slot,
 // leader = lowest lane of m.  acc/nvalid point at MY slot's blocks (only dereferenced by leaders,
 // or by every active lane for float / min / max).
-__device__ __forceinline__ void accumulate_slice(const AggPlan& plan, const VMCtx& cx, const Opnd* ops, int i, int64_t g,
+__device__ __forceinline__ void accumulate_slice(const AggPlan& plan, const VMCtx& cx, int i, int64_t g,
                                                  bool active, uint32_t m, bool leader, uint64_t* acc, uint32_t* nvalid) {
   for (int k = 0; k < plan.naggs; k++) {
     const AggD& a = plan.aggs[k];
     bool valid = active;
-    if (a.out_idx >= 0 && active) valid = opnd_valid(ops[k], i, g);
+    // operands are re-resolved per aggregate (a few shared-memory reads) instead of being kept in a
+    // dynamically indexed array, which would live in local memory
+    Opnd opk;
+    if (a.out_idx >= 0) opk = resolve(cx, cx.hdr->outs[a.out_idx], mt_width(a.in_mt));
+    if (a.out_idx >= 0 && active) valid = opnd_valid(opk, i, g);
     const uint32_t vcount = __popc(__ballot_sync(0xffffffffu, valid) & m);
     if (a.track_valid && leader && active && vcount) atomicAdd(&nvalid[a.valid_off], vcount);
     switch (a.kind) {
@@ -111,7 +115,7 @@ __device__ __forceinline__ void accumulate_slice(const AggPlan& plan, const VMCt
       case B2_AGG_SUM: {
         if (a.is_float) {
           double v = 0.0;
-          if (valid) v = a.in_mt == MT_F32 ? (double)opnd_ld<float>(ops[k], i) : opnd_ld<double>(ops[k], i);
+          if (valid) v = a.in_mt == MT_F32 ? (double)opnd_ld<float>(opk, i) : opnd_ld<double>(opk, i);
           if (valid) atomicAdd(reinterpret_cast<double*>(&acc[a.limb_off]), v);
           break;
         }
@@ -119,11 +123,11 @@ __device__ __forceinline__ void accumulate_slice(const AggPlan& plan, const VMCt
         uint64_t lo = 0, hi = 0;
         if (valid) {
           switch (a.in_mt) {
-            case MT_I8: lo = (uint64_t)(int64_t)opnd_ld<int8_t>(ops[k], i); break;
-            case MT_I16: lo = (uint64_t)(int64_t)opnd_ld<int16_t>(ops[k], i); break;
-            case MT_I32: lo = (uint64_t)(int64_t)opnd_ld<int32_t>(ops[k], i); break;
-            case MT_I64: lo = (uint64_t)opnd_ld<int64_t>(ops[k], i); break;
-            default: { i128 v = opnd_ld<i128>(ops[k], i); lo = (uint64_t)v; hi = (uint64_t)(v >> 64); } break;
+            case MT_I8: lo = (uint64_t)(int64_t)opnd_ld<int8_t>(opk, i); break;
+            case MT_I16: lo = (uint64_t)(int64_t)opnd_ld<int16_t>(opk, i); break;
+            case MT_I32: lo = (uint64_t)(int64_t)opnd_ld<int32_t>(opk, i); break;
+            case MT_I64: lo = (uint64_t)opnd_ld<int64_t>(opk, i); break;
+            default: { i128 v = opnd_ld<i128>(opk, i); lo = (uint64_t)v; hi = (uint64_t)(v >> 64); } break;
           }
           if (a.in_mt != MT_I128) hi = ((int64_t)lo < 0) ? ~0ull : 0ull;
         }
@@ -150,18 +154,83 @@ __device__ __forceinline__ void accumulate_slice(const AggPlan& plan, const VMCt
         if (!valid) break;
         uint64_t key;
         switch (a.in_mt) {
-          case MT_I8: key = ord_i64(opnd_ld<int8_t>(ops[k], i)); break;
-          case MT_I16: key = ord_i64(opnd_ld<int16_t>(ops[k], i)); break;
-          case MT_I32: key = ord_i64(opnd_ld<int32_t>(ops[k], i)); break;
-          case MT_I64: key = ord_i64(opnd_ld<int64_t>(ops[k], i)); break;
-          case MT_F32: key = ord_f64((double)opnd_ld<float>(ops[k], i)); break;
-          default: key = ord_f64(opnd_ld<double>(ops[k], i)); break;
+          case MT_I8: key = ord_i64(opnd_ld<int8_t>(opk, i)); break;
+          case MT_I16: key = ord_i64(opnd_ld<int16_t>(opk, i)); break;
+          case MT_I32: key = ord_i64(opnd_ld<int32_t>(opk, i)); break;
+          case MT_I64: key = ord_i64(opnd_ld<int64_t>(opk, i)); break;
+          case MT_F32: key = ord_f64((double)opnd_ld<float>(opk, i)); break;
+          default: key = ord_f64(opnd_ld<double>(opk, i)); break;
         }
         unsigned long long* p = reinterpret_cast<unsigned long long*>(&acc[a.limb_off]);
         if (a.kind == B2_AGG_MIN) atomicMin(p, (unsigned long long)key); else atomicMax(p, (unsigned long long)key);
       } break;
       default: break;
     }
+  }
+}
+
+// Keyless reduction: every thread folds its own rows into private shared-memory accumulators
+// (no atomics, no warp collectives); the CTA combines them once at the end.
+__device__ __forceinline__ void accumulate_private(const AggPlan& plan, const VMCtx& cx, uint32_t active_mask, uint64_t* priv, uint32_t* privv) {
+  const int K = cx.K;
+  for (int k = 0; k < plan.naggs; k++) {
+    const AggD& a = plan.aggs[k];
+    Opnd op;
+    if (a.out_idx >= 0) op = resolve(cx, cx.hdr->outs[a.out_idx], mt_width(a.in_mt));
+    uint64_t* p0 = &priv[a.limb_off * VM_NT + threadIdx.x];
+    uint32_t nvalid = 0;
+    uint64_t l0 = p0[0], l1 = a.nlimbs > 1 ? p0[VM_NT] : 0, l2 = a.nlimbs > 2 ? p0[2 * VM_NT] : 0;
+    for (int j = 0; j < K; j++) {
+      if (!((active_mask >> j) & 1u)) continue;
+      const int i = threadIdx.x + j * VM_NT;
+      const int64_t g = cx.tile_base + i;
+      if (a.out_idx >= 0 && !opnd_valid(op, i, g)) continue;
+      nvalid++;
+      switch (a.kind) {
+        case B2_AGG_COUNT: case B2_AGG_COUNT_ALL: l0 += 1; break;
+        case B2_AGG_SUM: {
+          if (a.is_float) {
+            const double v = a.in_mt == MT_F32 ? (double)opnd_ld<float>(op, i) : opnd_ld<double>(op, i);
+            l0 = (uint64_t)__double_as_longlong(__longlong_as_double((long long)l0) + v);
+            break;
+          }
+          uint64_t lo, hi;
+          switch (a.in_mt) {
+            case MT_I8: lo = (uint64_t)(int64_t)opnd_ld<int8_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+            case MT_I16: lo = (uint64_t)(int64_t)opnd_ld<int16_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+            case MT_I32: lo = (uint64_t)(int64_t)opnd_ld<int32_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+            case MT_I64: lo = (uint64_t)opnd_ld<int64_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+            default: { const i128 v = opnd_ld<i128>(op, i); lo = (uint64_t)v; hi = (uint64_t)(v >> 64); } break;
+          }
+          const uint64_t s0 = l0 + lo;
+          const uint64_t c0 = s0 < l0;
+          l0 = s0;
+          if (a.nlimbs > 1) {
+            const uint64_t t1 = l1 + hi, c1a = t1 < l1;
+            const uint64_t s1 = t1 + c0, c1b = s1 < t1;
+            l1 = s1;
+            if (a.nlimbs > 2) l2 += ((int64_t)hi < 0 ? ~0ull : 0ull) + c1a + c1b;
+          }
+        } break;
+        case B2_AGG_MIN: case B2_AGG_MAX: {
+          uint64_t key;
+          switch (a.in_mt) {
+            case MT_I8: key = ord_i64(opnd_ld<int8_t>(op, i)); break;
+            case MT_I16: key = ord_i64(opnd_ld<int16_t>(op, i)); break;
+            case MT_I32: key = ord_i64(opnd_ld<int32_t>(op, i)); break;
+            case MT_I64: key = ord_i64(opnd_ld<int64_t>(op, i)); break;
+            case MT_F32: key = ord_f64((double)opnd_ld<float>(op, i)); break;
+            default: key = ord_f64(opnd_ld<double>(op, i)); break;
+          }
+          l0 = a.kind == B2_AGG_MIN ? (key < l0 ? key : l0) : (key > l0 ? key : l0);
+        } break;
+        default: break;
+      }
+    }
+    p0[0] = l0;
+    if (a.nlimbs > 1) p0[VM_NT] = l1;
+    if (a.nlimbs > 2) p0[2 * VM_NT] = l2;
+    if (a.track_valid && nvalid) privv[a.valid_off * VM_NT + threadIdx.x] += nvalid;
   }
 }
 
@@ -192,7 +261,7 @@ __global__ void init_table_kernel(GTable gt, const __grid_constant__ AggPlan pla
 
 // SMEM = true: per-CTA shared table + merge; false: straight to the global table
 template <bool SMEM>
-__global__ void __launch_bounds__(VM_NT) aggregate_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
+__global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
                                                           const __grid_constant__ VMInputs in, const __grid_constant__ AggPlan plan,
                                                           GTable gt, int64_t nrows, int smem_regs_bytes) {
   __shared__ VMShared sh;
@@ -202,6 +271,10 @@ __global__ void __launch_bounds__(VM_NT) aggregate_kernel(const VMProgramHeader*
   int32_t* s_slots = reinterpret_cast<int32_t*>(dyn + smem_regs_bytes);
   uint64_t* s_acc = reinterpret_cast<uint64_t*>(dyn + smem_regs_bytes + SMEM_SLOTS * 4);
   uint32_t* s_nvalid = reinterpret_cast<uint32_t*>(s_acc + (SMEM ? SMEM_SLOTS * plan.limbs : 0));
+  // keyless reductions: one private accumulator set per thread, [limb][thread] / [valid][thread]
+  uint64_t* s_priv = reinterpret_cast<uint64_t*>(s_nvalid + SMEM_SLOTS * plan.nvalids + (SMEM_SLOTS * plan.nvalids & 1));
+  uint32_t* s_privv = reinterpret_cast<uint32_t*>(s_priv + plan.limbs * VM_NT);
+  const bool keyless = SMEM && plan.nkeys == 0;
   const VMInstr* code = vm_load_program(sh, g_hdr, g_code);
   const int lane = threadIdx.x & 31;
   // a keyless reduction always has its single group, even over zero rows (GpuAggregateExec.scala:1107-1126)
@@ -213,24 +286,44 @@ __global__ void __launch_bounds__(VM_NT) aggregate_kernel(const VMProgramHeader*
         for (int l = 0; l < plan.aggs[k].nlimbs; l++) s_acc[s * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
       for (int v = 0; v < plan.nvalids; v++) s_nvalid[s * plan.nvalids + v] = 0;
     }
+    if (keyless) {
+      for (int k = 0; k < plan.naggs; k++)
+        for (int l = 0; l < plan.aggs[k].nlimbs; l++) s_priv[(plan.aggs[k].limb_off + l) * VM_NT + threadIdx.x] = init_limb(plan.aggs[k]);
+      for (int v = 0; v < plan.nvalids; v++) s_privv[v * VM_NT + threadIdx.x] = 0;
+    }
     __syncthreads();
   }
-  const int64_t ntiles = (nrows + VM_TILE - 1) / VM_TILE;
+  const int64_t ntiles = (nrows + sh.hdr.tile_rows - 1) / sh.hdr.tile_rows;
+  const int first_post = plan.has_pred ? sh.hdr.npred : 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (SMEM && *reinterpret_cast<volatile int32_t*>(gt.overflow)) break;  // someone overflowed: the launch is void
-    VMCtx cx; cx.hdr = &sh.hdr; cx.in = &in; cx.smem = regs; cx.tile_base = tile * VM_TILE; cx.nrows = nrows;
-    vm_run(cx, code);
-    Opnd pred;
-    if (plan.has_pred) pred = resolve(cx, sh.hdr.outs[0], 1);
-    Opnd ops[AG_MAX_AGGS];
-    for (int k = 0; k < plan.naggs; k++)
-      if (plan.aggs[k].out_idx >= 0) ops[k] = resolve(cx, sh.hdr.outs[plan.aggs[k].out_idx], mt_width(plan.aggs[k].in_mt));
+    VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
+    uint32_t active_mask = 0;
+    if (plan.has_pred) {
+      // predicate first; the projection only runs for rows that survive it (per-thread row mask)
+      vm_run(cx, code, 0, first_post);
+      const Opnd pred = resolve(cx, sh.hdr.outs[0], 1);
+      for (int j = 0; j < cx.K; j++) {
+        const int i = threadIdx.x + j * VM_NT;
+        const int64_t g = cx.tile_base + i;
+        const bool a = g < nrows && opnd_valid(pred, i, g) && opnd_ld<int8_t>(pred, i) != 0;
+        active_mask |= (uint32_t)a << j;
+      }
+      cx.rowmask = active_mask;
+    } else {
+      for (int j = 0; j < cx.K; j++) active_mask |= (uint32_t)(cx.tile_base + threadIdx.x + j * VM_NT < nrows) << j;
+    }
+    vm_run(cx, code, first_post, sh.hdr.ninstr);
+    if (keyless) {
+      accumulate_private(plan, cx, active_mask, s_priv, s_privv);
+      continue;
+    }
 #pragma unroll 1
-    for (int j = 0; j < VM_K; j++) {
+    for (int j = 0; j < cx.K; j++) {
       const int i = threadIdx.x + j * VM_NT;
       const int64_t g = cx.tile_base + i;
-      bool active = g < nrows;
-      if (active && plan.has_pred) active = opnd_valid(pred, i, g) && opnd_ld<int8_t>(pred, i) != 0;
+      bool active = (active_mask >> j) & 1u;
+      if (__ballot_sync(0xffffffffu, active) == 0) continue;  // nothing selected in these 32 rows
       int32_t slot = -1;
       if (active) {
         if (SMEM) {
@@ -261,8 +354,24 @@ __global__ void __launch_bounds__(VM_NT) aggregate_kernel(const VMProgramHeader*
         acc = SMEM ? &s_acc[slot * plan.limbs] : &gt.acc[(int64_t)slot * plan.limbs];
         nv = SMEM ? &s_nvalid[slot * plan.nvalids] : &gt.nvalid[(int64_t)slot * plan.nvalids];
       }
-      accumulate_slice(plan, cx, ops, i, g, active && slot >= 0, m, leader, acc, nv);
+      accumulate_slice(plan, cx, i, g, active && slot >= 0, m, leader, acc, nv);
     }
+  }
+  if (keyless) {
+    s_slots[0] = 0;
+    __syncthreads();
+    for (int k = 0; k < plan.naggs; k++) {
+      const AggD& a = plan.aggs[k];
+      unsigned long long* p = reinterpret_cast<unsigned long long*>(&s_acc[a.limb_off]);
+      const uint64_t l0 = s_priv[a.limb_off * VM_NT + threadIdx.x];
+      if (a.kind == B2_AGG_MIN) atomicMin(p, (unsigned long long)l0);
+      else if (a.kind == B2_AGG_MAX) atomicMax(p, (unsigned long long)l0);
+      else if (a.is_float) atomicAdd(reinterpret_cast<double*>(p), __longlong_as_double((long long)l0));
+      else acc_add_limbs(&s_acc[a.limb_off], a.nlimbs, l0, a.nlimbs > 1 ? s_priv[(a.limb_off + 1) * VM_NT + threadIdx.x] : 0,
+                         a.nlimbs > 2 ? s_priv[(a.limb_off + 2) * VM_NT + threadIdx.x] : 0);
+    }
+    for (int v = 0; v < plan.nvalids; v++)
+      if (s_privv[v * VM_NT + threadIdx.x]) atomicAdd(&s_nvalid[v], s_privv[v * VM_NT + threadIdx.x]);
   }
   if (SMEM) {
     __syncthreads();
@@ -366,7 +475,7 @@ __global__ void finalize_kernel(GTable gt, const __grid_constant__ AggPlan plan,
 // ------------------------------------------------------------------------------------------------
 void check_program_inputs(const Program* p, const Table* t);
 void fill_inputs(VMInputs& in, const Table* t);
-int vm_grid(int64_t nrows, int smem_bytes);
+int vm_grid(int64_t nrows, int smem_bytes, int tile_rows);
 Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullify_oob, const std::vector<int>* only_cols);
 Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
 
@@ -459,16 +568,17 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   bool done = false;
   // regime 1: shared-memory tables (always right for reductions; optimistic for group-by)
   {
-    int table_bytes = SMEM_SLOTS * 4 + SMEM_SLOTS * plan.limbs * 8 + SMEM_SLOTS * plan.nvalids * 4;
+    int table_bytes = SMEM_SLOTS * 4 + SMEM_SLOTS * plan.limbs * 8 + SMEM_SLOTS * plan.nvalids * 4 + 8;
+    if (nkeys == 0) table_bytes += plan.limbs * VM_NT * 8 + plan.nvalids * VM_NT * 4;
     int smem = ((vm_smem + 15) & ~15) + table_bytes;
     if (smem <= 160 * 1024) {
-      int grid = n > 0 ? vm_grid(n, smem) : 1;
+      int grid = n > 0 ? vm_grid(n, smem, prog->hdr.tile_rows) : 1;
       cap = 1;
       while (cap < (int64_t)grid * SMEM_SLOTS * 2) cap <<= 1;
       if (nkeys == 0) cap = 1;
       alloc_table(cap, slots, acc, nv, ovf, gt);
       if (n > 0 || nkeys == 0) {
-        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (smem > 32 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         KernelTimer kt_aggregate_smem_kernel("aggregate_smem_kernel");
         aggregate_kernel<true><<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, plan, gt, n,
                                                                   (vm_smem + 15) & ~15);
@@ -484,9 +594,9 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
     cap = 1024;
     while (cap < n * 2) cap <<= 1;
     alloc_table(cap, slots, acc, nv, ovf, gt);
-    if (vm_smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem));
+    if (vm_smem > 32 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem));
     KernelTimer kt_aggregate_global_kernel("aggregate_global_kernel");
-    aggregate_kernel<false><<<vm_grid(n, vm_smem), VM_NT, vm_smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in,
+    aggregate_kernel<false><<<vm_grid(n, vm_smem, prog->hdr.tile_rows), VM_NT, vm_smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in,
                                                                                 plan, gt, n, (vm_smem + 15) & ~15);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -550,6 +660,7 @@ Program* make_passthrough_program(const Table* t, const std::vector<int>& cols) 
     maxc = std::max(maxc, c + 1);
   }
   p->hdr.ncols = maxc;
+  set_tile_geometry(p->hdr, 0);
   p->col_dtype.resize(maxc);
   p->d_hdr = DevBuf(sizeof(VMProgramHeader));
   h2d(p->d_hdr.p, &p->hdr, 1);

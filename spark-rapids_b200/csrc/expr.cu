@@ -81,9 +81,9 @@ struct Compiler {
   int alloc_slot(int width) {
     auto& fl = free_slots[width];
     if (!fl.empty()) { int o = fl.back(); fl.pop_back(); return o; }
-    int bytes = width * VM_TILE;
-    bump = (bump + 15) & ~15;
-    int o = bump; bump += bytes;
+    // offsets are in bytes PER ROW; the kernel scales them by the tile's row count (a multiple of
+    // 256), so every slot base stays 256-byte aligned
+    int o = bump; bump += width;
     return o;
   }
   int alloc_reg(int mt, bool nullable) {
@@ -314,6 +314,10 @@ struct Compiler {
         if (a.o.kind == OK_LIT) std::swap(a, b);
         if (a.o.kind == OK_LIT) a = emit(V_MOV, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, a.precision, a.scale);
         if (p <= 38) {
+          if (rmt == MT_I128 && a.mt <= MT_I64 && b.mt <= MT_I64) {  // exact 64x64 -> 128, no widened temporaries
+            a = widen_int(a, MT_I64); b = widen_int(b, MT_I64);
+            return emit(V_MULW, MT_I64, MT_I128, MT_I128, a.nullable || b.nullable, 0, &a, &b, nullptr, rdt, rp, rs);
+          }
           a = widen_int(a, rmt); b = widen_int(b, rmt);
           return emit(V_MUL, rmt, rmt, rmt, a.nullable || b.nullable, 0, &a, &b, nullptr, rdt, rp, rs);
         }
@@ -359,6 +363,17 @@ struct Compiler {
   }
 };
 
+// rows per tile: as many as fit the register budget (multiple of VM_NT, at most VM_MAX_K per thread)
+void set_tile_geometry(VMProgramHeader& hdr, int bytes_per_row) {
+  hdr.bytes_per_row = bytes_per_row;
+  int k = bytes_per_row > 0 ? VM_SMEM_BUDGET / (bytes_per_row * VM_NT) : VM_MAX_K;
+  if (k > VM_MAX_K) k = VM_MAX_K;
+  if (k < 1) k = 1;
+  hdr.tile_rows = k * VM_NT;
+  hdr.smem_bytes = bytes_per_row * hdr.tile_rows;
+  if (hdr.smem_bytes > 200 * 1024) throw Error(B2_ERR_UNSUPPORTED, "expression needs too much shared memory");
+}
+
 static Program* compile_program(const b2_handle* exprs, int n) {
   if (n <= 0 || n > VM_MAX_OUTS) throw Error(B2_ERR_INVALID, "bad number of output expressions");
   std::unique_ptr<Program> prog(new Program());
@@ -367,6 +382,7 @@ static Program* compile_program(const b2_handle* exprs, int n) {
   for (int i = 0; i < n; i++) {
     Val v = cc.compile(expr_from(exprs[i]));
     if (v.o.kind == OK_REG) cc.reg_pinned[v.o.idx] = true;  // outputs stay live
+    if (i == 0) prog->hdr.npred = (int)prog->code.size();
     prog->hdr.outs[i] = v.o;
     prog->hdr.out_mt[i] = (uint8_t)v.mt;
     prog->out_dtype.push_back(v.dtype); prog->out_scale.push_back(v.scale); prog->out_precision.push_back(v.precision);
@@ -376,8 +392,7 @@ static Program* compile_program(const b2_handle* exprs, int n) {
   prog->hdr.nregs = (int)cc.reg_width.size();
   prog->hdr.ncols = (int)prog->col_dtype.size();
   prog->hdr.nouts = n;
-  prog->hdr.smem_bytes = (cc.bump + 15) & ~15;
-  if (prog->hdr.smem_bytes > 200 * 1024) throw Error(B2_ERR_UNSUPPORTED, "expression needs too much shared memory");
+  set_tile_geometry(prog->hdr, cc.bump);
   prog->d_hdr = DevBuf(sizeof(VMProgramHeader));
   h2d(prog->d_hdr.p, &prog->hdr, 1);
   prog->d_code = DevBuf(std::max<size_t>(1, prog->code.size()) * sizeof(VMInstr));

@@ -205,16 +205,18 @@ __device__ __forceinline__ const uint8_t* page_ptr(const PageD& pg, const uint8_
   return pg.dst_off >= 0 ? scratch + pg.dst_off : file + pg.src_off;
 }
 
-// ---- snappy: one warp per page ------------------------------------------------------------------
-// LZ77 streams are sequential per page; pages are independent (tens of thousands per partition).
-// Per warp: the compressed input is staged through a shared-memory ring (refilled 512 B at a time,
-// coalesced), every lane decodes the element header redundantly from shared memory (broadcast
-// reads, no shuffles), and the output goes through a second ring that serves the back-references
-// (<= 1 KB back: the common case for column data) and is flushed to HBM as aligned 16-byte stores.
+// ---- snappy: one warp per page, 32 candidate element starts parsed per step ---------------------
+// An LZ77 stream is sequential per page; pages are independent (tens of thousands per partition).
+// Per warp the compressed input is staged through a shared-memory ring and the output through a
+// second ring that serves back-references up to 2 KB and is flushed to HBM as 16-byte stores.
+// Each step looks at a 32-byte window of the input: every lane decodes the element that WOULD start
+// at its byte (header size, lengths, offset), the true element chain is then walked from lane 0 with
+// shuffles (two elements per hop), output positions come from a warp scan, all short literals are
+// copied by their own lanes at once, and only the back-references are replayed in order.
 constexpr int SN_WARPS = 4;            // warps (pages) per CTA
 constexpr int SN_IN = 1024;            // input ring bytes
-constexpr int SN_OUT = 2048;           // output ring bytes
-constexpr int SN_HIST = 1024;          // back-reference distance served from the ring
+constexpr int SN_OUT = 8192;           // output ring bytes
+constexpr int SN_HIST = 4096;          // back-reference distance served from the ring (older bytes are already in HBM)
 
 struct SnappyWarp {
   uint8_t in[SN_IN];
@@ -222,7 +224,6 @@ struct SnappyWarp {
 };
 
 __device__ __forceinline__ void sn_refill(SnappyWarp& w, const uint8_t* __restrict__ src, uint32_t in_len, uint32_t& loaded, uint32_t ip, int lane) {
-  // keep [ip, loaded) valid; top up in 512-byte slabs while there is room
   while (loaded < in_len && loaded - ip <= SN_IN - 512) {
     const uint32_t n = min(512u, in_len - loaded);
     for (uint32_t k = lane; k < n; k += 32) w.in[(loaded + k) & (SN_IN - 1)] = src[loaded + k];
@@ -231,16 +232,28 @@ __device__ __forceinline__ void sn_refill(SnappyWarp& w, const uint8_t* __restri
   __syncwarp();
 }
 
-// flush complete 512-byte slabs of the output ring with 16-byte stores (dst is 16-byte aligned)
-__device__ __forceinline__ void sn_flush(SnappyWarp& w, uint8_t* __restrict__ dst, uint32_t& flushed, uint32_t op, int lane, bool final) {
-  while (op - flushed >= 512) {
-    const uint4 v = *reinterpret_cast<const uint4*>(&w.out[(flushed + lane * 16) & (SN_OUT - 1)]);
-    *reinterpret_cast<uint4*>(dst + flushed + lane * 16) = v;
-    flushed += 512;
+// write ring bytes [flushed, target) to HBM: byte head up to 16-byte alignment, 512-byte slabs of
+// 16-byte stores, and (when `all`) a byte tail
+__device__ __forceinline__ void sn_flush(SnappyWarp& w, uint8_t* __restrict__ dst, uint32_t& flushed, uint32_t target, int lane, bool all) {
+  if (flushed >= target) return;
+  // 16-byte stores need the HBM address and the ring index aligned together
+  const bool can_vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  if (!can_vec) all = true;
+  if (can_vec && (flushed & 15) && (all || target - flushed >= 512 + 16)) {
+    const uint32_t n = min(16 - (flushed & 15), target - flushed);
+    if (lane < (int)n) dst[flushed + lane] = w.out[(flushed + lane) & (SN_OUT - 1)];
+    flushed += n;
   }
-  if (final && flushed < op) {
-    for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)];
-    flushed = op;
+  if (can_vec && (flushed & 15) == 0) {
+    while (target - flushed >= 512) {
+      const uint4 v = *reinterpret_cast<const uint4*>(&w.out[(flushed + lane * 16) & (SN_OUT - 1)]);
+      *reinterpret_cast<uint4*>(dst + flushed + lane * 16) = v;
+      flushed += 512;
+    }
+  }
+  if (all) {
+    for (uint32_t k = flushed + lane; k < target; k += 32) dst[k] = w.out[k & (SN_OUT - 1)];
+    flushed = target;
   }
 }
 
@@ -256,25 +269,23 @@ __global__ void __launch_bounds__(SN_WARPS * 32) snappy_kernel(const PageD* __re
   const uint8_t* in = file + pg.src_off;
   uint8_t* out = scratch + pg.dst_off;
   uint32_t in_len = (uint32_t)pg.comp_size, out_len = (uint32_t)pg.uncomp_size;
-  uint32_t lvl = 0;
   if (pg.lvl_bytes) {  // v2: levels are stored uncompressed in front of the compressed values
-    lvl = (uint32_t)pg.lvl_bytes;
+    const uint32_t lvl = (uint32_t)pg.lvl_bytes;
     for (uint32_t k = lane; k < lvl; k += 32) out[k] = in[k];
-    in += lvl; in_len -= lvl; out_len -= lvl;
+    in += lvl; out += lvl; in_len -= lvl; out_len -= lvl;
   }
-  // the value part of a v2 page may start unaligned: fall back to byte stores for the flushes then
-  uint8_t* dst = out + lvl;
-  bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  uint8_t* dst = out;
   uint32_t ip = 0, op = 0, loaded = 0, flushed = 0;
   sn_refill(w, in, in_len, loaded, ip, lane);
   uint32_t ulen = 0;
   { int shift = 0; while (ip < in_len) { const uint8_t b = w.in[ip & (SN_IN - 1)]; ip++; ulen |= (uint32_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; } }
   bool bad = ulen != out_len;
   while (!bad && ip < in_len && op < out_len) {
-    if (loaded - ip < 8 && loaded < in_len) sn_refill(w, in, in_len, loaded, ip, lane);
-    // every lane decodes the same header from shared memory
-    const uint32_t tag = w.in[ip & (SN_IN - 1)];
-    const uint32_t b1 = w.in[(ip + 1) & (SN_IN - 1)], b2 = w.in[(ip + 2) & (SN_IN - 1)], b3 = w.in[(ip + 3) & (SN_IN - 1)], b4 = w.in[(ip + 4) & (SN_IN - 1)];
+    if (loaded - ip < 40 && loaded < in_len) sn_refill(w, in, in_len, loaded, ip, lane);
+    // ---- 1. every lane decodes the element that would start at byte ip + lane
+    const uint32_t q = ip + lane;
+    const uint32_t tag = w.in[q & (SN_IN - 1)];
+    const uint32_t b1 = w.in[(q + 1) & (SN_IN - 1)], b2 = w.in[(q + 2) & (SN_IN - 1)], b3 = w.in[(q + 3) & (SN_IN - 1)], b4 = w.in[(q + 4) & (SN_IN - 1)];
     const uint32_t t = tag & 3;
     uint32_t len, off = 0, hdr;
     if (t == 0) {
@@ -284,53 +295,89 @@ __global__ void __launch_bounds__(SN_WARPS * 32) snappy_kernel(const PageD* __re
     } else if (t == 1) { len = 4 + ((tag >> 2) & 7); off = ((tag >> 5) << 8) | b1; hdr = 2; }
     else if (t == 2) { len = (tag >> 2) + 1; off = b1 | (b2 << 8); hdr = 3; }
     else { len = (tag >> 2) + 1; off = b1 | (b2 << 8) | (b3 << 16) | (b4 << 24); hdr = 5; }
-    if (op + len > out_len || (t == 0 && ip + hdr + len > in_len) || (t != 0 && (off == 0 || off > op))) { bad = true; break; }
-    ip += hdr;
-    if (t == 0) {
-      // literal: stream it through the rings in <= 512-byte pieces
-      uint32_t left = len;
+    const bool is_lit = t == 0;
+    const uint32_t esz = hdr + (is_lit ? len : 0);          // compressed bytes of this element
+    const uint32_t avail = min(32u, in_len - ip);
+    // a literal whose data does not end inside the window is streamed separately ("long")
+    const bool is_long = is_lit && (lane + esz > 32 || len > 31);
+    const uint32_t n1 = (lane >= avail) ? 64u : (is_long ? 64u : min(lane + esz, 64u));  // next start, 64 = leaves the window
+    uint32_t n2 = __shfl_sync(0xffffffffu, n1, n1 & 31);
+    if (n1 >= 32) n2 = 64u;
+    // ---- 2. walk the true chain from lane 0, two elements per hop
+    uint32_t M = 0, cur = 0;
+    while (cur < 32) {
+      M |= 1u << cur;
+      const uint32_t a = __shfl_sync(0xffffffffu, n1, cur);
+      const uint32_t c2 = __shfl_sync(0xffffffffu, n2, cur);
+      if (a < 32) M |= 1u << a;
+      cur = c2;
+    }
+    M &= (avail >= 32 ? 0xffffffffu : ((1u << avail) - 1u));
+    const bool mine = (M >> lane) & 1u;
+    // the last true element may be a long literal (handled after the window) — never two of them
+    const uint32_t longmask = __ballot_sync(0xffffffffu, mine && is_long);
+    const int long_lane = longmask ? (__ffs(longmask) - 1) : -1;
+    // header bytes of a true element must be loaded; a truncated stream is an error
+    const bool trunc = mine && (q + hdr > in_len || (is_lit && !is_long && q + esz > in_len));
+    // ---- 3. output positions by warp scan over the true short elements
+    const uint32_t myo = (mine && !is_long) ? len : 0;
+    uint32_t inc = myo;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t opos = op + inc - myo;
+    const bool badcopy = mine && !is_lit && (off == 0 || off > opos);
+    if (__any_sync(0xffffffffu, trunc || badcopy) || op + total > out_len) { bad = true; break; }
+    // ---- 4a. everything that does not depend on this window's own output, all lanes at once:
+    //          short literals, back-references into earlier output (ring), far back-references (HBM:
+    //          anything older than SN_HIST is already flushed because < 1 KB is ever pending here)
+    const bool indep = mine && !is_lit && (opos - off + len <= op);
+    if (mine && is_lit && !is_long) {
+      for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = w.in[(q + hdr + k) & (SN_IN - 1)];
+    } else if (indep) {
+      if (off <= SN_HIST) { for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = w.out[(opos - off + k) & (SN_OUT - 1)]; }
+      else { const uint8_t* src = dst + opos - off; for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = src[k]; }
+    }
+    __syncwarp();
+    // ---- 4b. back-references into this window's output, replayed in stream order
+    uint32_t cm = __ballot_sync(0xffffffffu, mine && !is_lit && !indep);
+    while (cm) {
+      const int l = __ffs(cm) - 1;
+      cm &= cm - 1;
+      const uint32_t o = __shfl_sync(0xffffffffu, opos, l), f = __shfl_sync(0xffffffffu, off, l), n = __shfl_sync(0xffffffffu, len, l);
+      uint8_t v = 0, v2 = 0;  // f <= window span here, always inside the ring
+      if (lane < (int)n) v = w.out[(o - f + (f >= n ? lane : lane % f)) & (SN_OUT - 1)];
+      if (lane + 32 < (int)n) v2 = w.out[(o - f + (f >= n ? lane + 32 : (lane + 32) % f)) & (SN_OUT - 1)];
+      __syncwarp();
+      if (lane < (int)n) w.out[(o + lane) & (SN_OUT - 1)] = v;
+      if (lane + 32 < (int)n) w.out[(o + lane + 32) & (SN_OUT - 1)] = v2;
+      __syncwarp();
+    }
+    op += total;
+    // end of the short elements = start of the long literal, or the next window
+    const uint32_t endp = mine ? (is_long ? lane : lane + esz) : 0;
+    ip += __reduce_max_sync(0xffffffffu, endp);
+    // ---- 4c. a long literal streams through the rings
+    if (long_lane >= 0) {
+      const uint32_t llen = __shfl_sync(0xffffffffu, len, long_lane), lhdr = __shfl_sync(0xffffffffu, hdr, long_lane);
+      if (ip + lhdr + llen > in_len || op + llen > out_len) { bad = true; break; }
+      ip += lhdr;
+      uint32_t left = llen;
       while (left) {
         const uint32_t n = min(left, 512u);
         if (loaded - ip < n) sn_refill(w, in, in_len, loaded, ip, lane);
         const uint32_t have = min(n, loaded - ip);
+        if (have == 0) { bad = true; break; }
         for (uint32_t k = lane; k < have; k += 32) w.out[(op + k) & (SN_OUT - 1)] = w.in[(ip + k) & (SN_IN - 1)];
         __syncwarp();
         ip += have; op += have; left -= have;
-        if (op - flushed >= 512) {
-          if (aligned) sn_flush(w, dst, flushed, op, lane, false);
-          else { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; flushed = op; }
-          __syncwarp();
-        }
-        if (have == 0) { bad = true; break; }
-      }
-    } else {
-      if (off <= SN_HIST) {
-        // back-reference served from the ring; overlapping copies repeat with period `off`
-        uint8_t v = 0;
-        if (lane < (int)len) v = w.out[(op - off + (off >= len ? lane : lane % off)) & (SN_OUT - 1)];
-        uint8_t v2 = 0;
-        if (lane + 32 < (int)len) v2 = w.out[(op - off + (off >= len ? lane + 32 : (lane + 32) % off)) & (SN_OUT - 1)];
-        __syncwarp();
-        if (lane < (int)len) w.out[(op + lane) & (SN_OUT - 1)] = v;
-        if (lane + 32 < (int)len) w.out[(op + lane + 32) & (SN_OUT - 1)] = v2;
-      } else {
-        // far reference: the source is already in HBM except possibly its unflushed tail
-        if (flushed < op) { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; flushed = op; aligned = aligned && (flushed & 15) == 0; }
-        __syncwarp();
-        const uint8_t* src = dst + op - off;
-        for (uint32_t k = lane; k < len; k += 32) w.out[(op + k) & (SN_OUT - 1)] = src[k];  // off > len here (len <= 64 < 1024 < off)
-      }
-      __syncwarp();
-      op += len;
-      if (op - flushed >= 512) {
-        if (aligned) sn_flush(w, dst, flushed, op, lane, false);
-        else { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; flushed = op; }
-        __syncwarp();
+        if (op - flushed >= 1024) { sn_flush(w, dst, flushed, op, lane, false); __syncwarp(); }
       }
     }
+    if (op - flushed >= 512) { sn_flush(w, dst, flushed, op, lane, false); __syncwarp(); }
   }
   __syncwarp();
-  if (flushed < op) { for (uint32_t k = flushed + lane; k < op; k += 32) dst[k] = w.out[k & (SN_OUT - 1)]; }
+  sn_flush(w, dst, flushed, op, lane, true);
   if ((bad || op != out_len) && lane == 0) atomicExch(errors, 1);
 }
 

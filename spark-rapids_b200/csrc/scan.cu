@@ -22,8 +22,7 @@ struct OutCols {
 // project
 template <typename T>
 __device__ __forceinline__ void store_out(const VMCtx& cx, const Opnd& o, T* __restrict__ out, uint32_t* __restrict__ ovalid) {
-#pragma unroll
-  for (int j = 0; j < VM_K; j++) {
+  for (int j = 0; j < cx.K; j++) {
     const int i = threadIdx.x + j * VM_NT;
     const int64_t g = cx.tile_base + i;
     const bool in = g < cx.nrows;
@@ -39,17 +38,17 @@ __device__ __forceinline__ void store_out(const VMCtx& cx, const Opnd& o, T* __r
   }
 }
 
-__global__ void __launch_bounds__(VM_NT) project_kernel(const VMProgramHeader* __restrict__ g_hdr,
+__global__ void __launch_bounds__(VM_NT, 4) project_kernel(const VMProgramHeader* __restrict__ g_hdr,
                                                         const VMInstr* __restrict__ g_code,
                                                         const __grid_constant__ VMInputs in,
                                                         const __grid_constant__ OutCols outs, int64_t nrows) {
   __shared__ VMShared sh;
   extern __shared__ __align__(16) char regs[];
   const VMInstr* code = vm_load_program(sh, g_hdr, g_code);
-  const int64_t ntiles = (nrows + VM_TILE - 1) / VM_TILE;
+  const int64_t ntiles = (nrows + sh.hdr.tile_rows - 1) / sh.hdr.tile_rows;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    VMCtx cx; cx.hdr = &sh.hdr; cx.in = &in; cx.smem = regs; cx.tile_base = tile * VM_TILE; cx.nrows = nrows;
-    vm_run(cx, code);
+    VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
+    vm_run(cx, code, 0, sh.hdr.ninstr);
     for (int o = 0; o < sh.hdr.nouts; o++) {
       const int mt = sh.hdr.out_mt[o];
       Opnd op = resolve(cx, sh.hdr.outs[o], mt_width(mt));
@@ -123,61 +122,61 @@ struct FilterWork {
 };
 
 template <typename T>
-__device__ __forceinline__ void compact_col(const T* __restrict__ in, T* __restrict__ out, const int64_t (&g)[VM_K],
-                                            const int64_t (&pos)[VM_K], const bool (&sel)[VM_K]) {
-#pragma unroll
-  for (int j = 0; j < VM_K; j++)
-    if (sel[j]) out[pos[j]] = in[g[j]];
+__device__ __forceinline__ void compact_one(const void* in, void* out, int64_t g, int64_t pos) {
+  reinterpret_cast<T*>(out)[pos] = reinterpret_cast<const T*>(in)[g];
 }
 
 // COUNT_ONLY: basicPhysicalOperators.scala:1161-1169 (zero-column batch: just count the trues)
 template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(VM_NT) filter_kernel(const VMProgramHeader* __restrict__ g_hdr,
+__global__ void __launch_bounds__(VM_NT, 4) filter_kernel(const VMProgramHeader* __restrict__ g_hdr,
                                                        const VMInstr* __restrict__ g_code,
                                                        const __grid_constant__ VMInputs in,
                                                        const __grid_constant__ FilterCols fc, int64_t nrows,
                                                        uint64_t* __restrict__ status, FilterWork* __restrict__ work) {
+  constexpr int NW = VM_NT / 32;
   __shared__ VMShared sh;
-  __shared__ uint32_t s_counts[VM_K * (VM_NT / 32)];
+  __shared__ uint32_t s_counts[VM_MAX_K * NW];  // selected rows per (j, warp) slice, then exclusive offsets
   __shared__ int64_t s_tile_excl;
   __shared__ int64_t s_tile;
   __shared__ uint32_t s_tile_total;
   extern __shared__ __align__(16) char regs[];
   const VMInstr* code = vm_load_program(sh, g_hdr, g_code);
-  const int64_t ntiles = (nrows + VM_TILE - 1) / VM_TILE;
+  const int64_t ntiles = (nrows + sh.hdr.tile_rows - 1) / sh.hdr.tile_rows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NW = VM_NT / 32;
   unsigned long long local_count = 0;
 
   while (true) {
-    int64_t tile;
     // tiles are claimed in launch order so that look-back only waits on tiles already running
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(&work->tile_counter, 1ull);
     __syncthreads();
-    tile = s_tile;
+    const int64_t tile = s_tile;
     if (tile >= ntiles) break;
 
-    VMCtx cx; cx.hdr = &sh.hdr; cx.in = &in; cx.smem = regs; cx.tile_base = tile * VM_TILE; cx.nrows = nrows;
-    vm_run(cx, code);
-    Opnd p = resolve(cx, sh.hdr.outs[0], 1);
-    bool sel[VM_K];
-    int64_t g[VM_K];
-    uint32_t ballots[VM_K];
-#pragma unroll
-    for (int j = 0; j < VM_K; j++) {
+    VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
+    vm_run(cx, code, 0, sh.hdr.ninstr);
+    const Opnd p = resolve(cx, sh.hdr.outs[0], 1);
+    const int K = cx.K;
+    uint32_t selmask = 0;
+    for (int j = 0; j < K; j++) {
       const int i = threadIdx.x + j * VM_NT;
-      g[j] = cx.tile_base + i;
+      const int64_t g = cx.tile_base + i;
       // a NULL predicate drops the row (basicPhysicalOperators.scala:1198-1224)
-      sel[j] = g[j] < nrows && opnd_valid(p, i, g[j]) && opnd_ld<int8_t>(p, i) != 0;
-      ballots[j] = __ballot_sync(0xffffffffu, sel[j]);
-      if (lane == 0) s_counts[j * NW + warp] = __popc(ballots[j]);
+      const bool sel = g < nrows && opnd_valid(p, i, g) && opnd_ld<int8_t>(p, i) != 0;
+      selmask |= (uint32_t)sel << j;
+      const uint32_t b = __ballot_sync(0xffffffffu, sel);
+      if (lane == 0) s_counts[j * NW + warp] = __popc(b);
     }
     __syncthreads();
-    if (warp == 0) {  // exclusive scan of the 32 (j, warp) slices in row order
-      uint32_t c = s_counts[lane];
-      uint32_t inc = c;
+    if (warp == 0) {  // exclusive scan of the K*NW slices in row order (4 consecutive slices per lane)
+      const int n = K * NW;
+      uint32_t c[4], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int e = lane * 4 + k; c[k] = e < n ? s_counts[e] : 0; sum += c[k]; }
+      uint32_t inc = sum;
       for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-      s_counts[lane] = inc - c;
+      uint32_t run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int e = lane * 4 + k; if (e < n) s_counts[e] = run; run += c[k]; }
       const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
       if (COUNT_ONLY) {
         if (lane == 0) local_count += total;
@@ -188,31 +187,25 @@ __global__ void __launch_bounds__(VM_NT) filter_kernel(const VMProgramHeader* __
     }
     __syncthreads();
     if (!COUNT_ONLY) {
-      int64_t pos[VM_K];
       const int64_t base = s_tile_excl;
-#pragma unroll
-      for (int j = 0; j < VM_K; j++)
-        pos[j] = base + s_counts[j * NW + warp] + __popc(ballots[j] & ((1u << lane) - 1u));
-      for (int c = 0; c < fc.ncols; c++) {
-        switch (fc.width[c]) {
-          case 1: compact_col<int8_t>((const int8_t*)fc.in[c], (int8_t*)fc.out[c], g, pos, sel); break;
-          case 2: compact_col<int16_t>((const int16_t*)fc.in[c], (int16_t*)fc.out[c], g, pos, sel); break;
-          case 4: compact_col<int32_t>((const int32_t*)fc.in[c], (int32_t*)fc.out[c], g, pos, sel); break;
-          case 8: compact_col<int64_t>((const int64_t*)fc.in[c], (int64_t*)fc.out[c], g, pos, sel); break;
-          case 16: compact_col<int4>((const int4*)fc.in[c], (int4*)fc.out[c], g, pos, sel); break;
-          default: break;  // strings go through the row-id map
+      for (int j = 0; j < K; j++) {
+        const bool sel = (selmask >> j) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, sel);
+        if (!sel) continue;
+        const int64_t g = cx.tile_base + threadIdx.x + j * VM_NT;
+        const int64_t pos = base + s_counts[j * NW + warp] + __popc(b & ((1u << lane) - 1u));
+        for (int c = 0; c < fc.ncols; c++) {
+          switch (fc.width[c]) {
+            case 1: compact_one<int8_t>(fc.in[c], fc.out[c], g, pos); break;
+            case 2: compact_one<int16_t>(fc.in[c], fc.out[c], g, pos); break;
+            case 4: compact_one<int32_t>(fc.in[c], fc.out[c], g, pos); break;
+            case 8: compact_one<int64_t>(fc.in[c], fc.out[c], g, pos); break;
+            case 16: compact_one<int4>(fc.in[c], fc.out[c], g, pos); break;
+            default: break;  // strings go through the row-id map
+          }
+          if (fc.out_valid[c] && bit_get(fc.in_valid[c], g)) atomicOr(&fc.out_valid[c][pos >> 5], 1u << (pos & 31));
         }
-        if (fc.out_valid[c]) {
-          const uint32_t* iv = fc.in_valid[c];
-#pragma unroll
-          for (int j = 0; j < VM_K; j++)
-            if (sel[j] && bit_get(iv, g[j])) atomicOr(&fc.out_valid[c][pos[j] >> 5], 1u << (pos[j] & 31));
-        }
-      }
-      if (fc.row_ids) {
-#pragma unroll
-        for (int j = 0; j < VM_K; j++)
-          if (sel[j]) fc.row_ids[pos[j]] = (int32_t)g[j];
+        if (fc.row_ids) fc.row_ids[pos] = (int32_t)g;
       }
       if (tile == ntiles - 1 && threadIdx.x == 0) work->total = (unsigned long long)(base + s_tile_total);
     }
@@ -246,11 +239,12 @@ void fill_inputs(VMInputs& in, const Table* t) {
 
 template <typename K>
 static void set_dyn_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  // static (program image, ~10 KB) + dynamic must stay under 48 KB unless the kernel opts in
+  if (bytes > 32 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
-int vm_grid(int64_t nrows, int smem_bytes) {
-  int64_t ntiles = (nrows + VM_TILE - 1) / VM_TILE;
+int vm_grid(int64_t nrows, int smem_bytes, int tile_rows) {
+  int64_t ntiles = (nrows + tile_rows - 1) / tile_rows;
   int per_sm = 8;  // 2048 threads / 256
   int static_smem = (int)sizeof(VMShared) + 1024;
   int by_smem = (227 * 1024) / (smem_bytes + static_smem);
@@ -262,7 +256,7 @@ int vm_grid(int64_t nrows, int smem_bytes) {
 // runs the fused filter; returns the selected-row count.  outputs sized for nrows.
 static int64_t run_filter(const Program* prog, const VMInputs& in, FilterCols& fc, int64_t nrows, bool count_only) {
   if (nrows == 0) return 0;
-  int64_t ntiles = (nrows + VM_TILE - 1) / VM_TILE;
+  int64_t ntiles = (nrows + prog->hdr.tile_rows - 1) / prog->hdr.tile_rows;
   DevBuf work(sizeof(FilterWork));
   CUDA_CHECK(cudaMemsetAsync(work.p, 0, sizeof(FilterWork), stream()));
   DevBuf status;
@@ -271,7 +265,7 @@ static int64_t run_filter(const Program* prog, const VMInputs& in, FilterCols& f
     CUDA_CHECK(cudaMemsetAsync(status.p, 0, (size_t)ntiles * 8, stream()));
   }
   int smem = prog->hdr.smem_bytes;
-  int grid = vm_grid(nrows, smem);
+  int grid = vm_grid(nrows, smem, prog->hdr.tile_rows);
   if (count_only) {
     set_dyn_smem(filter_kernel<true>, smem);
     KernelTimer kt_filter_count_kernel("filter_count_kernel");
@@ -368,7 +362,7 @@ int b2_project(b2_handle program, b2_handle table, b2_handle* out_table) {
     int smem = prog->hdr.smem_bytes;
     set_dyn_smem(project_kernel, smem);
     KernelTimer kt_project_kernel("project_kernel");
-    project_kernel<<<vm_grid(n, smem), VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, oc, n);
+    project_kernel<<<vm_grid(n, smem, prog->hdr.tile_rows), VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, oc, n);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
@@ -406,6 +400,7 @@ int b2_filter_mask(b2_handle table, b2_handle bool_mask, b2_handle* out_table) {
   prog.hdr.nouts = 1; prog.hdr.ncols = 1;
   prog.hdr.outs[0].kind = OK_COL; prog.hdr.outs[0].idx = 0; prog.hdr.outs[0].nullable = 1;
   prog.hdr.out_mt[0] = MT_I8;
+  set_tile_geometry(prog.hdr, 0);
   prog.col_dtype = {B2_BOOL8};
   prog.out_dtype = {B2_BOOL8}; prog.out_scale = {0}; prog.out_precision = {0}; prog.out_nullable = {1};
   prog.d_hdr = DevBuf(sizeof(VMProgramHeader));

@@ -1,7 +1,10 @@
 // vm.cuh — the fused expression evaluator: a register machine whose registers are typed column
-// slices in shared memory.  One CTA owns a tile of VM_TILE rows; thread t owns rows t + j*VM_NT,
-// so every register access is thread-private (no barriers between instructions) and bank-conflict
-// free, while every global column access is fully coalesced (a warp reads 32 consecutive rows).
+// slices in shared memory.  One CTA owns a tile of hdr.tile_rows rows; thread t owns rows
+// t + j*VM_NT (j < K), so every register access is thread-private (no barriers between
+// instructions) and bank-conflict free, while every global column access is fully coalesced (a warp
+// reads 32 consecutive rows).  The tile is sized per program (as many rows as fit ~40 KB of
+// registers) so that one instruction dispatch — and one trip through the instruction cache — is
+// amortised over thousands of rows: a vectorised interpreter, with vectors living in shared memory.
 //
 // Replaces the reference's one-cudf-kernel-per-expression-node evaluation with full intermediate
 // columns (GpuExpressions.scala:397-413 CudfBinaryExpression.doColumnar): here the
@@ -13,8 +16,8 @@
 namespace b2 {
 
 constexpr int VM_NT = 256;           // threads per CTA
-constexpr int VM_K = 4;              // rows per thread per tile
-constexpr int VM_TILE = VM_NT * VM_K;
+constexpr int VM_MAX_K = 16;         // rows per thread per tile (tile_rows = K * VM_NT <= 4096)
+constexpr int VM_SMEM_BUDGET = 40 * 1024;
 constexpr int VM_MAX_REGS = 64;
 constexpr int VM_MAX_COLS = 64;
 constexpr int VM_MAX_OUTS = 32;
@@ -36,6 +39,7 @@ enum VOP : uint8_t {
   V_RESCALE_UP,  // integer * 10^aux with overflow -> null (decimal scale increase); mt=mt2 width
   V_RESCALE_DOWN,// integer / 10^aux HALF_UP (decimal scale decrease)
   V_CHECK_PREC,  // |x| >= 10^aux -> null  (CheckOverflow / GpuCheckOverflow)
+  V_MULW,        // widening multiply: two I64 operands -> exact I128 product
   V_MULDEC,      // 128x128 -> 256-bit product, / 10^aux HALF_UP, overflow -> null
   V_DEC2F64,     // decimal (mt) -> double, / 10^aux
   V_NORM_NAN_ZERO,
@@ -60,11 +64,12 @@ struct alignas(16) VMInstr {
   VMOperand a, b, c;
 };
 
-struct VMReg { int32_t off; int32_t voff; };  // byte offsets inside the tile's shared memory
+struct VMReg { int32_t off; int32_t voff; };  // offsets in BYTES PER ROW (x tile_rows = bytes inside the tile)
 
 struct VMProgramHeader {
   int32_t ninstr, nregs, ncols, nouts;
-  int32_t smem_bytes;
+  int32_t smem_bytes;   // = bytes_per_row * tile_rows
+  int32_t bytes_per_row, tile_rows, npred;  // npred: leading instructions that compute output 0 (the predicate)
   VMReg regs[VM_MAX_REGS];
   VMOperand outs[VM_MAX_OUTS];
   uint8_t out_mt[VM_MAX_OUTS];
@@ -102,16 +107,19 @@ struct VMCtx {
   char* smem;
   int64_t tile_base;  // first global row of this tile
   int64_t nrows;
+  int K;              // rows per thread in this tile
+  int tile_rows;
+  uint32_t rowmask;   // bit j set = this thread's row j is wanted (post-predicate instructions)
 };
 
 __device__ __forceinline__ Opnd resolve(const VMCtx& cx, const VMOperand& o, int width) {
   Opnd r;
   r.vbytes = nullptr; r.vbits = nullptr;
   if (o.kind == OK_REG) {
-    r.base = cx.smem + cx.hdr->regs[o.idx].off;
+    r.base = cx.smem + (size_t)cx.hdr->regs[o.idx].off * cx.tile_rows;
     r.stride = width;
     r.vkind = o.nullable ? 1 : 0;
-    r.vbytes = reinterpret_cast<const uint8_t*>(cx.smem + cx.hdr->regs[o.idx].voff);
+    r.vbytes = reinterpret_cast<const uint8_t*>(cx.smem + (size_t)cx.hdr->regs[o.idx].voff * cx.tile_rows);
   } else if (o.kind == OK_COL) {
     r.base = reinterpret_cast<const char*>(cx.in->data[o.idx]) + cx.tile_base * width;
     r.stride = width;
@@ -144,9 +152,9 @@ struct Dst {
 };
 __device__ __forceinline__ Dst resolve_dst(const VMCtx& cx, const VMInstr& ins, int width) {
   Dst d;
-  d.base = cx.smem + cx.hdr->regs[ins.dst].off;
+  d.base = cx.smem + (size_t)cx.hdr->regs[ins.dst].off * cx.tile_rows;
   d.stride = width;
-  d.vbytes = reinterpret_cast<uint8_t*>(cx.smem + cx.hdr->regs[ins.dst].voff);
+  d.vbytes = reinterpret_cast<uint8_t*>(cx.smem + (size_t)cx.hdr->regs[ins.dst].voff * cx.tile_rows);
   d.nullable = ins.dst_nullable;
   return d;
 }
@@ -155,11 +163,6 @@ __device__ __forceinline__ void dst_st(const Dst& d, int i, T v, bool valid) {
   *reinterpret_cast<T*>(d.base + (size_t)i * d.stride) = v;
   if (d.nullable) d.vbytes[i] = valid ? 1 : 0;
 }
-
-#define VM_ROWS(i, g)                                         \
-  _Pragma("unroll") for (int _j = 0; _j < VM_K; _j++)         \
-    if (const int i = threadIdx.x + _j * VM_NT; true)         \
-      if (const int64_t g = cx.tile_base + i; g < cx.nrows)
 
 template <typename T> struct UnsignedOf { typedef T type; };
 template <> struct UnsignedOf<int8_t> { typedef uint8_t type; };
@@ -171,6 +174,112 @@ template <typename T> struct IsFloat { static const bool v = false; };
 template <> struct IsFloat<float> { static const bool v = true; };
 template <> struct IsFloat<double> { static const bool v = true; };
 
+// row loops.  Rows are processed in batches of VM_B: all operand loads of a batch are issued before
+// any store (registers may alias: a destination slot can recycle a source slot), which also keeps
+// VM_B independent loads in flight per thread.
+constexpr int VM_B = 4;  // the VM_LD*/VM_ST* expansions below are written for exactly 4
+// The context lives in the caller's frame (local memory) and every store through a register
+// pointer could alias it, so handlers copy what the row loops need into registers ONCE.
+struct TileInfo { int K; uint32_t rowmask; int64_t tile_base, nrows; };
+__device__ __forceinline__ TileInfo tile_info(const VMCtx& cx) { TileInfo t; t.K = cx.K; t.rowmask = cx.rowmask; t.tile_base = cx.tile_base; t.nrows = cx.nrows; return t; }
+#define VM_ROW_ACTIVE(j, i, g) \
+  const int i = threadIdx.x + (j) * VM_NT; const int64_t g = ti.tile_base + i; \
+  const bool act = (j) < ti.K && g < ti.nrows && ((ti.rowmask >> (j)) & 1u)
+
+// Row loops come in two flavours, chosen once per instruction (uniformly for the CTA):
+//   fast    : full tile, every row wanted, no operand carries NULLs and the result cannot be NULL.
+//             Per-thread base pointers + compile-time offsets: a row costs its loads, the ALU op and
+//             one store.  Literals are read once, outside the loop.
+//   checked : everything else (last tile, post-predicate row mask, NULL propagation).
+// Both issue all loads of a 4-row batch before any store (a destination slot may recycle a source
+// slot) and keep the batch in named scalars — indexed arrays ended up in local memory.
+__device__ __forceinline__ bool vm_full_tile(const TileInfo& ti, int tile_rows) {
+  return ti.tile_base + tile_rows <= ti.nrows && ti.rowmask == 0xffffffffu;
+}
+template <typename T>
+__device__ __forceinline__ const char* thread_base(const Opnd& o) { return o.base + (size_t)threadIdx.x * o.stride; }
+
+#define VM_LD1(u)                                                                              \
+  const int i##u = threadIdx.x + (j0 + u) * VM_NT; const int64_t g##u = ti.tile_base + i##u;    \
+  const bool act##u = (j0 + u) < ti.K && g##u < ti.nrows && ((ti.rowmask >> (j0 + u)) & 1u);  \
+  T x##u = T(); bool v##u = false;                                                             \
+  if (act##u) { x##u = opnd_ld<T>(a, i##u); v##u = opnd_valid(a, i##u, g##u); }
+#define VM_ST1(u) if (act##u) { bool vv = v##u; const R r = f(x##u, vv); dst_st<R>(d, i##u, r, vv); }
+#define VM_LD2(u)                                                                              \
+  const int i##u = threadIdx.x + (j0 + u) * VM_NT; const int64_t g##u = ti.tile_base + i##u;    \
+  const bool act##u = (j0 + u) < ti.K && g##u < ti.nrows && ((ti.rowmask >> (j0 + u)) & 1u);  \
+  T x##u = T(), y##u = T(); bool va##u = false, vb##u = false;                                 \
+  if (act##u) { x##u = opnd_ld<T>(a, i##u); y##u = opnd_ld<T>(b, i##u); va##u = opnd_valid(a, i##u, g##u); vb##u = opnd_valid(b, i##u, g##u); }
+#define VM_ST2(u) if (act##u) { bool vv = va##u && vb##u; const R r = f(x##u, y##u, va##u, vb##u, vv); dst_st<R>(d, i##u, r, vv); }
+
+// unary: F(T x, bool& valid) -> R
+template <typename T, typename R, typename F>
+__device__ __forceinline__ void vm_loop1(const VMCtx& cx, const VMInstr& ins, F f) {
+  const Opnd a = resolve(cx, ins.a, sizeof(T));
+  const Dst d = resolve_dst(cx, ins, sizeof(R));
+  const TileInfo ti = tile_info(cx);
+  if (a.vkind == 0 && !d.nullable && a.stride != 0 && vm_full_tile(ti, cx.tile_rows)) {
+    const char* pa = thread_base<T>(a);
+    char* pd = d.base + (size_t)threadIdx.x * sizeof(R);
+    for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
+      const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
+              x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
+      bool vv = true;
+      *reinterpret_cast<R*>(pd) = f(x0, vv); *reinterpret_cast<R*>(pd + VM_NT * sizeof(R)) = f(x1, vv);
+      *reinterpret_cast<R*>(pd + 2 * VM_NT * sizeof(R)) = f(x2, vv); *reinterpret_cast<R*>(pd + 3 * VM_NT * sizeof(R)) = f(x3, vv);
+    }
+    for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pd += VM_NT * sizeof(R)) {
+      bool vv = true;
+      *reinterpret_cast<R*>(pd) = f(*reinterpret_cast<const T*>(pa), vv);
+    }
+    return;
+  }
+  for (int j0 = 0; j0 < ti.K; j0 += VM_B) {
+    VM_LD1(0) VM_LD1(1) VM_LD1(2) VM_LD1(3)
+    VM_ST1(0) VM_ST1(1) VM_ST1(2) VM_ST1(3)
+  }
+}
+// binary: F(T x, T y, bool va, bool vb, bool& valid) -> R
+template <typename T, typename R, typename F>
+__device__ __forceinline__ void vm_loop2(const VMCtx& cx, const VMInstr& ins, F f) {
+  const Opnd a = resolve(cx, ins.a, sizeof(T)), b = resolve(cx, ins.b, sizeof(T));
+  const Dst d = resolve_dst(cx, ins, sizeof(R));
+  const TileInfo ti = tile_info(cx);
+  if (a.vkind == 0 && b.vkind == 0 && !d.nullable && a.stride != 0 && vm_full_tile(ti, cx.tile_rows)) {
+    const char* pa = thread_base<T>(a);
+    char* pd = d.base + (size_t)threadIdx.x * sizeof(R);
+    bool vv = true;
+    if (b.stride == 0) {  // column/register (op) literal
+      const T y = *reinterpret_cast<const T*>(b.base);
+      for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
+        const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
+                x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
+        *reinterpret_cast<R*>(pd) = f(x0, y, true, true, vv); *reinterpret_cast<R*>(pd + VM_NT * sizeof(R)) = f(x1, y, true, true, vv);
+        *reinterpret_cast<R*>(pd + 2 * VM_NT * sizeof(R)) = f(x2, y, true, true, vv); *reinterpret_cast<R*>(pd + 3 * VM_NT * sizeof(R)) = f(x3, y, true, true, vv);
+      }
+      for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pd += VM_NT * sizeof(R))
+        *reinterpret_cast<R*>(pd) = f(*reinterpret_cast<const T*>(pa), y, true, true, vv);
+    } else {
+      const char* pb = thread_base<T>(b);
+      for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pb += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
+        const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
+                x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
+        const T y0 = *reinterpret_cast<const T*>(pb), y1 = *reinterpret_cast<const T*>(pb + VM_NT * sizeof(T)),
+                y2 = *reinterpret_cast<const T*>(pb + 2 * VM_NT * sizeof(T)), y3 = *reinterpret_cast<const T*>(pb + 3 * VM_NT * sizeof(T));
+        *reinterpret_cast<R*>(pd) = f(x0, y0, true, true, vv); *reinterpret_cast<R*>(pd + VM_NT * sizeof(R)) = f(x1, y1, true, true, vv);
+        *reinterpret_cast<R*>(pd + 2 * VM_NT * sizeof(R)) = f(x2, y2, true, true, vv); *reinterpret_cast<R*>(pd + 3 * VM_NT * sizeof(R)) = f(x3, y3, true, true, vv);
+      }
+      for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pb += VM_NT * sizeof(T), pd += VM_NT * sizeof(R))
+        *reinterpret_cast<R*>(pd) = f(*reinterpret_cast<const T*>(pa), *reinterpret_cast<const T*>(pb), true, true, vv);
+    }
+    return;
+  }
+  for (int j0 = 0; j0 < ti.K; j0 += VM_B) {
+    VM_LD2(0) VM_LD2(1) VM_LD2(2) VM_LD2(3)
+    VM_ST2(0) VM_ST2(1) VM_ST2(2) VM_ST2(3)
+  }
+}
+
 // Spark comparison semantics (predicates.scala:155-331): NaN == NaN, NaN greater than all, -0.0 == 0.0
 template <typename T>
 __device__ __forceinline__ int cmp3(T a, T b) {
@@ -181,138 +290,116 @@ __device__ __forceinline__ int cmp3(T a, T b) {
   return a < b ? -1 : (a > b ? 1 : 0);
 }
 
-template <typename T>
-__device__ __forceinline__ void vm_arith(const VMCtx& cx, const VMInstr& ins) {
+template <typename T, int OP>
+__device__ __noinline__ void vm_arith(const VMCtx& cx, const VMInstr& ins) {
   typedef typename UnsignedOf<T>::type U;
-  Opnd a = resolve(cx, ins.a, sizeof(T)), b = resolve(cx, ins.b, sizeof(T));
-  Dst d = resolve_dst(cx, ins, sizeof(T));
-  const int op = ins.op;
-  VM_ROWS(i, g) {
-    T x = opnd_ld<T>(a, i), y = opnd_ld<T>(b, i);
-    bool v = opnd_valid(a, i, g) && opnd_valid(b, i, g);
-    T r = x;
+  vm_loop2<T, T>(cx, ins, [](T x, T y, bool, bool, bool& v) -> T {
     if constexpr (IsFloat<T>::v) {
       // arithmetic.scala:309-340 — IEEE; Divide/Remainder by zero -> NULL (Spark non-ANSI)
-      switch (op) {
-        case V_ADD: r = x + y; break;
-        case V_SUB: r = x - y; break;
-        case V_MUL: r = x * y; break;
-        case V_DIV: if (y == (T)0) { v = false; r = 0; } else r = x / y; break;
-        default: if (y == (T)0) { v = false; r = 0; } else {
-          r = (T)fmod((double)x, (double)y);
-          if (op == V_PMOD && r != (T)0 && ((r < 0) != (y < 0))) r += y; } break;
+      if constexpr (OP == V_ADD) return x + y;
+      else if constexpr (OP == V_SUB) return x - y;
+      else if constexpr (OP == V_MUL) return x * y;
+      else if constexpr (OP == V_DIV) { if (y == (T)0) { v = false; return (T)0; } return x / y; }
+      else {
+        if (y == (T)0) { v = false; return (T)0; }
+        T r = (T)fmod((double)x, (double)y);
+        if (OP == V_PMOD && r != (T)0 && ((r < 0) != (y < 0))) r += y;
+        return r;
       }
     } else {
-      switch (op) {  // integer: two's-complement wrap (arithmetic.scala:38-75, non-ANSI)
-        case V_ADD: r = (T)((U)x + (U)y); break;
-        case V_SUB: r = (T)((U)x - (U)y); break;
-        case V_MUL: r = (T)((U)x * (U)y); break;
-        default:
-          if (y == (T)0) { v = false; r = 0; }
-          else if (y == (T)-1) { r = (op == V_DIV) ? (T)((U)0 - (U)x) : (T)0; }
-          else if (op == V_DIV) r = x / y;
-          else { r = x % y; if (op == V_PMOD && r != 0 && ((r < 0) != (y < 0))) r += y; }
-          break;
+      // integer: two's-complement wrap (arithmetic.scala:38-75, non-ANSI)
+      if constexpr (OP == V_ADD) return (T)((U)x + (U)y);
+      else if constexpr (OP == V_SUB) return (T)((U)x - (U)y);
+      else if constexpr (OP == V_MUL) return (T)((U)x * (U)y);
+      else {
+        if (y == (T)0) { v = false; return (T)0; }
+        if (y == (T)-1) return (OP == V_DIV) ? (T)((U)0 - (U)x) : (T)0;
+        if constexpr (OP == V_DIV) return x / y;
+        else { T r = x % y; if (OP == V_PMOD && r != 0 && ((r < 0) != (y < 0))) r += y; return r; }
       }
     }
-    dst_st<T>(d, i, r, v);
-  }
+  });
 }
 
-// 128-bit decimal add/sub with overflow -> null (arithmetic.scala:78-125)
-__device__ __forceinline__ void vm_arith128(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, 16), b = resolve(cx, ins.b, 16);
-  Dst d = resolve_dst(cx, ins, 16);
-  const int op = ins.op;
-  VM_ROWS(i, g) {
-    i128 x = opnd_ld<i128>(a, i), y = opnd_ld<i128>(b, i);
-    bool v = opnd_valid(a, i, g) && opnd_valid(b, i, g);
-    i128 r;
-    if (op == V_ADD) { r = (i128)((u128)x + (u128)y); if (((x ^ r) & (y ^ r)) < 0) v = false; }
-    else if (op == V_SUB) { r = (i128)((u128)x - (u128)y); if (((x ^ y) & (x ^ r)) < 0) v = false; }
-    else { r = (i128)((u128)x * (u128)y); }  // V_MUL: caller guarantees it fits (p1+p2+1 <= 38)
-    dst_st<i128>(d, i, r, v);
-  }
+// 128-bit decimal add/sub with overflow -> null (arithmetic.scala:78-125); V_MUL: product known to fit
+template <int OP>
+__device__ __noinline__ void vm_arith128(const VMCtx& cx, const VMInstr& ins) {
+  vm_loop2<i128, i128>(cx, ins, [](i128 x, i128 y, bool, bool, bool& v) -> i128 {
+    if constexpr (OP == V_ADD) { i128 r = (i128)((u128)x + (u128)y); if (((x ^ r) & (y ^ r)) < 0) v = false; return r; }
+    else if constexpr (OP == V_SUB) { i128 r = (i128)((u128)x - (u128)y); if (((x ^ y) & (x ^ r)) < 0) v = false; return r; }
+    else return (i128)((u128)x * (u128)y);
+  });
 }
 
-template <typename T>
-__device__ __forceinline__ void vm_compare(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, sizeof(T)), b = resolve(cx, ins.b, sizeof(T));
-  Dst d = resolve_dst(cx, ins, 1);
-  const int op = ins.op;
-  VM_ROWS(i, g) {
-    T x = opnd_ld<T>(a, i), y = opnd_ld<T>(b, i);
-    bool va = opnd_valid(a, i, g), vb = opnd_valid(b, i, g);
-    int c = cmp3<T>(x, y);
-    bool r, v = va && vb;
-    switch (op) {
-      case V_EQ: r = c == 0; break;
-      case V_NE: r = c != 0; break;
-      case V_LT: r = c < 0; break;
-      case V_LE: r = c <= 0; break;
-      case V_GT: r = c > 0; break;
-      case V_GE: r = c >= 0; break;
-      default:   r = (va && vb) ? (c == 0) : (va == vb); v = true; break;  // <=> EqualNullSafe
-    }
-    dst_st<int8_t>(d, i, (int8_t)(r && (v || op == V_EQNS)), v);
-  }
+static __device__ __noinline__ void vm_mulw(const VMCtx& cx, const VMInstr& ins) {
+  vm_loop2<int64_t, i128>(cx, ins, [](int64_t x, int64_t y, bool, bool, bool&) -> i128 { return (i128)x * (i128)y; });
 }
 
-__device__ __forceinline__ void vm_logic(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, 1);
-  Dst d = resolve_dst(cx, ins, 1);
-  if (ins.op == V_NOT) {
-    VM_ROWS(i, g) { bool v = opnd_valid(a, i, g); dst_st<int8_t>(d, i, (int8_t)(v && !opnd_ld<int8_t>(a, i)), v); }
-    return;
-  }
-  Opnd b = resolve(cx, ins.b, 1);
-  const bool is_and = ins.op == V_AND;
-  VM_ROWS(i, g) {  // Kleene logic, predicates.scala:54-153 (NULL_LOGICAL_AND / NULL_LOGICAL_OR)
-    bool va = opnd_valid(a, i, g), vb = opnd_valid(b, i, g);
-    bool x = va && opnd_ld<int8_t>(a, i), y = vb && opnd_ld<int8_t>(b, i);
-    bool r, v;
-    if (is_and) { bool fa = va && !x, fb = vb && !y; r = x && y; v = (va && vb) || fa || fb; }
-    else { r = x || y; v = (va && vb) || x || y; }
-    dst_st<int8_t>(d, i, (int8_t)(r && v), v);
+template <typename T, int OP>
+__device__ __noinline__ void vm_compare(const VMCtx& cx, const VMInstr& ins) {
+  vm_loop2<T, int8_t>(cx, ins, [](T x, T y, bool va, bool vb, bool& v) -> int8_t {
+    const int c = cmp3<T>(x, y);
+    bool r;
+    if constexpr (OP == V_EQ) r = c == 0;
+    else if constexpr (OP == V_NE) r = c != 0;
+    else if constexpr (OP == V_LT) r = c < 0;
+    else if constexpr (OP == V_LE) r = c <= 0;
+    else if constexpr (OP == V_GT) r = c > 0;
+    else if constexpr (OP == V_GE) r = c >= 0;
+    else { r = (va && vb) ? (c == 0) : (va == vb); v = true; return (int8_t)r; }  // <=> EqualNullSafe
+    return (int8_t)(r && v);
+  });
+}
+
+template <int OP>
+__device__ __noinline__ void vm_logic(const VMCtx& cx, const VMInstr& ins) {
+  if constexpr (OP == V_NOT) {
+    vm_loop1<int8_t, int8_t>(cx, ins, [](int8_t x, bool& v) -> int8_t { return (int8_t)(v && !x); });
+  } else {
+    // Kleene logic, predicates.scala:54-153 (NULL_LOGICAL_AND / NULL_LOGICAL_OR)
+    vm_loop2<int8_t, int8_t>(cx, ins, [](int8_t xa, int8_t ya, bool va, bool vb, bool& v) -> int8_t {
+      const bool x = va && xa, y = vb && ya;
+      bool r;
+      if constexpr (OP == V_AND) { const bool fa = va && !x, fb = vb && !y; r = x && y; v = (va && vb) || fa || fb; }
+      else { r = x || y; v = (va && vb) || x || y; }
+      return (int8_t)(r && v);
+    });
   }
 }
 
 template <typename T>
-__device__ __forceinline__ void vm_select(const VMCtx& cx, const VMInstr& ins) {
-  Dst d = resolve_dst(cx, ins, sizeof(T));
-  if (ins.op == V_COALESCE) {
-    Opnd a = resolve(cx, ins.a, sizeof(T)), b = resolve(cx, ins.b, sizeof(T));
-    VM_ROWS(i, g) {
-      bool va = opnd_valid(a, i, g);
-      T r = va ? opnd_ld<T>(a, i) : opnd_ld<T>(b, i);
-      dst_st<T>(d, i, r, va || opnd_valid(b, i, g));
-    }
-  } else if (ins.op == V_IF) {  // conditionalExpressions.scala GpuIf: null predicate takes the else branch
-    Opnd p = resolve(cx, ins.a, 1), a = resolve(cx, ins.b, sizeof(T)), b = resolve(cx, ins.c, sizeof(T));
-    VM_ROWS(i, g) {
-      bool t = opnd_valid(p, i, g) && opnd_ld<int8_t>(p, i);
-      T r = t ? opnd_ld<T>(a, i) : opnd_ld<T>(b, i);
-      dst_st<T>(d, i, r, t ? opnd_valid(a, i, g) : opnd_valid(b, i, g));
-    }
-  } else if (ins.op == V_MOV) {
-    Opnd a = resolve(cx, ins.a, sizeof(T));
-    VM_ROWS(i, g) { dst_st<T>(d, i, opnd_ld<T>(a, i), opnd_valid(a, i, g)); }
-  } else if (ins.op == V_NEG || ins.op == V_ABS) {
-    typedef typename UnsignedOf<T>::type U;
-    Opnd a = resolve(cx, ins.a, sizeof(T));
-    const bool neg = ins.op == V_NEG;
-    VM_ROWS(i, g) {
-      T x = opnd_ld<T>(a, i);
-      T r;
-      if constexpr (IsFloat<T>::v) r = neg ? -x : (x < 0 || (x == 0 && 1 / (double)x < 0) ? -x : x);
-      else r = (neg || x < 0) ? (T)((U)0 - (U)x) : x;
-      dst_st<T>(d, i, r, opnd_valid(a, i, g));
-    }
+__device__ __noinline__ void vm_select(const VMCtx& cx, const VMInstr& ins) {
+  typedef typename UnsignedOf<T>::type U;
+  switch (ins.op) {
+    case V_COALESCE:
+      vm_loop2<T, T>(cx, ins, [](T x, T y, bool va, bool vb, bool& v) -> T { v = va || vb; return va ? x : y; });
+      break;
+    case V_MOV: vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T { return x; }); break;
+    case V_NEG:
+      vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T { if constexpr (IsFloat<T>::v) return -x; else return (T)((U)0 - (U)x); });
+      break;
+    case V_ABS:
+      vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T {
+        if constexpr (IsFloat<T>::v) return (x < 0 || (x == 0 && 1 / (double)x < 0)) ? -x : x;
+        else return x < 0 ? (T)((U)0 - (U)x) : x;
+      });
+      break;
+    default: {  // V_IF (conditionalExpressions.scala GpuIf): a NULL predicate takes the else branch
+      const Opnd p = resolve(cx, ins.a, 1), a = resolve(cx, ins.b, sizeof(T)), b = resolve(cx, ins.c, sizeof(T));
+      const Dst d = resolve_dst(cx, ins, sizeof(T));
+      const TileInfo ti = tile_info(cx);
+      for (int j = 0; j < ti.K; j++) {
+        VM_ROW_ACTIVE(j, i, g);
+        if (!act) continue;
+        const bool t = opnd_valid(p, i, g) && opnd_ld<int8_t>(p, i);
+        const T r = t ? opnd_ld<T>(a, i) : opnd_ld<T>(b, i);
+        const bool v = t ? opnd_valid(a, i, g) : opnd_valid(b, i, g);
+        dst_st<T>(d, i, r, v);
+      }
+    } break;
   }
 }
 
-// GpuCast.scala:295 doCast, numeric subset.  Integral narrowing wraps (Java semantics); float ->
-// integral follows Java (NaN -> 0, saturating) via int/long then narrows.
 // correctly rounded signed 128-bit -> double (keep 64 significant bits + sticky, then scale)
 __device__ __forceinline__ double i128_to_double(i128 x) {
   bool neg = x < 0;
@@ -334,6 +421,8 @@ template <typename S, typename D> struct CastVia { __device__ static __forceinli
 template <> struct CastVia<i128, double> { __device__ static __forceinline__ double f(i128 x) { return i128_to_double(x); } };
 template <> struct CastVia<i128, float> { __device__ static __forceinline__ float f(i128 x) { return (float)i128_to_double(x); } };
 
+// GpuCast.scala:295 doCast, numeric subset.  Integral narrowing wraps (Java semantics); float ->
+// integral follows Java (NaN -> 0, saturating) via int/long then narrows.
 template <typename S, typename D>
 __device__ __forceinline__ D cast_val(S x) {
   if constexpr (IsFloat<S>::v && !IsFloat<D>::v) {
@@ -355,10 +444,8 @@ __device__ __forceinline__ D cast_val(S x) {
   }
 }
 template <typename S, typename D>
-__device__ __forceinline__ void vm_cast2(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, sizeof(S));
-  Dst d = resolve_dst(cx, ins, sizeof(D));
-  VM_ROWS(i, g) { dst_st<D>(d, i, cast_val<S, D>(opnd_ld<S>(a, i)), opnd_valid(a, i, g)); }
+__device__ __noinline__ void vm_cast2(const VMCtx& cx, const VMInstr& ins) {
+  vm_loop1<S, D>(cx, ins, [](S x, bool&) -> D { return cast_val<S, D>(x); });
 }
 template <typename S>
 __device__ __forceinline__ void vm_cast1(const VMCtx& cx, const VMInstr& ins) {
@@ -385,167 +472,150 @@ __device__ __forceinline__ uint64_t div256_u64(uint64_t q[4], uint64_t dv) {
 }
 
 template <typename T>
-__device__ __forceinline__ void vm_decimal(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, sizeof(T));
-  Dst d = resolve_dst(cx, ins, sizeof(T));
+__device__ __noinline__ void vm_decimal(const VMCtx& cx, const VMInstr& ins) {
   const i128 p = pow10_i128(ins.aux);
   if (ins.op == V_RESCALE_UP) {
-    VM_ROWS(i, g) {
-      i128 x = (i128)opnd_ld<T>(a, i);
-      bool v = opnd_valid(a, i, g);
-      // overflow if |x| * 10^aux does not fit T
-      const i128 maxv = (i128)((((u128)1) << (8 * sizeof(T) - 1)) - 1);
-      const i128 lim = maxv / p;
-      i128 r = (i128)((u128)x * (u128)p);
-      if (x > lim || x < -lim) v = false;
-      dst_st<T>(d, i, (T)r, v);
-    }
+    const i128 maxv = (i128)((((u128)1) << (8 * sizeof(T) - 1)) - 1);
+    const i128 lim = maxv / p;
+    vm_loop1<T, T>(cx, ins, [p, lim](T xx, bool& v) -> T {
+      const i128 x = (i128)xx;
+      if (x > lim || x < -lim) v = false;  // |x| * 10^aux does not fit T
+      return (T)(i128)((u128)x * (u128)p);
+    });
   } else if (ins.op == V_RESCALE_DOWN) {  // HALF_UP (away from zero), as BigDecimal.setScale
-    VM_ROWS(i, g) {
-      i128 x = (i128)opnd_ld<T>(a, i);
-      bool neg = x < 0;
-      u128 m = neg ? (u128)0 - (u128)x : (u128)x;
-      u128 q = m / (u128)p, r = m % (u128)p;
+    vm_loop1<T, T>(cx, ins, [p](T xx, bool&) -> T {
+      const i128 x = (i128)xx;
+      const bool neg = x < 0;
+      const u128 m = neg ? (u128)0 - (u128)x : (u128)x;
+      u128 q = m / (u128)p;
+      const u128 r = m % (u128)p;
       if (r * 2 >= (u128)p) q += 1;
-      i128 res = neg ? -(i128)q : (i128)q;
-      dst_st<T>(d, i, (T)res, opnd_valid(a, i, g));
-    }
+      return (T)(neg ? -(i128)q : (i128)q);
+    });
   } else {  // V_CHECK_PREC
-    VM_ROWS(i, g) {
-      T x = opnd_ld<T>(a, i);
-      bool v = opnd_valid(a, i, g);
-      i128 xx = (i128)x;
-      if (xx >= p || xx <= -p) v = false;
-      dst_st<T>(d, i, x, v);
-    }
+    vm_loop1<T, T>(cx, ins, [p](T x, bool& v) -> T { const i128 xx = (i128)x; if (xx >= p || xx <= -p) v = false; return x; });
   }
 }
 
 // DecimalUtils.multiply128 (arithmetic.scala:470-512 longMultiply): exact 256-bit product,
 // HALF_UP to the result scale, NULL when the result needs more than 38 digits.
-__device__ __forceinline__ void vm_muldec(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, 16), b = resolve(cx, ins.b, 16);
-  Dst d = resolve_dst(cx, ins, 16);
+static __device__ __noinline__ void vm_muldec(const VMCtx& cx, const VMInstr& ins) {
   const int k = ins.aux;
-  VM_ROWS(i, g) {
-    i128 x = opnd_ld<i128>(a, i), y = opnd_ld<i128>(b, i);
-    bool v = opnd_valid(a, i, g) && opnd_valid(b, i, g);
-    bool neg = (x < 0) != (y < 0);
-    u128 mx = x < 0 ? (u128)0 - (u128)x : (u128)x, my = y < 0 ? (u128)0 - (u128)y : (u128)y;
-    uint64_t x0 = (uint64_t)mx, x1 = (uint64_t)(mx >> 64), y0 = (uint64_t)my, y1 = (uint64_t)(my >> 64);
+  const u128 p38 = (u128)pow10_i128(38);
+  vm_loop2<i128, i128>(cx, ins, [k, p38](i128 x, i128 y, bool, bool, bool& v) -> i128 {
+    const bool neg = (x < 0) != (y < 0);
+    const u128 mx = x < 0 ? (u128)0 - (u128)x : (u128)x, my = y < 0 ? (u128)0 - (u128)y : (u128)y;
+    const uint64_t x0 = (uint64_t)mx, x1 = (uint64_t)(mx >> 64), y0 = (uint64_t)my, y1 = (uint64_t)(my >> 64);
     uint64_t q[4];
-    u128 p00 = (u128)x0 * y0, p01 = (u128)x0 * y1, p10 = (u128)x1 * y0, p11 = (u128)x1 * y1;
+    const u128 p00 = (u128)x0 * y0, p01 = (u128)x0 * y1, p10 = (u128)x1 * y0, p11 = (u128)x1 * y1;
     q[0] = (uint64_t)p00;
-    u128 mid = (p00 >> 64) + (uint64_t)p01 + (uint64_t)p10;
+    const u128 mid = (p00 >> 64) + (uint64_t)p01 + (uint64_t)p10;
     q[1] = (uint64_t)mid;
-    u128 hi = (mid >> 64) + (p01 >> 64) + (p10 >> 64) + (uint64_t)p11;
+    const u128 hi = (mid >> 64) + (p01 >> 64) + (p10 >> 64) + (uint64_t)p11;
     q[2] = (uint64_t)hi;
     q[3] = (uint64_t)((hi >> 64) + (p11 >> 64));
     if (k > 0) {
-      // divide by 10^k in up to three u64 steps, tracking whether remainder*2 >= 10^k
-      int k1 = k > 19 ? 19 : k;
+      // divide by 10^k in up to two u64 steps, tracking whether remainder*2 >= 10^k
+      const int k1 = k > 19 ? 19 : k;
       uint64_t d1 = 1; for (int t = 0; t < k1; t++) d1 *= 10ull;
-      uint64_t r1 = div256_u64(q, d1);
-      int k2 = k - k1;
+      const uint64_t r1 = div256_u64(q, d1);
+      const int k2 = k - k1;
+      bool up;
       if (k2 > 0) {
         uint64_t d2 = 1; for (int t = 0; t < k2; t++) d2 *= 10ull;
-        uint64_t r2 = div256_u64(q, d2);
-        // total remainder = r2*d1 + r1 vs (d1*d2)/2
-        u128 rem = (u128)r2 * d1 + r1, half = ((u128)d1 * d2) / 2;
-        if (rem >= half) { for (int t = 0; t < 4; t++) { if (++q[t] != 0) break; } }
+        const uint64_t r2 = div256_u64(q, d2);
+        const u128 rem = (u128)r2 * d1 + r1, half = ((u128)d1 * d2) / 2;
+        up = rem >= half;
       } else {
-        if ((u128)r1 * 2 >= (u128)d1) { for (int t = 0; t < 4; t++) { if (++q[t] != 0) break; } }
+        up = (u128)r1 * 2 >= (u128)d1;
       }
+      if (up) { for (int t = 0; t < 4; t++) { if (++q[t] != 0) break; } }
     }
-    u128 mag = ((u128)q[1] << 64) | q[0];
-    if (q[2] || q[3] || mag >= (u128)pow10_i128(38)) v = false;
-    i128 r = neg ? -(i128)mag : (i128)mag;
-    dst_st<i128>(d, i, r, v);
-  }
+    const u128 mag = ((u128)q[1] << 64) | q[0];
+    if (q[2] || q[3] || mag >= p38) v = false;
+    return neg ? -(i128)mag : (i128)mag;
+  });
 }
 
 template <typename T>
-__device__ __forceinline__ void vm_dec2f64(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, sizeof(T));
-  Dst d = resolve_dst(cx, ins, 8);
+__device__ __noinline__ void vm_dec2f64(const VMCtx& cx, const VMInstr& ins) {
   double dv = 1.0; for (int t = 0; t < ins.aux; t++) dv *= 10.0;
-  VM_ROWS(i, g) { dst_st<double>(d, i, CastVia<T, double>::f(opnd_ld<T>(a, i)) / dv, opnd_valid(a, i, g)); }
+  vm_loop1<T, double>(cx, ins, [dv](T x, bool&) -> double { return CastVia<T, double>::f(x) / dv; });
 }
 
 template <typename T>
-__device__ __forceinline__ void vm_normnz(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, sizeof(T));
-  Dst d = resolve_dst(cx, ins, sizeof(T));
-  VM_ROWS(i, g) {  // NormalizeFloatingNumbers.scala:29-38: canonical NaN, -0.0 -> 0.0
-    T x = opnd_ld<T>(a, i);
-    if (x != x) x = (T)__longlong_as_double(0x7ff8000000000000LL);
-    else if (x == (T)0) x = (T)0;
-    dst_st<T>(d, i, x, opnd_valid(a, i, g));
-  }
+__device__ __noinline__ void vm_normnz(const VMCtx& cx, const VMInstr& ins) {
+  vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T {  // NormalizeFloatingNumbers.scala:29-38: canonical NaN, -0.0 -> 0.0
+    if (x != x) return (T)__longlong_as_double(0x7ff8000000000000LL);
+    if (x == (T)0) return (T)0;
+    return x;
+  });
 }
 
-__device__ __forceinline__ void vm_year(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, 4);
-  Dst d = resolve_dst(cx, ins, 4);
-  VM_ROWS(i, g) {  // proleptic Gregorian civil-from-days
-    int z = opnd_ld<int32_t>(a, i) + 719468;
-    int era = (z >= 0 ? z : z - 146096) / 146097;
-    unsigned doe = (unsigned)(z - era * 146097);
-    unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-    int y = (int)yoe + era * 400;
-    unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
-    unsigned mp = (5 * doy + 2) / 153;
-    int m = mp < 10 ? mp + 3 : mp - 9;
-    dst_st<int32_t>(d, i, y + (m <= 2), opnd_valid(a, i, g));
-  }
+static __device__ __noinline__ void vm_year(const VMCtx& cx, const VMInstr& ins) {
+  vm_loop1<int32_t, int32_t>(cx, ins, [](int32_t days, bool&) -> int32_t {  // proleptic Gregorian civil-from-days
+    const int z = days + 719468;
+    const int era = (z >= 0 ? z : z - 146096) / 146097;
+    const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const int y = (int)yoe + era * 400;
+    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doy + 2) / 153;
+    const int m = mp < 10 ? mp + 3 : mp - 9;
+    return y + (m <= 2);
+  });
 }
 
-__device__ __forceinline__ void vm_isnull(const VMCtx& cx, const VMInstr& ins) {
-  Opnd a = resolve(cx, ins.a, mt_width(ins.mt));
-  Dst d = resolve_dst(cx, ins, 1);
+static __device__ __noinline__ void vm_isnull(const VMCtx& cx, const VMInstr& ins) {
+  const Opnd a = resolve(cx, ins.a, mt_width(ins.mt));
+  const Dst d = resolve_dst(cx, ins, 1);
   const bool want_null = ins.op == V_ISNULL;
-  VM_ROWS(i, g) { dst_st<int8_t>(d, i, (int8_t)(opnd_valid(a, i, g) != want_null), true); }
+  const TileInfo ti = tile_info(cx);
+  for (int j = 0; j < ti.K; j++) { VM_ROW_ACTIVE(j, i, g); if (act) dst_st<int8_t>(d, i, (int8_t)(opnd_valid(a, i, g) != want_null), true); }
 }
 
-#define VM_DISPATCH_INT_FLOAT(fn)                      \
-  switch (ins.mt) {                                    \
-    case MT_I8: fn<int8_t>(cx, ins); break;            \
-    case MT_I16: fn<int16_t>(cx, ins); break;          \
-    case MT_I32: fn<int32_t>(cx, ins); break;          \
-    case MT_I64: fn<int64_t>(cx, ins); break;          \
-    case MT_F32: fn<float>(cx, ins); break;            \
-    case MT_F64: fn<double>(cx, ins); break;           \
-    default: break;                                    \
+#define VM_TYPES_INT_FLOAT(fn, ...)                         \
+  switch (ins.mt) {                                         \
+    case MT_I8: fn<int8_t, ##__VA_ARGS__>(cx, ins); break;  \
+    case MT_I16: fn<int16_t, ##__VA_ARGS__>(cx, ins); break;\
+    case MT_I32: fn<int32_t, ##__VA_ARGS__>(cx, ins); break;\
+    case MT_I64: fn<int64_t, ##__VA_ARGS__>(cx, ins); break;\
+    case MT_F32: fn<float, ##__VA_ARGS__>(cx, ins); break;  \
+    case MT_F64: fn<double, ##__VA_ARGS__>(cx, ins); break; \
+    default: break;                                         \
   }
-#define VM_DISPATCH_ALL(fn)                            \
-  switch (ins.mt) {                                    \
-    case MT_I8: fn<int8_t>(cx, ins); break;            \
-    case MT_I16: fn<int16_t>(cx, ins); break;          \
-    case MT_I32: fn<int32_t>(cx, ins); break;          \
-    case MT_I64: fn<int64_t>(cx, ins); break;          \
-    case MT_I128: fn<i128>(cx, ins); break;            \
-    case MT_F32: fn<float>(cx, ins); break;            \
-    default: fn<double>(cx, ins); break;               \
+#define VM_TYPES_ALL(fn, ...)                               \
+  switch (ins.mt) {                                         \
+    case MT_I8: fn<int8_t, ##__VA_ARGS__>(cx, ins); break;  \
+    case MT_I16: fn<int16_t, ##__VA_ARGS__>(cx, ins); break;\
+    case MT_I32: fn<int32_t, ##__VA_ARGS__>(cx, ins); break;\
+    case MT_I64: fn<int64_t, ##__VA_ARGS__>(cx, ins); break;\
+    case MT_I128: fn<i128, ##__VA_ARGS__>(cx, ins); break;  \
+    case MT_F32: fn<float, ##__VA_ARGS__>(cx, ins); break;  \
+    default: fn<double, ##__VA_ARGS__>(cx, ins); break;     \
   }
+#define VM_ARITH_CASE(OP)                                                                       \
+  case OP: if (ins.mt == MT_I128) vm_arith128<OP>(cx, ins); else { VM_TYPES_INT_FLOAT(vm_arith, OP) } break;
+#define VM_CMP_CASE(OP) case OP: VM_TYPES_ALL(vm_compare, OP) break;
 
-// Run the whole program over this CTA's tile.  No barrier is needed: registers are thread private.
-static __device__ __noinline__ void vm_run(const VMCtx& cx, const VMInstr* __restrict__ code) {
-  const int n = cx.hdr->ninstr;
-  for (int pc = 0; pc < n; pc++) {
+// Execute instructions [first, last) over this CTA's tile.  No barrier is needed: registers are thread private.
+static __device__ __noinline__ void vm_run(const VMCtx& cx, const VMInstr* __restrict__ code, int first, int last) {
+  for (int pc = first; pc < last; pc++) {
     const VMInstr& ins = code[pc];
     switch (ins.op) {
-      case V_ADD: case V_SUB: case V_MUL: case V_DIV: case V_MOD: case V_PMOD:
-        if (ins.mt == MT_I128) vm_arith128(cx, ins); else { VM_DISPATCH_INT_FLOAT(vm_arith) }
-        break;
-      case V_EQ: case V_NE: case V_LT: case V_LE: case V_GT: case V_GE: case V_EQNS:
-        VM_DISPATCH_ALL(vm_compare)
-        break;
-      case V_AND: case V_OR: case V_NOT: vm_logic(cx, ins); break;
+      VM_ARITH_CASE(V_ADD) VM_ARITH_CASE(V_SUB) VM_ARITH_CASE(V_MUL)
+      case V_DIV: VM_TYPES_INT_FLOAT(vm_arith, V_DIV) break;
+      case V_MOD: VM_TYPES_INT_FLOAT(vm_arith, V_MOD) break;
+      case V_PMOD: VM_TYPES_INT_FLOAT(vm_arith, V_PMOD) break;
+      VM_CMP_CASE(V_EQ) VM_CMP_CASE(V_NE) VM_CMP_CASE(V_LT) VM_CMP_CASE(V_LE) VM_CMP_CASE(V_GT) VM_CMP_CASE(V_GE) VM_CMP_CASE(V_EQNS)
+      case V_AND: vm_logic<V_AND>(cx, ins); break;
+      case V_OR: vm_logic<V_OR>(cx, ins); break;
+      case V_NOT: vm_logic<V_NOT>(cx, ins); break;
       case V_ISNULL: case V_ISNOTNULL: vm_isnull(cx, ins); break;
       case V_COALESCE: case V_IF: case V_MOV: case V_NEG: case V_ABS:
-        VM_DISPATCH_ALL(vm_select)
+        VM_TYPES_ALL(vm_select)
         break;
-      case V_CAST: VM_DISPATCH_ALL(vm_cast1) break;
+      case V_CAST: VM_TYPES_ALL(vm_cast1) break;
       case V_RESCALE_UP: case V_RESCALE_DOWN: case V_CHECK_PREC:
         switch (ins.mt) {
           case MT_I32: vm_decimal<int32_t>(cx, ins); break;
@@ -553,6 +623,7 @@ static __device__ __noinline__ void vm_run(const VMCtx& cx, const VMInstr* __res
           default: vm_decimal<i128>(cx, ins); break;
         }
         break;
+      case V_MULW: vm_mulw(cx, ins); break;
       case V_MULDEC: vm_muldec(cx, ins); break;
       case V_DEC2F64:
         switch (ins.mt) {
@@ -566,6 +637,14 @@ static __device__ __noinline__ void vm_run(const VMCtx& cx, const VMInstr* __res
       default: break;
     }
   }
+}
+
+// context for one tile
+__device__ __forceinline__ VMCtx vm_ctx(const VMProgramHeader* hdr, const VMInputs* in, char* smem, int64_t tile, int64_t nrows) {
+  VMCtx cx;
+  cx.hdr = hdr; cx.in = in; cx.smem = smem; cx.tile_rows = hdr->tile_rows; cx.K = hdr->tile_rows / VM_NT;
+  cx.tile_base = tile * (int64_t)hdr->tile_rows; cx.nrows = nrows; cx.rowmask = 0xffffffffu;
+  return cx;
 }
 
 constexpr int VM_SMEM_CODE = 64;  // instructions cached in shared memory
@@ -589,9 +668,6 @@ static __device__ __forceinline__ const VMInstr* vm_load_program(VMShared& sh, c
   return sh.code;
 }
 
-// read output `o` of the program for tile row i (global row g)
-template <typename T>
-__device__ __forceinline__ T vm_out(const VMCtx& cx, const Opnd& o, int i) { return opnd_ld<T>(o, i); }
 #endif  // __CUDACC__
 
 // host-side compiled program
@@ -604,5 +680,6 @@ struct Program {
   DevBuf d_hdr, d_code;                // device copies
 };
 Program* program_from(b2_handle h);
+void set_tile_geometry(VMProgramHeader& hdr, int bytes_per_row);
 
 }  // namespace b2
