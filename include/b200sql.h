@@ -280,6 +280,31 @@ int b2_comm_close(b2_handle comm);
 int b2_exchange(b2_handle comm, b2_handle partitioned_table, const int32_t* offsets,
                 b2_handle* out_table);
 
+/* ---- host operator layer: C++ mirror of the GpuExec nodes of the hot path (exec.cu).  Every node is
+ * a pull iterator of batches — GpuExec.internalDoExecuteColumnar(): RDD[ColumnarBatch]
+ * (GpuExec.scala:106,190,380).  b2_exec_next returns 0 in *out_table when the node is exhausted. */
+int b2_exec_source(b2_handle* out);                                   /* child RDD stand-in */
+int b2_exec_source_push(b2_handle source, b2_handle table);
+int b2_exec_parquet_scan(const char* const* column_names, int32_t ncols, b2_handle* out);      /* GpuParquetScan.scala:3543-3600 */
+int b2_exec_parquet_scan_add(b2_handle scan, const uint8_t* host_buf, int64_t len);            /* buffer must outlive the scan */
+int b2_exec_filter(b2_handle child, b2_handle predicate_program, b2_handle* out);              /* GpuFilterExec :1238-1291 */
+int b2_exec_project(b2_handle child, b2_handle program, b2_handle* out);                       /* GpuProjectExec :755-884 */
+/* GpuHashAggregateExec (GpuAggregateExec.scala:1942-2085).  merge_mode 0: update aggregates over the
+ * program's outputs (Partial/Complete); 1: input batches are aggregation buffers, keys leading (Final) */
+int b2_exec_hash_aggregate(b2_handle child, b2_handle program, int32_t has_predicate, int32_t merge_mode,
+                           const int32_t* keys, int32_t nkeys, const b2_agg_spec* aggs, int32_t naggs, b2_handle* out);
+/* GpuShuffledHashJoinExec (GpuShuffledHashJoinExec.scala:228-385): output = stream columns ++ build columns */
+int b2_exec_shuffled_hash_join(b2_handle stream_child, b2_handle build_child, const int32_t* stream_keys,
+                               const int32_t* build_keys, int32_t nkeys, int32_t kind, int32_t nulls_equal, b2_handle* out);
+/* GpuSortExec (global != 0: full sort, else each batch) / GpuTopN when limit >= 0 */
+int b2_exec_sort(b2_handle child, const b2_order_by_arg* order, int32_t norder, int32_t global, int64_t limit, b2_handle* out);
+int b2_exec_coalesce(b2_handle child, int64_t target_rows, b2_handle* out);                    /* GpuCoalesceBatches */
+/* GpuShuffleExchangeExec: hash partition on key_cols (none = SinglePartition) + NCCL all-to-all */
+int b2_exec_shuffle_exchange(b2_handle child, const int32_t* key_cols, int32_t nkeys, b2_handle comm, int32_t world, b2_handle* out);
+int b2_exec_next(b2_handle exec, b2_handle* out_table);
+int b2_exec_metrics(b2_handle exec, int64_t* out3);  /* numOutputRows, numOutputBatches, opTime (ns) */
+int b2_exec_close(b2_handle exec);
+
 /* ---- timing hooks for bench.py (CUDA events on the library stream) ------------------------------ */
 int b2_event_create(b2_handle* out);
 int b2_event_record(b2_handle ev);

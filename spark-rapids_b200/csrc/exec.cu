@@ -1,0 +1,400 @@
+// exec.cu — host-side operator layer above the kernels: the C++ mirror of the reference's GpuExec
+// nodes for the hot path (the reference's host side is Scala; no JVM exists in this image, so the
+// compiled-language mirror is C++).  Contract copied from GpuExec.internalDoExecuteColumnar():
+// RDD[ColumnarBatch] (GpuExec.scala:106,190,380): every node is a pull iterator of batches; metrics
+// numOutputRows / numOutputBatches / opTime (GpuExec.scala:195-199, GpuMetrics.scala:49-62).
+//
+//   GpuBatchSource            the child RDD / scan output handed in by the caller
+//   GpuParquetScanExec        GpuParquetScan.scala:3543-3600 (PartitionReader.next -> Table.readParquet)
+//   GpuFilterExec             basicPhysicalOperators.scala:1238-1291
+//   GpuProjectExec            basicPhysicalOperators.scala:755-884
+//   GpuHashAggregateExec      GpuAggregateExec.scala:1942-2085; first pass per batch (:730-742) then
+//                             GpuMergeAggregateIterator (:896-1018): concat partials + merge-aggregate
+//   GpuShuffledHashJoinExec   GpuShuffledHashJoinExec.scala:228-385 + GpuHashJoin.doJoin (:2547-2628):
+//                             build side coalesced to ONE batch, hash table built once, stream probed
+//                             batch by batch, payload gathered
+//   GpuSortExec / GpuTopN     GpuSortExec.scala:87-165 (each-batch | full), limit.scala:234-330
+//   GpuCoalesceBatches        GpuCoalesceBatches.scala:160-239 (TargetSize goal by rows)
+//   GpuShuffleExchangeExec    GpuShuffleExchangeExecBase.scala:384-536 with the NCCL all-to-all
+#include <chrono>
+#include <deque>
+#include "vm.cuh"
+
+namespace b2 {
+
+Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullify_oob, const std::vector<int>* only_cols);
+Table* concat_tables(const std::vector<const Table*>& ts);
+Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const int* key_outs, int nkeys, const b2_agg_spec* specs, int naggs);
+Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
+
+struct TableRef {  // owning reference
+  Table* t = nullptr;
+  TableRef() {}
+  explicit TableRef(Table* t_) : t(t_) {}
+  TableRef(const TableRef&) = delete;
+  TableRef& operator=(const TableRef&) = delete;
+  TableRef(TableRef&& o) noexcept : t(o.t) { o.t = nullptr; }
+  TableRef& operator=(TableRef&& o) noexcept { if (this != &o) { reset(); t = o.t; o.t = nullptr; } return *this; }
+  ~TableRef() { reset(); }
+  void reset() { if (t) table_release(t); t = nullptr; }
+  Table* release() { Table* r = t; t = nullptr; return r; }
+};
+
+static Table* from_handle_owned(b2_handle h) { return h ? reinterpret_cast<Table*>((intptr_t)h) : nullptr; }
+
+struct GpuExec {
+  std::atomic<int> refs{1};
+  std::vector<GpuExec*> children;
+  int64_t num_output_rows = 0, num_output_batches = 0, op_time_ns = 0;
+  virtual ~GpuExec() { for (auto* c : children) c->release(); }
+  void release() { if (refs.fetch_sub(1) == 1) delete this; }
+  void add_child(GpuExec* c) { c->refs.fetch_add(1); children.push_back(c); }
+  virtual Table* do_next() = 0;  // nullptr when exhausted; returned table is owned by the caller
+  Table* next() {
+    auto t0 = std::chrono::steady_clock::now();
+    Table* t = do_next();
+    op_time_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    if (t) { num_output_rows += t->rows; num_output_batches++; }
+    return t;
+  }
+};
+static GpuExec* exec_from(b2_handle h) {
+  if (!h) throw Error(B2_ERR_INVALID, "null exec handle");
+  return reinterpret_cast<GpuExec*>((intptr_t)h);
+}
+
+struct GpuBatchSource : GpuExec {
+  std::deque<Table*> q;
+  ~GpuBatchSource() { for (auto* t : q) table_release(t); }
+  Table* do_next() override {
+    if (q.empty()) return nullptr;
+    Table* t = q.front(); q.pop_front();
+    return t;
+  }
+};
+
+struct GpuParquetScanExec : GpuExec {
+  struct Buf { const uint8_t* p; int64_t len; };
+  std::deque<Buf> bufs;
+  std::vector<std::string> names;
+  Table* do_next() override {
+    if (bufs.empty()) return nullptr;
+    Buf b = bufs.front(); bufs.pop_front();
+    std::vector<const char*> cn;
+    for (auto& s : names) cn.push_back(s.c_str());
+    b2_handle out = 0;
+    int rc = b2_parquet_decode(b.p, b.len, cn.data(), (int)cn.size(), &out);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    return from_handle_owned(out);
+  }
+};
+
+struct GpuFilterExec : GpuExec {
+  b2_handle program;
+  Table* do_next() override {
+    TableRef in(children[0]->next());
+    if (!in.t) return nullptr;
+    b2_handle out = 0;
+    int rc = b2_filter(program, to_handle(in.t), &out);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    return from_handle_owned(out);
+  }
+};
+struct GpuProjectExec : GpuExec {
+  b2_handle program;
+  Table* do_next() override {
+    TableRef in(children[0]->next());
+    if (!in.t) return nullptr;
+    b2_handle out = 0;
+    int rc = b2_project(program, to_handle(in.t), &out);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    return from_handle_owned(out);
+  }
+};
+
+// aggregate modes as in Spark: Partial/Complete run the update aggregates on raw input, Final merges
+// partial buffers (SUM of sums, SUM of counts, MIN of mins, MAX of maxes)
+struct GpuHashAggregateExec : GpuExec {
+  Program* program = nullptr;  // pre-step projection (+ fused predicate as output 0) for update mode; null in merge mode
+  bool has_pred = false, merge_mode = false, done = false;
+  std::vector<int> keys;               // update: program outputs; merge: leading input columns
+  std::vector<b2_agg_spec> aggs;       // update: columns = program outputs; merge: columns = input columns
+
+  static std::vector<b2_agg_spec> merge_specs(const std::vector<b2_agg_spec>& a, int nkeys) {
+    std::vector<b2_agg_spec> m = a;
+    for (size_t i = 0; i < m.size(); i++) {
+      m[i].column = nkeys + (int)i;
+      if (m[i].kind == B2_AGG_COUNT || m[i].kind == B2_AGG_COUNT_ALL) { m[i].kind = B2_AGG_SUM; m[i].out_dtype = B2_INT64; m[i].out_scale = 0; }
+    }
+    return m;
+  }
+  Table* merge(const Table* t) {  // keys are the leading columns
+    std::vector<int> cols, key_outs;
+    for (int k = 0; k < (int)keys.size(); k++) { key_outs.push_back(k); cols.push_back(k); }
+    std::vector<b2_agg_spec> m = merge_specs(aggs, (int)keys.size());
+    for (auto& s : m) cols.push_back(s.column);
+    std::unique_ptr<Program> p(make_passthrough_program(t, cols));
+    return scan_aggregate(p.get(), false, t, key_outs.data(), (int)key_outs.size(), m.data(), (int)m.size());
+  }
+  Table* do_next() override {
+    if (done) return nullptr;
+    done = true;
+    std::vector<TableRef> partials;
+    while (true) {
+      TableRef in(children[0]->next());
+      if (!in.t) break;
+      if (merge_mode) partials.emplace_back(in.release());   // inputs already are aggregation buffers
+      else partials.emplace_back(scan_aggregate(program, has_pred, in.t, keys.data(), (int)keys.size(), aggs.data(), (int)aggs.size()));
+    }
+    if (partials.empty()) {
+      // a keyless aggregate over no batches still emits its initial-value row (GpuAggregateExec.scala:1107-1126)
+      if (!keys.empty() || merge_mode) return nullptr;
+      throw Error(B2_ERR_UNSUPPORTED, "keyless aggregate over zero input batches needs the input schema");
+    }
+    if (partials.size() == 1 && !merge_mode) return partials[0].release();
+    std::vector<const Table*> ts;
+    for (auto& p : partials) ts.push_back(p.t);
+    TableRef cat(concat_tables(ts));
+    return merge(cat.t);
+  }
+};
+
+struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), children[1] = build (right)
+  std::vector<int> stream_keys, build_keys;
+  int kind = B2_JOIN_INNER;
+  bool nulls_equal = false, built = false;
+  TableRef build_table;
+  b2_handle ht = 0;
+  ~GpuShuffledHashJoinExec() { if (ht) b2_join_hash_table_close(ht); }
+  static Table* select(const Table* t, const std::vector<int>& idx) {
+    std::vector<Column*> cols;
+    for (int i : idx) { if (i < 0 || i >= (int)t->cols.size()) throw Error(B2_ERR_INVALID, "join key index out of range"); col_incref(t->cols[i]); cols.push_back(t->cols[i]); }
+    return new_table(std::move(cols));
+  }
+  void build() {
+    // prepareBuildBatchesForJoin: the whole build side becomes one batch
+    std::vector<TableRef> parts;
+    while (true) { TableRef b(children[1]->next()); if (!b.t) break; parts.emplace_back(b.release()); }
+    if (parts.empty()) throw Error(B2_ERR_UNSUPPORTED, "empty build side needs the build schema");
+    if (parts.size() == 1) build_table = std::move(parts[0]);
+    else { std::vector<const Table*> ts; for (auto& p : parts) ts.push_back(p.t); build_table = TableRef(concat_tables(ts)); }
+    TableRef bk(select(build_table.t, build_keys));
+    int rc = b2_join_build(to_handle(bk.t), nulls_equal, &ht);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    built = true;
+  }
+  Table* do_next() override {
+    if (!built) build();
+    TableRef s(children[0]->next());
+    if (!s.t) return nullptr;
+    TableRef sk(select(s.t, stream_keys));
+    b2_handle lm = 0, rm = 0;
+    int rc = b2_join_probe(ht, to_handle(sk.t), kind, &lm, &rm);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    ColGuard lmap(col_from(lm));
+    ColGuard rmap(rm ? col_from(rm) : nullptr);
+    TableRef left(gather_table(s.t, lmap.c->data.as<int32_t>(), lmap.c->size, false, nullptr));
+    if (!rmap.c) return left.release();  // semi / anti: stream columns only
+    TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER, nullptr));
+    std::vector<Column*> cols;  // output = left columns ++ right columns (GpuHashJoin.scala:2451-2470)
+    for (auto*& c : left.t->cols) { cols.push_back(c); c = nullptr; }
+    for (auto*& c : right.t->cols) { cols.push_back(c); c = nullptr; }
+    left.t->cols.clear(); right.t->cols.clear();
+    return new_table(std::move(cols));
+  }
+};
+
+DevBuf sort_order(const Table* t, const b2_order_by_arg* keys, int nkeys);
+struct GpuSortExec : GpuExec {
+  std::vector<b2_order_by_arg> order;
+  bool global = true;   // false: sort each batch (SortEachBatch); true: full sort of the partition
+  int64_t limit = -1;   // >= 0: GpuTopN
+  bool done = false;
+  Table* sorted(const Table* t, int64_t n) {
+    DevBuf perm = sort_order(t, order.data(), (int)order.size());
+    return gather_table(t, perm.as<int32_t>(), n < 0 ? t->rows : std::min<int64_t>(n, t->rows), false, nullptr);
+  }
+  Table* do_next() override {
+    if (!global && limit < 0) {
+      TableRef in(children[0]->next());
+      return in.t ? sorted(in.t, -1) : nullptr;
+    }
+    if (done) return nullptr;
+    done = true;
+    TableRef pending;
+    while (true) {
+      TableRef in(children[0]->next());
+      if (!in.t) break;
+      if (limit >= 0) {
+        // GpuTopN: sort the batch, keep N, fold into the running top-N
+        TableRef top(sorted(in.t, limit));
+        if (!pending.t) pending = std::move(top);
+        else { std::vector<const Table*> ts{pending.t, top.t}; TableRef cat(concat_tables(ts)); pending = TableRef(sorted(cat.t, limit)); }
+      } else {
+        if (!pending.t) pending = std::move(in);
+        else { std::vector<const Table*> ts{pending.t, in.t}; pending = TableRef(concat_tables(ts)); }
+      }
+    }
+    if (!pending.t) return nullptr;
+    return limit >= 0 ? pending.release() : sorted(pending.t, -1);
+  }
+};
+
+struct GpuCoalesceBatches : GpuExec {
+  int64_t target_rows = 1 << 30;
+  TableRef carry;
+  Table* do_next() override {
+    std::vector<TableRef> acc;
+    int64_t rows = 0;
+    if (carry.t) { rows += carry.t->rows; acc.emplace_back(carry.release()); }
+    while (rows < target_rows) {
+      TableRef in(children[0]->next());
+      if (!in.t) break;
+      if (rows > 0 && rows + in.t->rows > target_rows) { carry = std::move(in); break; }
+      rows += in.t->rows;
+      acc.emplace_back(in.release());
+    }
+    if (acc.empty()) return nullptr;
+    if (acc.size() == 1) return acc[0].release();
+    std::vector<const Table*> ts;
+    for (auto& a : acc) ts.push_back(a.t);
+    return concat_tables(ts);
+  }
+};
+
+struct GpuShuffleExchangeExec : GpuExec {
+  std::vector<int32_t> key_cols;   // empty = SinglePartition (everything to rank 0)
+  b2_handle comm = 0;
+  int world = 1;
+  Table* do_next() override {
+    TableRef in(children[0]->next());
+    if (!in.t) return nullptr;
+    std::vector<int32_t> offs(world + 1, 0);
+    TableRef part;
+    if (key_cols.empty()) {
+      in.t->refs.fetch_add(1);
+      part = TableRef(in.t);
+      for (int r = 1; r <= world; r++) offs[r] = (int32_t)in.t->rows;
+    } else {
+      b2_handle out = 0;
+      int rc = b2_hash_partition(to_handle(in.t), key_cols.data(), (int)key_cols.size(), 42, world, &out, offs.data());
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+      part = TableRef(from_handle_owned(out));
+    }
+    if (world == 1 || !comm) return part.release();
+    b2_handle out = 0;
+    int rc = b2_exchange(comm, to_handle(part.t), offs.data(), &out);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    return from_handle_owned(out);
+  }
+};
+
+}  // namespace b2
+
+using namespace b2;
+extern "C" {
+
+int b2_exec_source(b2_handle* out) {
+  B2_TRY
+  *out = to_handle(new GpuBatchSource());
+  B2_CATCH
+}
+int b2_exec_source_push(b2_handle src, b2_handle table) {
+  B2_TRY
+  auto* s = dynamic_cast<GpuBatchSource*>(exec_from(src));
+  B2_CHECK(s, "not a batch source");
+  Table* t = table_from(table);
+  t->refs.fetch_add(1);
+  s->q.push_back(t);
+  B2_CATCH
+}
+int b2_exec_parquet_scan(const char* const* column_names, int32_t ncols, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuParquetScanExec();
+  for (int i = 0; i < ncols; i++) e->names.push_back(column_names[i]);
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_parquet_scan_add(b2_handle scan, const uint8_t* host_buf, int64_t len) {
+  B2_TRY
+  auto* s = dynamic_cast<GpuParquetScanExec*>(exec_from(scan));
+  B2_CHECK(s, "not a parquet scan");
+  s->bufs.push_back({host_buf, len});
+  B2_CATCH
+}
+int b2_exec_filter(b2_handle child, b2_handle predicate_program, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuFilterExec();
+  e->add_child(exec_from(child)); e->program = predicate_program;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_project(b2_handle child, b2_handle program, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuProjectExec();
+  e->add_child(exec_from(child)); e->program = program;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_hash_aggregate(b2_handle child, b2_handle program, int32_t has_predicate, int32_t merge_mode, const int32_t* keys, int32_t nkeys,
+                           const b2_agg_spec* aggs, int32_t naggs, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuHashAggregateExec();
+  e->add_child(exec_from(child));
+  e->program = merge_mode ? nullptr : program_from(program);
+  e->has_pred = has_predicate != 0; e->merge_mode = merge_mode != 0;
+  e->keys.assign(keys, keys + nkeys); e->aggs.assign(aggs, aggs + naggs);
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_shuffled_hash_join(b2_handle stream_child, b2_handle build_child, const int32_t* stream_keys, const int32_t* build_keys, int32_t nkeys,
+                               int32_t kind, int32_t nulls_equal, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuShuffledHashJoinExec();
+  e->add_child(exec_from(stream_child)); e->add_child(exec_from(build_child));
+  e->stream_keys.assign(stream_keys, stream_keys + nkeys); e->build_keys.assign(build_keys, build_keys + nkeys);
+  e->kind = kind; e->nulls_equal = nulls_equal != 0;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_sort(b2_handle child, const b2_order_by_arg* order, int32_t norder, int32_t global, int64_t limit, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuSortExec();
+  e->add_child(exec_from(child));
+  e->order.assign(order, order + norder); e->global = global != 0; e->limit = limit;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_coalesce(b2_handle child, int64_t target_rows, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuCoalesceBatches();
+  e->add_child(exec_from(child)); e->target_rows = target_rows;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_shuffle_exchange(b2_handle child, const int32_t* key_cols, int32_t nkeys, b2_handle comm, int32_t world, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuShuffleExchangeExec();
+  e->add_child(exec_from(child));
+  e->key_cols.assign(key_cols, key_cols + nkeys); e->comm = comm; e->world = world;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_next(b2_handle exec, b2_handle* out_table) {
+  B2_TRY
+  *out_table = to_handle(exec_from(exec)->next());
+  B2_CATCH
+}
+int b2_exec_metrics(b2_handle exec, int64_t* out3) {
+  B2_TRY
+  GpuExec* e = exec_from(exec);
+  out3[0] = e->num_output_rows; out3[1] = e->num_output_batches; out3[2] = e->op_time_ns;
+  B2_CATCH
+}
+int b2_exec_close(b2_handle exec) {
+  B2_TRY
+  exec_from(exec)->release();
+  B2_CATCH
+}
+
+}  // extern "C"
