@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
   uint64_t* s_priv = reinterpret_cast<uint64_t*>(s_nvalid + SMEM_SLOTS * plan.nvalids + (SMEM_SLOTS * plan.nvalids & 1));
   uint32_t* s_privv = reinterpret_cast<uint32_t*>(s_priv + plan.limbs * VM_NT);
   const bool keyless = SMEM && plan.nkeys == 0;
-  const VMInstr* code = vm_load_program(sh, g_hdr, g_code);
+  const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs);
   const int lane = threadIdx.x & 31;
   // a keyless reduction always has its single group, even over zero rows (GpuAggregateExec.scala:1107-1126)
   if (plan.nkeys == 0 && blockIdx.x == 0 && threadIdx.x == 0) gt.slots[0] = 0;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
     uint32_t active_mask = 0;
     if (plan.has_pred) {
       // predicate first; the projection only runs for rows that survive it (per-thread row mask)
-      vm_run(cx, code, 0, first_post);
+      vm_run(tile_info(cx), code, 0, first_post);
       const Opnd pred = resolve(cx, sh.hdr.outs[0], 1);
       for (int j = 0; j < cx.K; j++) {
         const int i = threadIdx.x + j * VM_NT;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
     } else {
       for (int j = 0; j < cx.K; j++) active_mask |= (uint32_t)(cx.tile_base + threadIdx.x + j * VM_NT < nrows) << j;
     }
-    vm_run(cx, code, first_post, sh.hdr.ninstr);
+    vm_run(tile_info(cx), code, first_post, sh.hdr.ninstr);
     if (keyless) {
       accumulate_private(plan, cx, active_mask, s_priv, s_privv);
       continue;

@@ -388,6 +388,7 @@ static Program* compile_program(const b2_handle* exprs, int n) {
     prog->out_dtype.push_back(v.dtype); prog->out_scale.push_back(v.scale); prog->out_precision.push_back(v.precision);
     prog->out_nullable.push_back(v.nullable);
   }
+  if (prog->code.size() > (size_t)VM_SMEM_CODE) throw Error(B2_ERR_UNSUPPORTED, "expression list compiles to more than 64 instructions; split the projection");
   prog->hdr.ninstr = (int)prog->code.size();
   prog->hdr.nregs = (int)cc.reg_width.size();
   prog->hdr.ncols = (int)prog->col_dtype.size();

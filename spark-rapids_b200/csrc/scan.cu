@@ -44,11 +44,11 @@ __global__ void __launch_bounds__(VM_NT, 4) project_kernel(const VMProgramHeader
                                                         const __grid_constant__ OutCols outs, int64_t nrows) {
   __shared__ VMShared sh;
   extern __shared__ __align__(16) char regs[];
-  const VMInstr* code = vm_load_program(sh, g_hdr, g_code);
+  const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs);
   const int64_t ntiles = (nrows + sh.hdr.tile_rows - 1) / sh.hdr.tile_rows;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
-    vm_run(cx, code, 0, sh.hdr.ninstr);
+    vm_run(tile_info(cx), code, 0, sh.hdr.ninstr);
     for (int o = 0; o < sh.hdr.nouts; o++) {
       const int mt = sh.hdr.out_mt[o];
       Opnd op = resolve(cx, sh.hdr.outs[o], mt_width(mt));
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(VM_NT, 4) filter_kernel(const VMProgramHeader*
   __shared__ int64_t s_tile;
   __shared__ uint32_t s_tile_total;
   extern __shared__ __align__(16) char regs[];
-  const VMInstr* code = vm_load_program(sh, g_hdr, g_code);
+  const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs);
   const int64_t ntiles = (nrows + sh.hdr.tile_rows - 1) / sh.hdr.tile_rows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long local_count = 0;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(VM_NT, 4) filter_kernel(const VMProgramHeader*
     if (tile >= ntiles) break;
 
     VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
-    vm_run(cx, code, 0, sh.hdr.ninstr);
+    vm_run(tile_info(cx), code, 0, sh.hdr.ninstr);
     const Opnd p = resolve(cx, sh.hdr.outs[0], 1);
     const int K = cx.K;
     uint32_t selmask = 0;

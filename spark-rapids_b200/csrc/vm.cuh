@@ -80,6 +80,25 @@ struct VMInputs {
   const uint32_t* valid[VM_MAX_COLS];
 };
 
+// instruction with operands resolved once per CTA (shared memory): a row loop starts with two
+// 16-byte shared loads per operand instead of re-deriving pointers from the program header
+struct alignas(16) ROpnd {
+  const char* base;      // tile-0 address: register slice (shared), column data (global) or literal
+  const void* vptr;      // validity bytes (shared) or bitmask (global)
+  int32_t stride;        // bytes per row, 0 for a literal
+  int32_t tile_step;     // bytes per row to advance per tile row offset (columns only)
+  int32_t vkind;         // 0 valid, 1 bytes, 2 bitmask, 3 null
+  int32_t pad;
+};
+struct alignas(16) RInstr {
+  uint8_t op, mt, mt2, dst_nullable;
+  int32_t aux;
+  char* dbase;
+  uint8_t* dvb;
+  int64_t pad;
+  ROpnd a, b, c;
+};
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
 
@@ -180,8 +199,20 @@ template <> struct IsFloat<double> { static const bool v = true; };
 constexpr int VM_B = 4;  // the VM_LD*/VM_ST* expansions below are written for exactly 4
 // The context lives in the caller's frame (local memory) and every store through a register
 // pointer could alias it, so handlers copy what the row loops need into registers ONCE.
-struct TileInfo { int K; uint32_t rowmask; int64_t tile_base, nrows; };
-__device__ __forceinline__ TileInfo tile_info(const VMCtx& cx) { TileInfo t; t.K = cx.K; t.rowmask = cx.rowmask; t.tile_base = cx.tile_base; t.nrows = cx.nrows; return t; }
+struct TileInfo { int K; uint32_t rowmask; int64_t tile_base, nrows; int tile_rows; };
+__device__ __forceinline__ TileInfo tile_info(const VMCtx& cx) {
+  TileInfo t; t.K = cx.K; t.rowmask = cx.rowmask; t.tile_base = cx.tile_base; t.nrows = cx.nrows; t.tile_rows = cx.tile_rows; return t;
+}
+__device__ __forceinline__ Opnd ropnd(const ROpnd& o, const TileInfo& ti) {
+  Opnd r;
+  r.base = o.base + ti.tile_base * o.tile_step;
+  r.stride = o.stride; r.vkind = o.vkind;
+  r.vbytes = reinterpret_cast<const uint8_t*>(o.vptr); r.vbits = reinterpret_cast<const uint32_t*>(o.vptr);
+  return r;
+}
+__device__ __forceinline__ Dst rdst(const RInstr& ins, int width) {
+  Dst d; d.base = ins.dbase; d.stride = width; d.vbytes = ins.dvb; d.nullable = ins.dst_nullable; return d;
+}
 #define VM_ROW_ACTIVE(j, i, g) \
   const int i = threadIdx.x + (j) * VM_NT; const int64_t g = ti.tile_base + i; \
   const bool act = (j) < ti.K && g < ti.nrows && ((ti.rowmask >> (j)) & 1u)
@@ -214,11 +245,10 @@ __device__ __forceinline__ const char* thread_base(const Opnd& o) { return o.bas
 
 // unary: F(T x, bool& valid) -> R
 template <typename T, typename R, typename F>
-__device__ __forceinline__ void vm_loop1(const VMCtx& cx, const VMInstr& ins, F f) {
-  const Opnd a = resolve(cx, ins.a, sizeof(T));
-  const Dst d = resolve_dst(cx, ins, sizeof(R));
-  const TileInfo ti = tile_info(cx);
-  if (a.vkind == 0 && !d.nullable && a.stride != 0 && vm_full_tile(ti, cx.tile_rows)) {
+__device__ __forceinline__ void vm_loop1(const TileInfo ti, const RInstr& ins, F f) {
+  const Opnd a = ropnd(ins.a, ti);
+  const Dst d = rdst(ins, sizeof(R));
+  if (a.vkind == 0 && !d.nullable && a.stride != 0 && vm_full_tile(ti, ti.tile_rows)) {
     const char* pa = thread_base<T>(a);
     char* pd = d.base + (size_t)threadIdx.x * sizeof(R);
     for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
@@ -241,11 +271,10 @@ __device__ __forceinline__ void vm_loop1(const VMCtx& cx, const VMInstr& ins, F 
 }
 // binary: F(T x, T y, bool va, bool vb, bool& valid) -> R
 template <typename T, typename R, typename F>
-__device__ __forceinline__ void vm_loop2(const VMCtx& cx, const VMInstr& ins, F f) {
-  const Opnd a = resolve(cx, ins.a, sizeof(T)), b = resolve(cx, ins.b, sizeof(T));
-  const Dst d = resolve_dst(cx, ins, sizeof(R));
-  const TileInfo ti = tile_info(cx);
-  if (a.vkind == 0 && b.vkind == 0 && !d.nullable && a.stride != 0 && vm_full_tile(ti, cx.tile_rows)) {
+__device__ __forceinline__ void vm_loop2(const TileInfo ti, const RInstr& ins, F f) {
+  const Opnd a = ropnd(ins.a, ti), b = ropnd(ins.b, ti);
+  const Dst d = rdst(ins, sizeof(R));
+  if (a.vkind == 0 && b.vkind == 0 && !d.nullable && a.stride != 0 && vm_full_tile(ti, ti.tile_rows)) {
     const char* pa = thread_base<T>(a);
     char* pd = d.base + (size_t)threadIdx.x * sizeof(R);
     bool vv = true;
@@ -291,9 +320,9 @@ __device__ __forceinline__ int cmp3(T a, T b) {
 }
 
 template <typename T, int OP>
-__device__ __noinline__ void vm_arith(const VMCtx& cx, const VMInstr& ins) {
+__device__ __noinline__ void vm_arith(const TileInfo ti, const RInstr& ins) {
   typedef typename UnsignedOf<T>::type U;
-  vm_loop2<T, T>(cx, ins, [](T x, T y, bool, bool, bool& v) -> T {
+  vm_loop2<T, T>(ti, ins, [](T x, T y, bool, bool, bool& v) -> T {
     if constexpr (IsFloat<T>::v) {
       // arithmetic.scala:309-340 — IEEE; Divide/Remainder by zero -> NULL (Spark non-ANSI)
       if constexpr (OP == V_ADD) return x + y;
@@ -323,21 +352,21 @@ __device__ __noinline__ void vm_arith(const VMCtx& cx, const VMInstr& ins) {
 
 // 128-bit decimal add/sub with overflow -> null (arithmetic.scala:78-125); V_MUL: product known to fit
 template <int OP>
-__device__ __noinline__ void vm_arith128(const VMCtx& cx, const VMInstr& ins) {
-  vm_loop2<i128, i128>(cx, ins, [](i128 x, i128 y, bool, bool, bool& v) -> i128 {
+__device__ __noinline__ void vm_arith128(const TileInfo ti, const RInstr& ins) {
+  vm_loop2<i128, i128>(ti, ins, [](i128 x, i128 y, bool, bool, bool& v) -> i128 {
     if constexpr (OP == V_ADD) { i128 r = (i128)((u128)x + (u128)y); if (((x ^ r) & (y ^ r)) < 0) v = false; return r; }
     else if constexpr (OP == V_SUB) { i128 r = (i128)((u128)x - (u128)y); if (((x ^ y) & (x ^ r)) < 0) v = false; return r; }
     else return (i128)((u128)x * (u128)y);
   });
 }
 
-static __device__ __noinline__ void vm_mulw(const VMCtx& cx, const VMInstr& ins) {
-  vm_loop2<int64_t, i128>(cx, ins, [](int64_t x, int64_t y, bool, bool, bool&) -> i128 { return (i128)x * (i128)y; });
+static __device__ __noinline__ void vm_mulw(const TileInfo ti, const RInstr& ins) {
+  vm_loop2<int64_t, i128>(ti, ins, [](int64_t x, int64_t y, bool, bool, bool&) -> i128 { return (i128)x * (i128)y; });
 }
 
 template <typename T, int OP>
-__device__ __noinline__ void vm_compare(const VMCtx& cx, const VMInstr& ins) {
-  vm_loop2<T, int8_t>(cx, ins, [](T x, T y, bool va, bool vb, bool& v) -> int8_t {
+__device__ __noinline__ void vm_compare(const TileInfo ti, const RInstr& ins) {
+  vm_loop2<T, int8_t>(ti, ins, [](T x, T y, bool va, bool vb, bool& v) -> int8_t {
     const int c = cmp3<T>(x, y);
     bool r;
     if constexpr (OP == V_EQ) r = c == 0;
@@ -352,12 +381,12 @@ __device__ __noinline__ void vm_compare(const VMCtx& cx, const VMInstr& ins) {
 }
 
 template <int OP>
-__device__ __noinline__ void vm_logic(const VMCtx& cx, const VMInstr& ins) {
+__device__ __noinline__ void vm_logic(const TileInfo ti, const RInstr& ins) {
   if constexpr (OP == V_NOT) {
-    vm_loop1<int8_t, int8_t>(cx, ins, [](int8_t x, bool& v) -> int8_t { return (int8_t)(v && !x); });
+    vm_loop1<int8_t, int8_t>(ti, ins, [](int8_t x, bool& v) -> int8_t { return (int8_t)(v && !x); });
   } else {
     // Kleene logic, predicates.scala:54-153 (NULL_LOGICAL_AND / NULL_LOGICAL_OR)
-    vm_loop2<int8_t, int8_t>(cx, ins, [](int8_t xa, int8_t ya, bool va, bool vb, bool& v) -> int8_t {
+    vm_loop2<int8_t, int8_t>(ti, ins, [](int8_t xa, int8_t ya, bool va, bool vb, bool& v) -> int8_t {
       const bool x = va && xa, y = vb && ya;
       bool r;
       if constexpr (OP == V_AND) { const bool fa = va && !x, fb = vb && !y; r = x && y; v = (va && vb) || fa || fb; }
@@ -368,27 +397,26 @@ __device__ __noinline__ void vm_logic(const VMCtx& cx, const VMInstr& ins) {
 }
 
 template <typename T>
-__device__ __noinline__ void vm_select(const VMCtx& cx, const VMInstr& ins) {
+__device__ __noinline__ void vm_select(const TileInfo ti, const RInstr& ins) {
   typedef typename UnsignedOf<T>::type U;
   switch (ins.op) {
     case V_COALESCE:
-      vm_loop2<T, T>(cx, ins, [](T x, T y, bool va, bool vb, bool& v) -> T { v = va || vb; return va ? x : y; });
+      vm_loop2<T, T>(ti, ins, [](T x, T y, bool va, bool vb, bool& v) -> T { v = va || vb; return va ? x : y; });
       break;
-    case V_MOV: vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T { return x; }); break;
+    case V_MOV: vm_loop1<T, T>(ti, ins, [](T x, bool&) -> T { return x; }); break;
     case V_NEG:
-      vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T { if constexpr (IsFloat<T>::v) return -x; else return (T)((U)0 - (U)x); });
+      vm_loop1<T, T>(ti, ins, [](T x, bool&) -> T { if constexpr (IsFloat<T>::v) return -x; else return (T)((U)0 - (U)x); });
       break;
     case V_ABS:
-      vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T {
+      vm_loop1<T, T>(ti, ins, [](T x, bool&) -> T {
         if constexpr (IsFloat<T>::v) return (x < 0 || (x == 0 && 1 / (double)x < 0)) ? -x : x;
         else return x < 0 ? (T)((U)0 - (U)x) : x;
       });
       break;
     default: {  // V_IF (conditionalExpressions.scala GpuIf): a NULL predicate takes the else branch
-      const Opnd p = resolve(cx, ins.a, 1), a = resolve(cx, ins.b, sizeof(T)), b = resolve(cx, ins.c, sizeof(T));
-      const Dst d = resolve_dst(cx, ins, sizeof(T));
-      const TileInfo ti = tile_info(cx);
-      for (int j = 0; j < ti.K; j++) {
+      const Opnd p = ropnd(ins.a, ti), a = ropnd(ins.b, ti), b = ropnd(ins.c, ti);
+      const Dst d = rdst(ins, sizeof(T));
+          for (int j = 0; j < ti.K; j++) {
         VM_ROW_ACTIVE(j, i, g);
         if (!act) continue;
         const bool t = opnd_valid(p, i, g) && opnd_ld<int8_t>(p, i);
@@ -444,19 +472,19 @@ __device__ __forceinline__ D cast_val(S x) {
   }
 }
 template <typename S, typename D>
-__device__ __noinline__ void vm_cast2(const VMCtx& cx, const VMInstr& ins) {
-  vm_loop1<S, D>(cx, ins, [](S x, bool&) -> D { return cast_val<S, D>(x); });
+__device__ __noinline__ void vm_cast2(const TileInfo ti, const RInstr& ins) {
+  vm_loop1<S, D>(ti, ins, [](S x, bool&) -> D { return cast_val<S, D>(x); });
 }
 template <typename S>
-__device__ __forceinline__ void vm_cast1(const VMCtx& cx, const VMInstr& ins) {
+__device__ __forceinline__ void vm_cast1(const TileInfo ti, const RInstr& ins) {
   switch (ins.mt2) {
-    case MT_I8: vm_cast2<S, int8_t>(cx, ins); break;
-    case MT_I16: vm_cast2<S, int16_t>(cx, ins); break;
-    case MT_I32: vm_cast2<S, int32_t>(cx, ins); break;
-    case MT_I64: vm_cast2<S, int64_t>(cx, ins); break;
-    case MT_I128: vm_cast2<S, i128>(cx, ins); break;
-    case MT_F32: vm_cast2<S, float>(cx, ins); break;
-    default: vm_cast2<S, double>(cx, ins); break;
+    case MT_I8: vm_cast2<S, int8_t>(ti, ins); break;
+    case MT_I16: vm_cast2<S, int16_t>(ti, ins); break;
+    case MT_I32: vm_cast2<S, int32_t>(ti, ins); break;
+    case MT_I64: vm_cast2<S, int64_t>(ti, ins); break;
+    case MT_I128: vm_cast2<S, i128>(ti, ins); break;
+    case MT_F32: vm_cast2<S, float>(ti, ins); break;
+    default: vm_cast2<S, double>(ti, ins); break;
   }
 }
 
@@ -472,18 +500,18 @@ __device__ __forceinline__ uint64_t div256_u64(uint64_t q[4], uint64_t dv) {
 }
 
 template <typename T>
-__device__ __noinline__ void vm_decimal(const VMCtx& cx, const VMInstr& ins) {
+__device__ __noinline__ void vm_decimal(const TileInfo ti, const RInstr& ins) {
   const i128 p = pow10_i128(ins.aux);
   if (ins.op == V_RESCALE_UP) {
     const i128 maxv = (i128)((((u128)1) << (8 * sizeof(T) - 1)) - 1);
     const i128 lim = maxv / p;
-    vm_loop1<T, T>(cx, ins, [p, lim](T xx, bool& v) -> T {
+    vm_loop1<T, T>(ti, ins, [p, lim](T xx, bool& v) -> T {
       const i128 x = (i128)xx;
       if (x > lim || x < -lim) v = false;  // |x| * 10^aux does not fit T
       return (T)(i128)((u128)x * (u128)p);
     });
   } else if (ins.op == V_RESCALE_DOWN) {  // HALF_UP (away from zero), as BigDecimal.setScale
-    vm_loop1<T, T>(cx, ins, [p](T xx, bool&) -> T {
+    vm_loop1<T, T>(ti, ins, [p](T xx, bool&) -> T {
       const i128 x = (i128)xx;
       const bool neg = x < 0;
       const u128 m = neg ? (u128)0 - (u128)x : (u128)x;
@@ -493,16 +521,16 @@ __device__ __noinline__ void vm_decimal(const VMCtx& cx, const VMInstr& ins) {
       return (T)(neg ? -(i128)q : (i128)q);
     });
   } else {  // V_CHECK_PREC
-    vm_loop1<T, T>(cx, ins, [p](T x, bool& v) -> T { const i128 xx = (i128)x; if (xx >= p || xx <= -p) v = false; return x; });
+    vm_loop1<T, T>(ti, ins, [p](T x, bool& v) -> T { const i128 xx = (i128)x; if (xx >= p || xx <= -p) v = false; return x; });
   }
 }
 
 // DecimalUtils.multiply128 (arithmetic.scala:470-512 longMultiply): exact 256-bit product,
 // HALF_UP to the result scale, NULL when the result needs more than 38 digits.
-static __device__ __noinline__ void vm_muldec(const VMCtx& cx, const VMInstr& ins) {
+static __device__ __noinline__ void vm_muldec(const TileInfo ti, const RInstr& ins) {
   const int k = ins.aux;
   const u128 p38 = (u128)pow10_i128(38);
-  vm_loop2<i128, i128>(cx, ins, [k, p38](i128 x, i128 y, bool, bool, bool& v) -> i128 {
+  vm_loop2<i128, i128>(ti, ins, [k, p38](i128 x, i128 y, bool, bool, bool& v) -> i128 {
     const bool neg = (x < 0) != (y < 0);
     const u128 mx = x < 0 ? (u128)0 - (u128)x : (u128)x, my = y < 0 ? (u128)0 - (u128)y : (u128)y;
     const uint64_t x0 = (uint64_t)mx, x1 = (uint64_t)(mx >> 64), y0 = (uint64_t)my, y1 = (uint64_t)(my >> 64);
@@ -538,22 +566,22 @@ static __device__ __noinline__ void vm_muldec(const VMCtx& cx, const VMInstr& in
 }
 
 template <typename T>
-__device__ __noinline__ void vm_dec2f64(const VMCtx& cx, const VMInstr& ins) {
+__device__ __noinline__ void vm_dec2f64(const TileInfo ti, const RInstr& ins) {
   double dv = 1.0; for (int t = 0; t < ins.aux; t++) dv *= 10.0;
-  vm_loop1<T, double>(cx, ins, [dv](T x, bool&) -> double { return CastVia<T, double>::f(x) / dv; });
+  vm_loop1<T, double>(ti, ins, [dv](T x, bool&) -> double { return CastVia<T, double>::f(x) / dv; });
 }
 
 template <typename T>
-__device__ __noinline__ void vm_normnz(const VMCtx& cx, const VMInstr& ins) {
-  vm_loop1<T, T>(cx, ins, [](T x, bool&) -> T {  // NormalizeFloatingNumbers.scala:29-38: canonical NaN, -0.0 -> 0.0
+__device__ __noinline__ void vm_normnz(const TileInfo ti, const RInstr& ins) {
+  vm_loop1<T, T>(ti, ins, [](T x, bool&) -> T {  // NormalizeFloatingNumbers.scala:29-38: canonical NaN, -0.0 -> 0.0
     if (x != x) return (T)__longlong_as_double(0x7ff8000000000000LL);
     if (x == (T)0) return (T)0;
     return x;
   });
 }
 
-static __device__ __noinline__ void vm_year(const VMCtx& cx, const VMInstr& ins) {
-  vm_loop1<int32_t, int32_t>(cx, ins, [](int32_t days, bool&) -> int32_t {  // proleptic Gregorian civil-from-days
+static __device__ __noinline__ void vm_year(const TileInfo ti, const RInstr& ins) {
+  vm_loop1<int32_t, int32_t>(ti, ins, [](int32_t days, bool&) -> int32_t {  // proleptic Gregorian civil-from-days
     const int z = days + 719468;
     const int era = (z >= 0 ? z : z - 146096) / 146097;
     const unsigned doe = (unsigned)(z - era * 146097);
@@ -566,74 +594,73 @@ static __device__ __noinline__ void vm_year(const VMCtx& cx, const VMInstr& ins)
   });
 }
 
-static __device__ __noinline__ void vm_isnull(const VMCtx& cx, const VMInstr& ins) {
-  const Opnd a = resolve(cx, ins.a, mt_width(ins.mt));
-  const Dst d = resolve_dst(cx, ins, 1);
+static __device__ __noinline__ void vm_isnull(const TileInfo ti, const RInstr& ins) {
+  const Opnd a = ropnd(ins.a, ti);
+  const Dst d = rdst(ins, 1);
   const bool want_null = ins.op == V_ISNULL;
-  const TileInfo ti = tile_info(cx);
   for (int j = 0; j < ti.K; j++) { VM_ROW_ACTIVE(j, i, g); if (act) dst_st<int8_t>(d, i, (int8_t)(opnd_valid(a, i, g) != want_null), true); }
 }
 
 #define VM_TYPES_INT_FLOAT(fn, ...)                         \
   switch (ins.mt) {                                         \
-    case MT_I8: fn<int8_t, ##__VA_ARGS__>(cx, ins); break;  \
-    case MT_I16: fn<int16_t, ##__VA_ARGS__>(cx, ins); break;\
-    case MT_I32: fn<int32_t, ##__VA_ARGS__>(cx, ins); break;\
-    case MT_I64: fn<int64_t, ##__VA_ARGS__>(cx, ins); break;\
-    case MT_F32: fn<float, ##__VA_ARGS__>(cx, ins); break;  \
-    case MT_F64: fn<double, ##__VA_ARGS__>(cx, ins); break; \
+    case MT_I8: fn<int8_t, ##__VA_ARGS__>(ti, ins); break;  \
+    case MT_I16: fn<int16_t, ##__VA_ARGS__>(ti, ins); break;\
+    case MT_I32: fn<int32_t, ##__VA_ARGS__>(ti, ins); break;\
+    case MT_I64: fn<int64_t, ##__VA_ARGS__>(ti, ins); break;\
+    case MT_F32: fn<float, ##__VA_ARGS__>(ti, ins); break;  \
+    case MT_F64: fn<double, ##__VA_ARGS__>(ti, ins); break; \
     default: break;                                         \
   }
 #define VM_TYPES_ALL(fn, ...)                               \
   switch (ins.mt) {                                         \
-    case MT_I8: fn<int8_t, ##__VA_ARGS__>(cx, ins); break;  \
-    case MT_I16: fn<int16_t, ##__VA_ARGS__>(cx, ins); break;\
-    case MT_I32: fn<int32_t, ##__VA_ARGS__>(cx, ins); break;\
-    case MT_I64: fn<int64_t, ##__VA_ARGS__>(cx, ins); break;\
-    case MT_I128: fn<i128, ##__VA_ARGS__>(cx, ins); break;  \
-    case MT_F32: fn<float, ##__VA_ARGS__>(cx, ins); break;  \
-    default: fn<double, ##__VA_ARGS__>(cx, ins); break;     \
+    case MT_I8: fn<int8_t, ##__VA_ARGS__>(ti, ins); break;  \
+    case MT_I16: fn<int16_t, ##__VA_ARGS__>(ti, ins); break;\
+    case MT_I32: fn<int32_t, ##__VA_ARGS__>(ti, ins); break;\
+    case MT_I64: fn<int64_t, ##__VA_ARGS__>(ti, ins); break;\
+    case MT_I128: fn<i128, ##__VA_ARGS__>(ti, ins); break;  \
+    case MT_F32: fn<float, ##__VA_ARGS__>(ti, ins); break;  \
+    default: fn<double, ##__VA_ARGS__>(ti, ins); break;     \
   }
 #define VM_ARITH_CASE(OP)                                                                       \
-  case OP: if (ins.mt == MT_I128) vm_arith128<OP>(cx, ins); else { VM_TYPES_INT_FLOAT(vm_arith, OP) } break;
+  case OP: if (ins.mt == MT_I128) vm_arith128<OP>(ti, ins); else { VM_TYPES_INT_FLOAT(vm_arith, OP) } break;
 #define VM_CMP_CASE(OP) case OP: VM_TYPES_ALL(vm_compare, OP) break;
 
 // Execute instructions [first, last) over this CTA's tile.  No barrier is needed: registers are thread private.
-static __device__ __noinline__ void vm_run(const VMCtx& cx, const VMInstr* __restrict__ code, int first, int last) {
+static __device__ __noinline__ void vm_run(const TileInfo ti, const RInstr* __restrict__ code, int first, int last) {
   for (int pc = first; pc < last; pc++) {
-    const VMInstr& ins = code[pc];
+    const RInstr& ins = code[pc];
     switch (ins.op) {
       VM_ARITH_CASE(V_ADD) VM_ARITH_CASE(V_SUB) VM_ARITH_CASE(V_MUL)
       case V_DIV: VM_TYPES_INT_FLOAT(vm_arith, V_DIV) break;
       case V_MOD: VM_TYPES_INT_FLOAT(vm_arith, V_MOD) break;
       case V_PMOD: VM_TYPES_INT_FLOAT(vm_arith, V_PMOD) break;
       VM_CMP_CASE(V_EQ) VM_CMP_CASE(V_NE) VM_CMP_CASE(V_LT) VM_CMP_CASE(V_LE) VM_CMP_CASE(V_GT) VM_CMP_CASE(V_GE) VM_CMP_CASE(V_EQNS)
-      case V_AND: vm_logic<V_AND>(cx, ins); break;
-      case V_OR: vm_logic<V_OR>(cx, ins); break;
-      case V_NOT: vm_logic<V_NOT>(cx, ins); break;
-      case V_ISNULL: case V_ISNOTNULL: vm_isnull(cx, ins); break;
+      case V_AND: vm_logic<V_AND>(ti, ins); break;
+      case V_OR: vm_logic<V_OR>(ti, ins); break;
+      case V_NOT: vm_logic<V_NOT>(ti, ins); break;
+      case V_ISNULL: case V_ISNOTNULL: vm_isnull(ti, ins); break;
       case V_COALESCE: case V_IF: case V_MOV: case V_NEG: case V_ABS:
         VM_TYPES_ALL(vm_select)
         break;
       case V_CAST: VM_TYPES_ALL(vm_cast1) break;
       case V_RESCALE_UP: case V_RESCALE_DOWN: case V_CHECK_PREC:
         switch (ins.mt) {
-          case MT_I32: vm_decimal<int32_t>(cx, ins); break;
-          case MT_I64: vm_decimal<int64_t>(cx, ins); break;
-          default: vm_decimal<i128>(cx, ins); break;
+          case MT_I32: vm_decimal<int32_t>(ti, ins); break;
+          case MT_I64: vm_decimal<int64_t>(ti, ins); break;
+          default: vm_decimal<i128>(ti, ins); break;
         }
         break;
-      case V_MULW: vm_mulw(cx, ins); break;
-      case V_MULDEC: vm_muldec(cx, ins); break;
+      case V_MULW: vm_mulw(ti, ins); break;
+      case V_MULDEC: vm_muldec(ti, ins); break;
       case V_DEC2F64:
         switch (ins.mt) {
-          case MT_I32: vm_dec2f64<int32_t>(cx, ins); break;
-          case MT_I64: vm_dec2f64<int64_t>(cx, ins); break;
-          default: vm_dec2f64<i128>(cx, ins); break;
+          case MT_I32: vm_dec2f64<int32_t>(ti, ins); break;
+          case MT_I64: vm_dec2f64<int64_t>(ti, ins); break;
+          default: vm_dec2f64<i128>(ti, ins); break;
         }
         break;
-      case V_NORM_NAN_ZERO: if (ins.mt == MT_F32) vm_normnz<float>(cx, ins); else vm_normnz<double>(cx, ins); break;
-      case V_YEAR: vm_year(cx, ins); break;
+      case V_NORM_NAN_ZERO: if (ins.mt == MT_F32) vm_normnz<float>(ti, ins); else vm_normnz<double>(ti, ins); break;
+      case V_YEAR: vm_year(ti, ins); break;
       default: break;
     }
   }
@@ -647,23 +674,47 @@ __device__ __forceinline__ VMCtx vm_ctx(const VMProgramHeader* hdr, const VMInpu
   return cx;
 }
 
-constexpr int VM_SMEM_CODE = 64;  // instructions cached in shared memory
+constexpr int VM_SMEM_CODE = 64;  // instructions per program (resolved form lives in shared memory)
 struct VMShared {
   VMProgramHeader hdr;
-  VMInstr code[VM_SMEM_CODE];
+  RInstr code[VM_SMEM_CODE];
 };
-// cooperative copy of the program into shared memory; returns the code pointer to execute from
-static __device__ __forceinline__ const VMInstr* vm_load_program(VMShared& sh, const VMProgramHeader* g_hdr,
-                                                                 const VMInstr* g_code) {
+// cooperative load: header into shared memory, then one thread per instruction resolves its operands
+static __device__ __forceinline__ const RInstr* vm_load_program(VMShared& sh, const VMProgramHeader* g_hdr, const VMInstr* g_code,
+                                                                 const VMInputs& in, char* regs) {
   const int* src = reinterpret_cast<const int*>(g_hdr);
   int* dst = reinterpret_cast<int*>(&sh.hdr);
   for (int k = threadIdx.x; k < (int)(sizeof(VMProgramHeader) / 4); k += blockDim.x) dst[k] = src[k];
   __syncthreads();
   const int n = sh.hdr.ninstr;
-  if (n > VM_SMEM_CODE) return g_code;
-  const int4* s4 = reinterpret_cast<const int4*>(g_code);
-  int4* d4 = reinterpret_cast<int4*>(sh.code);
-  for (int k = threadIdx.x; k < n * (int)(sizeof(VMInstr) / 16); k += blockDim.x) d4[k] = s4[k];
+  const int tile_rows = sh.hdr.tile_rows;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const VMInstr& g = g_code[k];
+    RInstr r;
+    r.op = g.op; r.mt = g.mt; r.mt2 = g.mt2; r.dst_nullable = g.dst_nullable; r.aux = g.aux; r.pad = 0;
+    r.dbase = regs + (size_t)sh.hdr.regs[g.dst].off * tile_rows;
+    r.dvb = reinterpret_cast<uint8_t*>(regs + (size_t)sh.hdr.regs[g.dst].voff * tile_rows);
+    const VMOperand* ops[3] = {&g.a, &g.b, &g.c};
+    ROpnd* outs[3] = {&r.a, &r.b, &r.c};
+    // operand width = the instruction's input machine type, except boolean operands of logic ops / IF predicate
+    for (int j = 0; j < 3; j++) {
+      const VMOperand& o = *ops[j];
+      ROpnd q; q.pad = 0; q.vptr = nullptr; q.tile_step = 0;
+      int width = mt_width(g.mt);
+      if (g.op == V_AND || g.op == V_OR || g.op == V_NOT || (g.op == V_IF && j == 0)) width = 1;
+      if (o.kind == OK_REG) {
+        q.base = regs + (size_t)sh.hdr.regs[o.idx].off * tile_rows; q.stride = width;
+        q.vkind = o.nullable ? 1 : 0; q.vptr = regs + (size_t)sh.hdr.regs[o.idx].voff * tile_rows;
+      } else if (o.kind == OK_COL) {
+        q.base = reinterpret_cast<const char*>(in.data[o.idx]); q.stride = width; q.tile_step = width;
+        q.vptr = in.valid[o.idx]; q.vkind = (o.nullable && in.valid[o.idx]) ? 2 : 0;
+      } else {
+        q.base = reinterpret_cast<const char*>(&o.lo); q.stride = 0; q.vkind = o.lit_null ? 3 : 0;
+      }
+      *outs[j] = q;
+    }
+    sh.code[k] = r;
+  }
   __syncthreads();
   return sh.code;
 }
