@@ -258,6 +258,27 @@ def _arith(op, a, b):
                     valid[i] = False
                 out[i] = r if valid[i] else 0
             return OCol(out, valid, (decimal_dtype_for(rp), rp, rs))
+        if op == "div":  # arithmetic.scala:903-1000 (Spark Divide result type, HALF_UP, x / 0 -> NULL)
+            rs = max(6, s1 + p2 + 1)
+            rp, rs = adjust_precision_scale(p1 - s1 + s2 + rs, rs)
+            k = rs - s1 + s2
+            lim = 10 ** rp
+            for i in range(n):
+                d = int(b.values[i])
+                if d == 0 or not valid[i]:
+                    valid[i] = False
+                    out[i] = 0
+                    continue
+                num = int(a.values[i]) * 10 ** k
+                q, r = divmod(abs(num), abs(d))
+                if r * 2 >= abs(d):
+                    q += 1
+                q = -q if (num < 0) != (d < 0) else q
+                if abs(q) >= lim or abs(q) >= 10 ** 38:
+                    valid[i] = False
+                    q = 0
+                out[i] = q
+            return OCol(out, valid, (decimal_dtype_for(rp), rp, rs))
         raise NotImplementedError("decimal " + op)
     assert a.typ[0] == b.typ[0], (a.typ, b.typ)
     dt = a.typ[0]

@@ -24,7 +24,8 @@
 namespace b2 {
 
 constexpr int AG_MAX_AGGS = 24;
-constexpr int SMEM_SLOTS = 128;  // groups per CTA table (power of two)
+constexpr int SMEM_SLOTS_MAX = 2048;  // groups per CTA table (power of two, sized per plan)
+constexpr uint32_t KEY_READY = 0x80000000u;
 constexpr int32_t SLOT_EMPTY = -1;
 
 struct AggD {
@@ -39,6 +40,8 @@ struct AggD {
 };
 struct AggPlan {
   int32_t nkeys, naggs, limbs, nvalids, has_pred;
+  int32_t smem_slots;   // slots of the per-CTA table (power of two)
+  int32_t fast_keys;    // all keys fixed width, <= 8 bytes together: packed copy kept in the slot
   KeyCols keys;
   AggD aggs[AG_MAX_AGGS];
 };
@@ -84,87 +87,89 @@ __device__ __forceinline__ void acc_add_limbs(uint64_t* acc, int nlimbs, uint64_
   if (s2) atomicAdd(&a[2], (unsigned long long)s2);
 }
 
-// sum over the lanes in `m` of a 64-bit piece, as a 128-bit unsigned value (4 REDUX on 16-bit pieces)
-__device__ __forceinline__ u128 group_sum_u64(uint32_t m, uint64_t x) {
-  uint32_t s0 = __reduce_add_sync(m, (uint32_t)(x & 0xffff));
-  uint32_t s1 = __reduce_add_sync(m, (uint32_t)((x >> 16) & 0xffff));
-  uint32_t s2 = __reduce_add_sync(m, (uint32_t)((x >> 32) & 0xffff));
-  uint32_t s3 = __reduce_add_sync(m, (uint32_t)((x >> 48) & 0xffff));
+// Accumulate one warp-slice (32 rows) into per-slot accumulators.  Two regimes per slice:
+//   few distinct groups in the warp (<= 4, e.g. TPC-H q1): for each group the members' values are
+//     summed with full-mask REDUX (hardware) on 16-bit pieces and ONE lane updates the accumulator;
+//   many distinct groups: every lane updates its own slot (little contention by construction).
+// (A REDUX over an arbitrary lane subset is a software loop on this architecture: 20% of the
+//  kernel's stall samples in profiles/r1_agg_keyed_ncu_summary.txt before this split.)
+__device__ __forceinline__ u128 warp_sum_u64(uint64_t x) {
+  const uint32_t s0 = __reduce_add_sync(0xffffffffu, (uint32_t)(x & 0xffff));
+  const uint32_t s1 = __reduce_add_sync(0xffffffffu, (uint32_t)((x >> 16) & 0xffff));
+  const uint32_t s2 = __reduce_add_sync(0xffffffffu, (uint32_t)((x >> 32) & 0xffff));
+  const uint32_t s3 = __reduce_add_sync(0xffffffffu, (uint32_t)((x >> 48) & 0xffff));
   return (u128)s0 + ((u128)s1 << 16) + ((u128)s2 << 32) + ((u128)s3 << 48);
 }
 
-// Accumulate one warp-slice (32 rows) into per-slot accumulators.  `m` = lanes sharing my slot,
-// leader = lowest lane of m.  acc/nvalid point at MY slot's blocks (only dereferenced by leaders,
-// or by every active lane for float / min / max).
 __device__ __forceinline__ void accumulate_slice(const AggPlan& plan, const VMCtx& cx, int i, int64_t g,
-                                                 bool active, uint32_t m, bool leader, uint64_t* acc, uint32_t* nvalid) {
+                                                 bool active, int32_t slot, uint64_t* acc_base, uint32_t* nv_base) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t m = __match_any_sync(0xffffffffu, slot);
+  const bool leader = active && lane == (__ffs(m) - 1);
+  const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
+  const bool few = __popc(leaders) <= 4;
+  uint64_t* acc = active ? acc_base + (int64_t)slot * plan.limbs : nullptr;
+  uint32_t* nvalid = active ? nv_base + (int64_t)slot * plan.nvalids : nullptr;
   for (int k = 0; k < plan.naggs; k++) {
     const AggD& a = plan.aggs[k];
     bool valid = active;
-    // operands are re-resolved per aggregate (a few shared-memory reads) instead of being kept in a
-    // dynamically indexed array, which would live in local memory
     Opnd opk;
     if (a.out_idx >= 0) opk = resolve(cx, cx.hdr->outs[a.out_idx], mt_width(a.in_mt));
     if (a.out_idx >= 0 && active) valid = opnd_valid(opk, i, g);
-    const uint32_t vcount = __popc(__ballot_sync(0xffffffffu, valid) & m);
-    if (a.track_valid && leader && active && vcount) atomicAdd(&nvalid[a.valid_off], vcount);
-    switch (a.kind) {
-      case B2_AGG_COUNT: case B2_AGG_COUNT_ALL:
-        if (leader && active && vcount) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[a.limb_off]), (unsigned long long)vcount);
-        break;
-      case B2_AGG_SUM: {
-        if (a.is_float) {
-          double v = 0.0;
-          if (valid) v = a.in_mt == MT_F32 ? (double)opnd_ld<float>(opk, i) : opnd_ld<double>(opk, i);
-          if (valid) atomicAdd(reinterpret_cast<double*>(&acc[a.limb_off]), v);
-          break;
-        }
-        // integer / decimal: sign-extended value as (lo, hi)
-        uint64_t lo = 0, hi = 0;
-        if (valid) {
-          switch (a.in_mt) {
-            case MT_I8: lo = (uint64_t)(int64_t)opnd_ld<int8_t>(opk, i); break;
-            case MT_I16: lo = (uint64_t)(int64_t)opnd_ld<int16_t>(opk, i); break;
-            case MT_I32: lo = (uint64_t)(int64_t)opnd_ld<int32_t>(opk, i); break;
-            case MT_I64: lo = (uint64_t)opnd_ld<int64_t>(opk, i); break;
-            default: { i128 v = opnd_ld<i128>(opk, i); lo = (uint64_t)v; hi = (uint64_t)(v >> 64); } break;
+    // value of this row as sign-extended (lo, hi) or as an ordered key / double
+    uint64_t lo = 0, hi = 0;
+    double dv = 0.0;
+    if (valid && a.out_idx >= 0) {
+      switch (a.in_mt) {
+        case MT_I8: lo = (uint64_t)(int64_t)opnd_ld<int8_t>(opk, i); break;
+        case MT_I16: lo = (uint64_t)(int64_t)opnd_ld<int16_t>(opk, i); break;
+        case MT_I32: lo = (uint64_t)(int64_t)opnd_ld<int32_t>(opk, i); break;
+        case MT_I64: lo = (uint64_t)opnd_ld<int64_t>(opk, i); break;
+        case MT_I128: { const i128 v = opnd_ld<i128>(opk, i); lo = (uint64_t)v; hi = (uint64_t)(v >> 64); } break;
+        case MT_F32: dv = (double)opnd_ld<float>(opk, i); break;
+        default: dv = opnd_ld<double>(opk, i); break;
+      }
+      if (a.in_mt < MT_I128) hi = ((int64_t)lo < 0) ? ~0ull : 0ull;
+    }
+    const bool int_sum = a.kind == B2_AGG_SUM && !a.is_float;
+    const bool counting = a.kind == B2_AGG_COUNT || a.kind == B2_AGG_COUNT_ALL;
+    if (few && (int_sum || counting || a.track_valid)) {
+      // one pass per distinct group of this slice
+      uint32_t rem = leaders;
+      while (rem) {
+        const int L = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int32_t gs = __shfl_sync(0xffffffffu, slot, L);
+        const bool mem = active && slot == gs;
+        const uint32_t vc = __popc(__ballot_sync(0xffffffffu, mem && valid));
+        if (a.track_valid && lane == L && vc) atomicAdd(&nvalid[a.valid_off], vc);
+        if (counting) { if (lane == L && vc) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[a.limb_off]), (unsigned long long)vc); }
+        else if (int_sum) {
+          const bool mv = mem && valid;
+          const uint32_t nneg = __popc(__ballot_sync(0xffffffffu, mv && (int64_t)hi < 0));
+          const u128 slo = warp_sum_u64(mv ? lo : 0);
+          if (a.in_mt == MT_I128) {
+            const u128 shi = warp_sum_u64(mv ? hi : 0);
+            if (lane == L) {
+              const u128 mid = (slo >> 64) + (u128)(uint64_t)shi;
+              acc_add_limbs(&acc[a.limb_off], 3, (uint64_t)slo, (uint64_t)mid, (uint64_t)(mid >> 64) + (uint64_t)(shi >> 64) - (uint64_t)nneg);
+            }
+          } else if (lane == L) {
+            acc_add_limbs(&acc[a.limb_off], a.nlimbs, (uint64_t)slo, (uint64_t)(slo >> 64) - (uint64_t)nneg, 0);
           }
-          if (a.in_mt != MT_I128) hi = ((int64_t)lo < 0) ? ~0ull : 0ull;
         }
-        const bool neg = (int64_t)hi < 0;
-        const uint32_t nneg = __popc(__ballot_sync(0xffffffffu, neg) & m);
-        u128 slo = group_sum_u64(m, lo);
-        if (a.in_mt == MT_I128) {
-          // 192-bit: sum = slo + (shi << 64) - (nneg << 128)
-          u128 shi = group_sum_u64(m, hi);
-          if (leader && active) {
-            uint64_t l0 = (uint64_t)slo;
-            u128 mid = (slo >> 64) + (u128)(uint64_t)shi;
-            uint64_t l1 = (uint64_t)mid;
-            uint64_t l2 = (uint64_t)(mid >> 64) + (uint64_t)(shi >> 64) - (uint64_t)nneg;
-            acc_add_limbs(&acc[a.limb_off], 3, l0, l1, l2);
-          }
-        } else if (leader && active) {
-          uint64_t l0 = (uint64_t)slo;
-          uint64_t l1 = (uint64_t)(slo >> 64) - (uint64_t)nneg;  // each negative contributes -2^64
-          acc_add_limbs(&acc[a.limb_off], a.nlimbs, l0, l1, 0);
-        }
-      } break;
-      case B2_AGG_MIN: case B2_AGG_MAX: {
-        if (!valid) break;
-        uint64_t key;
-        switch (a.in_mt) {
-          case MT_I8: key = ord_i64(opnd_ld<int8_t>(opk, i)); break;
-          case MT_I16: key = ord_i64(opnd_ld<int16_t>(opk, i)); break;
-          case MT_I32: key = ord_i64(opnd_ld<int32_t>(opk, i)); break;
-          case MT_I64: key = ord_i64(opnd_ld<int64_t>(opk, i)); break;
-          case MT_F32: key = ord_f64((double)opnd_ld<float>(opk, i)); break;
-          default: key = ord_f64(opnd_ld<double>(opk, i)); break;
-        }
-        unsigned long long* p = reinterpret_cast<unsigned long long*>(&acc[a.limb_off]);
-        if (a.kind == B2_AGG_MIN) atomicMin(p, (unsigned long long)key); else atomicMax(p, (unsigned long long)key);
-      } break;
-      default: break;
+      }
+    } else if (valid) {
+      if (a.track_valid) atomicAdd(&nvalid[a.valid_off], 1u);
+      if (counting) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[a.limb_off]), 1ull);
+      else if (int_sum) acc_add_limbs(&acc[a.limb_off], a.nlimbs, lo, hi, (int64_t)hi < 0 ? ~0ull : 0ull);
+    }
+    if (!valid) continue;
+    if (a.kind == B2_AGG_SUM && a.is_float) atomicAdd(reinterpret_cast<double*>(&acc[a.limb_off]), dv);
+    else if (a.kind == B2_AGG_MIN || a.kind == B2_AGG_MAX) {
+      const uint64_t key = a.is_float ? ord_f64(dv) : ord_i64((int64_t)lo);
+      unsigned long long* p = reinterpret_cast<unsigned long long*>(&acc[a.limb_off]);
+      if (a.kind == B2_AGG_MIN) atomicMin(p, (unsigned long long)key); else atomicMax(p, (unsigned long long)key);
     }
   }
 }
@@ -234,6 +239,17 @@ __device__ __forceinline__ void accumulate_private(const AggPlan& plan, const VM
   }
 }
 
+// fixed-width keys of <= 8 bytes together: (packed bits, null mask) identify the group exactly
+__device__ __forceinline__ void pack_keys(const KeyCols& ks, int64_t r, uint64_t& bits, uint32_t& nulls) {
+  bits = 0; nulls = 0;
+  int shift = 0;
+  for (int i = 0; i < ks.n; i++) {
+    const KeyCol& k = ks.c[i];
+    if (row_valid(k.valid, r)) bits |= key_bits(k, r) << shift; else nulls |= 1u << i;
+    shift += 8 * k.width;
+  }
+}
+
 // find-or-insert row `row` in the global table; returns the slot
 __device__ __forceinline__ uint32_t global_insert(const GTable& gt, const KeyCols& keys, int64_t row) {
   if (keys.n == 0) { gt.slots[0] = 0; return 0; }
@@ -269,19 +285,24 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
   char* regs = dyn;
   // shared table lives after the VM registers
   int32_t* s_slots = reinterpret_cast<int32_t*>(dyn + smem_regs_bytes);
-  uint64_t* s_acc = reinterpret_cast<uint64_t*>(dyn + smem_regs_bytes + SMEM_SLOTS * 4);
-  uint32_t* s_nvalid = reinterpret_cast<uint32_t*>(s_acc + (SMEM ? SMEM_SLOTS * plan.limbs : 0));
+  const int SLOTS = plan.smem_slots;
+  uint64_t* s_acc = reinterpret_cast<uint64_t*>(dyn + smem_regs_bytes + SLOTS * 4);
+  uint32_t* s_nvalid = reinterpret_cast<uint32_t*>(s_acc + (SMEM ? SLOTS * plan.limbs : 0));
   // keyless reductions: one private accumulator set per thread, [limb][thread] / [valid][thread]
-  uint64_t* s_priv = reinterpret_cast<uint64_t*>(s_nvalid + SMEM_SLOTS * plan.nvalids + (SMEM_SLOTS * plan.nvalids & 1));
+  // after the table: keyless private accumulators, or the packed keys of the slots (fast keys)
+  uint64_t* s_priv = reinterpret_cast<uint64_t*>(s_nvalid + SLOTS * plan.nvalids + (SLOTS * plan.nvalids & 1));
   uint32_t* s_privv = reinterpret_cast<uint32_t*>(s_priv + plan.limbs * VM_NT);
+  uint64_t* s_keys = s_priv;                                             // [SLOTS]
+  uint32_t* s_knull = reinterpret_cast<uint32_t*>(s_keys + SLOTS);       // [SLOTS], KEY_READY once s_keys is valid
   const bool keyless = SMEM && plan.nkeys == 0;
   const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs);
   const int lane = threadIdx.x & 31;
   // a keyless reduction always has its single group, even over zero rows (GpuAggregateExec.scala:1107-1126)
   if (plan.nkeys == 0 && blockIdx.x == 0 && threadIdx.x == 0) gt.slots[0] = 0;
   if (SMEM) {
-    for (int s = threadIdx.x; s < SMEM_SLOTS; s += VM_NT) {
+    for (int s = threadIdx.x; s < SLOTS; s += VM_NT) {
       s_slots[s] = SLOT_EMPTY;
+      if (plan.fast_keys && plan.nkeys > 0) s_knull[s] = 0;
       for (int k = 0; k < plan.naggs; k++)
         for (int l = 0; l < plan.aggs[k].nlimbs; l++) s_acc[s * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
       for (int v = 0; v < plan.nvalids; v++) s_nvalid[s * plan.nvalids + v] = 0;
@@ -328,8 +349,33 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
       if (active) {
         if (SMEM) {
           if (plan.nkeys == 0) { slot = 0; s_slots[0] = 0; }
-          else {
-            uint32_t idx = row_hash(plan.keys, g) & (SMEM_SLOTS - 1);
+          else if (plan.fast_keys) {
+            uint64_t kb; uint32_t kn;
+            pack_keys(plan.keys, g, kb, kn);
+            uint32_t idx = (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) & (SLOTS - 1);
+            int probes = 0;
+            while (true) {
+              int32_t cur = s_slots[idx];
+              if (cur == SLOT_EMPTY) {
+                const int32_t old = atomicCAS(&s_slots[idx], SLOT_EMPTY, (int32_t)g);
+                if (old == SLOT_EMPTY) {  // mine: publish the packed key for later probes
+                  s_keys[idx] = kb;
+                  __threadfence_block();
+                  *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]) = kn | KEY_READY;
+                  slot = idx; break;
+                }
+                cur = old;
+              }
+              const uint32_t tag = *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]);
+              bool same;
+              if (tag & KEY_READY) { __threadfence_block(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&s_keys[idx]) == kb; }
+              else same = cur == (int32_t)g || rows_equal(plan.keys, g, plan.keys, cur, true);  // key not published yet
+              if (same) { slot = idx; break; }
+              idx = (idx + 1) & (SLOTS - 1);
+              if (++probes >= SLOTS / 2) { atomicExch(gt.overflow, 1); active = false; break; }
+            }
+          } else {
+            uint32_t idx = row_hash(plan.keys, g) & (SLOTS - 1);
             int probes = 0;
             while (true) {
               int32_t cur = s_slots[idx];
@@ -339,22 +385,15 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
                 cur = old;
               }
               if (cur == (int32_t)g || rows_equal(plan.keys, g, plan.keys, cur, true)) { slot = idx; break; }
-              idx = (idx + 1) & (SMEM_SLOTS - 1);
-              if (++probes >= SMEM_SLOTS * 3 / 4) { atomicExch(gt.overflow, 1); active = false; break; }
+              idx = (idx + 1) & (SLOTS - 1);
+              if (++probes >= SLOTS / 2) { atomicExch(gt.overflow, 1); active = false; break; }
             }
           }
         } else {
           slot = (int32_t)global_insert(gt, plan.keys, g);
         }
       }
-      const uint32_t m = __match_any_sync(0xffffffffu, slot);
-      const bool leader = lane == (__ffs(m) - 1);
-      uint64_t* acc = nullptr; uint32_t* nv = nullptr;
-      if (slot >= 0) {
-        acc = SMEM ? &s_acc[slot * plan.limbs] : &gt.acc[(int64_t)slot * plan.limbs];
-        nv = SMEM ? &s_nvalid[slot * plan.nvalids] : &gt.nvalid[(int64_t)slot * plan.nvalids];
-      }
-      accumulate_slice(plan, cx, i, g, active && slot >= 0, m, leader, acc, nv);
+      accumulate_slice(plan, cx, i, g, active && slot >= 0, active ? slot : -1, SMEM ? s_acc : gt.acc, SMEM ? s_nvalid : gt.nvalid);
     }
   }
   if (keyless) {
@@ -376,7 +415,7 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
   if (SMEM) {
     __syncthreads();
     if (*reinterpret_cast<volatile int32_t*>(gt.overflow)) return;
-    for (int s = threadIdx.x; s < SMEM_SLOTS; s += VM_NT) {
+    for (int s = threadIdx.x; s < SLOTS; s += VM_NT) {
       const int32_t row = s_slots[s];
       if (row == SLOT_EMPTY) continue;
       const uint32_t gs = global_insert(gt, plan.keys, row);
@@ -512,6 +551,11 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
     key_table_cols.push_back(op.idx);
   }
   plan.keys = key_cols_of(t, key_table_cols.data(), nkeys);
+  {
+    int kw = 0; bool fixed = nkeys > 0;
+    for (int k = 0; k < nkeys; k++) { if (plan.keys.c[k].dtype == B2_STRING || plan.keys.c[k].width == 16) fixed = false; kw += plan.keys.c[k].width; }
+    plan.fast_keys = fixed && kw <= 8;
+  }
   int limbs = 0, nvalids = 0;
   for (int k = 0; k < naggs; k++) {
     AggD& a = plan.aggs[k];
@@ -568,13 +612,20 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   bool done = false;
   // regime 1: shared-memory tables (always right for reductions; optimistic for group-by)
   {
-    int table_bytes = SMEM_SLOTS * 4 + SMEM_SLOTS * plan.limbs * 8 + SMEM_SLOTS * plan.nvalids * 4 + 8;
+    // table sized for <= ~24 KB: more slots = shorter probe chains and more groups before the global regime
+    int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + (plan.fast_keys ? 12 : 0);
+    int nslots = 128;
+    while (nslots * 2 <= SMEM_SLOTS_MAX && nslots * 2 * per_slot <= 24 * 1024) nslots *= 2;
+    if (nkeys == 0) nslots = 128;
+    plan.smem_slots = nslots;
+    int table_bytes = nslots * 4 + nslots * plan.limbs * 8 + nslots * plan.nvalids * 4 + 8;
     if (nkeys == 0) table_bytes += plan.limbs * VM_NT * 8 + plan.nvalids * VM_NT * 4;
+    else if (plan.fast_keys) table_bytes += nslots * 12;
     int smem = ((vm_smem + 15) & ~15) + table_bytes;
     if (smem <= 160 * 1024) {
       int grid = n > 0 ? vm_grid(n, smem, prog->hdr.tile_rows) : 1;
       cap = 1;
-      while (cap < (int64_t)grid * SMEM_SLOTS * 2) cap <<= 1;
+      while (cap < (int64_t)grid * nslots * 2) cap <<= 1;
       if (nkeys == 0) cap = 1;
       alloc_table(cap, slots, acc, nv, ovf, gt);
       if (n > 0 || nkeys == 0) {

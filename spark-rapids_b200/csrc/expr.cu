@@ -324,7 +324,20 @@ struct Compiler {
         a = widen_int(a, MT_I128); b = widen_int(b, MT_I128);
         return emit(V_MULDEC, MT_I128, MT_I128, MT_I128, true, s - rs, &a, &b, nullptr, B2_DECIMAL128, rp, rs);
       }
-      throw Error(B2_ERR_UNSUPPORTED, "decimal divide/remainder is not supported yet");
+      if (e->op == B2_OP_DIV) {
+        // Spark Divide: scale = max(6, s1 + p2 + 1), precision = p1 - s1 + s2 + scale (DecimalPrecision), adjusted
+        int rs = std::max(6, s1 + p2 + 1), rp = p1 - s1 + s2 + rs;
+        adjust_precision_scale(rp, rs);
+        const int k = rs - s1 + s2;
+        if (k < 0 || k > 38) throw Error(B2_ERR_UNSUPPORTED, "decimal divide with this precision/scale combination");
+        if (a.o.kind == OK_LIT) a = emit(V_MOV, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, a.precision, a.scale);
+        a = widen_int(a, MT_I128); b = widen_int(b, MT_I128);
+        Val r = emit(V_DIVDEC, MT_I128, MT_I128, MT_I128, true, k, &a, &b, nullptr, decimal_dtype_for(rp), rp, rs);
+        if (rp <= 18) r = widen_int(r, mt_of(decimal_dtype_for(rp)));
+        r.dtype = decimal_dtype_for(rp); r.precision = rp; r.scale = rs;
+        return r;
+      }
+      throw Error(B2_ERR_UNSUPPORTED, "decimal remainder is not supported yet");
     }
     if (a.dtype != b.dtype) throw Error(B2_ERR_INVALID, "arithmetic operand types differ");
     if (a.dtype == B2_BOOL8 || a.dtype == B2_STRING) throw Error(B2_ERR_INVALID, "arithmetic on non-numeric type");

@@ -40,6 +40,7 @@ enum VOP : uint8_t {
   V_RESCALE_DOWN,// integer / 10^aux HALF_UP (decimal scale decrease)
   V_CHECK_PREC,  // |x| >= 10^aux -> null  (CheckOverflow / GpuCheckOverflow)
   V_MULW,        // widening multiply: two I64 operands -> exact I128 product
+  V_DIVDEC,      // decimal divide: round_half_up(a * 10^aux / b), b == 0 or > 38 digits -> null
   V_MULDEC,      // 128x128 -> 256-bit product, / 10^aux HALF_UP, overflow -> null
   V_DEC2F64,     // decimal (mt) -> double, / 10^aux
   V_NORM_NAN_ZERO,
@@ -565,6 +566,36 @@ static __device__ __noinline__ void vm_muldec(const TileInfo ti, const RInstr& i
   });
 }
 
+// Decimal divide (arithmetic.scala:903-1000 GpuDecimalDivideBase.longDivide -> DecimalUtils.divide128):
+// exact 256-bit numerator |a| * 10^k, restoring long division by |b|, HALF_UP, NULL on zero divisor
+// or when the quotient needs more than 38 digits.
+static __device__ __noinline__ void vm_divdec(const TileInfo ti, const RInstr& ins) {
+  const int k = ins.aux;
+  const u128 p38 = (u128)pow10_i128(38);
+  const u128 pk = (u128)pow10_i128(k);
+  vm_loop2<i128, i128>(ti, ins, [pk, p38](i128 x, i128 y, bool, bool, bool& v) -> i128 {
+    if (y == 0) { v = false; return (i128)0; }
+    const bool neg = (x < 0) != (y < 0);
+    const u128 mx = x < 0 ? (u128)0 - (u128)x : (u128)x, my = y < 0 ? (u128)0 - (u128)y : (u128)y;
+    // 256-bit numerator = mx * pk
+    const uint64_t x0 = (uint64_t)mx, x1 = (uint64_t)(mx >> 64), y0 = (uint64_t)pk, y1 = (uint64_t)(pk >> 64);
+    const u128 p00 = (u128)x0 * y0, p01 = (u128)x0 * y1, p10 = (u128)x1 * y0, p11 = (u128)x1 * y1;
+    const u128 mid = (p00 >> 64) + (uint64_t)p01 + (uint64_t)p10;
+    const u128 lo = ((u128)(uint64_t)mid << 64) | (uint64_t)p00;
+    const u128 hi = (mid >> 64) + (p01 >> 64) + (p10 >> 64) + p11;
+    if (hi >= my) { v = false; return (i128)0; }  // quotient would not fit 128 bits
+    u128 rem = hi, q = 0;
+    for (int i = 127; i >= 0; i--) {
+      const bool top = (rem >> 127) != 0;
+      rem = (rem << 1) | ((lo >> i) & 1);
+      if (top || rem >= my) { rem -= my; q |= (u128)1 << i; }
+    }
+    if (rem >= my - rem) q += 1;  // 2*rem >= my, HALF_UP
+    if (q >= p38) { v = false; return (i128)0; }
+    return neg ? -(i128)q : (i128)q;
+  });
+}
+
 template <typename T>
 __device__ __noinline__ void vm_dec2f64(const TileInfo ti, const RInstr& ins) {
   double dv = 1.0; for (int t = 0; t < ins.aux; t++) dv *= 10.0;
@@ -652,6 +683,7 @@ static __device__ __noinline__ void vm_run(const TileInfo ti, const RInstr* __re
         break;
       case V_MULW: vm_mulw(ti, ins); break;
       case V_MULDEC: vm_muldec(ti, ins); break;
+      case V_DIVDEC: vm_divdec(ti, ins); break;
       case V_DEC2F64:
         switch (ins.mt) {
           case MT_I32: vm_dec2f64<int32_t>(ti, ins); break;

@@ -139,3 +139,27 @@ def test_type_errors(b2):
         b2.Program([a + b])
     with pytest.raises(b2.B2Error):
         b2.Program([b2.col(0, b2.STRING) + b2.col(1, b2.STRING)])
+
+
+@pytest.mark.parametrize("ta,tb", [((O.DECIMAL128, 22, 2), (O.DECIMAL128, 20, 0)), ((O.DECIMAL64, 12, 2), (O.DECIMAL64, 12, 2)),
+                                   ((O.DECIMAL128, 38, 6), (O.DECIMAL32, 5, 0)), ((O.DECIMAL64, 18, 4), (O.DECIMAL128, 25, 3))])
+def test_decimal_divide(b2, ta, tb):
+    """GpuDecimalDivide (arithmetic.scala:903-1000): Spark result type, HALF_UP, divide by zero -> NULL"""
+    rng = np.random.default_rng(ta[1] * 7 + tb[1])
+    n = 1500
+    a, b = G.gen_column(rng, ta, n), G.gen_column(rng, tb, n, small=True)
+    b.values[rng.choice(n, 20, replace=False)] = 0
+    ca, cb = G.b2_expr_col(b2, 0, a), G.b2_expr_col(b2, 1, b)
+    run(b2, [ca / cb], [a, b])
+
+
+def test_decimal_average_finalisation(b2):
+    """avg = sum / count evaluated on the aggregation buffers (aggregateFunctions.scala:1555-1556, 1606-1616):
+    decimal(22,2) sum / cast(count as decimal(20,0)), then cast to decimal(p+4, s+4) = (16,6)"""
+    rng = np.random.default_rng(9)
+    n = 800
+    s = G.gen_column(rng, (O.DECIMAL128, 22, 2), n, small=True)
+    c = O.OCol(rng.integers(0, 50, n).astype(np.int64), np.ones(n, bool), (O.INT64, 0, 0))
+    cs, cc = G.b2_expr_col(b2, 0, s), G.b2_expr_col(b2, 1, c)
+    avg = (cs / cc.cast(b2.DECIMAL128, 20, 0)).cast(b2.DECIMAL64, 16, 6)
+    run(b2, [avg], [s, c])
