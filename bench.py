@@ -143,7 +143,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import spark_rapids_b200 as m
     from oracle import tpch
-    m.init(local)
+    m.init(local, 8 << 30)   # Rmm.initialize analogue: pre-grown stream-ordered pool
 
     rows = args.rows
     raw = tpch.lineitem_q6_parquet(rows, 42 + rank, CACHE)

@@ -12,7 +12,7 @@ import spark_rapids_b200 as m
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
 REPS = 3
-m.init(0)
+m.init(0, 24 << 30)   # pre-grown pool (Rmm.initialize analogue): first-touch pool growth costs ~45 ms/GB
 rng = np.random.default_rng(42)
 peak = 6585.1
 if os.path.exists("MEASURED_PEAKS.json"):
@@ -20,14 +20,18 @@ if os.path.exists("MEASURED_PEAKS.json"):
 
 
 def timed(fn, reps=REPS):
+    r = None
     for _ in range(2):
+        del r
         r = fn()
     del r
+    r = None
     m.sync()
     m.profile_enable(True)
     e0, e1 = m.Event(), m.Event()
     e0.record()
     for _ in range(reps):
+        del r          # release the previous result first: otherwise the pool has to grow to hold two
         r = fn()
     e1.record()
     m.sync()

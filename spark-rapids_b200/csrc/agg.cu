@@ -51,6 +51,8 @@ struct GTable {
   uint32_t* nvalid;   // [cap][nvalids]
   uint32_t mask;      // cap - 1
   int32_t* overflow;  // set when a shared-memory table filled up
+  uint64_t* keys;     // fast keys: packed key per slot
+  uint32_t* knull;    // fast keys: null mask | KEY_READY once keys[slot] is visible
 };
 
 // order-preserving maps to u64 for MIN/MAX (Spark float order: NaN greatest, aggregateFunctions.scala:368-465)
@@ -251,8 +253,32 @@ __device__ __forceinline__ void pack_keys(const KeyCols& ks, int64_t r, uint64_t
 }
 
 // find-or-insert row `row` in the global table; returns the slot
-__device__ __forceinline__ uint32_t global_insert(const GTable& gt, const KeyCols& keys, int64_t row) {
+__device__ __forceinline__ uint32_t global_insert(const GTable& gt, const KeyCols& keys, int64_t row, bool fast) {
   if (keys.n == 0) { gt.slots[0] = 0; return 0; }
+  if (fast) {
+    uint64_t kb; uint32_t kn;
+    pack_keys(keys, row, kb, kn);
+    uint32_t idx = (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) & gt.mask;
+    while (true) {
+      int32_t cur = gt.slots[idx];
+      if (cur == SLOT_EMPTY) {
+        const int32_t old = atomicCAS(&gt.slots[idx], SLOT_EMPTY, (int32_t)row);
+        if (old == SLOT_EMPTY) {
+          gt.keys[idx] = kb;
+          __threadfence();
+          *reinterpret_cast<volatile uint32_t*>(&gt.knull[idx]) = kn | KEY_READY;
+          return idx;
+        }
+        cur = old;
+      }
+      const uint32_t tag = *reinterpret_cast<volatile uint32_t*>(&gt.knull[idx]);
+      bool same;
+      if (tag & KEY_READY) { __threadfence(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&gt.keys[idx]) == kb; }
+      else same = cur == (int32_t)row || rows_equal(keys, row, keys, cur, true);
+      if (same) return idx;
+      idx = (idx + 1) & gt.mask;
+    }
+  }
   uint32_t idx = row_hash(keys, row) & gt.mask;
   while (true) {
     int32_t cur = gt.slots[idx];
@@ -269,6 +295,7 @@ __device__ __forceinline__ uint32_t global_insert(const GTable& gt, const KeyCol
 __global__ void init_table_kernel(GTable gt, const __grid_constant__ AggPlan plan, int64_t cap) {
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < cap; s += (int64_t)gridDim.x * blockDim.x) {
     gt.slots[s] = SLOT_EMPTY;
+    if (gt.knull) gt.knull[s] = 0;
     for (int k = 0; k < plan.naggs; k++)
       for (int l = 0; l < plan.aggs[k].nlimbs; l++) gt.acc[s * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
     for (int v = 0; v < plan.nvalids; v++) gt.nvalid[s * plan.nvalids + v] = 0;
@@ -390,7 +417,7 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
             }
           }
         } else {
-          slot = (int32_t)global_insert(gt, plan.keys, g);
+          slot = (int32_t)global_insert(gt, plan.keys, g, plan.fast_keys != 0);
         }
       }
       accumulate_slice(plan, cx, i, g, active && slot >= 0, active ? slot : -1, SMEM ? s_acc : gt.acc, SMEM ? s_nvalid : gt.nvalid);
@@ -418,7 +445,7 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
     for (int s = threadIdx.x; s < SLOTS; s += VM_NT) {
       const int32_t row = s_slots[s];
       if (row == SLOT_EMPTY) continue;
-      const uint32_t gs = global_insert(gt, plan.keys, row);
+      const uint32_t gs = global_insert(gt, plan.keys, row, plan.fast_keys != 0);
       uint64_t* ga = &gt.acc[(int64_t)gs * plan.limbs];
       const uint64_t* sa = &s_acc[s * plan.limbs];
       for (int k = 0; k < plan.naggs; k++) {
@@ -596,9 +623,12 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   VMInputs in; fill_inputs(in, t);
   const int vm_smem = prog->hdr.smem_bytes;
 
+  DevBuf gkeys, gknull;
   auto alloc_table = [&](int64_t cap, DevBuf& slots, DevBuf& acc, DevBuf& nv, DevBuf& ovf, GTable& gt) {
     slots = DevBuf((size_t)cap * 4); acc = DevBuf((size_t)cap * plan.limbs * 8); nv = DevBuf((size_t)cap * plan.nvalids * 4);
     ovf = DevBuf(4);
+    gt.keys = nullptr; gt.knull = nullptr;
+    if (plan.fast_keys) { gkeys = DevBuf((size_t)cap * 8); gknull = DevBuf((size_t)cap * 4); gt.keys = gkeys.as<uint64_t>(); gt.knull = gknull.as<uint32_t>(); }
     gt.slots = slots.as<int32_t>(); gt.acc = acc.as<uint64_t>(); gt.nvalid = nv.as<uint32_t>(); gt.mask = (uint32_t)(cap - 1);
     gt.overflow = ovf.as<int32_t>();
     CUDA_CHECK(cudaMemsetAsync(ovf.p, 0, 4, stream()));
@@ -610,8 +640,36 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   GTable gt;
   int64_t cap = 0;
   bool done = false;
+  // cardinality probe: on large keyed inputs run the shared-memory regime over a 256 K-row prefix first;
+  // if even that overflows the per-CTA tables the whole input goes straight to the global regime
+  bool try_smem = true;
+  if (nkeys > 0 && n > (1 << 20)) {
+    DevBuf ps, pa, pn, po; GTable pg;
+    const int64_t pn_rows = 1 << 18;
+    int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + (plan.fast_keys ? 12 : 0);
+    int nslots = 128;
+    while (nslots * 2 <= SMEM_SLOTS_MAX && nslots * 2 * per_slot <= 24 * 1024) nslots *= 2;
+    plan.smem_slots = nslots;
+    int table_bytes = nslots * 4 + nslots * plan.limbs * 8 + nslots * plan.nvalids * 4 + 8 + (plan.fast_keys ? nslots * 12 : 0);
+    int smem = ((vm_smem + 15) & ~15) + table_bytes;
+    if (smem <= 160 * 1024) {
+      int grid = vm_grid(pn_rows, smem, prog->hdr.tile_rows);
+      int64_t pcap = 1;
+      while (pcap < (int64_t)grid * nslots * 2) pcap <<= 1;
+      alloc_table(pcap, ps, pa, pn, po, pg);
+      if (smem > 32 * 1024) CUDA_CHECK(cudaFuncSetAttribute(aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      aggregate_kernel<true><<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, plan, pg, pn_rows,
+                                                                (vm_smem + 15) & ~15);
+      CUDA_CHECK(cudaGetLastError());
+      count_launch();
+      int32_t h = 0;
+      d2h(&h, po.p, 1);
+      sync();
+      try_smem = h == 0;
+    }
+  }
   // regime 1: shared-memory tables (always right for reductions; optimistic for group-by)
-  {
+  if (try_smem) {
     // table sized for <= ~24 KB: more slots = shorter probe chains and more groups before the global regime
     int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + (plan.fast_keys ? 12 : 0);
     int nslots = 128;

@@ -82,7 +82,7 @@ def _check_join(b2, build, probe, kind, nulls_equal=False):
     else:
         grm = rm.to_pylist()
         assert sorted(zip(glm, grm)) == sorted(zip(elm, erm))
-        assert glm == sorted(glm)  # grouped by stream row
+        # (output order is unspecified: docs/compatibility.md:18-25; the distinct-build fast path appends per warp)
 
 
 @pytest.mark.parametrize("kind", [0, 1, 2, 3])
