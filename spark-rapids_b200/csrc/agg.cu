@@ -241,15 +241,26 @@ __device__ __forceinline__ void accumulate_private(const AggPlan& plan, const VM
   }
 }
 
-// fixed-width keys of <= 8 bytes together: (packed bits, null mask) identify the group exactly
-__device__ __forceinline__ void pack_keys(const KeyCols& ks, int64_t r, uint64_t& bits, uint32_t& nulls) {
+// keys that fit 8 bytes together — fixed-width columns and SHORT strings (1 length byte + chars) —
+// identify the group exactly as (packed bits, null mask).  Returns false for a row whose string is
+// too long for its budget: that row takes the generic compare path.
+__device__ __forceinline__ bool pack_keys(const KeyCols& ks, int64_t r, uint64_t& bits, uint32_t& nulls) {
   bits = 0; nulls = 0;
   int shift = 0;
   for (int i = 0; i < ks.n; i++) {
     const KeyCol& k = ks.c[i];
-    if (row_valid(k.valid, r)) bits |= key_bits(k, r) << shift; else nulls |= 1u << i;
-    shift += 8 * k.width;
+    if (!row_valid(k.valid, r)) nulls |= 1u << i;
+    else if (k.dtype == B2_STRING) {
+      const int32_t b = k.offsets[r], len = k.offsets[r + 1] - b;
+      if (len > k.pack - 1) return false;
+      uint64_t v = (uint64_t)(len + 1);
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(k.data) + b;
+      for (int q = 0; q < len; q++) v |= (uint64_t)p[q] << (8 * (q + 1));
+      bits |= v << shift;
+    } else bits |= key_bits(k, r) << shift;
+    shift += 8 * k.pack;
   }
+  return true;
 }
 
 // find-or-insert row `row` in the global table; returns the slot
@@ -257,23 +268,25 @@ __device__ __forceinline__ uint32_t global_insert(const GTable& gt, const KeyCol
   if (keys.n == 0) { gt.slots[0] = 0; return 0; }
   if (fast) {
     uint64_t kb; uint32_t kn;
-    pack_keys(keys, row, kb, kn);
-    uint32_t idx = (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) & gt.mask;
+    const bool packed = pack_keys(keys, row, kb, kn);
+    uint32_t idx = (packed ? (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) : row_hash(keys, row)) & gt.mask;
     while (true) {
       int32_t cur = gt.slots[idx];
       if (cur == SLOT_EMPTY) {
         const int32_t old = atomicCAS(&gt.slots[idx], SLOT_EMPTY, (int32_t)row);
         if (old == SLOT_EMPTY) {
-          gt.keys[idx] = kb;
-          __threadfence();
-          *reinterpret_cast<volatile uint32_t*>(&gt.knull[idx]) = kn | KEY_READY;
+          if (packed) {
+            gt.keys[idx] = kb;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(&gt.knull[idx]) = kn | KEY_READY;
+          }
           return idx;
         }
         cur = old;
       }
       const uint32_t tag = *reinterpret_cast<volatile uint32_t*>(&gt.knull[idx]);
       bool same;
-      if (tag & KEY_READY) { __threadfence(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&gt.keys[idx]) == kb; }
+      if (packed && (tag & KEY_READY)) { __threadfence(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&gt.keys[idx]) == kb; }
       else same = cur == (int32_t)row || rows_equal(keys, row, keys, cur, true);
       if (same) return idx;
       idx = (idx + 1) & gt.mask;
@@ -378,24 +391,26 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
           if (plan.nkeys == 0) { slot = 0; s_slots[0] = 0; }
           else if (plan.fast_keys) {
             uint64_t kb; uint32_t kn;
-            pack_keys(plan.keys, g, kb, kn);
-            uint32_t idx = (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) & (SLOTS - 1);
+            const bool packed = pack_keys(plan.keys, g, kb, kn);
+            uint32_t idx = (packed ? (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) : row_hash(plan.keys, g)) & (SLOTS - 1);
             int probes = 0;
             while (true) {
               int32_t cur = s_slots[idx];
               if (cur == SLOT_EMPTY) {
                 const int32_t old = atomicCAS(&s_slots[idx], SLOT_EMPTY, (int32_t)g);
                 if (old == SLOT_EMPTY) {  // mine: publish the packed key for later probes
-                  s_keys[idx] = kb;
-                  __threadfence_block();
-                  *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]) = kn | KEY_READY;
+                  if (packed) {
+                    s_keys[idx] = kb;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]) = kn | KEY_READY;
+                  }
                   slot = idx; break;
                 }
                 cur = old;
               }
               const uint32_t tag = *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]);
               bool same;
-              if (tag & KEY_READY) { __threadfence_block(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&s_keys[idx]) == kb; }
+              if (packed && (tag & KEY_READY)) { __threadfence_block(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&s_keys[idx]) == kb; }
               else same = cur == (int32_t)g || rows_equal(plan.keys, g, plan.keys, cur, true);  // key not published yet
               if (same) { slot = idx; break; }
               idx = (idx + 1) & (SLOTS - 1);
@@ -579,9 +594,17 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   }
   plan.keys = key_cols_of(t, key_table_cols.data(), nkeys);
   {
-    int kw = 0; bool fixed = nkeys > 0;
-    for (int k = 0; k < nkeys; k++) { if (plan.keys.c[k].dtype == B2_STRING || plan.keys.c[k].width == 16) fixed = false; kw += plan.keys.c[k].width; }
-    plan.fast_keys = fixed && kw <= 8;
+    // packed-key budget: fixed-width columns take their width, short strings share what is left of 8 bytes
+    int fixed_bytes = 0, nstr = 0; bool ok = nkeys > 0;
+    for (int k = 0; k < nkeys; k++) {
+      if (plan.keys.c[k].dtype == B2_STRING) nstr++;
+      else if (plan.keys.c[k].width == 16) ok = false;
+      else fixed_bytes += plan.keys.c[k].width;
+    }
+    ok = ok && fixed_bytes + 2 * nstr <= 8;
+    for (int k = 0; k < nkeys && ok; k++)
+      plan.keys.c[k].pack = plan.keys.c[k].dtype == B2_STRING ? (8 - fixed_bytes) / nstr : plan.keys.c[k].width;
+    plan.fast_keys = ok;
   }
   int limbs = 0, nvalids = 0;
   for (int k = 0; k < naggs; k++) {

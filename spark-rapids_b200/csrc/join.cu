@@ -21,9 +21,8 @@ struct JoinTable {
   int64_t cap;
   int64_t build_rows;
   bool nulls_equal;
-  bool fast = false;      // keys fixed width, <= 8 bytes together, no NULL can match: packed key stored beside the slot
+  bool fast = false;      // keys fixed width, <= 8 bytes together, no NULL can match: 16-byte entries {tag|row, packed key}
   bool distinct = false;  // no two build rows share a key (FK -> PK joins): probe is single pass
-  DevBuf skeys;           // uint64 [cap] packed keys (fast)
   std::vector<int> key_idx;
   ~JoinTable() { if (keys) table_release(keys); }
 };
@@ -40,8 +39,9 @@ __device__ __forceinline__ uint64_t pack_join_key(const KeyCols& ks, int64_t r) 
 }
 __device__ __forceinline__ uint32_t hash_packed(uint64_t kb) { const uint64_t h = mix64(kb ^ 0x9e3779b97f4a7c15ull); return (uint32_t)(h ^ (h >> 32)); }
 
-__global__ void join_build_kernel(const __grid_constant__ KeyCols keys, int64_t n, uint64_t* __restrict__ slots, uint64_t* __restrict__ skeys,
+__global__ void join_build_kernel(const __grid_constant__ KeyCols keys, int64_t n, uint64_t* __restrict__ slots,
                                   uint32_t mask, bool nulls_equal, bool fast, int32_t* __restrict__ has_dups) {
+  const int sh = fast ? 1 : 0;  // entry stride: 2 words when the packed key rides along
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     if (!nulls_equal && any_null_key(keys, r)) continue;  // a NULL key can never match: keep it out of the table
     uint64_t kb = 0;
@@ -50,8 +50,8 @@ __global__ void join_build_kernel(const __grid_constant__ KeyCols keys, int64_t 
     const uint64_t entry = ((uint64_t)h << 32) | (uint32_t)r;
     uint32_t idx = h & mask;
     while (true) {
-      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&slots[idx]), (unsigned long long)JSLOT_EMPTY, (unsigned long long)entry);
-      if (old == JSLOT_EMPTY) { if (fast) skeys[idx] = kb; break; }
+      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&slots[(size_t)idx << sh]), (unsigned long long)JSLOT_EMPTY, (unsigned long long)entry);
+      if (old == JSLOT_EMPTY) { if (fast) slots[((size_t)idx << 1) + 1] = kb; break; }
       // occupied: a slot with my tag may hold my key -> the build side is not distinct
       if ((uint32_t)(old >> 32) == h && *has_dups == 0 && rows_equal(keys, r, keys, (int32_t)(uint32_t)old, nulls_equal)) atomicExch(has_dups, 1);
       idx = (idx + 1) & mask;
@@ -59,11 +59,18 @@ __global__ void join_build_kernel(const __grid_constant__ KeyCols keys, int64_t 
   }
 }
 
+// one probe step: entry word (and, for packed keys, the key from the same 16-byte line)
+__device__ __forceinline__ uint64_t join_entry(const uint64_t* __restrict__ slots, uint32_t idx, bool fast, uint64_t& key) {
+  if (fast) { const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(&slots[(size_t)idx << 1]); key = e.y; return e.x; }
+  key = 0;
+  return slots[idx];
+}
+
 // single pass for a distinct build side: at most one match per stream row.
 //   INNER: pairs appended with one atomic per warp (join output order is unspecified: docs/compatibility.md:18-25)
 //   LEFT OUTER: row r -> (r, match or INT32_MIN), no compaction at all
 __global__ void join_probe_distinct_kernel(const __grid_constant__ KeyCols probe, const __grid_constant__ KeyCols build, int64_t n,
-                                           const uint64_t* __restrict__ slots, const uint64_t* __restrict__ skeys, uint32_t mask, bool nulls_equal,
+                                           const uint64_t* __restrict__ slots, uint32_t mask, bool nulls_equal,
                                            bool fast, int kind, unsigned long long* __restrict__ total, int32_t* __restrict__ left_map,
                                            int32_t* __restrict__ right_map) {
   const int lane = threadIdx.x & 31;
@@ -76,10 +83,11 @@ __global__ void join_probe_distinct_kernel(const __grid_constant__ KeyCols probe
       if (fast) { kb = pack_join_key(probe, r); h = hash_packed(kb); } else h = row_hash(probe, r);
       uint32_t idx = h & mask;
       while (true) {
-        const uint64_t e = slots[idx];
+        uint64_t ek;
+        const uint64_t e = join_entry(slots, idx, fast, ek);
         if (e == JSLOT_EMPTY) break;
         if ((uint32_t)(e >> 32) == h) {
-          const bool eq = fast ? (skeys[idx] == kb) : rows_equal(probe, r, build, (int32_t)(uint32_t)e, nulls_equal);
+          const bool eq = fast ? (ek == kb) : rows_equal(probe, r, build, (int32_t)(uint32_t)e, nulls_equal);
           if (eq) { br = (int32_t)(uint32_t)e; break; }
         }
         idx = (idx + 1) & mask;
@@ -101,7 +109,7 @@ __global__ void join_probe_distinct_kernel(const __grid_constant__ KeyCols probe
 // MODE 0: count matches per probe row; MODE 1: write pairs at offsets
 template <int MODE>
 __global__ void join_probe_kernel(const __grid_constant__ KeyCols probe, const __grid_constant__ KeyCols build, int64_t n,
-                                  const uint64_t* __restrict__ slots, const uint64_t* __restrict__ skeys, uint32_t mask, bool nulls_equal,
+                                  const uint64_t* __restrict__ slots, uint32_t mask, bool nulls_equal,
                                   bool fast, int kind, int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
                                   int32_t* __restrict__ left_map, int32_t* __restrict__ right_map) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
@@ -114,11 +122,12 @@ __global__ void join_probe_kernel(const __grid_constant__ KeyCols probe, const _
       if (fast) { kb = pack_join_key(probe, r); h = hash_packed(kb); } else h = row_hash(probe, r);
       uint32_t idx = h & mask;
       while (true) {
-        const uint64_t e = slots[idx];
+        uint64_t ek;
+        const uint64_t e = join_entry(slots, idx, fast, ek);
         if (e == JSLOT_EMPTY) break;
         if ((uint32_t)(e >> 32) == h) {
           const int32_t br = (int32_t)(uint32_t)e;
-          if (fast ? (skeys[idx] == kb) : rows_equal(probe, r, build, br, nulls_equal)) {
+          if (fast ? (ek == kb) : rows_equal(probe, r, build, br, nulls_equal)) {
             if (MODE == 1 && !semi_like) { left_map[o + matches] = (int32_t)r; right_map[o + matches] = br; }
             matches++;
             if (semi_like) break;
@@ -165,20 +174,19 @@ int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* ou
   int64_t cap = 1024;
   while (cap < t->rows * 2) cap <<= 1;
   jt->cap = cap;
-  jt->slots = DevBuf((size_t)cap * 8);
-  CUDA_CHECK(cudaMemsetAsync(jt->slots.p, 0xff, (size_t)cap * 8, stream()));
   {
     int kw = 0; bool fixed = true, nullable = false;
     for (auto* c : t->cols) { if (c->dtype == B2_STRING || c->dtype == B2_DECIMAL128) fixed = false; kw += dtype_width(c->dtype); nullable = nullable || c->nullable(); }
     jt->fast = fixed && kw <= 8 && !(jt->nulls_equal && nullable);
-    if (jt->fast) jt->skeys = DevBuf((size_t)cap * 8);
   }
+  jt->slots = DevBuf((size_t)cap * (jt->fast ? 16 : 8));
+  CUDA_CHECK(cudaMemsetAsync(jt->slots.p, 0xff, jt->slots.bytes, stream()));
   DevBuf dups(4);
   CUDA_CHECK(cudaMemsetAsync(dups.p, 0, 4, stream()));
   if (t->rows) {
     KeyCols keys = key_cols_of(t, jt->key_idx.data(), (int)jt->key_idx.size());
     KernelTimer kt_join_build_kernel("join_build_kernel");
-    join_build_kernel<<<grid_for(t->rows, 256), 256, 0, stream()>>>(keys, t->rows, jt->slots.as<uint64_t>(), jt->skeys.as<uint64_t>(), (uint32_t)(cap - 1),
+    join_build_kernel<<<grid_for(t->rows, 256), 256, 0, stream()>>>(keys, t->rows, jt->slots.as<uint64_t>(), (uint32_t)(cap - 1),
                                                                     jt->nulls_equal, jt->fast, dups.as<int32_t>());
     CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -218,7 +226,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
       DevBuf tot(8);
       CUDA_CHECK(cudaMemsetAsync(tot.p, 0, 8, stream()));
       KernelTimer kt("join_probe_distinct_kernel");
-      join_probe_distinct_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), jt->skeys.as<uint64_t>(), (uint32_t)(jt->cap - 1),
+      join_probe_distinct_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1),
                                                                           jt->nulls_equal, jt->fast, kind, tot.as<unsigned long long>(),
                                                                           lm.c->data.as<int32_t>(), rm.c->data.as<int32_t>());
       CUDA_CHECK(cudaGetLastError());
@@ -234,7 +242,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
   int64_t total = 0;
   if (n) {
     KernelTimer kt_join_probe_count_kernel("join_probe_count_kernel");
-    join_probe_kernel<0><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), jt->skeys.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, jt->fast, kind,
+    join_probe_kernel<0><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, jt->fast, kind,
                                                                   counts.as<int32_t>(), nullptr, nullptr, nullptr);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -249,7 +257,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
   ColGuard rm(semi_like ? nullptr : new_column(B2_INT32, 0, total, false));
   if (n && total) {
     KernelTimer kt_join_probe_write_kernel("join_probe_write_kernel");
-    join_probe_kernel<1><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), jt->skeys.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, jt->fast, kind,
+    join_probe_kernel<1><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, jt->fast, kind,
                                                                   nullptr, offsets.as<int64_t>(), lm.c->data.as<int32_t>(),
                                                                   semi_like ? nullptr : rm.c->data.as<int32_t>());
     CUDA_CHECK(cudaGetLastError());

@@ -16,6 +16,8 @@ struct KeyCol {
   const int32_t* offsets;
   int32_t dtype;
   int32_t width;
+  int32_t pack;   // bytes this column takes in a packed 8-byte group key (0 = not packable); strings: 1 length byte + chars
+  int32_t pad;
 };
 struct KeyCols {
   int32_t n;

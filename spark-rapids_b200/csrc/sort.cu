@@ -22,18 +22,18 @@ constexpr int RS_TILE = RS_NT * RS_ITEMS;  // 4096 items per CTA
 constexpr int RS_WARPS = RS_NT / 32;
 constexpr int RS_WARP_ITEMS = RS_TILE / RS_WARPS;  // 512 consecutive items per warp
 
-// histogram of all eight digits of the chunk in one read
-__global__ void __launch_bounds__(256) hist8_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ hist) {
+// histogram of the first `ndigits` digits of the chunk in one read (shared-memory atomics; a
+// match_any pre-aggregation was measured slower for 8-bit digits of random keys)
+__global__ void __launch_bounds__(256) hist8_kernel(const uint64_t* __restrict__ keys, int64_t n, int ndigits, unsigned long long* __restrict__ hist) {
   __shared__ uint32_t s_h[8 * 256];
   for (int k = threadIdx.x; k < 8 * 256; k += blockDim.x) s_h[k] = 0;
   __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t k = keys[i];
-#pragma unroll
-    for (int d = 0; d < 8; d++) atomicAdd(&s_h[d * 256 + ((k >> (8 * d)) & 255)], 1u);
+    const uint64_t k = keys[i];
+    for (int d = 0; d < ndigits; d++) atomicAdd(&s_h[d * 256 + ((k >> (8 * d)) & 255)], 1u);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < 8 * 256; k += blockDim.x)
+  for (int k = threadIdx.x; k < ndigits * 256; k += blockDim.x)
     if (s_h[k]) atomicAdd(&hist[k], (unsigned long long)s_h[k]);
 }
 
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(RS_NT) tile_hist_kernel(const uint64_t* __rest
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
-    int64_t i = base + k * RS_NT + threadIdx.x;
+    const int64_t i = base + k * RS_NT + threadIdx.x;
     if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 255], 1u);
   }
   __syncthreads();
@@ -111,7 +111,7 @@ int radix_sort_pairs(uint64_t* keys_a, int32_t* vals_a, uint64_t* keys_b, int32_
   if (n <= 1) return 0;
   DevBuf hist(8 * 256 * 8);
   CUDA_CHECK(cudaMemsetAsync(hist.p, 0, hist.bytes, stream()));
-  hist8_kernel<<<grid_for(n, 256 * 8), 256, 0, stream()>>>(keys_a, n, hist.as<unsigned long long>());
+  hist8_kernel<<<grid_for(n, 256 * 8), 256, 0, stream()>>>(keys_a, n, nbytes, hist.as<unsigned long long>());
   count_launch();
   std::vector<unsigned long long> h(8 * 256);
   d2h(h.data(), hist.p, h.size());
