@@ -46,9 +46,11 @@ void dev_free(void* p);
 void count_launch(int n = 1);
 struct KernelTimer {  // scoped CUDA-event timer around a kernel launch; no-op unless profiling is on
   void* rec;
-  explicit KernelTimer(const char* name);
+  cudaStream_t st;
+  explicit KernelTimer(const char* name, cudaStream_t on = nullptr);
   ~KernelTimer();
 };
+cudaStream_t aux_stream();   // second per-thread stream for work that may overlap the main stream
 int sm_count();
 
 struct DevBuf {  // RAII stream-ordered device buffer

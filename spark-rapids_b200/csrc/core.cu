@@ -63,18 +63,19 @@ struct ProfRec { const char* name; cudaEvent_t a, b; };
 static std::atomic<bool> g_prof{false};
 static std::mutex g_prof_mu;
 static std::vector<ProfRec*> g_prof_recs;
-KernelTimer::KernelTimer(const char* name) : rec(nullptr) {
+KernelTimer::KernelTimer(const char* name, cudaStream_t on) : rec(nullptr), st(on) {
   if (!g_prof.load(std::memory_order_relaxed)) return;
+  if (!st) st = stream();
   ProfRec* r = new ProfRec();
   r->name = name;
   cudaEventCreate(&r->a); cudaEventCreate(&r->b);
-  cudaEventRecord(r->a, stream());
+  cudaEventRecord(r->a, st);
   rec = r;
 }
 KernelTimer::~KernelTimer() {
   if (!rec) return;
   ProfRec* r = reinterpret_cast<ProfRec*>(rec);
-  cudaEventRecord(r->b, stream());
+  cudaEventRecord(r->b, st);
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_recs.push_back(r);
 }
@@ -99,6 +100,12 @@ static void ensure_init() {
   uint64_t thr = UINT64_MAX;  // keep freed memory in the pool: Rmm pool behaviour
   CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   g_inited = true;
+}
+
+static thread_local cudaStream_t t_aux = nullptr;
+cudaStream_t aux_stream() {
+  if (!t_aux) { stream(); CUDA_CHECK(cudaStreamCreateWithFlags(&t_aux, cudaStreamNonBlocking)); }
+  return t_aux;
 }
 
 cudaStream_t stream() {

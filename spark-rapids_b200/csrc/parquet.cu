@@ -11,6 +11,8 @@
 // one CTA per page: one thread parses a batch of run headers, all warps expand the runs;
 // (4) strings: lengths -> scan -> chars copy; (5) only if a column really has NULLs, scatter the
 // dense values to their rows.  Flat schemas (what Spark/TPC-H tables are); nested -> UNSUPPORTED.
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include "prim.cuh"
 
@@ -258,12 +260,14 @@ __device__ __forceinline__ void sn_flush(SnappyWarp& w, uint8_t* __restrict__ ds
 }
 
 __global__ void __launch_bounds__(SN_WARPS * 32) snappy_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, int ntodo,
-                                                               const uint8_t* __restrict__ file, uint8_t* __restrict__ scratch, int32_t* __restrict__ errors) {
+                                                               const uint8_t* __restrict__ file, uint8_t* __restrict__ scratch, int32_t* __restrict__ errors,
+                                                               const int32_t* __restrict__ gate) {
   __shared__ __align__(16) SnappyWarp s_w[SN_WARPS];
   const int lane = threadIdx.x & 31;
   const int wi = threadIdx.x >> 5;
   const int wg = blockIdx.x * SN_WARPS + wi;
   if (wg >= ntodo) return;
+  if (gate && gate[wg] == 0) return;  // big page already decoded by the CTA-wide kernel
   SnappyWarp& w = s_w[wi];
   const PageD pg = pages[todo[wg]];
   const uint8_t* in = file + pg.src_off;
@@ -379,6 +383,205 @@ __global__ void __launch_bounds__(SN_WARPS * 32) snappy_kernel(const PageD* __re
   __syncwarp();
   sn_flush(w, dst, flushed, op, lane, true);
   if ((bad || op != out_len) && lane == 0) atomicExch(errors, 1);
+}
+
+// ---- snappy for LARGE pages: one CTA (32 warps) per page, fully parallel LZ77 --------------------
+// A 1 MB dictionary page is ~260 k LZ77 elements; on one warp it is the critical path of the whole
+// decode.  Here the compressed stream is cut into 32 chunks.  (1) Each warp finds an element boundary
+// near its chunk start by self-synchronisation: 32 lanes parse forward from 32 consecutive byte offsets
+// until they agree.  (2) Each warp walks its chunk from its boundary and must land EXACTLY on the next
+// warp's boundary; warp 0 starts at the true stream start, so success of every check proves every
+// boundary by induction (otherwise the page falls back to the one-warp kernel).  (3) Output offsets
+// by prefix sum.  (4) Second walk: literal bytes go to their final place, and every output byte j gets
+// a source S[j] (itself for literals, j - offset for back-references).  (5) Pointer jumping
+// S[j] = S[S[j]] until every byte points at a literal byte (log2(chain depth) rounds).
+// (6) out[j] = out[S[j]].
+constexpr int SB_WARPS = 32;
+constexpr uint32_t SB_MIN_BYTES = 192 * 1024;   // uncompressed size from which a page takes this path
+
+struct SnE { uint32_t esz, len, off, hdr; bool lit, ok; };
+__device__ __forceinline__ SnE sn_parse(const uint8_t* __restrict__ in, uint32_t q, uint32_t in_len) {
+  SnE e; e.esz = 1; e.len = 0; e.off = 0; e.hdr = 1; e.lit = true; e.ok = false;
+  if (q >= in_len) return e;
+  const uint32_t tag = in[q];
+  const uint32_t b1 = q + 1 < in_len ? in[q + 1] : 0, b2 = q + 2 < in_len ? in[q + 2] : 0, b3 = q + 3 < in_len ? in[q + 3] : 0, b4 = q + 4 < in_len ? in[q + 4] : 0;
+  const uint32_t t = tag & 3;
+  if (t == 0) {
+    uint32_t len = tag >> 2;
+    if (len < 60) { e.len = len + 1; e.hdr = 1; }
+    else { const uint32_t nb = len - 59; const uint32_t v = b1 | (b2 << 8) | (b3 << 16) | (b4 << 24); e.len = (nb == 4 ? v : (v & ((1u << (8 * nb)) - 1))) + 1; e.hdr = 1 + nb; }
+    e.lit = true; e.esz = e.hdr + e.len;
+    e.ok = (uint64_t)q + e.esz <= in_len;
+  } else {
+    e.lit = false;
+    if (t == 1) { e.len = 4 + ((tag >> 2) & 7); e.off = ((tag >> 5) << 8) | b1; e.hdr = 2; }
+    else if (t == 2) { e.len = (tag >> 2) + 1; e.off = b1 | (b2 << 8); e.hdr = 3; }
+    else { e.len = (tag >> 2) + 1; e.off = b1 | (b2 << 8) | (b3 << 16) | (b4 << 24); e.hdr = 5; }
+    e.esz = e.hdr;
+    e.ok = q + e.hdr <= in_len && e.off != 0;
+  }
+  return e;
+}
+
+// Walk elements [ip_start, ip_stop) with the 32-byte window method.  EMIT = false: only sum output
+// lengths.  EMIT = true: place literals and write the source map.  Returns false on any inconsistency
+// (including not landing exactly on ip_stop).
+template <bool EMIT>
+__device__ bool sn_walk(const uint8_t* __restrict__ in, uint32_t in_len, uint32_t ip_start, uint32_t ip_stop, uint32_t op_start, uint32_t out_len,
+                        uint8_t* __restrict__ out, uint32_t* __restrict__ S, uint32_t sbase, uint32_t& out_total) {
+  const int lane = threadIdx.x & 31;
+  uint32_t ip = ip_start, op = op_start;
+  while (ip < ip_stop) {
+    const uint32_t q = ip + lane;
+    const uint32_t avail = min(32u, ip_stop - ip);
+    const SnE e = sn_parse(in, q, in_len);
+    const bool is_long = e.lit && (lane + e.esz > 32 || e.len > 31);
+    const uint32_t n1 = (lane >= avail) ? 64u : (is_long ? 64u : min(lane + e.esz, 64u));
+    uint32_t n2 = __shfl_sync(0xffffffffu, n1, n1 & 31);
+    if (n1 >= 32) n2 = 64u;
+    uint32_t M = 0, cur = 0;
+    while (cur < 32) {
+      M |= 1u << cur;
+      const uint32_t a = __shfl_sync(0xffffffffu, n1, cur);
+      const uint32_t c2 = __shfl_sync(0xffffffffu, n2, cur);
+      if (a < 32) M |= 1u << a;
+      cur = c2;
+    }
+    M &= (avail >= 32 ? 0xffffffffu : ((1u << avail) - 1u));
+    const bool mine = (M >> lane) & 1u;
+    const uint32_t longmask = __ballot_sync(0xffffffffu, mine && is_long);
+    const int long_lane = longmask ? (__ffs(longmask) - 1) : -1;
+    const uint32_t myo = (mine && !is_long) ? e.len : 0;
+    uint32_t inc = myo;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t opos = op + inc - myo;
+    const bool bad = mine && (!e.ok || (EMIT && !e.lit && e.off > opos));  // offsets can only be checked with absolute positions
+    if (__any_sync(0xffffffffu, bad) || (uint64_t)op + total > out_len) return false;
+    if (EMIT && mine && !is_long) {
+      if (e.lit) { for (uint32_t k = 0; k < e.len; k++) { out[opos + k] = in[q + e.hdr + k]; S[opos + k] = sbase + opos + k; } }
+      else { for (uint32_t k = 0; k < e.len; k++) S[opos + k] = sbase + opos + k - e.off; }
+    }
+    op += total;
+    const uint32_t endp = mine ? (is_long ? lane : lane + e.esz) : 0;
+    ip += __reduce_max_sync(0xffffffffu, endp);
+    if (long_lane >= 0) {
+      const uint32_t llen = __shfl_sync(0xffffffffu, e.len, long_lane), lhdr = __shfl_sync(0xffffffffu, e.hdr, long_lane);
+      const bool lok = __shfl_sync(0xffffffffu, (uint32_t)e.ok, long_lane) != 0;
+      if (!lok || (uint64_t)op + llen > out_len) return false;
+      if (EMIT) for (uint32_t k = lane; k < llen; k += 32) { out[op + k] = in[ip + lhdr + k]; S[op + k] = sbase + op + k; }
+      ip += lhdr + llen; op += llen;
+    }
+  }
+  out_total = op - op_start;
+  return ip == ip_stop;
+}
+
+__global__ void __launch_bounds__(SB_WARPS * 32) snappy_big_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo,
+                                                                   const int64_t* __restrict__ s_off, const uint8_t* __restrict__ file,
+                                                                   uint8_t* __restrict__ scratch, uint32_t* __restrict__ S_all, int32_t* __restrict__ fail) {
+  __shared__ uint32_t s_cand[SB_WARPS + 1], s_olen[SB_WARPS], s_op[SB_WARPS + 1];
+  __shared__ int s_bad;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const PageD pg = pages[todo[blockIdx.x]];
+  const uint8_t* in = file + pg.src_off;
+  uint8_t* out = scratch + pg.dst_off;
+  uint32_t in_len = (uint32_t)pg.comp_size, out_len = (uint32_t)pg.uncomp_size;
+  if (pg.lvl_bytes) {
+    const uint32_t lvl = (uint32_t)pg.lvl_bytes;
+    for (uint32_t k = threadIdx.x; k < lvl; k += blockDim.x) out[k] = in[k];
+    in += lvl; out += lvl; in_len -= lvl; out_len -= lvl;
+  }
+  uint32_t* S = S_all + s_off[blockIdx.x];
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  // preamble
+  uint32_t ip0 = 0, ulen = 0;
+  { int shift = 0; while (ip0 < in_len) { const uint8_t b = in[ip0++]; ulen |= (uint32_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; } }
+  if (ulen != out_len) { if (threadIdx.x == 0) fail[blockIdx.x] = 1; return; }  // fail codes: 1 preamble, 2 boundary, 3 verify, 4 length, 5 emit
+  const uint32_t C = (in_len - ip0 + SB_WARPS - 1) / SB_WARPS;
+  // ---- (1) boundary near each chunk start
+  {
+    uint32_t cand;
+    if (w == 0) cand = ip0;
+    else {
+      const uint32_t b = min(ip0 + (uint32_t)w * C, in_len);
+      uint32_t pos = min(b + lane, in_len);
+      uint32_t T = b + 256;
+      bool agreed = false;
+      uint32_t best = in_len;
+      // chains that start inside literal bytes misparse; most re-synchronise within a few elements,
+      // a few run off the end.  Take the position a majority of the 32 chains agrees on — the
+      // verification walk of the previous warp proves (or refutes) it.
+      for (int att = 0; att < 16 && !agreed; att++, T += 512) {
+        while (pos < T && pos < in_len) { const SnE e = sn_parse(in, pos, in_len); if (!e.ok) { pos = 0xffffffffu; break; } pos += e.esz; }
+        const uint32_t grp = __match_any_sync(0xffffffffu, pos);
+        const bool maj = pos != 0xffffffffu && __popc(grp) >= 17;
+        const uint32_t who = __ballot_sync(0xffffffffu, maj);
+        if (who) { best = __shfl_sync(0xffffffffu, pos, __ffs(who) - 1); agreed = true; }
+      }
+      cand = min(best, in_len);
+      if (!agreed && lane == 0) s_bad = 1;
+    }
+    if (lane == 0) s_cand[w] = cand;
+    if (threadIdx.x == 0) s_cand[SB_WARPS] = in_len;
+  }
+  __syncthreads();
+  if (s_bad) { if (threadIdx.x == 0) fail[blockIdx.x] = 2; return; }
+  // boundaries must be non-decreasing (a later chunk may start inside an earlier warp's overshoot)
+  // ---- (2) verification walk + output length per chunk
+  {
+    const uint32_t a = s_cand[w], b = s_cand[w + 1];
+    uint32_t olen = 0;
+    bool ok = a <= b;
+    if (ok && a < b) ok = sn_walk<false>(in, in_len, a, b, 0, 0xffffffffu, nullptr, nullptr, 0, olen);
+    if (lane == 0) { s_olen[w] = olen; if (!ok) s_bad = 1; }
+  }
+  __syncthreads();
+  if (s_bad) { if (threadIdx.x == 0) fail[blockIdx.x] = 3; return; }
+  // ---- (3) output offsets
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int k = 0; k < SB_WARPS; k++) { s_op[k] = run; run += s_olen[k]; }
+    s_op[SB_WARPS] = run;
+    if (run != out_len) s_bad = 1;
+  }
+  __syncthreads();
+  if (s_bad) { if (threadIdx.x == 0) fail[blockIdx.x] = 4; return; }
+  // ---- (4) emit literals + source map
+  {
+    const uint32_t a = s_cand[w], b = s_cand[w + 1];
+    uint32_t olen = 0;
+    bool ok = true;
+    if (a < b) ok = sn_walk<true>(in, in_len, a, b, s_op[w], out_len, out, S, (uint32_t)s_off[blockIdx.x], olen);
+    if (lane == 0 && !ok) s_bad = 1;
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (s_bad) { if (threadIdx.x == 0) fail[blockIdx.x] = 5; return; }
+}
+
+// (5) one pointer-jumping round over the source maps of ALL large pages (values are absolute indexes
+// into S): S[j] = S[S[j]].  20 rounds resolve chains of up to 2^20 back-references.
+__global__ void __launch_bounds__(256) snappy_jump_kernel(uint32_t* __restrict__ S, uint32_t total) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x; j0 < total; j0 += 4 * stride) {
+    uint32_t j[4], s1[4], s2[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { j[u] = j0 + u * stride; s1[u] = j[u] < total ? S[j[u]] : j[u]; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) s2[u] = (s1[u] != j[u] && s1[u] < total) ? *reinterpret_cast<volatile uint32_t*>(&S[s1[u]]) : s1[u];
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (s2[u] != s1[u]) S[j[u]] = s2[u];
+  }
+}
+// (6) every non-literal byte copies the literal byte its chain ends at
+__global__ void __launch_bounds__(256) snappy_resolve_kernel(const uint32_t* __restrict__ S, uint8_t* __restrict__ out, uint32_t total) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+    const uint32_t s1 = S[j];
+    if (s1 != j && s1 < total) out[j] = out[s1];
+  }
 }
 
 // ---- RLE / bit-packed hybrid ---------------------------------------------------------------------
@@ -791,6 +994,23 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
     }
     t_pq_stats[0] = comp; t_pq_stats[1] = prod; t_pq_stats[2] = unc; t_pq_stats[3] = 0; t_pq_stats[4] = (int64_t)pages.size();
   }
+  std::vector<int32_t> todo_snappy, todo_big, todo_levels, todo_values;
+  std::vector<int64_t> big_soff;
+  int64_t big_S = 0;
+  for (size_t i = 0; i < pages.size(); i++) {
+    if (pages[i].compressed) {
+      if ((uint32_t)pages[i].uncomp_size >= SB_MIN_BYTES && pages[i].lvl_bytes == 0) {
+        // large pages decode into one contiguous region at the end of the scratch buffer so that the
+        // source map and the output share one index space
+        todo_big.push_back((int32_t)i); big_soff.push_back(big_S);
+        pages[i].dst_off = scratch_bytes + big_S;   // scratch_bytes = start of the large-page region
+        big_S += ((int64_t)pages[i].uncomp_size + 15) & ~15LL;
+      } else todo_snappy.push_back((int32_t)i);
+    }
+    if (pages[i].kind != PG_DICT) { todo_values.push_back((int32_t)i); if (chunks[pages[i].chunk].max_def > 0) todo_levels.push_back((int32_t)i); }
+  }
+  const int64_t big_region = scratch_bytes;
+  scratch_bytes += big_S;
   cudaStream_t s = stream();
   // device copy of the file bytes (H2D inside the call unless the caller already has them resident)
   DevBuf file_buf;
@@ -825,23 +1045,63 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   DevBuf d_cols((size_t)ncols * sizeof(ColD));
   h2d(d_cols.p, cold.data(), cold.size());
 
-  std::vector<int32_t> todo_snappy, todo_levels, todo_values;
-  for (size_t i = 0; i < pages.size(); i++) {
-    if (pages[i].compressed) todo_snappy.push_back((int32_t)i);
-    if (pages[i].kind != PG_DICT) { todo_values.push_back((int32_t)i); if (chunks[pages[i].chunk].max_def > 0) todo_levels.push_back((int32_t)i); }
-  }
   // value_base is only known after the level pass when a column has NULLs; start with rows
   for (auto& pg : pages) pg.value_base = pg.row_start;
   if (!pages.empty()) h2d(d_pages.p, pages.data(), pages.size());
   auto upload = [&](const std::vector<int32_t>& v, DevBuf& b) { b = DevBuf(std::max<size_t>(1, v.size()) * 4); if (!v.empty()) h2d(b.p, v.data(), v.size()); };
   DevBuf d_todo_s, d_todo_l, d_todo_v;
   upload(todo_snappy, d_todo_s); upload(todo_levels, d_todo_l); upload(todo_values, d_todo_v);
+  DevBuf d_todo_b, d_big_soff, d_big_S, d_big_fail;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!todo_big.empty()) {
+    // large pages: CTA-wide parallel decode on a second stream, overlapping the one-warp-per-page kernel;
+    // pages it declines are redone by the one-warp kernel
+    cudaStream_t a = aux_stream();
+    upload(todo_big, d_todo_b);
+    d_big_soff = DevBuf(big_soff.size() * 8);
+    h2d(d_big_soff.p, big_soff.data(), big_soff.size());
+    d_big_S = DevBuf((size_t)big_S * 4);
+    d_big_fail = DevBuf(todo_big.size() * 4);
+    CUDA_CHECK(cudaMemsetAsync(d_big_fail.p, 0, d_big_fail.bytes, s));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(ev_fork, s));
+    CUDA_CHECK(cudaStreamWaitEvent(a, ev_fork, 0));
+    {
+      KernelTimer kt("snappy_big_kernel", a);
+      snappy_big_kernel<<<(int)todo_big.size(), SB_WARPS * 32, 0, a>>>(d_pages.as<PageD>(), d_todo_b.as<int32_t>(), d_big_soff.as<int64_t>(), d_file,
+                                                                        scratch.as<uint8_t>(), d_big_S.as<uint32_t>(), d_big_fail.as<int32_t>());
+      CUDA_CHECK(cudaGetLastError());
+      count_launch();
+    }
+    {
+      KernelTimer kt("snappy_jump_resolve_kernels", a);
+      const uint32_t total = (uint32_t)big_S;
+      const int grid = grid_for((int64_t)total, 256 * 4, 8);
+      for (int round = 0; round < 20; round++) snappy_jump_kernel<<<grid, 256, 0, a>>>(d_big_S.as<uint32_t>(), total);
+      snappy_resolve_kernel<<<grid_for((int64_t)total, 256, 8), 256, 0, a>>>(d_big_S.as<uint32_t>(), scratch.as<uint8_t>() + big_region, total);
+      CUDA_CHECK(cudaGetLastError());
+      count_launch(21);
+    }
+    {
+      KernelTimer kt_fb("snappy_fallback_kernel", a);
+      snappy_kernel<<<((int)todo_big.size() + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, 0, a>>>(d_pages.as<PageD>(), d_todo_b.as<int32_t>(), (int)todo_big.size(), d_file,
+                                                                                               scratch.as<uint8_t>(), d_err.as<int32_t>(), d_big_fail.as<int32_t>());
+      CUDA_CHECK(cudaGetLastError());
+      count_launch();
+    }
+    CUDA_CHECK(cudaEventRecord(ev_join, a));
+  }
   if (!todo_snappy.empty()) {
     KernelTimer kt_snappy_kernel("snappy_kernel");
     snappy_kernel<<<((int)todo_snappy.size() + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, 0, s>>>(d_pages.as<PageD>(), d_todo_s.as<int32_t>(), (int)todo_snappy.size(), d_file,
-                                                                              scratch.as<uint8_t>(), d_err.as<int32_t>());
+                                                                              scratch.as<uint8_t>(), d_err.as<int32_t>(), nullptr);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
+  }
+  if (ev_join) {
+    CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
+    cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
   }
   std::vector<int64_t> col_nonnull(ncols, 0);
   std::vector<bool> has_nulls(ncols, false);
