@@ -38,3 +38,25 @@ for _ in range(5):
 for k in m.profile_report():
     per = k["ms"] / k["launches"]
     print("%-28s %.4f ms  %8.1f GB/s  %8.1f Mrows/s" % (k["name"], per, n * 46 / 1e9 / (per / 1e3), n / per / 1e3))
+
+# ---- breakdown
+def tm(name, fn, bpr):
+    for _ in range(2):
+        fn()
+    m.profile_enable(True)
+    for _ in range(3):
+        fn()
+    for k in m.profile_report():
+        per = k["ms"] / k["launches"]
+        print("%-44s %-24s %.4f ms %8.1f GB/s" % (name, k["name"], per, n * bpr / 1e9 / (per / 1e3)))
+    m.profile_enable(False)
+p_proj = m.Program([disc_price, charge])
+tm("project disc_price, charge", lambda: m.project(p_proj, t), 24 + 32)
+p_dp = m.Program([disc_price])
+tm("project disc_price only", lambda: m.project(p_dp, t), 16 + 16)
+p_keys = m.Program([pred, c[0], c[1]])
+tm("group-by keys only, count(*)", lambda: m.scan_aggregate(p_keys, True, t, [0, 1], [(m.AGG_COUNT_ALL, 0)]), 14)
+p_one = m.Program([pred, c[0], c[1], c[2]])
+tm("group-by, sum(qty)", lambda: m.scan_aggregate(p_one, True, t, [0, 1], [(m.AGG_SUM, 2, m.DECIMAL128, 2, 22)]), 22)
+p_four = m.Program([pred, c[0], c[1], c[2], c[3], c[4], c[5]])
+tm("group-by, 4 plain sums", lambda: m.scan_aggregate(p_four, True, t, [0, 1], [(m.AGG_SUM, k, m.DECIMAL128, 2, 22) for k in (2, 3, 4, 5)]), 46)

@@ -315,6 +315,38 @@ __global__ void init_table_kernel(GTable gt, const __grid_constant__ AggPlan pla
   }
 }
 
+// find-or-insert row g in the CTA's shared-memory table; -1 when the table is too full (overflow flagged)
+__device__ __forceinline__ int32_t smem_find_slot(const AggPlan& plan, int64_t g, int32_t* s_slots, uint64_t* s_keys, uint32_t* s_knull, int SLOTS,
+                                                  int32_t* overflow, uint32_t* s_nocc) {
+  uint64_t kb = 0; uint32_t kn = 0;
+  const bool packed = plan.fast_keys && pack_keys(plan.keys, g, kb, kn);
+  uint32_t idx = (packed ? (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) : row_hash(plan.keys, g)) & (SLOTS - 1);
+  int probes = 0;
+  while (true) {
+    int32_t cur = s_slots[idx];
+    if (cur == SLOT_EMPTY) {
+      const int32_t old = atomicCAS(&s_slots[idx], SLOT_EMPTY, (int32_t)g);
+      if (old == SLOT_EMPTY) {  // mine: publish the packed key for later probes
+        if (packed) {
+          s_keys[idx] = kb;
+          __threadfence_block();
+          *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]) = kn | KEY_READY;
+        }
+        atomicAdd(s_nocc, 1u);
+        return (int32_t)idx;
+      }
+      cur = old;
+    }
+    bool same;
+    const uint32_t tag = plan.fast_keys ? *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]) : 0u;
+    if (packed && (tag & KEY_READY)) { __threadfence_block(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&s_keys[idx]) == kb; }
+    else same = cur == (int32_t)g || rows_equal(plan.keys, g, plan.keys, cur, true);  // generic compare / key not published yet
+    if (same) return (int32_t)idx;
+    idx = (idx + 1) & (SLOTS - 1);
+    if (++probes >= SLOTS / 2) { atomicExch(overflow, 1); return -1; }
+  }
+}
+
 // SMEM = true: per-CTA shared table + merge; false: straight to the global table
 template <bool SMEM>
 __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
@@ -335,7 +367,14 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
   uint64_t* s_keys = s_priv;                                             // [SLOTS]
   uint32_t* s_knull = reinterpret_cast<uint32_t*>(s_keys + SLOTS);       // [SLOTS], KEY_READY once s_keys is valid
   const bool keyless = SMEM && plan.nkeys == 0;
+  // keyed: sort area after the packed keys: counts/offsets per slot, slot per row, permutation, scalars
+  uint32_t* s_cnt = s_knull + SLOTS;
+  uint32_t* s_total = s_cnt + SLOTS;
+  uint32_t* s_nocc = s_total + 1;
+  uint16_t* s_rowslot = reinterpret_cast<uint16_t*>(s_nocc + 1);
   const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs);
+  uint16_t* s_perm = s_rowslot + sh.hdr.tile_rows;
+  if (SMEM && threadIdx.x == 0 && !keyless) *s_nocc = 0;
   const int lane = threadIdx.x & 31;
   // a keyless reduction always has its single group, even over zero rows (GpuAggregateExec.scala:1107-1126)
   if (plan.nkeys == 0 && blockIdx.x == 0 && threadIdx.x == 0) gt.slots[0] = 0;
@@ -370,7 +409,10 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
         const bool a = g < nrows && opnd_valid(pred, i, g) && opnd_ld<int8_t>(pred, i) != 0;
         active_mask |= (uint32_t)a << j;
       }
-      cx.rowmask = active_mask;
+      // the row mask only pays off when few rows survive: every VM op is side-effect free, so when most
+      // rows pass the projection runs unmasked (fast row loops) and the filtered rows are simply not aggregated
+      const int passed = __syncthreads_count(active_mask != 0) ;
+      cx.rowmask = (passed * 4 > VM_NT) ? 0xffffffffu : active_mask;
     } else {
       for (int j = 0; j < cx.K; j++) active_mask |= (uint32_t)(cx.tile_base + threadIdx.x + j * VM_NT < nrows) << j;
     }
@@ -378,6 +420,52 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
     if (keyless) {
       accumulate_private(plan, cx, active_mask, s_priv, s_privv);
       continue;
+    }
+    if (SMEM) {
+      // group-sorted tile: when the CTA has seen few groups relative to the tile, rows are counting-sorted
+      // by slot in shared memory so that a warp slice holds one or two groups instead of a random mix —
+      // the per-(group, aggregate) REDUX work then drops by the number of groups per slice
+      const int T = cx.tile_rows;
+      if ((int)(*s_nocc) * 16 <= T) {
+        for (int k = threadIdx.x; k < SLOTS; k += VM_NT) s_cnt[k] = 0;
+        __syncthreads();
+        for (int j = 0; j < cx.K; j++) {
+          const int i = threadIdx.x + j * VM_NT;
+          int32_t slot = -1;
+          if ((active_mask >> j) & 1u) slot = smem_find_slot(plan, cx.tile_base + i, s_slots, s_keys, s_knull, SLOTS, gt.overflow, s_nocc);
+          s_rowslot[i] = (uint16_t)(slot < 0 ? 0xffff : slot);
+          if (slot >= 0) atomicAdd(&s_cnt[slot], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // exclusive scan of the slot counts, SLOTS/32 consecutive slots per lane
+          const int per = SLOTS / 32;
+          uint32_t sum = 0;
+          for (int k = 0; k < per; k++) sum += s_cnt[lane * per + k];
+          uint32_t inc = sum;
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+          uint32_t run = inc - sum;
+          for (int k = 0; k < per; k++) { const uint32_t c = s_cnt[lane * per + k]; s_cnt[lane * per + k] = run; run += c; }
+          if (lane == 31) *s_total = inc;
+        }
+        __syncthreads();
+        for (int j = 0; j < cx.K; j++) {
+          const int i = threadIdx.x + j * VM_NT;
+          const uint32_t sl = s_rowslot[i];
+          if (sl != 0xffff) s_perm[atomicAdd(&s_cnt[sl], 1u)] = (uint16_t)i;
+        }
+        __syncthreads();
+        const int total = (int)*s_total;
+        for (int p0 = 0; p0 < total; p0 += VM_NT) {
+          const int p = p0 + threadIdx.x;
+          const bool act = p < total;
+          const int i = act ? (int)s_perm[p] : 0;
+          const int32_t slot = act ? (int32_t)s_rowslot[i] : -1;
+          if (__ballot_sync(0xffffffffu, act) == 0) continue;
+          accumulate_slice(plan, cx, i, cx.tile_base + i, act, slot, s_acc, s_nvalid);
+        }
+        __syncthreads();
+        continue;
+      }
     }
 #pragma unroll 1
     for (int j = 0; j < cx.K; j++) {
@@ -387,53 +475,9 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
       if (__ballot_sync(0xffffffffu, active) == 0) continue;  // nothing selected in these 32 rows
       int32_t slot = -1;
       if (active) {
-        if (SMEM) {
-          if (plan.nkeys == 0) { slot = 0; s_slots[0] = 0; }
-          else if (plan.fast_keys) {
-            uint64_t kb; uint32_t kn;
-            const bool packed = pack_keys(plan.keys, g, kb, kn);
-            uint32_t idx = (packed ? (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) : row_hash(plan.keys, g)) & (SLOTS - 1);
-            int probes = 0;
-            while (true) {
-              int32_t cur = s_slots[idx];
-              if (cur == SLOT_EMPTY) {
-                const int32_t old = atomicCAS(&s_slots[idx], SLOT_EMPTY, (int32_t)g);
-                if (old == SLOT_EMPTY) {  // mine: publish the packed key for later probes
-                  if (packed) {
-                    s_keys[idx] = kb;
-                    __threadfence_block();
-                    *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]) = kn | KEY_READY;
-                  }
-                  slot = idx; break;
-                }
-                cur = old;
-              }
-              const uint32_t tag = *reinterpret_cast<volatile uint32_t*>(&s_knull[idx]);
-              bool same;
-              if (packed && (tag & KEY_READY)) { __threadfence_block(); same = (tag & ~KEY_READY) == kn && *reinterpret_cast<volatile uint64_t*>(&s_keys[idx]) == kb; }
-              else same = cur == (int32_t)g || rows_equal(plan.keys, g, plan.keys, cur, true);  // key not published yet
-              if (same) { slot = idx; break; }
-              idx = (idx + 1) & (SLOTS - 1);
-              if (++probes >= SLOTS / 2) { atomicExch(gt.overflow, 1); active = false; break; }
-            }
-          } else {
-            uint32_t idx = row_hash(plan.keys, g) & (SLOTS - 1);
-            int probes = 0;
-            while (true) {
-              int32_t cur = s_slots[idx];
-              if (cur == SLOT_EMPTY) {
-                int32_t old = atomicCAS(&s_slots[idx], SLOT_EMPTY, (int32_t)g);
-                if (old == SLOT_EMPTY) { slot = idx; break; }
-                cur = old;
-              }
-              if (cur == (int32_t)g || rows_equal(plan.keys, g, plan.keys, cur, true)) { slot = idx; break; }
-              idx = (idx + 1) & (SLOTS - 1);
-              if (++probes >= SLOTS / 2) { atomicExch(gt.overflow, 1); active = false; break; }
-            }
-          }
-        } else {
-          slot = (int32_t)global_insert(gt, plan.keys, g, plan.fast_keys != 0);
-        }
+        if (SMEM) slot = smem_find_slot(plan, g, s_slots, s_keys, s_knull, SLOTS, gt.overflow, s_nocc);
+        else slot = (int32_t)global_insert(gt, plan.keys, g, plan.fast_keys != 0);
+        if (slot < 0) active = false;
       }
       accumulate_slice(plan, cx, i, g, active && slot >= 0, active ? slot : -1, SMEM ? s_acc : gt.acc, SMEM ? s_nvalid : gt.nvalid);
     }
@@ -669,11 +713,11 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   if (nkeys > 0 && n > (1 << 20)) {
     DevBuf ps, pa, pn, po; GTable pg;
     const int64_t pn_rows = 1 << 18;
-    int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + (plan.fast_keys ? 12 : 0);
+    int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + 16;
     int nslots = 128;
     while (nslots * 2 <= SMEM_SLOTS_MAX && nslots * 2 * per_slot <= 24 * 1024) nslots *= 2;
     plan.smem_slots = nslots;
-    int table_bytes = nslots * 4 + nslots * plan.limbs * 8 + nslots * plan.nvalids * 4 + 8 + (plan.fast_keys ? nslots * 12 : 0);
+    int table_bytes = nslots * 4 + nslots * plan.limbs * 8 + nslots * plan.nvalids * 4 + 8 + nslots * 12 + nslots * 4 + 8 + 2 * 2 * prog->hdr.tile_rows + 16;
     int smem = ((vm_smem + 15) & ~15) + table_bytes;
     if (smem <= 160 * 1024) {
       int grid = vm_grid(pn_rows, smem, prog->hdr.tile_rows);
@@ -694,14 +738,14 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   // regime 1: shared-memory tables (always right for reductions; optimistic for group-by)
   if (try_smem) {
     // table sized for <= ~24 KB: more slots = shorter probe chains and more groups before the global regime
-    int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + (plan.fast_keys ? 12 : 0);
+    int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + 16;
     int nslots = 128;
     while (nslots * 2 <= SMEM_SLOTS_MAX && nslots * 2 * per_slot <= 24 * 1024) nslots *= 2;
     if (nkeys == 0) nslots = 128;
     plan.smem_slots = nslots;
     int table_bytes = nslots * 4 + nslots * plan.limbs * 8 + nslots * plan.nvalids * 4 + 8;
     if (nkeys == 0) table_bytes += plan.limbs * VM_NT * 8 + plan.nvalids * VM_NT * 4;
-    else if (plan.fast_keys) table_bytes += nslots * 12;
+    else table_bytes += nslots * 12 + nslots * 4 + 8 + 2 * 2 * prog->hdr.tile_rows + 16;
     int smem = ((vm_smem + 15) & ~15) + table_bytes;
     if (smem <= 160 * 1024) {
       int grid = n > 0 ? vm_grid(n, smem, prog->hdr.tile_rows) : 1;

@@ -162,6 +162,18 @@ struct Compiler {
     int from_scale = is_decimal(v.dtype) ? v.scale : 0;
     int from_prec = is_decimal(v.dtype) ? v.precision : default_precision(v.dtype);
     if (v.mt == MT_F32 || v.mt == MT_F64) throw Error(B2_ERR_UNSUPPORTED, "float -> decimal cast is not supported");
+    if (v.o.kind == OK_LIT && !v.o.lit_null && scale >= from_scale && scale - from_scale <= 18) {
+      // fold literal rescaling at compile time (GpuLiteral arithmetic is constant-folded by Catalyst too)
+      __int128 x = ((__int128)v.o.hi << 64) | (unsigned __int128)(uint64_t)v.o.lo;
+      for (int t = 0; t < scale - from_scale; t++) x *= 10;
+      __int128 lim = 1; for (int t = 0; t < precision; t++) lim *= 10;
+      if (x < lim && x > -lim) {
+        Val r = v;
+        r.o.lo = (int64_t)(uint64_t)x; r.o.hi = (int64_t)(x >> 64);
+        r.mt = target_mt; r.dtype = target_dt; r.precision = precision; r.scale = scale;
+        return r;
+      }
+    }
     Val cur = v;
     if (scale >= from_scale) {
       cur = widen_int(cur, target_mt >= cur.mt ? target_mt : cur.mt);
@@ -321,8 +333,10 @@ struct Compiler {
           a = widen_int(a, rmt); b = widen_int(b, rmt);
           return emit(V_MUL, rmt, rmt, rmt, a.nullable || b.nullable, 0, &a, &b, nullptr, rdt, rp, rs);
         }
-        a = widen_int(a, MT_I128); b = widen_int(b, MT_I128);
-        return emit(V_MULDEC, MT_I128, MT_I128, MT_I128, true, s - rs, &a, &b, nullptr, B2_DECIMAL128, rp, rs);
+        if (a.mt != MT_I128 && b.mt == MT_I128) std::swap(a, b);   // the wide side goes left
+        a = widen_int(a, MT_I128);
+        if (b.mt != MT_I128) b = widen_int(b, MT_I64);              // 64-bit right operand: no widened temporary
+        return emit(V_MULDEC, MT_I128, b.mt, MT_I128, true, s - rs, &a, &b, nullptr, B2_DECIMAL128, rp, rs);
       }
       if (e->op == B2_OP_DIV) {
         // Spark Divide: scale = max(6, s1 + p2 + 1), precision = p1 - s1 + s2 + scale (DecimalPrecision), adjusted
@@ -379,7 +393,8 @@ struct Compiler {
 // rows per tile: as many as fit the register budget (multiple of VM_NT, at most VM_MAX_K per thread)
 void set_tile_geometry(VMProgramHeader& hdr, int bytes_per_row) {
   hdr.bytes_per_row = bytes_per_row;
-  int k = bytes_per_row > 0 ? VM_SMEM_BUDGET / (bytes_per_row * VM_NT) : VM_MAX_K;
+  const int budget = bytes_per_row >= 24 ? VM_SMEM_BUDGET_WIDE : VM_SMEM_BUDGET;
+  int k = bytes_per_row > 0 ? budget / (bytes_per_row * VM_NT) : VM_MAX_K;
   if (k > VM_MAX_K) k = VM_MAX_K;
   if (k < 1) k = 1;
   hdr.tile_rows = k * VM_NT;

@@ -17,7 +17,8 @@ namespace b2 {
 
 constexpr int VM_NT = 256;           // threads per CTA
 constexpr int VM_MAX_K = 16;         // rows per thread per tile (tile_rows = K * VM_NT <= 4096)
-constexpr int VM_SMEM_BUDGET = 40 * 1024;
+constexpr int VM_SMEM_BUDGET = 40 * 1024;        // register bytes per tile (narrow programs: 4 CTAs/SM)
+constexpr int VM_SMEM_BUDGET_WIDE = 72 * 1024;   // programs with wide rows (>= 24 B/row of registers): 2 CTAs/SM, more rows per dispatch
 constexpr int VM_MAX_REGS = 64;
 constexpr int VM_MAX_COLS = 64;
 constexpr int VM_MAX_OUTS = 32;
@@ -240,8 +241,8 @@ __device__ __forceinline__ const char* thread_base(const Opnd& o) { return o.bas
 #define VM_LD2(u)                                                                              \
   const int i##u = threadIdx.x + (j0 + u) * VM_NT; const int64_t g##u = ti.tile_base + i##u;    \
   const bool act##u = (j0 + u) < ti.K && g##u < ti.nrows && ((ti.rowmask >> (j0 + u)) & 1u);  \
-  T x##u = T(), y##u = T(); bool va##u = false, vb##u = false;                                 \
-  if (act##u) { x##u = opnd_ld<T>(a, i##u); y##u = opnd_ld<T>(b, i##u); va##u = opnd_valid(a, i##u, g##u); vb##u = opnd_valid(b, i##u, g##u); }
+  T x##u = T(); TB y##u = TB(); bool va##u = false, vb##u = false;                             \
+  if (act##u) { x##u = opnd_ld<T>(a, i##u); y##u = opnd_ld<TB>(b, i##u); va##u = opnd_valid(a, i##u, g##u); vb##u = opnd_valid(b, i##u, g##u); }
 #define VM_ST2(u) if (act##u) { bool vv = va##u && vb##u; const R r = f(x##u, y##u, va##u, vb##u, vv); dst_st<R>(d, i##u, r, vv); }
 
 // unary: F(T x, bool& valid) -> R
@@ -270,9 +271,9 @@ __device__ __forceinline__ void vm_loop1(const TileInfo ti, const RInstr& ins, F
     VM_ST1(0) VM_ST1(1) VM_ST1(2) VM_ST1(3)
   }
 }
-// binary: F(T x, T y, bool va, bool vb, bool& valid) -> R
-template <typename T, typename R, typename F>
-__device__ __forceinline__ void vm_loop2(const TileInfo ti, const RInstr& ins, F f) {
+// binary: F(T x, TB y, bool va, bool vb, bool& valid) -> R
+template <typename T, typename R, typename TB, typename F>
+__device__ __forceinline__ void vm_loop2x(const TileInfo ti, const RInstr& ins, F f) {
   const Opnd a = ropnd(ins.a, ti), b = ropnd(ins.b, ti);
   const Dst d = rdst(ins, sizeof(R));
   if (a.vkind == 0 && b.vkind == 0 && !d.nullable && a.stride != 0 && vm_full_tile(ti, ti.tile_rows)) {
@@ -280,7 +281,7 @@ __device__ __forceinline__ void vm_loop2(const TileInfo ti, const RInstr& ins, F
     char* pd = d.base + (size_t)threadIdx.x * sizeof(R);
     bool vv = true;
     if (b.stride == 0) {  // column/register (op) literal
-      const T y = *reinterpret_cast<const T*>(b.base);
+      const TB y = *reinterpret_cast<const TB*>(b.base);
       for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
         const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
                 x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
@@ -290,17 +291,17 @@ __device__ __forceinline__ void vm_loop2(const TileInfo ti, const RInstr& ins, F
       for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pd += VM_NT * sizeof(R))
         *reinterpret_cast<R*>(pd) = f(*reinterpret_cast<const T*>(pa), y, true, true, vv);
     } else {
-      const char* pb = thread_base<T>(b);
-      for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pb += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
+      const char* pb = thread_base<TB>(b);
+      for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pb += 4 * VM_NT * sizeof(TB), pd += 4 * VM_NT * sizeof(R)) {
         const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
                 x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
-        const T y0 = *reinterpret_cast<const T*>(pb), y1 = *reinterpret_cast<const T*>(pb + VM_NT * sizeof(T)),
-                y2 = *reinterpret_cast<const T*>(pb + 2 * VM_NT * sizeof(T)), y3 = *reinterpret_cast<const T*>(pb + 3 * VM_NT * sizeof(T));
+        const TB y0 = *reinterpret_cast<const TB*>(pb), y1 = *reinterpret_cast<const TB*>(pb + VM_NT * sizeof(TB)),
+                 y2 = *reinterpret_cast<const TB*>(pb + 2 * VM_NT * sizeof(TB)), y3 = *reinterpret_cast<const TB*>(pb + 3 * VM_NT * sizeof(TB));
         *reinterpret_cast<R*>(pd) = f(x0, y0, true, true, vv); *reinterpret_cast<R*>(pd + VM_NT * sizeof(R)) = f(x1, y1, true, true, vv);
         *reinterpret_cast<R*>(pd + 2 * VM_NT * sizeof(R)) = f(x2, y2, true, true, vv); *reinterpret_cast<R*>(pd + 3 * VM_NT * sizeof(R)) = f(x3, y3, true, true, vv);
       }
-      for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pb += VM_NT * sizeof(T), pd += VM_NT * sizeof(R))
-        *reinterpret_cast<R*>(pd) = f(*reinterpret_cast<const T*>(pa), *reinterpret_cast<const T*>(pb), true, true, vv);
+      for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pb += VM_NT * sizeof(TB), pd += VM_NT * sizeof(R))
+        *reinterpret_cast<R*>(pd) = f(*reinterpret_cast<const T*>(pa), *reinterpret_cast<const TB*>(pb), true, true, vv);
     }
     return;
   }
@@ -309,6 +310,9 @@ __device__ __forceinline__ void vm_loop2(const TileInfo ti, const RInstr& ins, F
     VM_ST2(0) VM_ST2(1) VM_ST2(2) VM_ST2(3)
   }
 }
+
+template <typename T, typename R, typename F>
+__device__ __forceinline__ void vm_loop2(const TileInfo ti, const RInstr& ins, F f) { vm_loop2x<T, R, T>(ti, ins, f); }
 
 // Spark comparison semantics (predicates.scala:155-331): NaN == NaN, NaN greater than all, -0.0 == 0.0
 template <typename T>
@@ -528,10 +532,12 @@ __device__ __noinline__ void vm_decimal(const TileInfo ti, const RInstr& ins) {
 
 // DecimalUtils.multiply128 (arithmetic.scala:470-512 longMultiply): exact 256-bit product,
 // HALF_UP to the result scale, NULL when the result needs more than 38 digits.
+template <typename TB>
 static __device__ __noinline__ void vm_muldec(const TileInfo ti, const RInstr& ins) {
   const int k = ins.aux;
   const u128 p38 = (u128)pow10_i128(38);
-  vm_loop2<i128, i128>(ti, ins, [k, p38](i128 x, i128 y, bool, bool, bool& v) -> i128 {
+  vm_loop2x<i128, i128, TB>(ti, ins, [k, p38](i128 x, TB yy, bool, bool, bool& v) -> i128 {
+    const i128 y = (i128)yy;
     const bool neg = (x < 0) != (y < 0);
     const u128 mx = x < 0 ? (u128)0 - (u128)x : (u128)x, my = y < 0 ? (u128)0 - (u128)y : (u128)y;
     const uint64_t x0 = (uint64_t)mx, x1 = (uint64_t)(mx >> 64), y0 = (uint64_t)my, y1 = (uint64_t)(my >> 64);
@@ -682,7 +688,7 @@ static __device__ __noinline__ void vm_run(const TileInfo ti, const RInstr* __re
         }
         break;
       case V_MULW: vm_mulw(ti, ins); break;
-      case V_MULDEC: vm_muldec(ti, ins); break;
+      case V_MULDEC: if (ins.mt2 == MT_I64) vm_muldec<int64_t>(ti, ins); else vm_muldec<i128>(ti, ins); break;
       case V_DIVDEC: vm_divdec(ti, ins); break;
       case V_DEC2F64:
         switch (ins.mt) {
@@ -734,6 +740,7 @@ static __device__ __forceinline__ const RInstr* vm_load_program(VMShared& sh, co
       ROpnd q; q.pad = 0; q.vptr = nullptr; q.tile_step = 0;
       int width = mt_width(g.mt);
       if (g.op == V_AND || g.op == V_OR || g.op == V_NOT || (g.op == V_IF && j == 0)) width = 1;
+      if (g.op == V_MULDEC && j == 1) width = mt_width(g.mt2);
       if (o.kind == OK_REG) {
         q.base = regs + (size_t)sh.hdr.regs[o.idx].off * tile_rows; q.stride = width;
         q.vkind = o.nullable ? 1 : 0; q.vptr = regs + (size_t)sh.hdr.regs[o.idx].voff * tile_rows;
