@@ -322,6 +322,13 @@ int b2_host_unregister(void* ptr);
 int b2_device_alloc(int64_t bytes, void** out);
 int b2_device_free(void* ptr);
 int b2_memcpy_h2d(void* dst, const void* src, int64_t bytes);
+/* asynchronous staging of a host buffer on a dedicated copy stream, so the H2D of the next scan batch
+ * overlaps the decode of the current one (what the reference's multithreaded Parquet reader does with
+ * its host buffers: GpuMultiFileReader.scala).  b2_upload_wait orders the calling thread's compute
+ * stream after the copy without blocking the host. */
+int b2_upload_start(const void* pinned_host, int64_t bytes, b2_handle* out_upload);
+int b2_upload_wait(b2_handle upload, void** out_device_ptr);
+int b2_upload_free(b2_handle upload);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -639,3 +639,28 @@ def parquet_last_stats():
     out = (ctypes.c_int64 * 5)()
     check(lib.b2_parquet_last_stats(out))
     return {"compressed_in": out[0], "decompressed_out": out[1], "page_bytes": out[2], "column_bytes": out[3], "pages": out[4]}
+
+
+class AsyncUpload:
+    """pinned host buffer -> device on the copy stream (overlaps the compute stream)"""
+
+    def __init__(self, arr):
+        out = ctypes.c_int64()
+        check(lib.b2_upload_start(_ptr(arr), arr.nbytes, ctypes.byref(out)))
+        self.h = ctypes.c_int64(out.value)
+
+    def wait(self):
+        """order the compute stream after the copy; returns the device pointer"""
+        p = ctypes.c_void_p()
+        check(lib.b2_upload_wait(self.h, ctypes.byref(p)))
+        return p.value
+
+    def free(self):
+        if self.h.value:
+            check(lib.b2_upload_free(self.h))
+            self.h = ctypes.c_int64(0)
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_upload_free(self.h)
+            self.h = ctypes.c_int64(0)

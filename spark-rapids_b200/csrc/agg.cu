@@ -315,6 +315,88 @@ __global__ void init_table_kernel(GTable gt, const __grid_constant__ AggPlan pla
   }
 }
 
+// Group-sorted tile, blocked: thread t owns C consecutive sorted positions, so it sees one group (two at
+// a boundary).  It folds its rows into a private 192-bit partial per aggregate (plain adds, no collectives);
+// when the whole warp ended on the same group the 32 partials are combined with 12 REDUX and ONE lane
+// touches the table, otherwise each lane flushes its own run.
+struct AggPart { uint64_t l0, l1, l2, mm; double d; uint32_t cnt; };
+__device__ __forceinline__ void part_reset(AggPart& p, const AggD& a) { p.l0 = p.l1 = p.l2 = 0; p.cnt = 0; p.d = 0.0; p.mm = init_limb(a); }
+__device__ __forceinline__ void part_flush(const AggPlan& plan, const AggD& a, const AggPart& p, int32_t slot, uint64_t* s_acc, uint32_t* s_nvalid) {
+  if (slot < 0 || p.cnt == 0) return;
+  uint64_t* acc = s_acc + (int64_t)slot * plan.limbs + a.limb_off;
+  if (a.track_valid) atomicAdd(&s_nvalid[(int64_t)slot * plan.nvalids + a.valid_off], p.cnt);
+  if (a.kind == B2_AGG_COUNT || a.kind == B2_AGG_COUNT_ALL) atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)p.cnt);
+  else if (a.kind == B2_AGG_SUM && a.is_float) atomicAdd(reinterpret_cast<double*>(acc), p.d);
+  else if (a.kind == B2_AGG_SUM) acc_add_limbs(acc, a.nlimbs, p.l0, p.l1, p.l2);
+  else if (a.kind == B2_AGG_MIN) atomicMin(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)p.mm);
+  else if (a.kind == B2_AGG_MAX) atomicMax(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)p.mm);
+}
+__device__ __forceinline__ void accumulate_sorted(const AggPlan& plan, const VMCtx& cx, const uint16_t* s_perm, const uint16_t* s_rowslot, int total,
+                                                  uint64_t* s_acc, uint32_t* s_nvalid) {
+  const int C = (total + VM_NT - 1) / VM_NT;
+  const int p0 = threadIdx.x * C, p1 = min(p0 + C, total);
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < plan.naggs; k++) {
+    const AggD& a = plan.aggs[k];
+    Opnd op;
+    if (a.out_idx >= 0) op = resolve(cx, cx.hdr->outs[a.out_idx], mt_width(a.in_mt));
+    AggPart part; part_reset(part, a);
+    int32_t run = -1;
+    for (int p = p0; p < p1; p++) {
+      const int i = s_perm[p];
+      const int32_t slot = (int32_t)s_rowslot[i];
+      if (slot != run) { part_flush(plan, a, part, run, s_acc, s_nvalid); part_reset(part, a); run = slot; }
+      const int64_t g = cx.tile_base + i;
+      if (a.out_idx >= 0 && !opnd_valid(op, i, g)) continue;
+      part.cnt++;
+      if (a.kind == B2_AGG_SUM && !a.is_float) {
+        uint64_t lo, hi;
+        switch (a.in_mt) {
+          case MT_I8: lo = (uint64_t)(int64_t)opnd_ld<int8_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+          case MT_I16: lo = (uint64_t)(int64_t)opnd_ld<int16_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+          case MT_I32: lo = (uint64_t)(int64_t)opnd_ld<int32_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+          case MT_I64: lo = (uint64_t)opnd_ld<int64_t>(op, i); hi = (int64_t)lo < 0 ? ~0ull : 0; break;
+          default: { const i128 v = opnd_ld<i128>(op, i); lo = (uint64_t)v; hi = (uint64_t)(v >> 64); } break;
+        }
+        const uint64_t s0 = part.l0 + lo, c0 = s0 < part.l0;
+        const uint64_t t1 = part.l1 + hi, c1a = t1 < part.l1;
+        const uint64_t s1 = t1 + c0, c1b = s1 < t1;
+        part.l0 = s0; part.l1 = s1; part.l2 += ((int64_t)hi < 0 ? ~0ull : 0ull) + c1a + c1b;
+      } else if (a.kind == B2_AGG_SUM) {
+        part.d += a.in_mt == MT_F32 ? (double)opnd_ld<float>(op, i) : opnd_ld<double>(op, i);
+      } else if (a.kind == B2_AGG_MIN || a.kind == B2_AGG_MAX) {
+        uint64_t key;
+        switch (a.in_mt) {
+          case MT_I8: key = ord_i64(opnd_ld<int8_t>(op, i)); break;
+          case MT_I16: key = ord_i64(opnd_ld<int16_t>(op, i)); break;
+          case MT_I32: key = ord_i64(opnd_ld<int32_t>(op, i)); break;
+          case MT_I64: key = ord_i64(opnd_ld<int64_t>(op, i)); break;
+          case MT_F32: key = ord_f64((double)opnd_ld<float>(op, i)); break;
+          default: key = ord_f64(opnd_ld<double>(op, i)); break;
+        }
+        part.mm = a.kind == B2_AGG_MIN ? (key < part.mm ? key : part.mm) : (key > part.mm ? key : part.mm);
+      }
+    }
+    // last run of every lane: one combined update when the warp agrees on the group
+    const int32_t wslot = __reduce_max_sync(0xffffffffu, run);
+    const bool uniform = __ballot_sync(0xffffffffu, run != wslot && run != -1) == 0;
+    const bool int_sum = a.kind == B2_AGG_SUM && !a.is_float;
+    if (uniform && wslot >= 0 && (int_sum || a.kind == B2_AGG_COUNT || a.kind == B2_AGG_COUNT_ALL)) {
+      const uint32_t cnt = __reduce_add_sync(0xffffffffu, part.cnt);
+      AggPart w; part_reset(w, a); w.cnt = cnt;
+      if (int_sum) {
+        const u128 S0 = warp_sum_u64(part.l0), S1 = warp_sum_u64(part.l1);
+        const uint64_t S2 = (uint64_t)warp_sum_u64(part.l2);
+        const u128 mid = (S0 >> 64) + (u128)(uint64_t)S1;
+        w.l0 = (uint64_t)S0; w.l1 = (uint64_t)mid; w.l2 = (uint64_t)(mid >> 64) + (uint64_t)(S1 >> 64) + S2;
+      }
+      if (lane == 0) part_flush(plan, a, w, wslot, s_acc, s_nvalid);
+    } else {
+      part_flush(plan, a, part, run, s_acc, s_nvalid);
+    }
+  }
+}
+
 // find-or-insert row g in the CTA's shared-memory table; -1 when the table is too full (overflow flagged)
 __device__ __forceinline__ int32_t smem_find_slot(const AggPlan& plan, int64_t g, int32_t* s_slots, uint64_t* s_keys, uint32_t* s_knull, int SLOTS,
                                                   int32_t* overflow, uint32_t* s_nocc) {
@@ -454,15 +536,7 @@ __global__ void __launch_bounds__(VM_NT, 4) aggregate_kernel(const VMProgramHead
           if (sl != 0xffff) s_perm[atomicAdd(&s_cnt[sl], 1u)] = (uint16_t)i;
         }
         __syncthreads();
-        const int total = (int)*s_total;
-        for (int p0 = 0; p0 < total; p0 += VM_NT) {
-          const int p = p0 + threadIdx.x;
-          const bool act = p < total;
-          const int i = act ? (int)s_perm[p] : 0;
-          const int32_t slot = act ? (int32_t)s_rowslot[i] : -1;
-          if (__ballot_sync(0xffffffffu, act) == 0) continue;
-          accumulate_slice(plan, cx, i, cx.tile_base + i, act, slot, s_acc, s_nvalid);
-        }
+        accumulate_sorted(plan, cx, s_perm, s_rowslot, (int)*s_total, s_acc, s_nvalid);
         __syncthreads();
         continue;
       }

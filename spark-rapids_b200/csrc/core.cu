@@ -498,6 +498,37 @@ int b2_memcpy_h2d(void* dst, const void* src, int64_t bytes) {
   B2_CATCH
 }
 
+struct Upload { void* dev; size_t bytes; cudaEvent_t done; };
+static thread_local cudaStream_t t_copy = nullptr;
+int b2_upload_start(const void* pinned_host, int64_t bytes, b2_handle* out_upload) {
+  B2_TRY
+  stream();
+  if (!t_copy) CUDA_CHECK(cudaStreamCreateWithFlags(&t_copy, cudaStreamNonBlocking));
+  std::unique_ptr<Upload> u(new Upload());
+  u->bytes = (size_t)bytes + 64;
+  CUDA_CHECK(cudaMallocAsync(&u->dev, u->bytes, t_copy));
+  CUDA_CHECK(cudaMemcpyAsync(u->dev, pinned_host, (size_t)bytes, cudaMemcpyHostToDevice, t_copy));
+  CUDA_CHECK(cudaEventCreateWithFlags(&u->done, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(u->done, t_copy));
+  *out_upload = to_handle(u.release());
+  B2_CATCH
+}
+int b2_upload_wait(b2_handle upload, void** out_device_ptr) {
+  B2_TRY
+  Upload* u = reinterpret_cast<Upload*>((intptr_t)upload);
+  CUDA_CHECK(cudaStreamWaitEvent(stream(), u->done, 0));
+  *out_device_ptr = u->dev;
+  B2_CATCH
+}
+int b2_upload_free(b2_handle upload) {
+  B2_TRY
+  Upload* u = reinterpret_cast<Upload*>((intptr_t)upload);
+  cudaFreeAsync(u->dev, stream());   // after everything queued on the compute stream that read it
+  cudaEventDestroy(u->done);
+  delete u;
+  B2_CATCH
+}
+
 struct Event { cudaEvent_t ev; };
 int b2_event_create(b2_handle* out) {
   B2_TRY
