@@ -253,6 +253,13 @@ int b2_parquet_decode(const uint8_t* host_buf, int64_t len, const char* const* c
 int b2_parquet_decode_device(const uint8_t* host_buf, const uint8_t* dev_buf, int64_t len,
                              const char* const* column_names, int32_t ncols, b2_handle* out_table);
 
+/* one task's split of the file: only row groups [rg_begin, rg_end) are decoded (GpuParquetScan.scala filterBlocks /
+ * clipBlocksToSchema: a Spark task reads the row groups of its input split); dev_buf may be NULL (bytes on the host) */
+int b2_parquet_decode_row_groups(const uint8_t* host_buf, const uint8_t* dev_buf, int64_t len,
+                                 const char* const* column_names, int32_t ncols, int32_t rg_begin, int32_t rg_end,
+                                 b2_handle* out_table);
+int b2_parquet_num_row_groups(const uint8_t* host_buf, int64_t len, int32_t* out_count);
+
 /* byte accounting of this thread's last decode (roofline numerators of bench.py):
  * out[0] compressed bytes fed to the decompressor, out[1] bytes it produced, out[2] uncompressed
  * bytes of all data+dictionary pages, out[3] bytes of the output columns, out[4] pages */

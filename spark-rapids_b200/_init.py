@@ -600,6 +600,23 @@ def parquet_decode_device(buf, dev_ptr, columns):
     return Table(out.value)
 
 
+def parquet_num_row_groups(buf):
+    arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    n = ctypes.c_int32()
+    check(lib.b2_parquet_num_row_groups(_ptr(arr), arr.nbytes, ctypes.byref(n)))
+    return n.value
+
+
+def parquet_decode_row_groups(buf, columns, rg_begin, rg_end, dev_ptr=None):
+    """one input split: decode row groups [rg_begin, rg_end) only (dev_ptr: file bytes already in HBM)"""
+    arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    names = (ctypes.c_char_p * len(columns))(*[c.encode() for c in columns])
+    out = ctypes.c_int64()
+    check(lib.b2_parquet_decode_row_groups(_ptr(arr), ctypes.c_void_p(dev_ptr) if dev_ptr else None, arr.nbytes, names, len(columns),
+                                           int(rg_begin), int(rg_end), ctypes.byref(out)))
+    return Table(out.value)
+
+
 # ---- profiling / raw buffers (bench.py) ---------------------------------------------------------------
 def profile_enable(on=True):
     check(lib.b2_profile_enable(int(on)))

@@ -156,10 +156,12 @@ inline ColView view_of(const Column* c) {
   return v;
 }
 
+// Descriptor-sized uploads (page tables, programs, plans) do not use the DMA engine: it serves copies in issue
+// order, so a 100-byte upload would wait behind the next batch's 0.5 GB file copy.  The bytes are staged in a
+// mapped pinned ring and pulled over by a small kernel on the compute stream (core.cu).
+void h2d_bytes(void* dst, const void* src, size_t bytes);
 template <typename T>
-inline void h2d(void* dst, const T* src, size_t n) {
-  CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, stream()));
-}
+inline void h2d(void* dst, const T* src, size_t n) { h2d_bytes(dst, src, n * sizeof(T)); }
 template <typename T>
 inline void d2h(T* dst, const void* src, size_t n) {
   CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, stream()));

@@ -3,6 +3,7 @@
 // (Rmm.initialize, ASYNC allocator mode), GpuColumnVector.java:621-660, HostColumnarToGpu.scala,
 // GpuColumnarToRowExec.scala:337-384 (copyToHost).
 #include <mutex>
+#include <algorithm>
 #include <unordered_map>
 #include <cstdio>
 #include "common.cuh"
@@ -116,6 +117,52 @@ cudaStream_t stream() {
     t_stream_owned = true;
   }
   return t_stream;
+}
+
+// ---- staged descriptor uploads ------------------------------------------------------------------------------
+static constexpr size_t STAGE_BYTES = 32u << 20, STAGE_MAX = 4u << 20;
+struct StageRing {
+  char* host = nullptr; char* dev = nullptr; size_t head = 0;
+  cudaEvent_t half[2] = {nullptr, nullptr};   // recorded after the last reader of each half
+  bool armed[2] = {false, false};
+};
+static thread_local StageRing t_stage;
+
+__global__ void stage_pull_kernel(char* dst, const char* src, size_t bytes) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+    const size_t n16 = bytes >> 4;
+    for (size_t i = i0; i < n16; i += step) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = (n16 << 4) + i0; i < bytes; i += step) dst[i] = src[i];
+  } else {
+    for (size_t i = i0; i < bytes; i += step) dst[i] = src[i];
+  }
+}
+
+void h2d_bytes(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return;
+  cudaStream_t s = stream();
+  if (bytes > STAGE_MAX) { CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s)); return; }
+  StageRing& r = t_stage;
+  if (!r.host) {
+    CUDA_CHECK(cudaHostAlloc((void**)&r.host, STAGE_BYTES, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer((void**)&r.dev, r.host, 0));
+    for (int i = 0; i < 2; i++) CUDA_CHECK(cudaEventCreateWithFlags(&r.half[i], cudaEventDisableTiming | cudaEventBlockingSync));
+  }
+  const size_t half = STAGE_BYTES / 2, need = (bytes + 15) & ~size_t(15);
+  size_t at = r.head;
+  int h = (int)std::min<size_t>(1, at / half);
+  if (at + need > (size_t)(h + 1) * half) {          // does not fit in the rest of this half: close it, move on
+    CUDA_CHECK(cudaEventRecord(r.half[h], s)); r.armed[h] = true;
+    h ^= 1; at = (size_t)h * half;
+    if (r.armed[h]) { CUDA_CHECK(cudaEventSynchronize(r.half[h])); r.armed[h] = false; }
+  }
+  memcpy(r.host + at, src, bytes);
+  r.head = at + need;
+  const int threads = 256;
+  const int blocks = (int)std::min<size_t>(64, (bytes / 16 + threads - 1) / threads + 1);
+  stage_pull_kernel<<<blocks, threads, 0, s>>>((char*)dst, r.dev + at, bytes);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 void* dev_alloc(size_t bytes) {
@@ -507,7 +554,11 @@ int b2_upload_start(const void* pinned_host, int64_t bytes, b2_handle* out_uploa
   std::unique_ptr<Upload> u(new Upload());
   u->bytes = (size_t)bytes + 64;
   CUDA_CHECK(cudaMallocAsync(&u->dev, u->bytes, t_copy));
-  CUDA_CHECK(cudaMemcpyAsync(u->dev, pinned_host, (size_t)bytes, cudaMemcpyHostToDevice, t_copy));
+  // in 8 MB pieces: the DMA engine serves work items in order, and the decode of the batch in flight issues
+  // small descriptor uploads that must not queue behind one 0.5 GB copy
+  const size_t piece = 8u << 20;
+  for (size_t off = 0; off < (size_t)bytes; off += piece)
+    CUDA_CHECK(cudaMemcpyAsync((char*)u->dev + off, (const char*)pinned_host + off, std::min(piece, (size_t)bytes - off), cudaMemcpyHostToDevice, t_copy));
   CUDA_CHECK(cudaEventCreateWithFlags(&u->done, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventRecord(u->done, t_copy));
   *out_upload = to_handle(u.release());

@@ -13,6 +13,8 @@
 // dense values to their rows.  Flat schemas (what Spark/TPC-H tables are); nested -> UNSUPPORTED.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <chrono>
 #include <map>
 #include "prim.cuh"
 
@@ -215,7 +217,7 @@ __device__ __forceinline__ const uint8_t* page_ptr(const PageD& pg, const uint8_
 // at its byte (header size, lengths, offset), the true element chain is then walked from lane 0 with
 // shuffles (two elements per hop), output positions come from a warp scan, all short literals are
 // copied by their own lanes at once, and only the back-references are replayed in order.
-constexpr int SN_WARPS = 4;            // warps (pages) per CTA
+constexpr int SN_WARPS = 1;            // pages (warps) per CTA: finest scheduling grain, ~24 pages resident per SM
 constexpr int SN_IN = 1024;            // input ring bytes
 constexpr int SN_OUT = 8192;           // output ring bytes
 constexpr int SN_HIST = 4096;          // back-reference distance served from the ring (older bytes are already in HBM)
@@ -879,7 +881,8 @@ static std::string lower(std::string s) { for (auto& c : s) c = (char)tolower(c)
 
 static thread_local int64_t t_pq_stats[5];
 
-Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, const char* const* names, int ncols) {
+Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, const char* const* names, int ncols, int rg_begin = 0, int rg_end = 0x7fffffff) {
+  const auto t_host0 = std::chrono::steady_clock::now();
   FileMeta fm = parse_footer(host, len);
   if (fm.schema.empty()) throw Error(B2_ERR_INVALID, "parquet: empty schema");
   // leaves in depth-first order = column-chunk order; only top-level (flat) leaves can be selected
@@ -910,6 +913,13 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
     if (!leaf_flat[found]) throw Error(B2_ERR_UNSUPPORTED, std::string("parquet: column '") + names[c] + "' is nested");
     plans.push_back(plan_column(fm.schema[leaf_schema[found]], leaf_schema[found]));
     leaf_of_col.push_back(found);
+  }
+  // split clipping (GpuParquetScan.scala filterBlocks: a task reads the row groups whose midpoint falls in its split)
+  rg_begin = std::max(0, rg_begin); rg_end = std::min<int>(rg_end, (int)fm.row_groups.size());
+  if (rg_begin > 0 || rg_end < (int)fm.row_groups.size()) {
+    std::vector<RowGroupMeta> sel;
+    for (int g = rg_begin; g < rg_end; g++) sel.push_back(fm.row_groups[g]);
+    fm.row_groups.swap(sel);
   }
   int64_t total_rows = 0;
   for (auto& rg : fm.row_groups) total_rows += rg.num_rows;
@@ -985,6 +995,9 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   }
   for (int c = 0; c < ncols; c++)
     if (col_rows[c] != total_rows) throw Error(B2_ERR_INVALID, "parquet: page row counts disagree with the footer");
+  if (getenv("B2_PQ_DEBUG"))
+    fprintf(stderr, "[b2 parquet] footer + page-header walk: %.3f ms for %zu pages\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(), pages.size());
 
   {
     int64_t comp = 0, prod = 0, unc = 0;
@@ -1050,6 +1063,8 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   if (!pages.empty()) h2d(d_pages.p, pages.data(), pages.size());
   auto upload = [&](const std::vector<int32_t>& v, DevBuf& b) { b = DevBuf(std::max<size_t>(1, v.size()) * 4); if (!v.empty()) h2d(b.p, v.data(), v.size()); };
   DevBuf d_todo_s, d_todo_l, d_todo_v;
+  // longest pages first: a page is one serial LZ77 chain, so the kernel ends when the slowest page does
+  std::stable_sort(todo_snappy.begin(), todo_snappy.end(), [&](int32_t a, int32_t b) { return pages[a].uncomp_size > pages[b].uncomp_size; });
   upload(todo_snappy, d_todo_s); upload(todo_levels, d_todo_l); upload(todo_values, d_todo_v);
   DevBuf d_todo_b, d_big_soff, d_big_S, d_big_fail;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1216,6 +1231,21 @@ int b2_parquet_decode_device(const uint8_t* host_buf, const uint8_t* dev_buf, in
   B2_TRY
   B2_CHECK(host_buf && dev_buf && len > 0 && ncols >= 1, "bad arguments");
   *out_table = to_handle(parquet_decode(host_buf, dev_buf, len, column_names, ncols));
+  B2_CATCH
+}
+
+int b2_parquet_decode_row_groups(const uint8_t* host_buf, const uint8_t* dev_buf, int64_t len, const char* const* column_names, int32_t ncols,
+                                 int32_t rg_begin, int32_t rg_end, b2_handle* out_table) {
+  B2_TRY
+  B2_CHECK(host_buf && len > 0 && ncols >= 1 && rg_begin >= 0 && rg_end >= rg_begin, "bad arguments");
+  *out_table = to_handle(parquet_decode(host_buf, dev_buf, len, column_names, ncols, rg_begin, rg_end));
+  B2_CATCH
+}
+
+int b2_parquet_num_row_groups(const uint8_t* host_buf, int64_t len, int32_t* out_count) {
+  B2_TRY
+  B2_CHECK(host_buf && len >= 12 && out_count, "bad arguments");
+  *out_count = (int32_t)parse_footer(host_buf, len).row_groups.size();
   B2_CATCH
 }
 

@@ -149,3 +149,40 @@ def test_q6_from_parquet_end_to_end(b2):
     keep = O.eval_expr(pred.sexpr, oc)
     exp = O.rows_of(O.reduce_cols(O.filter_cols([O.eval_expr(rev.sexpr, oc)], keep), spec))
     assert got == exp
+
+
+def test_row_group_splits(b2):
+    """a task decodes only the row groups of its split (GpuParquetScan.scala filterBlocks); the union is the file"""
+    rng = np.random.default_rng(11)
+    tbl = _tpch_like(25000, rng, True)
+    raw = _write(tbl, compression="snappy", row_group_size=6000)
+    cols = ["l_orderkey", "l_comment", "l_extendedprice"]
+    n = b2.parquet_num_row_groups(raw)
+    assert n == 5
+    exp = P.read_parquet(raw, cols)
+    parts = [b2.parquet_decode_row_groups(raw, cols, g, min(n, g + 2)) for g in range(0, n, 2)]
+    assert [p.num_rows for p in parts] == [12000, 12000, 1000]
+    whole = b2.concat(parts)
+    for i in range(len(cols)):
+        G.assert_col_equal(whole.column(i), exp[i])
+    assert b2.parquet_decode_row_groups(raw, cols, 5, 9).num_rows == 0
+
+
+@pytest.mark.parametrize("page", [8 << 10, 200 << 10, 2 << 20])
+def test_snappy_patterns(b2, page):
+    """LZ77 shapes the decoder treats differently: long literals, in-window chains (small int64 PLAIN), runs
+    (offset < length), far back-references (beyond the 4 KB ring history), mixed, across page sizes that take
+    the warp-pair kernel and the CTA-wide kernel"""
+    rng = np.random.default_rng(page)
+    n = 120_000
+    small = rng.integers(0, 1 << 20, n)                               # 3 data bytes + 5 zero bytes per value
+    runs = np.repeat(rng.integers(0, 1 << 40, n // 500 + 1), 500)[:n]  # long runs: overlapping copies
+    period = np.tile(rng.integers(0, 1 << 62, 1500), n // 1500 + 1)[:n]  # 12 KB period: far back-references
+    noise = rng.integers(-2**62, 2**62, n)                             # incompressible: long literals
+    mixed = np.where((np.arange(n) // 3000) % 2 == 0, noise, small)
+    tbl = pa.table({"small": pa.array(small), "runs": pa.array(runs), "period": pa.array(period), "noise": pa.array(noise), "mixed": pa.array(mixed)})
+    raw = _write(tbl, compression="snappy", use_dictionary=False, data_page_size=page)
+    cols = tbl.column_names
+    t = b2.parquet_decode(raw, cols)
+    for i, c in enumerate(cols):
+        assert np.array_equal(t.column(i).to_numpy()[0], tbl.column(c).to_numpy()), c
