@@ -815,7 +815,7 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
     int per_slot = 4 + plan.limbs * 8 + plan.nvalids * 4 + 16;
     int nslots = 128;
     while (nslots * 2 <= SMEM_SLOTS_MAX && nslots * 2 * per_slot <= 24 * 1024) nslots *= 2;
-    if (nkeys == 0) nslots = 128;
+    if (nkeys == 0) nslots = 8;   // a reduction uses slot 0 only; the freed shared memory buys a 4th CTA per SM
     plan.smem_slots = nslots;
     int table_bytes = nslots * 4 + nslots * plan.limbs * 8 + nslots * plan.nvalids * 4 + 8;
     if (nkeys == 0) table_bytes += plan.limbs * VM_NT * 8 + plan.nvalids * VM_NT * 4;

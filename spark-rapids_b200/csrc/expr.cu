@@ -232,6 +232,28 @@ struct Compiler {
         Val a = compile(e->kids[0]), b = compile(e->kids[1]);
         if (a.dtype != B2_BOOL8 || b.dtype != B2_BOOL8) throw Error(B2_ERR_INVALID, "AND/OR need boolean operands");
         if (a.o.kind == OK_LIT) std::swap(a, b);
+        if (e->op == B2_OP_AND && !a.nullable && !b.nullable && !prog->code.empty()) {
+          // conjunct fusion: acc AND (x cmp y) in one pass when the comparison was the instruction just emitted
+          // and feeds only this AND (its register dies here)
+          const VMInstr& last = prog->code.back();
+          if (a.o.kind == OK_REG && a.o.idx == last.dst && !(b.o.kind == OK_REG && b.o.idx == last.dst)) std::swap(a, b);
+          const bool cmp = last.op >= V_EQ && last.op <= V_GE && !last.dst_nullable;
+          if (cmp && b.o.kind == OK_REG && b.o.idx == last.dst && a.o.kind != OK_LIT && !(a.o.kind == OK_REG && a.o.idx == last.dst)) {
+            static const int truth[6] = {2, 5, 1, 3, 4, 6};   // EQ NE LT LE GT GE over {<, ==, >}
+            VMInstr ins = last;
+            ins.aux = truth[last.op - V_EQ];
+            ins.op = V_ANDCMP;
+            ins.c = a.o;
+            prog->code.pop_back();
+            release(a); release(b);
+            const int r = alloc_reg(MT_I8, false);
+            ins.dst = r; ins.dst_nullable = 0;
+            prog->code.push_back(ins);
+            Val v; v.o = none(); v.o.kind = OK_REG; v.o.idx = r; v.o.nullable = 0;
+            v.mt = MT_I8; v.dtype = B2_BOOL8; v.precision = 0; v.scale = 0; v.nullable = false;
+            return v;
+          }
+        }
         return emit(e->op == B2_OP_AND ? V_AND : V_OR, MT_I8, MT_I8, MT_I8, a.nullable || b.nullable, 0, &a, &b, nullptr, B2_BOOL8, 0, 0);
       }
       case B2_OP_NOT: {

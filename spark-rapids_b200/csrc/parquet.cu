@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <atomic>
 #include <map>
 #include "prim.cuh"
 
@@ -925,73 +927,115 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   for (auto& rg : fm.row_groups) total_rows += rg.num_rows;
   if (total_rows > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "parquet: more than 2^31-1 rows in one read; use chunked reads");
 
-  // walk page headers
+  // walk page headers.  Column chunks are independent page chains, so they are walked by a few host threads;
+  // offsets that depend on the chunks in front (scratch position, first row, dictionary-string base) are local
+  // to the chunk here and rebased in file order below.
+  struct ChunkWalk {
+    ChunkD cd; std::vector<PageD> pages; int64_t rows = 0, scratch = 0, dict_strs = 0;
+    int err = 0; std::string msg;
+  };
+  struct ChunkRef { const ChunkMeta* cm; int c; };
+  std::vector<ChunkRef> refs;
+  for (auto& rg : fm.row_groups)
+    for (int c = 0; c < ncols; c++) {
+      if (leaf_of_col[c] >= (int)rg.chunks.size()) throw Error(B2_ERR_INVALID, "parquet: row group lacks a column chunk");
+      refs.push_back({&rg.chunks[leaf_of_col[c]], c});
+    }
+  std::vector<ChunkWalk> walks(refs.size());
+  auto walk_chunk = [&](const ChunkRef& ref, ChunkWalk& w) {
+    const ChunkMeta& cm = *ref.cm;
+    const int c = ref.c;
+    if (cm.codec != CODEC_NONE && cm.codec != CODEC_SNAPPY) throw Error(B2_ERR_UNSUPPORTED, "parquet: codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED / SNAPPY)");
+    ChunkD& cd = w.cd; memset(&cd, 0, sizeof(cd));
+    cd.col = c; cd.phys = cm.type; cd.type_length = plans[c].type_length; cd.max_def = plans[c].max_def; cd.dict_page = -1;
+    int64_t pos = cm.data_page_offset;
+    if (cm.dict_page_offset > 0 && cm.dict_page_offset < pos) pos = cm.dict_page_offset;
+    const int64_t chunk_end = pos + cm.total_compressed;
+    if (cm.num_values == 0) return;  // empty row group
+    if (pos < 4 || chunk_end > len - 8) throw Error(B2_ERR_INVALID, "parquet: column chunk outside the buffer");
+    int64_t values_seen = 0;
+    while (pos < chunk_end && values_seen < cm.num_values) {
+      TReader r(host + pos, host + chunk_end);
+      int id, t, last = 0;
+      int ptype = -1, usize = 0, csize = 0, nvals = 0, enc = 0, v2_def_len = 0, v2_rep_len = 0, v2_compressed = 1;
+      while (r.field(id, t, last)) {
+        if (id == 1) ptype = (int)r.zigzag();
+        else if (id == 2) usize = (int)r.zigzag();
+        else if (id == 3) csize = (int)r.zigzag();
+        else if ((id == 5 || id == 7 || id == 8) && t == 12) {
+          int id2, t2, last2 = 0;
+          while (r.field(id2, t2, last2)) {
+            if (id2 == 1) nvals = (int)r.zigzag();
+            else if (id == 5 && id2 == 2) enc = (int)r.zigzag();
+            else if (id == 7 && id2 == 2) enc = (int)r.zigzag();
+            else if (id == 8 && id2 == 4) enc = (int)r.zigzag();
+            else if (id == 8 && id2 == 5) v2_def_len = (int)r.zigzag();
+            else if (id == 8 && id2 == 6) v2_rep_len = (int)r.zigzag();
+            else if (id == 8 && id2 == 7) v2_compressed = (t2 == 1);
+            else r.skip(t2);
+          }
+        } else r.skip(t);
+      }
+      const int64_t payload = r.p - host;
+      if (payload + csize > chunk_end) throw Error(B2_ERR_INVALID, "parquet: page runs past its chunk");
+      if (ptype == PG_INDEX) { pos = payload + csize; continue; }
+      PageD pg; memset(&pg, 0, sizeof(pg));
+      pg.src_off = payload; pg.comp_size = csize; pg.uncomp_size = usize; pg.num_values = nvals; pg.encoding = enc; pg.kind = ptype;
+      pg.lvl_bytes = ptype == PG_DATA_V2 ? v2_def_len + v2_rep_len : 0;
+      pg.compressed = cm.codec == CODEC_SNAPPY && (ptype != PG_DATA_V2 || v2_compressed);
+      if (ptype == PG_DATA_V2 && v2_rep_len) throw Error(B2_ERR_UNSUPPORTED, "parquet: repetition levels");
+      if (pg.compressed) { pg.dst_off = w.scratch; w.scratch += ((int64_t)usize + 15) & ~15LL; }
+      else pg.dst_off = -1;
+      if (ptype == PG_DICT) {
+        if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT) throw Error(B2_ERR_UNSUPPORTED, "parquet: dictionary page encoding " + std::to_string(enc));
+        cd.dict_page = (int)w.pages.size(); cd.dict_count = nvals;
+        if (cm.type == PT_BYTE_ARRAY) w.dict_strs += nvals;
+      } else if (ptype == PG_DATA || ptype == PG_DATA_V2) {
+        if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT && enc != ENC_RLE_DICT && !(enc == ENC_RLE && cm.type == PT_BOOLEAN))
+          throw Error(B2_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(enc) + " (DELTA_* / BYTE_STREAM_SPLIT are not supported)");
+        pg.row_start = w.rows;
+        w.rows += nvals; values_seen += nvals;
+      } else throw Error(B2_ERR_INVALID, "parquet: unknown page type");
+      w.pages.push_back(pg);
+      pos = payload + csize;
+    }
+  };
+  {
+    int64_t walk_bytes = 0;
+    for (auto& ref : refs) walk_bytes += ref.cm->total_compressed;
+    const int nthreads = (refs.size() >= 4 && walk_bytes >= (8 << 20)) ? (int)std::min<size_t>({8, refs.size(), std::max(1u, std::thread::hardware_concurrency())}) : 1;
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      for (size_t i = next.fetch_add(1); i < refs.size(); i = next.fetch_add(1)) {
+        try { walk_chunk(refs[i], walks[i]); }
+        catch (const Error& e) { walks[i].err = e.code; walks[i].msg = e.what(); }
+        catch (const std::exception& e) { walks[i].err = B2_ERR_INVALID; walks[i].msg = e.what(); }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+  }
   std::vector<PageD> pages;
   std::vector<ChunkD> chunks;
   std::vector<int64_t> col_rows(ncols, 0);
   int64_t scratch_bytes = 0, dict_str_total = 0;
-  for (auto& rg : fm.row_groups) {
-    for (int c = 0; c < ncols; c++) {
-      if (leaf_of_col[c] >= (int)rg.chunks.size()) throw Error(B2_ERR_INVALID, "parquet: row group lacks a column chunk");
-      const ChunkMeta& cm = rg.chunks[leaf_of_col[c]];
-      if (cm.codec != CODEC_NONE && cm.codec != CODEC_SNAPPY) throw Error(B2_ERR_UNSUPPORTED, "parquet: codec " + std::to_string(cm.codec) + " (only UNCOMPRESSED / SNAPPY)");
-      ChunkD cd; memset(&cd, 0, sizeof(cd));
-      cd.col = c; cd.phys = cm.type; cd.type_length = plans[c].type_length; cd.max_def = plans[c].max_def; cd.dict_page = -1;
-      cd.dict_str_off = dict_str_total;
-      const int chunk_idx = (int)chunks.size();
-      int64_t pos = cm.data_page_offset;
-      if (cm.dict_page_offset > 0 && cm.dict_page_offset < pos) pos = cm.dict_page_offset;
-      const int64_t chunk_end = pos + cm.total_compressed;
-      if (cm.num_values == 0) { chunks.push_back(cd); continue; }  // empty row group
-      if (pos < 4 || chunk_end > len - 8) throw Error(B2_ERR_INVALID, "parquet: column chunk outside the buffer");
-      int64_t values_seen = 0;
-      while (pos < chunk_end && values_seen < cm.num_values) {
-        TReader r(host + pos, host + chunk_end);
-        int id, t, last = 0;
-        int ptype = -1, usize = 0, csize = 0, nvals = 0, enc = 0, v2_def_len = 0, v2_rep_len = 0, v2_compressed = 1;
-        while (r.field(id, t, last)) {
-          if (id == 1) ptype = (int)r.zigzag();
-          else if (id == 2) usize = (int)r.zigzag();
-          else if (id == 3) csize = (int)r.zigzag();
-          else if ((id == 5 || id == 7 || id == 8) && t == 12) {
-            int id2, t2, last2 = 0;
-            while (r.field(id2, t2, last2)) {
-              if (id2 == 1) nvals = (int)r.zigzag();
-              else if (id == 5 && id2 == 2) enc = (int)r.zigzag();
-              else if (id == 7 && id2 == 2) enc = (int)r.zigzag();
-              else if (id == 8 && id2 == 4) enc = (int)r.zigzag();
-              else if (id == 8 && id2 == 5) v2_def_len = (int)r.zigzag();
-              else if (id == 8 && id2 == 6) v2_rep_len = (int)r.zigzag();
-              else if (id == 8 && id2 == 7) v2_compressed = (t2 == 1);
-              else r.skip(t2);
-            }
-          } else r.skip(t);
-        }
-        const int64_t payload = r.p - host;
-        if (payload + csize > chunk_end) throw Error(B2_ERR_INVALID, "parquet: page runs past its chunk");
-        if (ptype == PG_INDEX) { pos = payload + csize; continue; }
-        PageD pg; memset(&pg, 0, sizeof(pg));
-        pg.src_off = payload; pg.comp_size = csize; pg.uncomp_size = usize; pg.num_values = nvals; pg.encoding = enc; pg.kind = ptype; pg.chunk = chunk_idx;
-        pg.lvl_bytes = ptype == PG_DATA_V2 ? v2_def_len + v2_rep_len : 0;
-        pg.compressed = cm.codec == CODEC_SNAPPY && (ptype != PG_DATA_V2 || v2_compressed);
-        if (ptype == PG_DATA_V2 && v2_rep_len) throw Error(B2_ERR_UNSUPPORTED, "parquet: repetition levels");
-        if (pg.compressed) { pg.dst_off = scratch_bytes; scratch_bytes += ((int64_t)usize + 15) & ~15LL; }
-        else pg.dst_off = -1;
-        if (ptype == PG_DICT) {
-          if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT) throw Error(B2_ERR_UNSUPPORTED, "parquet: dictionary page encoding " + std::to_string(enc));
-          cd.dict_page = (int)pages.size(); cd.dict_count = nvals;
-          if (cm.type == PT_BYTE_ARRAY) dict_str_total += nvals;
-        } else if (ptype == PG_DATA || ptype == PG_DATA_V2) {
-          if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT && enc != ENC_RLE_DICT && !(enc == ENC_RLE && cm.type == PT_BOOLEAN))
-            throw Error(B2_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(enc) + " (DELTA_* / BYTE_STREAM_SPLIT are not supported)");
-          pg.row_start = col_rows[c];
-          col_rows[c] += nvals; values_seen += nvals;
-        } else throw Error(B2_ERR_INVALID, "parquet: unknown page type");
-        pages.push_back(pg);
-        pos = payload + csize;
-      }
-      chunks.push_back(cd);
+  for (size_t i = 0; i < walks.size(); i++) {
+    ChunkWalk& w = walks[i];
+    if (w.err) throw Error(w.err, w.msg);   // first failing chunk in file order, as a serial walk would report
+    const int c = refs[i].c;
+    const int chunk_idx = (int)chunks.size();
+    w.cd.dict_str_off = dict_str_total;
+    if (w.cd.dict_page >= 0) w.cd.dict_page += (int)pages.size();
+    for (PageD& pg : w.pages) {
+      pg.chunk = chunk_idx;
+      if (pg.compressed) pg.dst_off += scratch_bytes;
+      if (pg.kind == PG_DATA || pg.kind == PG_DATA_V2) pg.row_start += col_rows[c];
+      pages.push_back(pg);
     }
+    scratch_bytes += w.scratch; dict_str_total += w.dict_strs; col_rows[c] += w.rows;
+    chunks.push_back(w.cd);
   }
   for (int c = 0; c < ncols; c++)
     if (col_rows[c] != total_rows) throw Error(B2_ERR_INVALID, "parquet: page row counts disagree with the footer");

@@ -46,7 +46,8 @@ enum VOP : uint8_t {
   V_DEC2F64,     // decimal (mt) -> double, / 10^aux
   V_NORM_NAN_ZERO,
   V_YEAR,
-  V_MOV
+  V_MOV,
+  V_ANDCMP      // c AND (a <cmp> b), all operands non-null: aux = 3-bit truth mask over sign(a ? b) = {<, ==, >}
 };
 
 struct alignas(16) VMOperand {
@@ -385,6 +386,42 @@ __device__ __noinline__ void vm_compare(const TileInfo ti, const RInstr& ins) {
   });
 }
 
+// fused conjunct: dst = acc AND (x <cmp> y).  The compiler emits it only when nothing can be NULL, so a WHERE
+// chain of n comparisons costs n register passes instead of 2n - 1.
+template <typename T>
+__device__ __noinline__ void vm_andcmp(const TileInfo ti, const RInstr& ins) {
+  const Opnd a = ropnd(ins.a, ti), b = ropnd(ins.b, ti), c = ropnd(ins.c, ti);
+  const uint32_t m = (uint32_t)ins.aux;
+  char* const dbase = ins.dbase;
+  auto f = [m](T x, T y, int8_t acc) -> int8_t { return (int8_t)(acc && ((m >> (cmp3<T>(x, y) + 1)) & 1u)); };
+  if (a.stride != 0 && c.stride != 0 && vm_full_tile(ti, ti.tile_rows)) {
+    const char* pa = thread_base<T>(a);
+    const char* pc = thread_base<int8_t>(c);
+    char* pd = dbase + threadIdx.x;
+    if (b.stride == 0) {
+      const T y = *reinterpret_cast<const T*>(b.base);
+      for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pc += 4 * VM_NT, pd += 4 * VM_NT) {
+        const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
+                x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
+        const int8_t c0 = *reinterpret_cast<const int8_t*>(pc), c1 = *reinterpret_cast<const int8_t*>(pc + VM_NT),
+                     c2 = *reinterpret_cast<const int8_t*>(pc + 2 * VM_NT), c3 = *reinterpret_cast<const int8_t*>(pc + 3 * VM_NT);
+        pd[0] = f(x0, y, c0); pd[VM_NT] = f(x1, y, c1); pd[2 * VM_NT] = f(x2, y, c2); pd[3 * VM_NT] = f(x3, y, c3);
+      }
+      for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pc += VM_NT, pd += VM_NT)
+        pd[0] = f(*reinterpret_cast<const T*>(pa), y, *reinterpret_cast<const int8_t*>(pc));
+    } else {
+      const char* pb = thread_base<T>(b);
+      for (int j = 0; j < ti.K; j++, pa += VM_NT * sizeof(T), pb += VM_NT * sizeof(T), pc += VM_NT, pd += VM_NT)
+        pd[0] = f(*reinterpret_cast<const T*>(pa), *reinterpret_cast<const T*>(pb), *reinterpret_cast<const int8_t*>(pc));
+    }
+    return;
+  }
+  for (int j = 0; j < ti.K; j++) {   // a row is read before it is written and rows are thread private
+    VM_ROW_ACTIVE(j, i, g);
+    if (act) dbase[i] = f(opnd_ld<T>(a, i), opnd_ld<T>(b, i), opnd_ld<int8_t>(c, i));
+  }
+}
+
 template <int OP>
 __device__ __noinline__ void vm_logic(const TileInfo ti, const RInstr& ins) {
   if constexpr (OP == V_NOT) {
@@ -699,6 +736,7 @@ static __device__ __noinline__ void vm_run(const TileInfo ti, const RInstr* __re
         break;
       case V_NORM_NAN_ZERO: if (ins.mt == MT_F32) vm_normnz<float>(ti, ins); else vm_normnz<double>(ti, ins); break;
       case V_YEAR: vm_year(ti, ins); break;
+      case V_ANDCMP: VM_TYPES_ALL(vm_andcmp) break;
       default: break;
     }
   }
@@ -741,6 +779,7 @@ static __device__ __forceinline__ const RInstr* vm_load_program(VMShared& sh, co
       int width = mt_width(g.mt);
       if (g.op == V_AND || g.op == V_OR || g.op == V_NOT || (g.op == V_IF && j == 0)) width = 1;
       if (g.op == V_MULDEC && j == 1) width = mt_width(g.mt2);
+      if (g.op == V_ANDCMP && j == 2) width = 1;   // the accumulated predicate
       if (o.kind == OK_REG) {
         q.base = regs + (size_t)sh.hdr.regs[o.idx].off * tile_rows; q.stride = width;
         q.vkind = o.nullable ? 1 : 0; q.vptr = regs + (size_t)sh.hdr.regs[o.idx].voff * tile_rows;
