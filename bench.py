@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--rows", type=int, default=SF10_ROWS, help="lineitem rows per GPU (default: SF10)")
@@ -135,6 +135,10 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: anything a library prints (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch  # plumbing only: rendezvous, barrier, max-over-ranks
     import torch.distributed as dist
@@ -250,8 +254,17 @@ def main():
         kernels.append(ent)
     kernels.sort(key=lambda e: -e["share"])
     dom = kernels[0] if kernels else {"name": None, "alg_GBps": 0.0}
+    # DRAM traffic of the dominant kernel: one `ncu --set full` capture of this very workload, committed under profiles/
+    traffic = None
+    try:
+        if rows == SF10_ROWS:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_sf10_traffic.json")))[dom["name"]]["traffic_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom.get("alg_GBps", 0.0), "peak": peak, "unit": "GB/s",
-            "frac": dom.get("alg_GBps", 0.0) / peak, "traffic": None, "peak_source": peak_src,
+            "frac": dom.get("alg_GBps", 0.0) / peak, "traffic": traffic, "algorithmic_bytes": alg.get(dom["name"]),
+            "traffic_source": "profiles/r1_ncu_sf10_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)" if traffic else None,
+            "peak_source": peak_src,
             "note": "dominant kernel by CUDA-event share of the step; per-kernel list in `kernels`"}
     line = {"metric": "tpch_q6_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "query_sec": ms / args.steps / 1000, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -272,7 +285,10 @@ def main():
         assert cres == res or world > 1, ("CPU restatement disagrees with the GPU result", cres, res)
         line["cpu_baseline"] = {"value": rows / dt, "unit": "rows/s", "cores": cores, "kind": "port",
                                 "sample": "one full %d-row partition, %d reps; pyarrow scan+compute on %d threads (CPU restatement, NOT Spark)" % (rows, reps, cores)}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if comm:
         comm.close()
     if world > 1:
