@@ -229,14 +229,29 @@ struct SnappyWarp {
   uint8_t out[SN_OUT];
 };
 
-__device__ __forceinline__ void sn_refill(SnappyWarp& w, const uint8_t* __restrict__ src, uint32_t in_len, uint32_t& loaded, uint32_t ip, int lane) {
-  while (loaded < in_len && loaded - ip <= SN_IN - 512) {
-    const uint32_t n = min(512u, in_len - loaded);
-    for (uint32_t k = lane; k < n; k += 32) w.in[(loaded + k) & (SN_IN - 1)] = src[loaded + k];
-    loaded += n;
+// Input positions are counted from the 16-byte aligned address at or below the page's first byte (the caller
+// starts ip at that misalignment), so a refill is one 16-byte load + one 16-byte shared store per lane.
+// Reads up to 15 bytes outside [in, in + len): inside the file buffer (>= 16 bytes in front: "PAR1" + the first
+// page header; >= 16 bytes of slack behind, see b2_parquet_decode_device).
+__device__ __forceinline__ void sn_refill(SnappyWarp& w, const uint8_t* __restrict__ src_al, uint32_t in_len, uint32_t& loaded, uint32_t ip, int lane) {
+  while (loaded < in_len && loaded <= ip + (SN_IN - 512)) {   // (ip starts at the misalignment, above loaded == 0)
+    const uint32_t pos = loaded + lane * 16;
+    if (pos < in_len) *reinterpret_cast<uint4*>(&w.in[pos & (SN_IN - 1)]) = *reinterpret_cast<const uint4*>(src_al + pos);
+    loaded = min(loaded + 512u, in_len);
   }
   __syncwarp();
 }
+
+// byte copy between two non-overlapping ranges that do not wrap: loads of a group are issued before its stores
+__device__ __forceinline__ void sn_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t len) {
+  uint32_t k = 0;
+  for (; k + 4 <= len; k += 4) {
+    const uint8_t a = s[k], b = s[k + 1], c = s[k + 2], e = s[k + 3];
+    d[k] = a; d[k + 1] = b; d[k + 2] = c; d[k + 3] = e;
+  }
+  for (; k < len; k++) d[k] = s[k];
+}
+__device__ __forceinline__ bool sn_nowrap(uint32_t p, uint32_t len, uint32_t size) { return (p & (size - 1)) + len <= size; }
 
 // write ring bytes [flushed, target) to HBM: byte head up to 16-byte alignment, 512-byte slabs of
 // 16-byte stores, and (when `all`) a byte tail
@@ -283,7 +298,9 @@ __global__ void __launch_bounds__(SN_WARPS * 32) snappy_kernel(const PageD* __re
     in += lvl; out += lvl; in_len -= lvl; out_len -= lvl;
   }
   uint8_t* dst = out;
-  uint32_t ip = 0, op = 0, loaded = 0, flushed = 0;
+  const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15);
+  in -= a0; in_len += a0;                 // positions are relative to the aligned address from here on
+  uint32_t ip = a0, op = 0, loaded = 0, flushed = 0;
   sn_refill(w, in, in_len, loaded, ip, lane);
   uint32_t ulen = 0;
   { int shift = 0; while (ip < in_len) { const uint8_t b = w.in[ip & (SN_IN - 1)]; ip++; ulen |= (uint32_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; } }
@@ -341,10 +358,26 @@ __global__ void __launch_bounds__(SN_WARPS * 32) snappy_kernel(const PageD* __re
     //          anything older than SN_HIST is already flushed because < 1 KB is ever pending here)
     const bool indep = mine && !is_lit && (opos - off + len <= op);
     if (mine && is_lit && !is_long) {
-      for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = w.in[(q + hdr + k) & (SN_IN - 1)];
+      if (sn_nowrap(opos, len, SN_OUT) && sn_nowrap(q + hdr, len, SN_IN)) sn_copy(&w.out[opos & (SN_OUT - 1)], &w.in[(q + hdr) & (SN_IN - 1)], len);
+      else for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = w.in[(q + hdr + k) & (SN_IN - 1)];
     } else if (indep) {
-      if (off <= SN_HIST) { for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = w.out[(opos - off + k) & (SN_OUT - 1)]; }
-      else { const uint8_t* src = dst + opos - off; for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = src[k]; }
+      if (off <= SN_HIST) {
+        if (sn_nowrap(opos, len, SN_OUT) && sn_nowrap(opos - off, len, SN_OUT)) sn_copy(&w.out[opos & (SN_OUT - 1)], &w.out[(opos - off) & (SN_OUT - 1)], len);
+        else for (uint32_t k = 0; k < len; k++) w.out[(opos + k) & (SN_OUT - 1)] = w.out[(opos - off + k) & (SN_OUT - 1)];
+      } else {
+        // far back-reference: the bytes are in HBM (flushed by this warp).  Two aligned 8-byte loads cover 8 source
+        // bytes at any alignment: 4x fewer L1 transactions than byte loads, and both loads are in flight together.
+        const uint8_t* src = dst + opos - off;
+        for (uint32_t k = 0; k < len; k += 8) {
+          const uintptr_t ad = reinterpret_cast<uintptr_t>(src + k);
+          const uint64_t* al = reinterpret_cast<const uint64_t*>(ad & ~uintptr_t(7));
+          const uint32_t sh = (uint32_t)(ad & 7) * 8;
+          const uint64_t w0 = al[0], w1 = al[1];
+          const uint64_t v = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+          const uint32_t n = min(8u, len - k);
+          for (uint32_t b = 0; b < n; b++) w.out[(opos + k + b) & (SN_OUT - 1)] = (uint8_t)(v >> (8 * b));
+        }
+      }
     }
     __syncwarp();
     // ---- 4b. back-references into this window's output, replayed in stream order
