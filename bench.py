@@ -86,7 +86,7 @@ class ClockSampler:
 def build_q6(m):
     c_ship = m.col(0, m.DATE32, nullable=False)
     c_disc, c_qty, c_price = (m.col(i, m.DECIMAL64, 12, 2, nullable=False) for i in (1, 2, 3))
-    from oracle import tpch
+    from benchdata import tpch
     pred = ((c_ship >= m.lit(tpch.Q6_DATE_LO, m.DATE32)) & (c_ship < m.lit(tpch.Q6_DATE_HI, m.DATE32)) & (c_disc >= m.lit(5, m.DECIMAL64, 3, 2))
             & (c_disc <= m.lit(7, m.DECIMAL64, 3, 2)) & (c_qty < m.lit(2400, m.DECIMAL64, 12, 2)))
     rev = c_price * c_disc
@@ -97,9 +97,10 @@ def run_reference(args, rank, world):
     """CPU arm: rank 0 only."""
     if rank != 0:
         return
-    from oracle import tpch
+    from benchdata import tpch as gen
+    from oracle import tpch          # the CPU arm IS the restatement (no JVM/Spark on the box)
     rows = args.rows
-    raw = tpch.lineitem_q6_parquet(rows, 42, CACHE)
+    raw = gen.lineitem_q6_parquet(rows, 42, CACHE)
     cores = os.cpu_count() or 1
     # bounded sample per step: the whole partition if it is small enough, else its first row groups
     sample_rows = rows
@@ -146,7 +147,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import spark_rapids_b200 as m
-    from oracle import tpch
+    from benchdata import tpch       # synthetic inputs only; oracle/ is touched by the cpu_baseline leg alone
     m.init(local, 8 << 30)   # Rmm.initialize analogue: pre-grown stream-ordered pool
 
     rows = args.rows
@@ -214,10 +215,6 @@ def main():
 
     for _ in range(args.warmup):
         res_w = step(True)
-    # correctness: exact integer restatement of the same partition (rank-local)
-    expect = tpch.q6_numpy_chunks(tpch.lineitem_q6_chunks(rows, 42 + rank)) if rows <= SF10_ROWS else None
-    if world == 1 and expect is not None:
-        assert res_w == expect, ("q6 result mismatch", res_w, expect)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -275,14 +272,19 @@ def main():
             "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": int(nbytes) * world, "d2h_bytes_per_step": 16 * world,
                     "ms_per_step": ms_e2e / args.steps},
             "parquet_stats": st, "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps, "clocks": clocks, "roofline": roof, "kernels": kernels[:8]}
+    assert res_w == res and (world > 1 or res_e2e == res), ("q6 result differs between steps", res_w, res, res_e2e)
     if args.cpu_baseline and world >= 1:
+        from oracle import tpch as cpu   # checker + reported baseline: the only use of oracle/ in this arm
         cores = os.cpu_count() or 1
-        tpch.q6_cpu(raw, cores)
+        cpu.q6_cpu(raw, cores)
         t0 = time.perf_counter(); reps = 2
         for _ in range(reps):
-            cres = tpch.q6_cpu(raw, cores)
+            cres = cpu.q6_cpu(raw, cores)
         dt = (time.perf_counter() - t0) / reps
         assert cres == res or world > 1, ("CPU restatement disagrees with the GPU result", cres, res)
+        if world == 1 and rows <= SF10_ROWS:   # exact integer restatement over the raw columns pins both
+            expect = cpu.q6_numpy_chunks(tpch.lineitem_q6_chunks(rows, 42 + rank))
+            assert res == expect, ("q6 result mismatch", res, expect)
         line["cpu_baseline"] = {"value": rows / dt, "unit": "rows/s", "cores": cores, "kind": "port",
                                 "sample": "one full %d-row partition, %d reps; pyarrow scan+compute on %d threads (CPU restatement, NOT Spark)" % (rows, reps, cores)}
     sys.stdout.flush()

@@ -4,7 +4,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 sys.path.insert(0, ".")
 import spark_rapids_b200 as m
-from oracle import tpch
+from benchdata import tpch
 import bench
 m.init(0, 12 << 30)
 rows = 59_986_052

@@ -2,7 +2,7 @@ import sys, time
 import numpy as np
 sys.path.insert(0, ".")
 import spark_rapids_b200 as m
-from oracle import tpch
+from benchdata import tpch
 import bench
 m.init(0, 8 << 30)
 rows = 59_986_052
