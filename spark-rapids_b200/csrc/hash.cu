@@ -105,10 +105,131 @@ __global__ void part_hist_kernel(const int32_t* __restrict__ pids, int64_t n, in
 int radix_sort_pairs(uint64_t* keys_a, int32_t* vals_a, uint64_t* keys_b, int32_t* vals_b, int64_t n, int nbytes);
 Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullify_oob, const std::vector<int>* only_cols);
 
+// ---- direct stable partition (<= 1024 partitions) -------------------------------------------------------------
+// Two passes over the partition ids and ONE over the payload: per-tile histogram -> exclusive scan of the
+// partition-major [partition][tile] counts -> every tile recomputes stable ranks (warp match_any + per-warp counts in
+// shared memory, 256 rows at a time in row order) and writes each fixed-width NOT NULL column straight to its final
+// place.  Reads are coalesced, writes are coalesced per run of equal ids.  Other columns (strings, nullable) go
+// through the gather map the same kernel can emit.  Replaces id->key expansion + radix pass + random-read gather.
+constexpr int PT_NT = 256, PT_STEPS = 16, PT_TILE = PT_NT * PT_STEPS, PT_MAXP = 1024, PT_MAXC = 8;
+struct ScatterCols {
+  int32_t n;
+  int32_t width[PT_MAXC];
+  const void* in[PT_MAXC];
+  void* out[PT_MAXC];
+};
+
+__global__ void __launch_bounds__(PT_NT) part_tile_hist_kernel(const int32_t* __restrict__ pids, int64_t n, int32_t nparts, int64_t ntiles,
+                                                               int32_t* __restrict__ tile_cnt) {
+  __shared__ int32_t h[PT_MAXP];
+  for (int p = threadIdx.x; p < nparts; p += PT_NT) h[p] = 0;
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  for (int j = 0; j < PT_STEPS; j++) {
+    const int64_t i = tile * PT_TILE + (int64_t)j * PT_NT + threadIdx.x;
+    if (i < n) { const int32_t p = pids[i]; if ((uint32_t)p < (uint32_t)nparts) atomicAdd(&h[p], 1); }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < nparts; p += PT_NT) tile_cnt[(int64_t)p * ntiles + tile] = h[p];
+}
+
+__global__ void __launch_bounds__(PT_NT) part_scatter_kernel(const int32_t* __restrict__ pids, int64_t n, int32_t nparts, int64_t ntiles,
+                                                             const int32_t* __restrict__ base, const __grid_constant__ ScatterCols sc,
+                                                             int32_t* __restrict__ map_out) {
+  __shared__ int32_t run[PT_MAXP];              // next free output row of partition p for this tile
+  __shared__ uint16_t wcnt[PT_NT / 32][PT_MAXP];  // rows of partition p per warp in the current 256-row step
+  const int64_t tile = blockIdx.x;
+  for (int p = threadIdx.x; p < nparts; p += PT_NT) {
+    run[p] = base[(int64_t)p * ntiles + tile];
+    for (int w = 0; w < PT_NT / 32; w++) wcnt[w][p] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int j = 0; j < PT_STEPS; j++) {
+    const int64_t i = tile * PT_TILE + (int64_t)j * PT_NT + threadIdx.x;
+    int32_t p = -1;
+    if (i < n) { p = pids[i]; if ((uint32_t)p >= (uint32_t)nparts) p = -1; }
+    const uint32_t mask = __match_any_sync(0xffffffffu, p);
+    const int rank = __popc(mask & ((1u << lane) - 1u));
+    const int cnt = __popc(mask);
+    if (p >= 0 && rank == 0) wcnt[w][p] = (uint16_t)cnt;
+    __syncthreads();
+    int32_t dest = 0;
+    if (p >= 0) {
+      int pre = 0;
+      for (int w2 = 0; w2 < w; w2++) pre += wcnt[w2][p];
+      dest = run[p] + pre + rank;
+    }
+    __syncthreads();
+    if (p >= 0 && rank == 0) { atomicAdd(&run[p], cnt); wcnt[w][p] = 0; }
+    if (p >= 0) {
+      for (int c = 0; c < sc.n; c++) {
+        switch (sc.width[c]) {
+          case 1: reinterpret_cast<uint8_t*>(sc.out[c])[dest] = reinterpret_cast<const uint8_t*>(sc.in[c])[i]; break;
+          case 2: reinterpret_cast<uint16_t*>(sc.out[c])[dest] = reinterpret_cast<const uint16_t*>(sc.in[c])[i]; break;
+          case 4: reinterpret_cast<uint32_t*>(sc.out[c])[dest] = reinterpret_cast<const uint32_t*>(sc.in[c])[i]; break;
+          case 8: reinterpret_cast<uint64_t*>(sc.out[c])[dest] = reinterpret_cast<const uint64_t*>(sc.in[c])[i]; break;
+          default: reinterpret_cast<uint4*>(sc.out[c])[dest] = reinterpret_cast<const uint4*>(sc.in[c])[i]; break;
+        }
+      }
+      if (map_out) map_out[dest] = (int32_t)i;
+    }
+    __syncthreads();
+  }
+}
+
+static Table* partition_table_direct(const Table* t, const int32_t* d_pids, int32_t nparts, int32_t* offsets_out) {
+  const int64_t n = t->rows;
+  const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
+  const int64_t cells = (int64_t)nparts * ntiles;
+  DevBuf cnt((size_t)(cells + 1) * 4);
+  {
+    KernelTimer kt("part_tile_hist_kernel");
+    part_tile_hist_kernel<<<(int)ntiles, PT_NT, 0, stream()>>>(d_pids, n, nparts, ntiles, cnt.as<int32_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  DevBuf sums = exclusive_scan<int32_t, int32_t>(cnt.as<int32_t>(), cnt.as<int32_t>(), cells, true);
+  std::vector<int32_t> h(nparts + 1, 0);
+  CUDA_CHECK(cudaMemcpy2DAsync(h.data(), 4, cnt.p, (size_t)ntiles * 4, 4, (size_t)nparts, cudaMemcpyDeviceToHost, stream()));
+  d2h(&h[nparts], cnt.as<int32_t>() + cells, 1);
+  // outputs: fixed-width NOT NULL columns are written by the scatter kernel itself, the rest through the gather map
+  ColsGuard outs;
+  outs.v.resize(t->cols.size(), nullptr);
+  ScatterCols sc; memset(&sc, 0, sizeof(sc));
+  std::vector<int> via_map;
+  for (size_t c = 0; c < t->cols.size(); c++) {
+    const Column* ic = t->cols[c];
+    if (ic->dtype != B2_STRING && !ic->nullable() && sc.n < PT_MAXC) {
+      Column* oc = new_column(ic->dtype, ic->scale, n, false);
+      outs.v[c] = oc;
+      sc.width[sc.n] = dtype_width(ic->dtype); sc.in[sc.n] = ic->data.p; sc.out[sc.n] = oc->data.p; sc.n++;
+    } else via_map.push_back((int)c);
+  }
+  DevBuf map;
+  if (!via_map.empty()) map = DevBuf((size_t)n * 4);
+  {
+    KernelTimer kt("part_scatter_kernel");
+    part_scatter_kernel<<<(int)ntiles, PT_NT, 0, stream()>>>(d_pids, n, nparts, ntiles, cnt.as<int32_t>(), sc, map.as<int32_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  sync();
+  if (h[nparts] != n) throw Error(B2_ERR_INVALID, "partition ids out of range");
+  for (int p = 0; p <= nparts; p++) offsets_out[p] = h[p];
+  if (!via_map.empty()) {
+    Table* g = gather_table(t, map.as<int32_t>(), n, false, &via_map);
+    for (size_t k = 0; k < via_map.size(); k++) { outs.v[via_map[k]] = g->cols[k]; col_incref(g->cols[k]); }
+    table_release(g);
+  }
+  return new_table(outs.release());
+}
+
 // Table.partition: stable reorder so each partition is contiguous + partition start offsets
 Table* partition_table(const Table* t, const int32_t* d_pids, int32_t nparts, int32_t* offsets_out) {
   const int64_t n = t->rows;
   B2_CHECK(nparts >= 1, "need at least one partition");
+  if (nparts <= PT_MAXP && n >= PT_TILE) return partition_table_direct(t, d_pids, nparts, offsets_out);
   DevBuf counts((size_t)nparts * 4);
   CUDA_CHECK(cudaMemsetAsync(counts.p, 0, counts.bytes, stream()));
   std::vector<int32_t> h(nparts, 0);
