@@ -342,6 +342,29 @@ static Table* filter_impl(const Program* prog, const Table* pred_table, const Ta
 
 }  // namespace b2
 
+namespace b2 {
+// Table.filter(mask): order-preserving compaction of every column by a BOOL8 mask (NULL = drop)
+Table* filter_by_mask(const Table* t, Column* m) {
+  B2_CHECK(m->dtype == B2_BOOL8, "filter mask must be BOOL8");
+  B2_CHECK(m->size == t->rows, "mask length differs from the table");
+  // a zero-instruction program whose single output is input column 0 (the mask)
+  Program prog; memset(&prog.hdr, 0, sizeof(prog.hdr));
+  prog.hdr.nouts = 1; prog.hdr.ncols = 1;
+  prog.hdr.outs[0].kind = OK_COL; prog.hdr.outs[0].idx = 0; prog.hdr.outs[0].nullable = 1;
+  prog.hdr.out_mt[0] = MT_I8;
+  set_tile_geometry(prog.hdr, 0);
+  prog.col_dtype = {B2_BOOL8};
+  prog.out_dtype = {B2_BOOL8}; prog.out_scale = {0}; prog.out_precision = {0}; prog.out_nullable = {1};
+  prog.d_hdr = DevBuf(sizeof(VMProgramHeader));
+  h2d(prog.d_hdr.p, &prog.hdr, 1);
+  prog.d_code = DevBuf(sizeof(VMInstr));
+  Table mt; mt.cols = {m}; mt.rows = m->size;
+  struct Unhook { Table& t; ~Unhook() { t.cols.clear(); } } unhook{mt};  // mt does not own m
+  return filter_impl(&prog, &mt, t);
+}
+
+}  // namespace b2
+
 extern "C" {
 
 int b2_project(b2_handle program, b2_handle table, b2_handle* out_table) {
@@ -391,24 +414,7 @@ int b2_filter_count(b2_handle predicate_program, b2_handle table, int64_t* out_c
 
 int b2_filter_mask(b2_handle table, b2_handle bool_mask, b2_handle* out_table) {
   B2_TRY
-  Table* t = table_from(table);
-  Column* m = col_from(bool_mask);
-  B2_CHECK(m->dtype == B2_BOOL8, "filter mask must be BOOL8");
-  B2_CHECK(m->size == t->rows, "mask length differs from the table");
-  // a zero-instruction program whose single output is input column 0 (the mask)
-  Program prog; memset(&prog.hdr, 0, sizeof(prog.hdr));
-  prog.hdr.nouts = 1; prog.hdr.ncols = 1;
-  prog.hdr.outs[0].kind = OK_COL; prog.hdr.outs[0].idx = 0; prog.hdr.outs[0].nullable = 1;
-  prog.hdr.out_mt[0] = MT_I8;
-  set_tile_geometry(prog.hdr, 0);
-  prog.col_dtype = {B2_BOOL8};
-  prog.out_dtype = {B2_BOOL8}; prog.out_scale = {0}; prog.out_precision = {0}; prog.out_nullable = {1};
-  prog.d_hdr = DevBuf(sizeof(VMProgramHeader));
-  h2d(prog.d_hdr.p, &prog.hdr, 1);
-  prog.d_code = DevBuf(sizeof(VMInstr));
-  Table mt; mt.cols = {m}; mt.rows = m->size;
-  struct Unhook { Table& t; ~Unhook() { t.cols.clear(); } } unhook{mt};  // mt does not own m
-  *out_table = to_handle(filter_impl(&prog, &mt, t));
+  *out_table = to_handle(filter_by_mask(table_from(table), col_from(bool_mask)));
   B2_CATCH
 }
 

@@ -208,7 +208,7 @@ __device__ __forceinline__ uint32_t norm_byte(const SortCol& c, int64_t row, int
 __global__ void build_chunk_kernel(const __grid_constant__ SortPlan plan, const int32_t* __restrict__ perm, int64_t n, int chunk,
                                    uint64_t* __restrict__ keys) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = perm[i];
+    const int64_t row = perm ? perm[i] : i;
     uint64_t k = 0;
     const int b0 = chunk * 8;
     for (int ci = 0; ci < plan.ncols; ci++) {
@@ -313,6 +313,53 @@ __global__ void bounds_kernel(const __grid_constant__ SortPlan sorted, const __g
 
 Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullify_oob, const std::vector<int>* only_cols);
 Table* concat_tables(const std::vector<const Table*>& ts);
+Table* filter_by_mask(const Table* t, Column* m);
+
+__global__ void topn_mask_kernel(const uint64_t* __restrict__ keys, int64_t n, uint64_t thr, int8_t* __restrict__ mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mask[i] = keys[i] <= thr;
+}
+
+// Top-N without sorting the batch: radix-select on the most significant varying byte of the row key.  One histogram
+// pass over the leading 8 key bytes gives the smallest byte value b whose cumulative count reaches the limit; every
+// row of the answer has a key prefix <= b, so the batch is compacted (in input order: ties stay stable) to those
+// candidates and only they are sorted.  Returns nullptr when the prefix does not discriminate (caller sorts).
+static Table* top_n_select(const Table* t, const b2_order_by_arg* keys, int nkeys, int64_t limit) {
+  const int64_t n = t->rows;
+  if (n < (1 << 18) || limit <= 0 || limit > n / 16) return nullptr;
+  SortPlan plan = make_sort_plan(t, keys, nkeys);
+  DevBuf k0((size_t)n * 8);
+  build_chunk_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(plan, nullptr, n, 0, k0.as<uint64_t>());
+  DevBuf hist(8 * 256 * 8);
+  CUDA_CHECK(cudaMemsetAsync(hist.p, 0, hist.bytes, stream()));
+  hist8_kernel<<<grid_for(n, 256 * 8), 256, 0, stream()>>>(k0.as<uint64_t>(), n, 8, hist.as<unsigned long long>());
+  CUDA_CHECK(cudaGetLastError());
+  count_launch(2);
+  std::vector<unsigned long long> h(8 * 256);
+  d2h(h.data(), hist.p, h.size());
+  sync();
+  uint64_t thr = 0;
+  int64_t m = -1;
+  for (int d = 7; d >= 0 && m < 0; d--) {
+    int constant = -1;
+    for (int b = 0; b < 256; b++) if (h[d * 256 + b] == (unsigned long long)n) constant = b;
+    if (constant >= 0) { thr |= (uint64_t)constant << (8 * d); continue; }
+    int64_t cum = 0;
+    for (int b = 0; b < 256; b++) {
+      cum += (int64_t)h[d * 256 + b];
+      if (cum >= limit) { thr |= (uint64_t)b << (8 * d); if (d > 0) thr |= (1ull << (8 * d)) - 1; m = cum; break; }
+    }
+  }
+  if (m < 0 || m > n / 4) return nullptr;   // all leading bytes equal, or one value dominates: sort everything
+  ColGuard mask(new_column(B2_BOOL8, 0, n, false));
+  topn_mask_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(k0.as<uint64_t>(), n, thr, mask.c->data.as<int8_t>());
+  CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  std::unique_ptr<Table, void (*)(Table*)> sub(filter_by_mask(t, mask.c), table_release);
+  if (sub->rows < std::min<int64_t>(limit, n)) throw Error(B2_ERR_INVALID, "top-n selection lost rows");
+  DevBuf perm = sort_order(sub.get(), keys, nkeys);
+  return gather_table(sub.get(), perm.as<int32_t>(), std::min<int64_t>(limit, sub->rows), false, nullptr);
+}
+
 
 }  // namespace b2
 
@@ -339,9 +386,10 @@ int b2_order_by(b2_handle table, const b2_order_by_arg* keys, int32_t nkeys, b2_
 
 int b2_top_n(b2_handle table, const b2_order_by_arg* keys, int32_t nkeys, int64_t n, b2_handle* out_table) {
   B2_TRY
-  // GpuTopN (limit.scala:234-330): sort the batch and keep the first n rows
+  // GpuTopN (limit.scala:234-330): the first n rows of the sorted batch
   Table* t = table_from(table);
   B2_CHECK(n >= 0, "negative limit");
+  if (Table* sel = top_n_select(t, keys, nkeys, n)) { *out_table = to_handle(sel); return B2_OK; }
   DevBuf perm = sort_order(t, keys, nkeys);
   *out_table = to_handle(gather_table(t, perm.as<int32_t>(), std::min<int64_t>(n, t->rows), false, nullptr));
   B2_CATCH

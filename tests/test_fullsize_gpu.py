@@ -146,3 +146,42 @@ def test_join_full_size(b2, big):
     o = np.argsort(l, kind="stable")
     assert np.array_equal(l[o], np.nonzero(hit >= 0)[0])                # every matching probe row exactly once
     assert int(bval[r].sum()) == int(bval[hit[hit >= 0]].sum())
+
+
+@pytest.mark.parametrize("limit", [1, 10, 1000])
+def test_top_n_full_size(b2, big, limit):
+    """GpuTopN over 30 M rows takes the radix-select path (no full sort): same rows, same order as a stable
+    lexicographic sort (price desc, group asc, input order on ties)"""
+    key, val, grp, t = big
+    n = 30_000_000
+    sub = b2.slice_table(t, 0, n)
+    top = b2.top_n(sub, [(1, 0, 0), (2, 1, 1)], limit)
+    assert top.num_rows == limit
+    order = np.lexsort((np.arange(n), grp[:n], -val[:n]))[:limit]     # last key is the primary one
+    assert np.array_equal(top.column(0).to_numpy()[0], key[:n][order])
+    assert np.array_equal(top.column(1).to_numpy()[0], val[:n][order])
+    assert np.array_equal(top.column(2).to_numpy()[0], grp[:n][order])
+
+
+def test_top_n_select_with_nulls_ties_and_skew(b2):
+    """the selection must keep every tie of the threshold prefix, honour nulls_first / nulls_last and fall back to the
+    full sort when one value dominates"""
+    rng = np.random.default_rng(77)
+    n = 400_000
+    v = rng.integers(-1000, 1000, n).astype(np.int64)
+    valid = rng.random(n) > 0.01
+    f = rng.standard_normal(n)
+    col_v = b2.Column.from_numpy(v, valid=valid)
+    t = b2.Table.from_columns([col_v, b2.Column.from_numpy(f), b2.Column.from_numpy(np.arange(n, dtype=np.int32))])
+    big_first = np.where(valid, v, np.iinfo(np.int64).min)                 # asc, nulls first
+    exp = np.lexsort((np.arange(n), f, big_first))[:50]
+    got = b2.top_n(t, [(0, 1, 1), (1, 1, 1)], 50).column(2).to_numpy()[0]
+    assert np.array_equal(got, exp)
+    last = np.where(valid, -v, np.iinfo(np.int64).max)                     # desc, nulls last
+    exp = np.lexsort((np.arange(n), last))[:200]
+    got = b2.top_n(t, [(0, 0, 0)], 200).column(2).to_numpy()[0]
+    assert np.array_equal(got, exp)
+    skew = np.zeros(n, dtype=np.int64); skew[rng.integers(0, n, 20)] = -5   # one dominant value: prefix does not discriminate
+    t2 = b2.Table.from_columns([b2.Column.from_numpy(skew), b2.Column.from_numpy(np.arange(n, dtype=np.int32))])
+    exp = np.lexsort((np.arange(n), skew))[:100]
+    assert np.array_equal(b2.top_n(t2, [(0, 1, 1)], 100).column(1).to_numpy()[0], exp)
