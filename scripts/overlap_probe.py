@@ -31,4 +31,7 @@ def pipelined(n=6):
         r = m.scan_aggregate(prog, True, tb, [], spec).to_rows()
         cur.free()
 m.sync(); t0 = time.perf_counter(); pipelined(6); m.sync(); print("pipelined ms/step", (time.perf_counter() - t0) / 6 * 1e3)
+for name, fn in (("resident", lambda: [dec_only() for _ in range(6)]), ("pipelined", lambda: pipelined(6))):
+    m.sync(); m.profile_enable(True); fn(); m.sync(); rep = m.profile_report(); m.profile_enable(False)
+    print(name, {k["name"]: round(k["ms"] / 6, 3) for k in rep})
 t0 = time.perf_counter(); u = m.AsyncUpload(raw); t1 = time.perf_counter(); u.wait(); m.sync(); print("AsyncUpload call returns in ms", (t1 - t0) * 1e3); u.free()

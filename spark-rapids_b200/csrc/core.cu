@@ -161,6 +161,7 @@ void h2d_bytes(void* dst, const void* src, size_t bytes) {
   r.head = at + need;
   const int threads = 256;
   const int blocks = (int)std::min<size_t>(64, (bytes / 16 + threads - 1) / threads + 1);
+  KernelTimer kt_stage_pull("stage_pull_kernel");
   stage_pull_kernel<<<blocks, threads, 0, s>>>((char*)dst, r.dev + at, bytes);
   CUDA_CHECK(cudaGetLastError());
 }
