@@ -1019,6 +1019,22 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
       pg.lvl_bytes = ptype == PG_DATA_V2 ? v2_def_len + v2_rep_len : 0;
       pg.compressed = cm.codec == CODEC_SNAPPY && (ptype != PG_DATA_V2 || v2_compressed);
       if (ptype == PG_DATA_V2 && v2_rep_len) throw Error(B2_ERR_UNSUPPORTED, "parquet: repetition levels");
+      if (pg.compressed && pg.lvl_bytes == 0 && csize > usize && usize > 0) {
+        // Incompressible pages (bit-packed dictionary indexes, mostly) are stored by snappy as ONE literal: the
+        // page bytes sit verbatim in the file behind the length preamble and the literal header.  Read them in
+        // place instead of copying them through the decompressor.
+        const uint8_t* p = host + payload;
+        const uint8_t* pend = p + csize;
+        uint64_t ulen = 0; int shift = 0;
+        while (p < pend && shift < 35) { const uint8_t b = *p++; ulen |= (uint64_t)(b & 0x7f) << shift; if (!(b & 0x80)) break; shift += 7; }
+        if (ulen == (uint64_t)usize && p < pend && (*p & 3) == 0) {
+          uint64_t len = *p >> 2; int nb = 0;
+          if (len >= 60) { nb = (int)len - 59; len = 0; for (int k = 0; k < nb && p + 1 + k < pend; k++) len |= (uint64_t)p[1 + k] << (8 * k); }
+          len += 1;
+          const uint8_t* data = p + 1 + nb;
+          if (len == (uint64_t)usize && data + len == pend) { pg.compressed = 0; pg.src_off = data - host; pg.comp_size = usize; }
+        }
+      }
       if (pg.compressed) { pg.dst_off = w.scratch; w.scratch += ((int64_t)usize + 15) & ~15LL; }
       else pg.dst_off = -1;
       if (ptype == PG_DICT) {
@@ -1038,7 +1054,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   {
     int64_t walk_bytes = 0;
     for (auto& ref : refs) walk_bytes += ref.cm->total_compressed;
-    const int nthreads = (refs.size() >= 4 && walk_bytes >= (8 << 20)) ? (int)std::min<size_t>({8, refs.size(), std::max(1u, std::thread::hardware_concurrency())}) : 1;
+    const int nthreads = (refs.size() >= 4 && walk_bytes >= (8 << 20)) ? (int)std::min<size_t>({(size_t)(getenv("B2_PQ_WALK_THREADS") ? atoi(getenv("B2_PQ_WALK_THREADS")) : 8), refs.size(), std::max(1u, std::thread::hardware_concurrency())}) : 1;
     std::atomic<size_t> next{0};
     auto worker = [&]() {
       for (size_t i = next.fetch_add(1); i < refs.size(); i = next.fetch_add(1)) {
