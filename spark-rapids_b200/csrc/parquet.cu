@@ -63,7 +63,7 @@ struct TReader {
 };
 
 enum { PT_BOOLEAN = 0, PT_INT32 = 1, PT_INT64 = 2, PT_INT96 = 3, PT_FLOAT = 4, PT_DOUBLE = 5, PT_BYTE_ARRAY = 6, PT_FLBA = 7 };
-enum { ENC_PLAIN = 0, ENC_PLAIN_DICT = 2, ENC_RLE = 3, ENC_BIT_PACKED = 4, ENC_RLE_DICT = 8 };
+enum { ENC_PLAIN = 0, ENC_PLAIN_DICT = 2, ENC_RLE = 3, ENC_BIT_PACKED = 4, ENC_DELTA_BINARY = 5, ENC_RLE_DICT = 8 };
 enum { PG_DATA = 0, PG_INDEX = 1, PG_DICT = 2, PG_DATA_V2 = 3 };
 enum { CODEC_NONE = 0, CODEC_SNAPPY = 1 };
 
@@ -761,6 +761,94 @@ struct DictSink {
   }
 };
 
+// ---- DELTA_BINARY_PACKED (INT32 / INT64) ----------------------------------------------------------------------
+// header: block size, miniblocks per block, value count, first value (zigzag); then per block: min delta (zigzag),
+// one bit width per miniblock, the bit-packed miniblocks.  value[i] = value[i-1] + min_delta + delta[i], wrapping.
+// Block headers are varints, so one thread walks them — PQ_NT miniblocks at a time; then every thread sums its own
+// miniblock, an exclusive scan of the miniblock totals gives each thread its starting value, and the miniblocks
+// are expanded in parallel.
+__device__ __forceinline__ uint64_t dl_uleb(const uint8_t*& p, const uint8_t* end) {
+  uint64_t v = 0; int sh = 0;
+  while (p < end) { const uint8_t b = *p++; v |= (uint64_t)(b & 0x7f) << sh; if (!(b & 0x80)) break; sh += 7; if (sh > 63) break; }
+  return v;
+}
+__device__ __forceinline__ int64_t dl_zigzag(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
+__device__ __forceinline__ uint64_t extract_bits64(const uint8_t* data, uint64_t bitpos, int bw) {
+  if (bw == 0) return 0;
+  const uint8_t* a = data + (bitpos >> 3);
+  const uintptr_t base = reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)7;
+  const uint64_t w0 = *reinterpret_cast<const uint64_t*>(base), w1 = *reinterpret_cast<const uint64_t*>(base + 8);
+  const int sh = (int)((reinterpret_cast<uintptr_t>(a) & 7) * 8 + (bitpos & 7));
+  uint64_t v = w0 >> sh;
+  if (sh) v |= w1 << (64 - sh);
+  return bw >= 64 ? v : (v & ((1ull << bw) - 1));
+}
+
+__device__ void decode_delta_binary(const uint8_t* p, const uint8_t* end, int nvals, ValueWriter w, int32_t* errors) {
+  __shared__ const uint8_t* s_ptr[PQ_NT];
+  __shared__ int64_t s_md[PQ_NT];
+  __shared__ uint64_t s_tot[PQ_NT];
+  __shared__ uint8_t s_bw[PQ_NT];
+  __shared__ uint64_t s_carry;
+  __shared__ const uint8_t* s_p;
+  __shared__ int s_n, s_vpm, s_mpb, s_j, s_bad;
+  __shared__ int64_t s_cur_md;
+  __shared__ const uint8_t* s_bws;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    const uint64_t block = dl_uleb(p, end), mpb = dl_uleb(p, end), total = dl_uleb(p, end);
+    const int64_t first = dl_zigzag(dl_uleb(p, end));
+    s_bad = (mpb == 0 || block == 0 || block % 128 != 0 || block % mpb != 0 || (block / mpb) % 32 != 0 || (nvals > 0 && total < (uint64_t)nvals)) ? 1 : 0;
+    s_vpm = s_bad ? 32 : (int)(block / mpb); s_mpb = (int)mpb; s_j = (int)mpb;   // j == mpb: a block header comes next
+    s_carry = (uint64_t)first; s_p = p; s_cur_md = 0; s_bws = p;
+    if (!s_bad && nvals > 0) { const uint64_t v = (uint64_t)first; w.write_fixed(0, reinterpret_cast<const uint8_t*>(&v)); }
+  }
+  __syncthreads();
+  if (s_bad) { if (t == 0) atomicExch(errors, 5); return; }
+  const int vpm = s_vpm;
+  int done = 1;   // values written so far
+  while (done < nvals) {
+    if (t == 0) {
+      const uint8_t* q = s_p;
+      int m = 0, sched = done;
+      while (m < PQ_NT && sched < nvals) {
+        if (s_j == s_mpb) {   // block header: min delta + one bit width per miniblock
+          if (q >= end) break;
+          s_cur_md = dl_zigzag(dl_uleb(q, end)); s_bws = q; q += s_mpb; s_j = 0;
+          if (q > end) { s_bad = 1; break; }
+        }
+        const int bw = s_bws[s_j];
+        if (bw > 64 || q + (size_t)vpm * bw / 8 > end) { s_bad = 1; break; }   // (width-0 miniblocks occupy no bytes)
+        s_ptr[m] = q; s_bw[m] = (uint8_t)bw; s_md[m] = s_cur_md;
+        q += (size_t)vpm * bw / 8;
+        s_j++; m++; sched += vpm;
+      }
+      if (m == 0) s_bad = 1;   // ran out of bytes before the announced value count
+      s_n = m; s_p = q;
+    }
+    __syncthreads();
+    if (s_bad) { if (t == 0) atomicExch(errors, 5); return; }
+    const int n = s_n;
+    uint64_t tot = 0;
+    if (t < n) { const uint64_t md = (uint64_t)s_md[t]; const int bw = s_bw[t]; for (int i = 0; i < vpm; i++) tot += md + extract_bits64(s_ptr[t], (uint64_t)i * bw, bw); }
+    s_tot[t] = t < n ? tot : 0;
+    __syncthreads();
+    if (t == 0) { uint64_t run = s_carry; for (int u = 0; u < n; u++) { const uint64_t x = s_tot[u]; s_tot[u] = run; run += x; } s_carry = run; }
+    __syncthreads();
+    if (t < n) {
+      uint64_t v = s_tot[t];
+      const uint64_t md = (uint64_t)s_md[t]; const int bw = s_bw[t];
+      const int k0 = done + t * vpm;
+      for (int i = 0; i < vpm && k0 + i < nvals; i++) {
+        v += md + extract_bits64(s_ptr[t], (uint64_t)i * bw, bw);
+        w.write_fixed(k0 + i, reinterpret_cast<const uint8_t*>(&v));
+      }
+    }
+    __syncthreads();
+    done += n * vpm;
+  }
+}
+
 __global__ void __launch_bounds__(PQ_NT) values_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, const ChunkD* __restrict__ chunks,
                                                        const ColD* __restrict__ cols, const uint8_t* __restrict__ file, const uint8_t* __restrict__ scratch,
                                                        const int32_t* __restrict__ nonnull, const int64_t* __restrict__ dict_src,
@@ -803,6 +891,8 @@ __global__ void __launch_bounds__(PQ_NT) values_kernel(const PageD* __restrict__
     } else {
       for (int k = threadIdx.x; k < nvals; k += PQ_NT) w.write_fixed(k, vals + (size_t)k * src_width);
     }
+  } else if (pg.encoding == ENC_DELTA_BINARY && (ch.phys == PT_INT32 || ch.phys == PT_INT64)) {
+    decode_delta_binary(vals, pend, nvals, w, errors);
   } else if (pg.encoding == ENC_RLE && ch.phys == PT_BOOLEAN) {
     // RLE booleans (data page v2 writers): 4-byte length, then the hybrid stream at bit width 1
     struct BoolSink { int8_t* out; __device__ __forceinline__ void put(int k, uint32_t v) { out[k] = (int8_t)(v & 1); } };
@@ -1042,8 +1132,9 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
         cd.dict_page = (int)w.pages.size(); cd.dict_count = nvals;
         if (cm.type == PT_BYTE_ARRAY) w.dict_strs += nvals;
       } else if (ptype == PG_DATA || ptype == PG_DATA_V2) {
-        if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT && enc != ENC_RLE_DICT && !(enc == ENC_RLE && cm.type == PT_BOOLEAN))
-          throw Error(B2_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(enc) + " (DELTA_* / BYTE_STREAM_SPLIT are not supported)");
+        if (enc != ENC_PLAIN && enc != ENC_PLAIN_DICT && enc != ENC_RLE_DICT && !(enc == ENC_RLE && cm.type == PT_BOOLEAN) &&
+            !(enc == ENC_DELTA_BINARY && (cm.type == PT_INT32 || cm.type == PT_INT64)))
+          throw Error(B2_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(enc) + " (DELTA_BYTE_ARRAY / DELTA_LENGTH_BYTE_ARRAY / BYTE_STREAM_SPLIT are not supported)");
         pg.row_start = w.rows;
         w.rows += nvals; values_seen += nvals;
       } else throw Error(B2_ERR_INVALID, "parquet: unknown page type");
