@@ -700,7 +700,20 @@ __global__ void __launch_bounds__(PQ_NT) levels_kernel(const PageD* __restrict__
   const uint8_t* d = page_ptr(pg, file, scratch);
   const uint8_t *lv_end, *vals;
   const uint8_t* lv = levels_of(pg, d, lv_end, vals);
-  LevelSink sink{cols[ch.col].lvl + pg.row_start, ch.max_def, &s_cnt};
+  uint8_t* out_lvl = cols[ch.col].lvl + pg.row_start;
+  // the usual page of a nullable column without NULLs: one RLE run "every level = max_def" — no per-row work
+  {
+    const uint8_t* q = lv;
+    uint32_t hdr = 0; int sh = 0;
+    while (q < lv_end && sh < 35) { const uint8_t b = *q++; hdr |= (uint32_t)(b & 0x7f) << sh; if (!(b & 0x80)) break; sh += 7; }
+    if (q < lv_end && (hdr & 1u) == 0 && (int)(hdr >> 1) >= pg.num_values && pg.num_values > 0) {
+      const bool ok = (int)(*q & 1u) == ch.max_def;
+      for (int k = threadIdx.x; k < pg.num_values; k += PQ_NT) out_lvl[k] = ok;
+      if (threadIdx.x == 0) nonnull[pi] = ok ? pg.num_values : 0;
+      return;
+    }
+  }
+  LevelSink sink{out_lvl, ch.max_def, &s_cnt};
   decode_hybrid(lv, lv_end, 1, pg.num_values, sink);  // flat schema: max_def == 1 -> bit width 1
   __syncthreads();
   if (threadIdx.x == 0) nonnull[pi] = (int32_t)s_cnt;
