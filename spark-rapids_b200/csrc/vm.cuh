@@ -283,13 +283,23 @@ __device__ __forceinline__ void vm_loop2x(const TileInfo ti, const RInstr& ins, 
     bool vv = true;
     if (b.stride == 0) {  // column/register (op) literal
       const TB y = *reinterpret_cast<const TB*>(b.base);
-      for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
+      int j0 = 0;
+      if constexpr (sizeof(T) <= 8 && sizeof(R) <= 8) {
+        for (; j0 + 8 <= ti.K; j0 += 8, pa += 8 * VM_NT * sizeof(T), pd += 8 * VM_NT * sizeof(R)) {
+          T x[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) x[u] = *reinterpret_cast<const T*>(pa + u * VM_NT * sizeof(T));
+#pragma unroll
+          for (int u = 0; u < 8; u++) *reinterpret_cast<R*>(pd + u * VM_NT * sizeof(R)) = f(x[u], y, true, true, vv);
+        }
+      }
+      for (; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pd += 4 * VM_NT * sizeof(R)) {
         const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
                 x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
         *reinterpret_cast<R*>(pd) = f(x0, y, true, true, vv); *reinterpret_cast<R*>(pd + VM_NT * sizeof(R)) = f(x1, y, true, true, vv);
         *reinterpret_cast<R*>(pd + 2 * VM_NT * sizeof(R)) = f(x2, y, true, true, vv); *reinterpret_cast<R*>(pd + 3 * VM_NT * sizeof(R)) = f(x3, y, true, true, vv);
       }
-      for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pd += VM_NT * sizeof(R))
+      for (; j0 < ti.K; j0++, pa += VM_NT * sizeof(T), pd += VM_NT * sizeof(R))
         *reinterpret_cast<R*>(pd) = f(*reinterpret_cast<const T*>(pa), y, true, true, vv);
     } else {
       const char* pb = thread_base<TB>(b);
@@ -400,14 +410,27 @@ __device__ __noinline__ void vm_andcmp(const TileInfo ti, const RInstr& ins) {
     char* pd = dbase + threadIdx.x;
     if (b.stride == 0) {
       const T y = *reinterpret_cast<const T*>(b.base);
-      for (int j0 = 0; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pc += 4 * VM_NT, pd += 4 * VM_NT) {
+      int j0 = 0;
+      if constexpr (sizeof(T) <= 8) {
+        // column operands come straight from HBM: eight rows per thread in flight before the first use
+        for (; j0 + 8 <= ti.K; j0 += 8, pa += 8 * VM_NT * sizeof(T), pc += 8 * VM_NT, pd += 8 * VM_NT) {
+          T x[8]; int8_t c[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) x[u] = *reinterpret_cast<const T*>(pa + u * VM_NT * sizeof(T));
+#pragma unroll
+          for (int u = 0; u < 8; u++) c[u] = *reinterpret_cast<const int8_t*>(pc + u * VM_NT);
+#pragma unroll
+          for (int u = 0; u < 8; u++) pd[u * VM_NT] = f(x[u], y, c[u]);
+        }
+      }
+      for (; j0 + 4 <= ti.K; j0 += 4, pa += 4 * VM_NT * sizeof(T), pc += 4 * VM_NT, pd += 4 * VM_NT) {
         const T x0 = *reinterpret_cast<const T*>(pa), x1 = *reinterpret_cast<const T*>(pa + VM_NT * sizeof(T)),
                 x2 = *reinterpret_cast<const T*>(pa + 2 * VM_NT * sizeof(T)), x3 = *reinterpret_cast<const T*>(pa + 3 * VM_NT * sizeof(T));
         const int8_t c0 = *reinterpret_cast<const int8_t*>(pc), c1 = *reinterpret_cast<const int8_t*>(pc + VM_NT),
                      c2 = *reinterpret_cast<const int8_t*>(pc + 2 * VM_NT), c3 = *reinterpret_cast<const int8_t*>(pc + 3 * VM_NT);
         pd[0] = f(x0, y, c0); pd[VM_NT] = f(x1, y, c1); pd[2 * VM_NT] = f(x2, y, c2); pd[3 * VM_NT] = f(x3, y, c3);
       }
-      for (int j = ti.K & ~3; j < ti.K; j++, pa += VM_NT * sizeof(T), pc += VM_NT, pd += VM_NT)
+      for (; j0 < ti.K; j0++, pa += VM_NT * sizeof(T), pc += VM_NT, pd += VM_NT)
         pd[0] = f(*reinterpret_cast<const T*>(pa), y, *reinterpret_cast<const int8_t*>(pc));
     } else {
       const char* pb = thread_base<T>(b);
