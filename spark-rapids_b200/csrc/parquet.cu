@@ -707,8 +707,9 @@ __global__ void __launch_bounds__(PQ_NT) levels_kernel(const PageD* __restrict__
     uint32_t hdr = 0; int sh = 0;
     while (q < lv_end && sh < 35) { const uint8_t b = *q++; hdr |= (uint32_t)(b & 0x7f) << sh; if (!(b & 0x80)) break; sh += 7; }
     if (q < lv_end && (hdr & 1u) == 0 && (int)(hdr >> 1) >= pg.num_values && pg.num_values > 0) {
+      // (the per-row bytes are not written here: when the column turns out to have NULLs in other pages,
+      //  fill_uniform_levels_kernel writes them for the all-valid / all-NULL pages afterwards)
       const bool ok = (int)(*q & 1u) == ch.max_def;
-      for (int k = threadIdx.x; k < pg.num_values; k += PQ_NT) out_lvl[k] = ok;
       if (threadIdx.x == 0) nonnull[pi] = ok ? pg.num_values : 0;
       return;
     }
@@ -717,6 +718,22 @@ __global__ void __launch_bounds__(PQ_NT) levels_kernel(const PageD* __restrict__
   decode_hybrid(lv, lv_end, 1, pg.num_values, sink);  // flat schema: max_def == 1 -> bit width 1
   __syncthreads();
   if (threadIdx.x == 0) nonnull[pi] = (int32_t)s_cnt;
+}
+
+// per-row validity bytes of the pages levels_kernel short-cut (every row valid, or every row NULL); launched only for
+// columns that do contain NULLs somewhere
+__global__ void __launch_bounds__(PQ_NT) fill_uniform_levels_kernel(const PageD* __restrict__ pages, const int32_t* __restrict__ todo, const ChunkD* __restrict__ chunks,
+                                                                    const ColD* __restrict__ cols, const int32_t* __restrict__ nonnull,
+                                                                    const uint8_t* __restrict__ col_has_nulls) {
+  const int pi = todo[blockIdx.x];
+  const PageD pg = pages[pi];
+  const ChunkD ch = chunks[pg.chunk];
+  if (!col_has_nulls[ch.col]) return;
+  const int nn = nonnull[pi];
+  if (nn != 0 && nn != pg.num_values) return;   // mixed page: the level decoder wrote its bytes
+  uint8_t* out_lvl = cols[ch.col].lvl + pg.row_start;
+  const uint8_t v = nn != 0;
+  for (int k = threadIdx.x; k < pg.num_values; k += PQ_NT) out_lvl[k] = v;
 }
 
 // ---- pass 2: values ---------------------------------------------------------------------------------
@@ -1344,8 +1361,19 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
       const int c = chunks[pg.chunk].col;
       if (chunks[pg.chunk].max_def > 0) { pg.value_base = run[c]; run[c] += nn[i]; }
     }
-    for (int c = 0; c < ncols; c++) if (plans[c].max_def > 0) { col_nonnull[c] = run[c]; has_nulls[c] = run[c] != total_rows; }
+    bool any_nulls = false;
+    for (int c = 0; c < ncols; c++) if (plans[c].max_def > 0) { col_nonnull[c] = run[c]; has_nulls[c] = run[c] != total_rows; any_nulls = any_nulls || has_nulls[c]; }
     h2d(d_pages.p, pages.data(), pages.size());
+    if (any_nulls) {
+      std::vector<uint8_t> hn(ncols, 0);
+      for (int c = 0; c < ncols; c++) hn[c] = has_nulls[c] ? 1 : 0;
+      DevBuf d_hn((size_t)ncols);
+      h2d(d_hn.p, hn.data(), hn.size());
+      fill_uniform_levels_kernel<<<(int)todo_levels.size(), PQ_NT, 0, s>>>(d_pages.as<PageD>(), d_todo_l.as<int32_t>(), d_chunks.as<ChunkD>(), d_cols.as<ColD>(),
+                                                                           d_nonnull.as<int32_t>(), d_hn.as<uint8_t>());
+      CUDA_CHECK(cudaGetLastError());
+      count_launch();
+    }
   }
   DevBuf d_dict_src((size_t)std::max<int64_t>(dict_str_total, 1) * 8), d_dict_len((size_t)std::max<int64_t>(dict_str_total, 1) * 4);
   if (dict_str_total) {
