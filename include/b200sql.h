@@ -208,7 +208,10 @@ typedef enum {
 int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* out_hash_table);
 int b2_join_hash_table_close(b2_handle ht);
 /* probe: stream side is "left".  Returns INT32 gather-map columns (right map NULL for semi/anti).
- * For LEFT_OUTER unmatched rows carry INT32_MIN in the right map (OutOfBoundsPolicy.NULLIFY). */
+ * For LEFT_OUTER unmatched rows carry INT32_MIN in the right map (OutOfBoundsPolicy.NULLIFY).
+ * FULL_OUTER = the LEFT_OUTER maps followed by one row per build row that no stream row matched, in build order,
+ * with INT32_MIN in the left map (Table.fullJoinGatherMaps; across stream batches the caller keeps the union of
+ * matched build rows itself, as GpuHashJoin.scala's HashFullJoinIterator does). */
 int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind,
                   b2_handle* out_left_map, b2_handle* out_right_map);
 /* Table.gather(map, OutOfBoundsPolicy): out-of-range index -> null row when nullify != 0 */

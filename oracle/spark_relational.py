@@ -34,7 +34,8 @@ def _join_key(cols, i, nulls_equal):
 
 def hash_join(build_keys, probe_keys, kind, nulls_equal=False):
     """-> (left_map, right_map|None) as python lists; stream/probe side is 'left'.
-    kind: 0 inner, 1 left outer, 2 left semi, 3 left anti."""
+    kind: 0 inner, 1 left outer, 2 left semi, 3 left anti, 4 full outer (left outer rows, then the unmatched build
+    rows in build order with left = INT32_MIN; GpuHashJoin.scala full-join gather maps)."""
     table = {}
     nb = len(build_keys[0])
     for i in range(nb):
@@ -60,6 +61,13 @@ def hash_join(build_keys, probe_keys, kind, nulls_equal=False):
         else:
             if not m:
                 lm.append(r)
+    if kind == 4:
+        lm, rm = hash_join(build_keys, probe_keys, 1, nulls_equal)
+        hit = set(b for b in rm if b >= 0)
+        for b in range(nb):
+            if b not in hit:
+                lm.append(INT32_MIN); rm.append(b)
+        return lm, rm
     return lm, (rm if kind in (0, 1) else None)
 
 

@@ -151,6 +151,22 @@ __global__ void join_probe_kernel(const __grid_constant__ KeyCols probe, const _
   }
 }
 
+// ---- full outer = left outer + the build rows no stream row matched (GpuHashJoin.scala full-join gather maps) -----
+__global__ void mark_matched_kernel(const int32_t* __restrict__ right_map, int64_t n, uint8_t* __restrict__ matched) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = right_map[i];
+    if (r >= 0) matched[r] = 1;
+  }
+}
+__global__ void unmatched_flags_kernel(const uint8_t* __restrict__ matched, int64_t nb, int32_t* __restrict__ flags) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) flags[i] = matched[i] ? 0 : 1;
+}
+__global__ void append_unmatched_kernel(const uint8_t* __restrict__ matched, const int32_t* __restrict__ pos, int64_t nb, int64_t base,
+                                        int32_t* __restrict__ left_map, int32_t* __restrict__ right_map) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x)
+    if (!matched[i]) { left_map[base + pos[i]] = INT32_MIN; right_map[base + pos[i]] = (int32_t)i; }
+}
+
 static JoinTable* jt_from(b2_handle h) {
   if (!h) throw Error(B2_ERR_INVALID, "null hash table handle");
   return reinterpret_cast<JoinTable*>((intptr_t)h);
@@ -212,7 +228,41 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
   B2_CHECK(pt->cols.size() == jt->keys->cols.size(), "probe and build key counts differ");
   for (size_t i = 0; i < pt->cols.size(); i++)
     B2_CHECK(pt->cols[i]->dtype == jt->keys->cols[i]->dtype, "probe and build key dtypes differ");
-  if (kind == B2_JOIN_FULL_OUTER) throw Error(B2_ERR_UNSUPPORTED, "full outer join is not supported yet");
+  if (kind == B2_JOIN_FULL_OUTER) {
+    // left outer maps, then one extra row (left = out of bounds -> NULLs) per build row that nothing matched
+    B2_CHECK(out_right_map != nullptr, "a full outer join needs both gather maps");
+    b2_handle hl = 0, hr = 0;
+    int rc = b2_join_probe(ht, probe_keys_table, B2_JOIN_LEFT_OUTER, &hl, &hr);
+    if (rc != B2_OK) return rc;
+    ColGuard lo(col_from(hl)), ro(col_from(hr));
+    const int64_t m = lo.c->size, nb = jt->keys->rows;
+    DevBuf matched((size_t)std::max<int64_t>(nb, 1)), pos((size_t)(nb + 1) * 4);
+    CUDA_CHECK(cudaMemsetAsync(matched.p, 0, matched.bytes, stream()));
+    int32_t extra = 0;
+    if (nb) {
+      if (m) mark_matched_kernel<<<grid_for(m, 256), 256, 0, stream()>>>(ro.c->data.as<int32_t>(), m, matched.as<uint8_t>());
+      unmatched_flags_kernel<<<grid_for(nb, 256), 256, 0, stream()>>>(matched.as<uint8_t>(), nb, pos.as<int32_t>());
+      count_launch(2);
+      exclusive_scan<int32_t, int32_t>(pos.as<int32_t>(), pos.as<int32_t>(), nb, true);
+      d2h(&extra, pos.as<int32_t>() + nb, 1);
+      sync();
+    }
+    if (m + extra > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "join output exceeds 2^31-1 rows; split the stream batch");
+    ColGuard lm(new_column(B2_INT32, 0, m + extra, false)), rm(new_column(B2_INT32, 0, m + extra, false));
+    if (m) {
+      CUDA_CHECK(cudaMemcpyAsync(lm.c->data.p, lo.c->data.p, (size_t)m * 4, cudaMemcpyDeviceToDevice, stream()));
+      CUDA_CHECK(cudaMemcpyAsync(rm.c->data.p, ro.c->data.p, (size_t)m * 4, cudaMemcpyDeviceToDevice, stream()));
+    }
+    if (extra) {
+      append_unmatched_kernel<<<grid_for(nb, 256), 256, 0, stream()>>>(matched.as<uint8_t>(), pos.as<int32_t>(), nb, m, lm.c->data.as<int32_t>(),
+                                                                        rm.c->data.as<int32_t>());
+      CUDA_CHECK(cudaGetLastError());
+      count_launch();
+    }
+    *out_left_map = to_handle(lm.release());
+    *out_right_map = to_handle(rm.release());
+    return B2_OK;
+  }
   B2_CHECK(kind >= B2_JOIN_INNER && kind <= B2_JOIN_LEFT_ANTI, "bad join kind");
   const int64_t n = pt->rows;
   const bool semi_like = kind == B2_JOIN_LEFT_SEMI || kind == B2_JOIN_LEFT_ANTI;

@@ -85,7 +85,7 @@ def _check_join(b2, build, probe, kind, nulls_equal=False):
         # (output order is unspecified: docs/compatibility.md:18-25; the distinct-build fast path appends per warp)
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("typ", [(O.INT64, 0, 0), (O.INT32, 0, 0), (O.STRING, 0, 0), (O.FLOAT64, 0, 0), (O.DECIMAL128, 30, 2)])
 def test_join_single_key(b2, kind, typ):
     rng = np.random.default_rng(kind * 10 + typ[0])
@@ -234,3 +234,28 @@ def test_concat_and_slice(b2):
         G.assert_col_equal(out.column(i), exp)
         sl = b2.slice_table(out, 90, 150).column(i)
         G.assert_col_equal(sl, O.OCol(exp.values[90:150], exp.valid[90:150], t))
+
+
+def test_full_outer_join_then_gather(b2):
+    """FullOuter: every stream row and every build row appears; the unmatched side is NULL after the gather with
+    out-of-bounds -> NULL (JoinGatherer.scala:585-599); distinct and duplicate build keys, NULL keys on both sides"""
+    rng = np.random.default_rng(21)
+    for distinct in (True, False):
+        bkey = gen(rng, (O.INT64, 0, 0), 4000, distinct=4000 if distinct else 500)
+        pkey = gen(rng, (O.INT64, 0, 0), 9000, distinct=3000)
+        bval = gen(rng, (O.DECIMAL64, 12, 2), 4000)
+        ht = b2.JoinHashTable(G.to_b2_table(b2, [bkey]))
+        lm, rm = ht.probe(G.to_b2_table(b2, [pkey]), 4)
+        elm, erm = R.hash_join([bkey], [pkey], 4)
+        assert sorted(zip(lm.to_pylist(), rm.to_pylist())) == sorted(zip(elm, erm))
+        left = b2.gather(G.to_b2_table(b2, [pkey]), lm, True)
+        right = b2.gather(G.to_b2_table(b2, [bkey, bval]), rm, True)
+        order = np.lexsort((rm.to_numpy()[0], lm.to_numpy()[0]))
+        eorder = np.lexsort((np.array(erm), np.array(elm)))
+        el = R.gather([pkey], np.array(elm)[eorder], True)
+        er = R.gather([bkey, bval], np.array(erm)[eorder], True)
+        gl = b2.gather(left, b2.Column.from_numpy(order.astype(np.int32)))
+        gr = b2.gather(right, b2.Column.from_numpy(order.astype(np.int32)))
+        G.assert_col_equal(gl.column(0), el[0])
+        G.assert_col_equal(gr.column(0), er[0])
+        G.assert_col_equal(gr.column(1), er[1])
