@@ -162,7 +162,7 @@ struct GpuHashAggregateExec : GpuExec {
 struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), children[1] = build (right)
   std::vector<int> stream_keys, build_keys;
   int kind = B2_JOIN_INNER;
-  bool nulls_equal = false, built = false;
+  bool nulls_equal = false, built = false, full_done = false;
   TableRef build_table;
   b2_handle ht = 0;
   ~GpuShuffledHashJoinExec() { if (ht) b2_join_hash_table_close(ht); }
@@ -185,7 +185,20 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
   }
   Table* do_next() override {
     if (!built) build();
-    TableRef s(children[0]->next());
+    TableRef s;
+    if (kind == B2_JOIN_FULL_OUTER) {
+      // the unmatched build rows can only be emitted once every stream row has been seen: the stream side is
+      // coalesced into one batch (the reference tracks matched build rows across batches instead)
+      if (full_done) return nullptr;
+      full_done = true;
+      std::vector<TableRef> parts;
+      while (true) { TableRef b(children[0]->next()); if (!b.t) break; parts.emplace_back(b.release()); }
+      if (parts.empty()) throw Error(B2_ERR_UNSUPPORTED, "empty stream side of a full outer join needs the stream schema");
+      if (parts.size() == 1) s = std::move(parts[0]);
+      else { std::vector<const Table*> ts; for (auto& q : parts) ts.push_back(q.t); s = TableRef(concat_tables(ts)); }
+    } else {
+      s = TableRef(children[0]->next());
+    }
     if (!s.t) return nullptr;
     TableRef sk(select(s.t, stream_keys));
     b2_handle lm = 0, rm = 0;
@@ -193,9 +206,9 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
     if (rc != B2_OK) throw Error(rc, b2_last_error());
     ColGuard lmap(col_from(lm));
     ColGuard rmap(rm ? col_from(rm) : nullptr);
-    TableRef left(gather_table(s.t, lmap.c->data.as<int32_t>(), lmap.c->size, false, nullptr));
+    TableRef left(gather_table(s.t, lmap.c->data.as<int32_t>(), lmap.c->size, kind == B2_JOIN_FULL_OUTER, nullptr));
     if (!rmap.c) return left.release();  // semi / anti: stream columns only
-    TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER, nullptr));
+    TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER || kind == B2_JOIN_FULL_OUTER, nullptr));
     std::vector<Column*> cols;  // output = left columns ++ right columns (GpuHashJoin.scala:2451-2470)
     for (auto*& c : left.t->cols) { cols.push_back(c); c = nullptr; }
     for (auto*& c : right.t->cols) { cols.push_back(c); c = nullptr; }

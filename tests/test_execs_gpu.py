@@ -122,3 +122,28 @@ def test_each_batch_sort_and_coalesce(b2):
     assert [t.num_rows for t in co] == [2000, 2000, 2000, 2000, 2000]
     co2 = list(E.GpuCoalesceBatches(E.GpuBatchSource(batches(b2, [c], 10)), 10**9))
     assert [t.num_rows for t in co2] == [10000]
+
+
+def test_full_outer_join_exec_multi_batch(b2):
+    """GpuShuffledHashJoinExec FullOuter over a stream side that arrives in several batches: every stream row and
+    every build row exactly once, the missing side NULL"""
+    from spark_rapids_b200 import execs as E
+    rng = np.random.default_rng(8)
+    i64 = (O.INT64, 0, 0)
+    ns, nb = 9000, 2500
+    stream = [O.OCol(rng.integers(0, 4000, ns).astype(np.int64), rng.random(ns) > 0.05, i64), O.OCol(np.arange(ns, dtype=np.int64), np.ones(ns, bool), i64)]
+    build = [O.OCol(rng.permutation(6000)[:nb].astype(np.int64), rng.random(nb) > 0.05, i64), O.OCol(np.arange(nb, dtype=np.int64) + 10**6, np.ones(nb, bool), i64)]
+    j = E.GpuShuffledHashJoinExec([0], [0], b2.JOIN_FULL_OUTER, E.GpuBatchSource(batches(b2, stream, 4)), E.GpuBatchSource(batches(b2, build, 2)))
+    got = sorted(j.collect().to_rows(), key=lambda r: tuple((x is None, x) for x in r))
+    bmap = {int(k): int(v) for k, v, ok in zip(build[0].values, build[1].values, build[0].valid) if ok}
+    exp, hit = [], set()
+    for k, sid, ok in zip(stream[0].values, stream[1].values, stream[0].valid):
+        if ok and int(k) in bmap:
+            exp.append((int(k), int(sid), int(k), bmap[int(k)])); hit.add(int(k))
+        else:
+            exp.append((int(k) if ok else None, int(sid), None, None))
+    for k, v, ok in zip(build[0].values, build[1].values, build[0].valid):
+        if not ok or int(k) not in hit:
+            exp.append((None, None, int(k) if ok else None, int(v)))
+    exp = sorted(exp, key=lambda r: tuple((x is None, x) for x in r))
+    assert got == exp
