@@ -408,7 +408,9 @@ __device__ __forceinline__ int32_t smem_find_slot(const AggPlan& plan, int64_t g
     int32_t cur = s_slots[idx];
     if (cur == SLOT_EMPTY) {
       const int32_t old = atomicCAS(&s_slots[idx], SLOT_EMPTY, (int32_t)g);
-      if (old == SLOT_EMPTY) {  // mine: publish the packed key for later probes
+      if (old == SLOT_EMPTY) {  // mine: publish the packed key for later probes (key, fence, then the READY flag: a reader
+                                // that does not see the flag yet compares the rows themselves; racecheck reports this
+                                // flag+fence hand-off as a hazard pair, see profiles/r1_racecheck.txt)
         if (packed) {
           s_keys[idx] = kb;
           __threadfence_block();
