@@ -669,8 +669,16 @@ __device__ void decode_hybrid(const uint8_t* p, const uint8_t* end, int bw, int 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < n; r += PQ_NT / 32) {
       const RunD run = s_runs[r];
-      if (run.packed) for (int k = lane; k < run.count; k += 32) sink.put(run.start + k, extract_bits(run.data, (uint64_t)k * bw, bw));
-      else for (int k = lane; k < run.count; k += 32) sink.put(run.start + k, run.value);
+      if (run.packed) {
+        // four values per lane in flight: bits -> index -> dictionary entry -> store is a chain of dependent loads
+        int k = lane;
+        for (; k + 96 < run.count; k += 128) {
+          const uint32_t v0 = extract_bits(run.data, (uint64_t)k * bw, bw), v1 = extract_bits(run.data, (uint64_t)(k + 32) * bw, bw),
+                         v2 = extract_bits(run.data, (uint64_t)(k + 64) * bw, bw), v3 = extract_bits(run.data, (uint64_t)(k + 96) * bw, bw);
+          sink.put4(run.start + k, v0, v1, v2, v3);
+        }
+        for (; k < run.count; k += 32) sink.put(run.start + k, extract_bits(run.data, (uint64_t)k * bw, bw));
+      } else for (int k = lane; k < run.count; k += 32) sink.put(run.start + k, run.value);
     }
     __syncthreads();
     if (s_done >= count) break;
@@ -681,6 +689,7 @@ __device__ void decode_hybrid(const uint8_t* p, const uint8_t* end, int bw, int 
 struct LevelSink {
   uint8_t* lvl; int max_def; unsigned int* cnt;
   __device__ __forceinline__ void put(int k, uint32_t v) { const bool ok = (int)v == max_def; lvl[k] = ok; if (ok) atomicAdd(cnt, 1u); }
+  __device__ __forceinline__ void put4(int k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { put(k, a); put(k + 32, b); put(k + 64, c); put(k + 96, d); }
 };
 __device__ __forceinline__ const uint8_t* levels_of(const PageD& pg, const uint8_t* d, const uint8_t*& lv_end, const uint8_t*& values) {
   if (pg.kind == PG_DATA_V2) { lv_end = d + pg.lvl_bytes; values = d + pg.lvl_bytes; return d; }
@@ -788,6 +797,23 @@ struct DictSink {
     if ((int)idx >= w.dict_count) { atomicExch(errors, 2); return; }
     if (w.col.conv == 5) { w.col.str_src[w.base + k] = w.dict_src[idx]; w.col.str_len[w.base + k] = w.dict_len[idx]; }
     else w.write_fixed(k, w.dict + (size_t)idx * src_width);
+  }
+  // rows k, k+32, k+64, k+96: the four dictionary entries are fetched before the first store
+  __device__ __forceinline__ void put4(int k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (w.col.conv == 0 && (src_width == 4 || src_width == 8) && w.col.out_width == src_width &&
+        (reinterpret_cast<uintptr_t>(w.dict) & (uintptr_t)(src_width - 1)) == 0 && (int)max(max(a, b), max(c, d)) < w.dict_count) {
+      if (src_width == 4) {
+        const uint32_t* dp = reinterpret_cast<const uint32_t*>(w.dict);
+        const uint32_t x0 = dp[a], x1 = dp[b], x2 = dp[c], x3 = dp[d];
+        uint32_t* o = reinterpret_cast<uint32_t*>(w.col.dense) + w.base + k; o[0] = x0; o[32] = x1; o[64] = x2; o[96] = x3;
+      } else {
+        const uint64_t* dp = reinterpret_cast<const uint64_t*>(w.dict);
+        const uint64_t x0 = dp[a], x1 = dp[b], x2 = dp[c], x3 = dp[d];
+        uint64_t* o = reinterpret_cast<uint64_t*>(w.col.dense) + w.base + k; o[0] = x0; o[32] = x1; o[64] = x2; o[96] = x3;
+      }
+      return;
+    }
+    put(k, a); put(k + 32, b); put(k + 64, c); put(k + 96, d);
   }
 };
 
@@ -925,7 +951,11 @@ __global__ void __launch_bounds__(PQ_NT) values_kernel(const PageD* __restrict__
     decode_delta_binary(vals, pend, nvals, w, errors);
   } else if (pg.encoding == ENC_RLE && ch.phys == PT_BOOLEAN) {
     // RLE booleans (data page v2 writers): 4-byte length, then the hybrid stream at bit width 1
-    struct BoolSink { int8_t* out; __device__ __forceinline__ void put(int k, uint32_t v) { out[k] = (int8_t)(v & 1); } };
+    struct BoolSink {
+      int8_t* out;
+      __device__ __forceinline__ void put(int k, uint32_t v) { out[k] = (int8_t)(v & 1); }
+      __device__ __forceinline__ void put4(int k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { put(k, a); put(k + 32, b); put(k + 64, c); put(k + 96, d); }
+    };
     BoolSink sink{reinterpret_cast<int8_t*>(col.dense) + w.base};
     decode_hybrid(vals + 4, pend, 1, nvals, sink);
   } else {
