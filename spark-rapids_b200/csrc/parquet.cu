@@ -752,6 +752,17 @@ __device__ __forceinline__ uint64_t load_le(const uint8_t* p, int nbytes) {
     if (nbytes == 8) return *reinterpret_cast<const uint64_t*>(p);
     if (nbytes == 4) return *reinterpret_cast<const uint32_t*>(p);
   }
+  if (nbytes == 8 || nbytes == 4) {
+    // PLAIN values start right behind the (odd-sized) level bytes, so they are rarely aligned: two aligned 8-byte
+    // loads and a funnel shift instead of a byte loop (the page buffers have >= 16 bytes of slack)
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+    const uint64_t* al = reinterpret_cast<const uint64_t*>(ad & ~uintptr_t(7));
+    const int sh = (int)(ad & 7) * 8;
+    const uint64_t w0 = al[0];
+    uint64_t x = w0 >> sh;
+    if (sh + nbytes * 8 > 64) x |= al[1] << (64 - sh);
+    return nbytes == 8 ? x : (x & 0xffffffffull);
+  }
   for (int k = 0; k < nbytes; k++) v |= (uint64_t)p[k] << (8 * k);
   return v;
 }
