@@ -75,3 +75,61 @@ def lineitem_q6_parquet(rows, seed=42, cache_dir=None, row_group_rows=4_800_000)
         raw.tofile(path + ".tmp%d" % os.getpid())
         os.replace(path + ".tmp%d" % os.getpid(), path)
     return raw
+
+
+# ---- TPC-H q3 tables (customer 150k*SF, orders 1.5M*SF, lineitem 6,001,215*SF; dense i64 keys, uniform
+# foreign keys, c_mktsegment 5 values, uniform dates, seed 42).  Tables are produced chunk by chunk so that a rank of an N-GPU
+# run (and the chunked CPU check) can make exactly its share: chunk i of a table is seeded by (seed, table, i).
+SEGMENTS = [b"AUTOMOBILE", b"BUILDING", b"FURNITURE", b"MACHINERY", b"HOUSEHOLD"]
+Q3_SEGMENT = b"BUILDING"
+Q3_DATE = 9204                      # 1995-03-15
+DATE_1992_01_01, DATE_1998_08_02 = 8035, 10440
+Q3_CHUNKS = {"customer": 8, "orders": 8, "lineitem": 16}
+_TABLE_ID = {"customer": 1, "orders": 2, "lineitem": 3}
+
+
+def q3_rows(sf):
+    """row counts at scale factor sf (fractional sf allowed for tests)"""
+    li = SF_ROWS.get(sf, int(round(6001215 * sf)))
+    return {"customer": int(round(150_000 * sf)), "orders": int(round(1_500_000 * sf)), "lineitem": li}
+
+
+def chunk_range(n, nchunks, i):
+    return n * i // nchunks, n * (i + 1) // nchunks
+
+
+def _segment_strings(codes):
+    """codes -> (chars uint8, offsets int32) of the Arrow string column"""
+    seg_len = np.array([len(s) for s in SEGMENTS], dtype=np.int32)
+    width = int(seg_len.max())
+    mat = np.zeros((len(SEGMENTS), width), dtype=np.uint8)
+    for k, s in enumerate(SEGMENTS):
+        mat[k, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+    lens = seg_len[codes]
+    offsets = np.zeros(len(codes) + 1, dtype=np.int32)
+    np.cumsum(lens, out=offsets[1:])
+    keep = np.arange(width, dtype=np.int32)[None, :] < lens[:, None]
+    chars = mat[codes][keep]
+    return np.ascontiguousarray(chars), offsets
+
+
+def q3_chunk(table, sf, i, seed=42):
+    """chunk i of a q3 table -> dict of numpy columns (c_mktsegment: (chars, offsets) plus the raw codes)"""
+    rows = q3_rows(sf)
+    lo, hi = chunk_range(rows[table], Q3_CHUNKS[table], i)
+    n = hi - lo
+    rng = np.random.default_rng([seed, _TABLE_ID[table], i])
+    if table == "customer":
+        codes = rng.integers(0, len(SEGMENTS), n, dtype=np.int8)
+        chars, offsets = _segment_strings(codes)
+        return {"c_custkey": np.arange(lo, hi, dtype=np.int64), "c_mktsegment": (chars, offsets), "c_mktsegment_code": codes}
+    if table == "orders":
+        return {"o_orderkey": np.arange(lo, hi, dtype=np.int64), "o_custkey": rng.integers(0, rows["customer"], n, dtype=np.int64),
+                "o_orderdate": rng.integers(DATE_1992_01_01, DATE_1998_08_02 + 1, n, dtype=np.int32), "o_shippriority": np.zeros(n, dtype=np.int32)}
+    return {"l_orderkey": rng.integers(0, rows["orders"], n, dtype=np.int64), "l_extendedprice": rng.integers(90000, 10494951, n, dtype=np.int64),
+            "l_discount": rng.integers(0, 11, n, dtype=np.int64), "l_shipdate": rng.integers(DATE_1992_01_02, DATE_1998_12_01 + 1, n, dtype=np.int32)}
+
+
+def q3_chunks_of_rank(table, rank, world):
+    """the chunks a rank of a strong-scaled run owns (round robin, so every rank gets the same number)"""
+    return [i for i in range(Q3_CHUNKS[table]) if i % world == rank]

@@ -133,7 +133,11 @@ typedef enum {
   /* NormalizeFloatingNumbers.scala:29-38 */
   B2_OP_NORMALIZE_NAN_ZERO = 41,
   /* datetimeExpressions.scala GpuYear */
-  B2_OP_YEAR = 42
+  B2_OP_YEAR = 42,
+  /* stringFunctions.scala:163 GpuStartsWith, :189 GpuEndsWith, :396 GpuContains, :972 GpuLike, :524 GpuSubstring.
+   * String comparisons (EQ..GE) follow UTF8String.compareTo (unsigned bytes).  Strings are consumed by predicates;
+   * a Substring is a window a predicate looks through (b2_substring materialises one as a column).            */
+  B2_OP_STARTS_WITH = 50, B2_OP_ENDS_WITH = 51, B2_OP_CONTAINS = 52, B2_OP_LIKE = 53, B2_OP_SUBSTRING = 54
 } b2_expr_op;
 
 int b2_expr_column(int32_t index, int32_t dtype, int32_t precision, int32_t scale,
@@ -146,6 +150,14 @@ int b2_expr_binary(int32_t op, b2_handle left, b2_handle right, b2_handle* out);
 int b2_expr_ternary(int32_t op, b2_handle a, b2_handle b, b2_handle c, b2_handle* out);
 int b2_expr_cast(b2_handle child, int32_t dtype, int32_t precision, int32_t scale,
                  b2_handle* out);
+int b2_expr_string_literal(const char* utf8, int32_t len, int32_t is_null, b2_handle* out); /* GpuLiteral(StringType) */
+int b2_expr_like(b2_handle child, b2_handle pattern_literal, int32_t escape_char, b2_handle* out);   /* GpuLike */
+int b2_expr_substring(b2_handle child, int32_t pos, int32_t len, b2_handle* out);  /* GpuSubstring, literal pos/len (1-based) */
+/* GpuInSet.scala / In over a literal list: Kleene OR of equalities */
+int b2_expr_in(b2_handle child, const b2_handle* literals, int32_t n, b2_handle* out);
+/* conditionalExpressions.scala:322 GpuCaseWhen; else_value = 0 -> NULL */
+int b2_expr_case_when(const b2_handle* conds, const b2_handle* values, int32_t n, b2_handle else_value,
+                      b2_handle* out);
 int b2_expr_type(b2_handle expr, int32_t* dtype, int32_t* precision, int32_t* scale,
                  int32_t* nullable);
 int b2_expr_close(b2_handle expr);
@@ -156,10 +168,17 @@ int b2_program_close(b2_handle program);
 /* GpuProjectExec.project: table -> table of nexprs columns, one launch */
 int b2_project(b2_handle program, b2_handle table, b2_handle* out_table);
 
+/* GpuSubstring (stringFunctions.scala:524-620) with literal pos (1-based, negative = from the end) and len, materialised
+ * as a new STRING column (code-point semantics of UTF8String.substringSQL) */
+int b2_substring(b2_handle string_column, int32_t pos, int32_t len, b2_handle* out_column);
+
 /* ---- a2: filter (basicPhysicalOperators.scala:1148-1224 GpuFilter; Table.filter(mask)) -------- */
 int b2_filter_mask(b2_handle table, b2_handle bool_mask, b2_handle* out_table);
 /* fused: predicate program (1 BOOL8 output) evaluated and compacted in one kernel */
 int b2_filter(b2_handle predicate_program, b2_handle table, b2_handle* out_table);
+/* GpuFilterExec under a column-pruning GpuProjectExec, fused: only keep_cols (in that order) are compacted */
+int b2_filter_select(b2_handle predicate_program, b2_handle table, const int32_t* keep_cols, int32_t nkeep,
+                     b2_handle* out_table);
 /* count-only path, basicPhysicalOperators.scala:1161-1169 */
 int b2_filter_count(b2_handle predicate_program, b2_handle table, int64_t* out_count);
 
@@ -289,15 +308,44 @@ int b2_comm_close(b2_handle comm);
  * the concatenation of what every rank sent to me. */
 int b2_exchange(b2_handle comm, b2_handle partitioned_table, const int32_t* offsets,
                 b2_handle* out_table);
+/* same with the termination protocol of GpuShuffleExchangeExec: partitioned_table = 0 (offsets NULL) when this rank has no
+ * batch for this call; *any_data = some rank had one (0: the exchange is over everywhere, *out_table = 0) */
+int b2_exchange_ex(b2_handle comm, b2_handle partitioned_table, const int32_t* offsets,
+                   b2_handle* out_table, int32_t* any_data);
+/* FUSED GpuHashPartitioning + shuffle write + read for fixed-width tables: one kernel hashes the keys (Spark Murmur3 pmod
+ * world; nkeys = 0: SinglePartition -> rank 0) and stores every row straight into the destination GPU's receive arena
+ * over NVLink peer mappings; one 400-byte header all-gather is the size exchange and the completion barrier.
+ * (GpuShuffleExchangeExecBase.scala:384-536, GpuHashPartitioningBase.scala:36-54, GpuPartitioning.scala:66-99) */
+int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* key_cols, int32_t nkeys, int32_t seed,
+                     b2_handle* out_table, int32_t* any_data);
+int b2_comm_fused_ready(b2_handle comm, int32_t* ok);        /* collective: peer arenas mapped on every rank? */
+int b2_comm_allmax(b2_handle comm, int32_t value, int32_t* out);   /* collective max of one int per rank */
+/* out4: payload bytes sent to / received from OTHER ranks so far, exchange calls, arena bytes (0 = NCCL path) */
+int b2_comm_stats(b2_handle comm, int64_t* out4);
+/* GpuBroadcastExchangeExec data movement: root's table to every rank (ncclBroadcast); non-root pass table = 0 */
+int b2_broadcast_table(b2_handle comm, b2_handle table, int32_t root, b2_handle* out_table);
 
 /* ---- host operator layer: C++ mirror of the GpuExec nodes of the hot path (exec.cu).  Every node is
  * a pull iterator of batches — GpuExec.internalDoExecuteColumnar(): RDD[ColumnarBatch]
  * (GpuExec.scala:106,190,380).  b2_exec_next returns 0 in *out_table when the node is exhausted. */
 int b2_exec_source(b2_handle* out);                                   /* child RDD stand-in */
 int b2_exec_source_push(b2_handle source, b2_handle table);
+/* HostColumnarToGpu (HostColumnarToGpu.scala): host columnar batches -> device, the copy of batch k+1 overlapping the
+ * consumption of batch k.  The host buffers (pinned for full PCIe speed) must outlive the node. */
+typedef struct {
+  int32_t dtype, scale;
+  int64_t rows;
+  const void* data;              /* values, or chars for STRING */
+  const uint8_t* validity_bits;  /* NULL = no nulls */
+  const int32_t* offsets;        /* STRING: rows + 1 offsets */
+} b2_host_column;
+int b2_exec_host_source(b2_handle* out);
+int b2_exec_host_source_push(b2_handle source, const b2_host_column* cols, int32_t ncols);
 int b2_exec_parquet_scan(const char* const* column_names, int32_t ncols, b2_handle* out);      /* GpuParquetScan.scala:3543-3600 */
 int b2_exec_parquet_scan_add(b2_handle scan, const uint8_t* host_buf, int64_t len);            /* buffer must outlive the scan */
 int b2_exec_filter(b2_handle child, b2_handle predicate_program, b2_handle* out);              /* GpuFilterExec :1238-1291 */
+/* GpuProjectExec(column pruning) over GpuFilterExec, fused: only keep_cols are compacted */
+int b2_exec_filter_select(b2_handle child, b2_handle predicate_program, const int32_t* keep_cols, int32_t nkeep, b2_handle* out);
 int b2_exec_project(b2_handle child, b2_handle program, b2_handle* out);                       /* GpuProjectExec :755-884 */
 /* GpuHashAggregateExec (GpuAggregateExec.scala:1942-2085).  merge_mode 0: update aggregates over the
  * program's outputs (Partial/Complete); 1: input batches are aggregation buffers, keys leading (Final) */
@@ -306,6 +354,14 @@ int b2_exec_hash_aggregate(b2_handle child, b2_handle program, int32_t has_predi
 /* GpuShuffledHashJoinExec (GpuShuffledHashJoinExec.scala:228-385): output = stream columns ++ build columns */
 int b2_exec_shuffled_hash_join(b2_handle stream_child, b2_handle build_child, const int32_t* stream_keys,
                                const int32_t* build_keys, int32_t nkeys, int32_t kind, int32_t nulls_equal, b2_handle* out);
+/* same with a column-pruning GpuProjectExec above the join fused into the gathers: output = stream_out ++ build_out */
+int b2_exec_shuffled_hash_join_select(b2_handle stream_child, b2_handle build_child, const int32_t* stream_keys,
+                                      const int32_t* build_keys, int32_t nkeys, int32_t kind, int32_t nulls_equal,
+                                      const int32_t* stream_out, int32_t nstream_out, const int32_t* build_out,
+                                      int32_t nbuild_out, b2_handle* out);
+/* GpuBroadcastExchangeExec (GpuBroadcastExchangeExec.scala): every rank gets the whole child relation, one batch.  Used as
+ * the build child of a join it makes GpuBroadcastHashJoinExec (GpuBroadcastHashJoinExecBase.scala:1-203). */
+int b2_exec_broadcast_exchange(b2_handle child, b2_handle comm, int32_t rank, int32_t world, b2_handle* out);
 /* GpuSortExec (global != 0: full sort, else each batch) / GpuTopN when limit >= 0 */
 int b2_exec_sort(b2_handle child, const b2_order_by_arg* order, int32_t norder, int32_t global, int64_t limit, b2_handle* out);
 int b2_exec_coalesce(b2_handle child, int64_t target_rows, b2_handle* out);                    /* GpuCoalesceBatches */
@@ -313,6 +369,9 @@ int b2_exec_coalesce(b2_handle child, int64_t target_rows, b2_handle* out);     
 int b2_exec_shuffle_exchange(b2_handle child, const int32_t* key_cols, int32_t nkeys, b2_handle comm, int32_t world, b2_handle* out);
 int b2_exec_next(b2_handle exec, b2_handle* out_table);
 int b2_exec_metrics(b2_handle exec, int64_t* out3);  /* numOutputRows, numOutputBatches, opTime (ns) */
+/* device time of the node while b2_profile_enable(1) was on: out2[0] = self ms (children pulled from inside next() excluded),
+ * out2[1] = total ms */
+int b2_exec_device_time(b2_handle exec, double* out2);
 int b2_exec_close(b2_handle exec);
 
 /* ---- timing hooks for bench.py (CUDA events on the library stream) ------------------------------ */

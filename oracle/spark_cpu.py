@@ -142,9 +142,16 @@ def eval_expr(sx, cols):
     if op == "col":
         c = cols[sx[1]]
         return OCol(c.values, c.valid, sx[2])
+    if op == "lit" and sx[2][0] == STRING:
+        v = sx[1]
+        vals = np.empty(n, dtype=object)
+        vals[:] = b"" if v is None else (v.encode() if isinstance(v, str) else v)
+        return OCol(vals, np.full(n, v is not None), (STRING, 0, 0))
     if op == "lit":
         v, typ = sx[1], sx[2]
         dt = typ[0]
+        if v is None and dt < 0:   # untyped NULL (CASE without ELSE)
+            return OCol(np.zeros(n, dtype=np.int8), np.zeros(n, bool), typ)
         if v is None:
             vals = np.zeros(n, dtype=object if is_decimal(dt) else _NP[dt])
             return OCol(vals, np.zeros(n, bool), typ)
@@ -205,6 +212,34 @@ def eval_expr(sx, cols):
         v[np.isnan(v)] = np.nan
         v[v == 0] = 0.0
         return OCol(v, a.valid, a.typ)
+    if op in ("startswith", "endswith", "contains", "like"):
+        # stringFunctions.scala:163 GpuStartsWith, :189 GpuEndsWith, :396 GpuContains, :972 GpuLike: NULL in, NULL out
+        a, b = eval_expr(sx[1], cols), eval_expr(sx[2], cols)
+        valid = a.valid & b.valid
+        esc = sx[3] if op == "like" and len(sx) > 3 else "\\"
+        fn = {"startswith": lambda x, y: x.startswith(y), "endswith": lambda x, y: x.endswith(y), "contains": lambda x, y: y in x,
+              "like": lambda x, y: _like(x, y, esc)}[op]
+        r = np.array([bool(ok and fn(x, y)) for x, y, ok in zip(a.values, b.values, valid)], dtype=bool) if n else np.zeros(0, bool)
+        return OCol(r.astype(np.int8), valid, (BOOL8, 0, 0))
+    if op == "substr":
+        a = eval_expr(sx[1], cols)
+        vals = np.empty(n, dtype=object)
+        for i in range(n):
+            vals[i] = substring_sql(a.values[i], sx[2], sx[3]) if a.valid[i] else b""
+        return OCol(vals, a.valid, (STRING, 0, 0))
+    if op == "in":   # GpuInSet / In: Kleene OR of equalities
+        acc = None
+        for lit_sx in sx[2]:
+            e = ("eq", sx[1], lit_sx)
+            acc = e if acc is None else ("or", acc, e)
+        if acc is None:
+            acc = ("ne", sx[1], sx[1])
+        return eval_expr(acc, cols)
+    if op == "case":   # GpuCaseWhen (conditionalExpressions.scala:322): first TRUE branch, else `else` (NULL when absent)
+        tail = sx[2] if sx[2] is not None else ("lit", None, (-1, 0, 0))
+        for c, v in reversed(sx[1]):
+            tail = ("if", c, v, tail)
+        return eval_expr(tail, cols)
     if op == "year":
         a = eval_expr(sx[1], cols)
         d = a.values.astype("datetime64[D]")
@@ -212,7 +247,38 @@ def eval_expr(sx, cols):
     raise NotImplementedError(op)
 
 
+def substring_sql(b, pos, length):
+    """UTF8String.substringSQL as GpuSubstring restates it (stringFunctions.scala:540-600): code points, 1-based pos,
+    negative pos counts from the end"""
+    s = b.decode("utf-8", "surrogateescape")
+    nchars = len(s)
+    start = pos + nchars if pos < 0 else (pos - 1 if pos > 0 else 0)
+    end = max(0, min(start + length, 2**31 - 1))
+    start = max(start, 0)
+    if start >= end or start >= nchars:
+        return b""
+    return s[start:end].encode("utf-8", "surrogateescape")
+
+
+def _like(x, pat, esc="\\"):
+    """SQL LIKE on bytes (UTF-8): % any sequence, _ exactly one code point, esc escapes the next pattern character"""
+    import re
+    xs, ps = x.decode("utf-8", "surrogateescape"), pat.decode("utf-8", "surrogateescape")
+    out, i = [], 0
+    while i < len(ps):
+        ch = ps[i]
+        if ch == esc and i + 1 < len(ps):
+            out.append(re.escape(ps[i + 1])); i += 2; continue
+        out.append(".*" if ch == "%" else ("." if ch == "_" else re.escape(ch)))
+        i += 1
+    return re.fullmatch("".join(out), xs, flags=re.S) is not None
+
+
 def _unify(a, b):
+    if a.typ[0] < 0:   # untyped NULL takes its sibling's type
+        return OCol(np.zeros(len(a), dtype=b.values.dtype), a.valid, b.typ), b
+    if b.typ[0] < 0:
+        return a, OCol(np.zeros(len(b), dtype=a.values.dtype), b.valid, a.typ)
     if is_decimal(a.typ[0]) and is_decimal(b.typ[0]):
         s = max(a.typ[2], b.typ[2])
         p = max(a.typ[1] - a.typ[2], b.typ[1] - b.typ[2]) + s
@@ -300,8 +366,8 @@ def _arith(op, a, b):
                     r = x / ys
                 else:
                     r = np.fmod(x, ys)
-                    if op == "pmod":
-                        r = np.where((r != 0) & ((r < 0) != (ys < 0)), r + ys, r)
+                    if op == "pmod":   # Spark Pmod: r = a % n; if (r < 0) (r + n) % n else r  (arithmetic.scala:1177 BinaryOp.PMOD)
+                        r = np.where(r < 0, np.fmod(r + ys, ys), r)
                 r = np.where(zero, 0, r)
         return OCol(r.astype(x.dtype), valid, a.typ)
     bits = _INT_BITS[dt]
@@ -326,8 +392,11 @@ def _arith(op, a, b):
                     res[i] = _wrap(q, bits)
                 else:
                     rem = xi - q * yi
-                    if op == "pmod" and rem != 0 and ((rem < 0) != (yi < 0)):
-                        rem += yi
+                    if op == "pmod" and rem < 0:   # (r + n) % n, the add wrapping in the operand type (int/long; byte/short add as int)
+                        s2 = _wrap(rem + yi, max(bits, 32))
+                        q2 = abs(s2) // abs(yi)
+                        q2 = q2 if (s2 < 0) == (yi < 0) else -q2
+                        rem = s2 - q2 * yi
                     res[i] = _wrap(rem, bits)
             r = np.where(zero, 0, res).astype(x.dtype)
     return OCol(r.astype(x.dtype), valid, a.typ)

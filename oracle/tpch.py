@@ -49,3 +49,129 @@ def q6_numpy(cols):
     if not m.any():
         return None
     return int((cols["l_extendedprice"][m].astype(object) * cols["l_discount"][m].astype(object)).sum())
+
+
+# ---- TPC-H q3 ----------------------------------------------------------------------------------------
+#   select l_orderkey, sum(l_extendedprice * (1 - l_discount)) as revenue, o_orderdate, o_shippriority
+#   from customer, orders, lineitem
+#   where c_mktsegment = 'BUILDING' and c_custkey = o_custkey and l_orderkey = o_orderkey
+#     and o_orderdate < date '1995-03-15' and l_shipdate > date '1995-03-15'
+#   group by l_orderkey, o_orderdate, o_shippriority order by revenue desc, o_orderdate limit 10
+# revenue is decimal(12,2) * decimal(13,2) = decimal(26,4), summed as decimal(36,4): unscaled value = price * (100 - disc).
+def q3_numpy(customer_chunks, orders_chunks, lineitem_chunks, date=None, segment=None, limit=10):
+    """exact integer restatement over the raw numpy columns, one chunk at a time (never holds a whole table).
+    -> list of (l_orderkey, revenue_unscaled_dec36_4, o_orderdate, o_shippriority), ordered by revenue desc, o_orderdate asc,
+    (then l_orderkey asc to make ties deterministic for the comparison)."""
+    import numpy as np
+    from benchdata import tpch as gen
+    date = gen.Q3_DATE if date is None else date
+    segment = gen.Q3_SEGMENT if segment is None else segment
+    seg_code = gen.SEGMENTS.index(segment)
+    # customer: keys of the wanted segment (sorted unique array -> membership by binary search; no dense-key assumption)
+    ckeys = []
+    for c in customer_chunks:
+        chars, offsets = c["c_mktsegment"]
+        lens = np.diff(offsets)
+        ok = lens == len(segment)
+        if ok.any():  # compare the bytes of the candidates
+            starts = offsets[:-1][ok]
+            mat = chars[starts[:, None] + np.arange(len(segment))[None, :]]
+            same = (mat == np.frombuffer(segment, dtype=np.uint8)[None, :]).all(axis=1)
+            sel = np.flatnonzero(ok)[same]
+            ckeys.append(c["c_custkey"][sel])
+            assert (c["c_mktsegment_code"][sel] == seg_code).all()
+    ckeys = np.sort(np.concatenate(ckeys)) if ckeys else np.zeros(0, np.int64)
+    okeys, odate, oprio = [], [], []
+    for o in orders_chunks:
+        m = o["o_orderdate"] < date
+        pos = np.searchsorted(ckeys, o["o_custkey"])
+        pos[pos >= len(ckeys)] = max(len(ckeys) - 1, 0)
+        m &= (ckeys[pos] == o["o_custkey"]) if len(ckeys) else False
+        okeys.append(o["o_orderkey"][m]); odate.append(o["o_orderdate"][m]); oprio.append(o["o_shippriority"][m])
+    okeys = np.concatenate(okeys); odate = np.concatenate(odate); oprio = np.concatenate(oprio)
+    order = np.argsort(okeys, kind="stable")
+    okeys, odate, oprio = okeys[order], odate[order], oprio[order]
+    assert len(okeys) == 0 or (np.diff(okeys) > 0).all(), "o_orderkey must be unique"
+    keys, revs = [], []
+    for li in lineitem_chunks:
+        m = li["l_shipdate"] > date
+        k = li["l_orderkey"][m]
+        pos = np.searchsorted(okeys, k)
+        pos[pos >= len(okeys)] = max(len(okeys) - 1, 0)
+        hit = (okeys[pos] == k) if len(okeys) else np.zeros(len(k), bool)
+        keys.append(pos[hit])     # index into the qualifying orders = group id
+        revs.append((li["l_extendedprice"][m][hit] * (100 - li["l_discount"][m][hit])).astype(np.int64))
+    gid = np.concatenate(keys); rev = np.concatenate(revs)
+    srt = np.argsort(gid, kind="stable")
+    gid, rev = gid[srt], rev[srt]
+    if len(gid) == 0:
+        return []
+    starts = np.flatnonzero(np.concatenate(([True], gid[1:] != gid[:-1])))
+    sums = np.add.reduceat(rev, starts)            # int64, exact (<= 7 lines x 1.05e9 per group)
+    g = gid[starts]
+    top = np.lexsort((okeys[g], odate[g], -sums))[:limit]
+    return [(int(okeys[g[i]]), int(sums[i]), int(odate[g[i]]), int(oprio[g[i]])) for i in top]
+
+
+def q3_expected(sf, seed=42, threads=8):
+    """q3_numpy over every chunk of the synthetic tables at scale factor sf (chunks generated on `threads` host threads)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from benchdata import tpch as gen
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        cust = list(ex.map(lambda i: gen.q3_chunk("customer", sf, i, seed), range(gen.Q3_CHUNKS["customer"])))
+        orders = list(ex.map(lambda i: gen.q3_chunk("orders", sf, i, seed), range(gen.Q3_CHUNKS["orders"])))
+    def line():
+        for i in range(gen.Q3_CHUNKS["lineitem"]):
+            yield gen.q3_chunk("lineitem", sf, i, seed)
+    return q3_numpy(cust, orders, line())
+
+
+def q3_cpu(customer, orders, lineitem, threads=None, date=None, segment=None, limit=10):
+    """The "vanilla CPU plan" stand-in for q3 when no JVM/Spark exists on the box: the same Filter -> HashJoin -> HashJoin ->
+    HashAggregate -> TakeOrdered pipeline, executed by pyarrow's multi-threaded Acero engine on all host cores.  NOT Spark.
+    Inputs are pyarrow Tables (built once, outside the timed region, like Spark's cached columnar input).
+    Money columns are int64 unscaled decimals and revenue is computed in int64 (exact here; cheaper than Spark's Decimal
+    arithmetic, i.e. favourable to the CPU side)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from benchdata import tpch as gen
+    if threads:
+        pa.set_cpu_count(threads)
+    date = gen.Q3_DATE if date is None else date
+    segment = gen.Q3_SEGMENT if segment is None else segment
+    cust = customer.filter(pc.equal(customer["c_mktsegment"], pa.scalar(segment, type=pa.binary()))).select(["c_custkey"])
+    ords = orders.filter(pc.less(orders["o_orderdate"], pa.scalar(date, type=pa.int32())))
+    j1 = ords.join(cust, keys="o_custkey", right_keys="c_custkey", join_type="inner").select(["o_orderkey", "o_orderdate", "o_shippriority"])
+    li = lineitem.filter(pc.greater(lineitem["l_shipdate"], pa.scalar(date, type=pa.int32()))).select(["l_orderkey", "l_extendedprice", "l_discount"])
+    j2 = li.join(j1, keys="l_orderkey", right_keys="o_orderkey", join_type="inner")
+    rev = pc.multiply(j2["l_extendedprice"], pc.subtract(pa.scalar(100, type=pa.int64()), j2["l_discount"]))
+    j2 = j2.append_column("rev", rev)
+    agg = j2.group_by(["l_orderkey", "o_orderdate", "o_shippriority"]).aggregate([("rev", "sum")])
+    idx = pc.select_k_unstable(agg, k=limit, sort_keys=[("rev_sum", "descending"), ("o_orderdate", "ascending"), ("l_orderkey", "ascending")])
+    top = agg.take(idx)
+    return [(int(a), int(b), int(c), int(d)) for a, b, c, d in zip(top["l_orderkey"].to_pylist(), top["rev_sum"].to_pylist(), top["o_orderdate"].to_pylist(),
+                                                                  top["o_shippriority"].to_pylist())]
+
+
+def q3_arrow_tables(sf, seed=42, threads=8):
+    """the synthetic q3 tables as pyarrow Tables (the CPU arm's cached input)"""
+    import numpy as np
+    import pyarrow as pa
+    from concurrent.futures import ThreadPoolExecutor
+    from benchdata import tpch as gen
+    def table(name, cols):
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            chunks = list(ex.map(lambda i: gen.q3_chunk(name, sf, i, seed), range(gen.Q3_CHUNKS[name])))
+        arrays = {}
+        for c in cols:
+            if c == "c_mktsegment":
+                parts = []
+                for ch in chunks:
+                    chars, offsets = ch[c]
+                    parts.append(pa.Array.from_buffers(pa.binary(), len(offsets) - 1, [None, pa.py_buffer(offsets), pa.py_buffer(chars)]))
+                arrays[c] = pa.chunked_array(parts)
+            else:
+                arrays[c] = pa.chunked_array([pa.array(ch[c]) for ch in chunks])
+        return pa.table(arrays)
+    return (table("customer", ["c_custkey", "c_mktsegment"]), table("orders", ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"]),
+            table("lineitem", ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"]))

@@ -6,7 +6,7 @@ implementation here: every operation goes to the library, which fails loudly wit
 import ctypes
 import numpy as np
 
-from ._lib import lib, check, B2Error, B2ColumnInfo, B2AggSpec, B2OrderByArg, parse_header, LIB_PATH  # noqa: F401
+from ._lib import lib, check, B2Error, B2ColumnInfo, B2AggSpec, B2OrderByArg, B2HostColumn, parse_header, LIB_PATH  # noqa: F401
 
 # b2_dtype
 BOOL8, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, DATE32, TIMESTAMP_US, DECIMAL32, DECIMAL64, DECIMAL128, STRING = range(13)
@@ -21,6 +21,7 @@ OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_EQ_NULLSAFE = 10, 11, 12, 13, 14, 1
 OP_AND, OP_OR, OP_NOT = 20, 21, 22
 OP_IS_NULL, OP_IS_NOT_NULL, OP_COALESCE, OP_IF = 30, 31, 32, 33
 OP_NORMALIZE_NAN_ZERO, OP_YEAR = 41, 42
+OP_STARTS_WITH, OP_ENDS_WITH, OP_CONTAINS, OP_LIKE, OP_SUBSTRING = 50, 51, 52, 53, 54
 # b2_agg_kind
 AGG_SUM, AGG_COUNT, AGG_MIN, AGG_MAX, AGG_COUNT_ALL = 1, 2, 3, 4, 5
 # b2_join_kind
@@ -107,6 +108,16 @@ class Column:
         vb = None if valid.all() else np.ascontiguousarray(pack_bits(valid))
         out = ctypes.c_int64()
         check(lib.b2_column_from_host(STRING, 0, len(enc), _ptr(chars) if len(chars) else None, _ptr(vb), _ptr(offsets), ctypes.byref(out)))
+        return Column(out.value)
+
+    @staticmethod
+    def from_string_buffers(chars, offsets, valid=None):
+        """Arrow string buffers (uint8 chars, int32 offsets[n+1]) -> STRING column"""
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        vb = None if valid is None else np.ascontiguousarray(pack_bits(valid))
+        out = ctypes.c_int64()
+        check(lib.b2_column_from_host(STRING, 0, len(offsets) - 1, _ptr(chars) if len(chars) else None, _ptr(vb), _ptr(offsets), ctypes.byref(out)))
         return Column(out.value)
 
     # ---- inspection
@@ -237,7 +248,7 @@ class Expr:
         return dt.value, p.value, s.value, bool(nl.value)
 
     def _bin(self, op, name, other):
-        other = other if isinstance(other, Expr) else lit(other)
+        other = other if isinstance(other, Expr) else (strlit(other) if isinstance(other, (str, bytes)) else lit(other))
         out = ctypes.c_int64()
         check(lib.b2_expr_binary(op, self.h, other.h, ctypes.byref(out)))
         return Expr(out.value, (name, self.sexpr, other.sexpr))
@@ -270,6 +281,28 @@ class Expr:
     def normalize_nan_zero(self): return self._un(OP_NORMALIZE_NAN_ZERO, "normnz")
     def year(self): return self._un(OP_YEAR, "year")
     def coalesce(self, o): return self._bin(OP_COALESCE, "coalesce", o)
+    # string predicates (stringFunctions.scala:163,189,396,972) — the right side is a literal
+    def startswith(self, s): return self._bin(OP_STARTS_WITH, "startswith", s if isinstance(s, Expr) else strlit(s))
+    def endswith(self, s): return self._bin(OP_ENDS_WITH, "endswith", s if isinstance(s, Expr) else strlit(s))
+    def contains(self, s): return self._bin(OP_CONTAINS, "contains", s if isinstance(s, Expr) else strlit(s))
+
+    def like(self, pattern, escape="\\"):
+        pat = pattern if isinstance(pattern, Expr) else strlit(pattern)
+        out = ctypes.c_int64()
+        check(lib.b2_expr_like(self.h, pat.h, ord(escape), ctypes.byref(out)))
+        return Expr(out.value, ("like", self.sexpr, pat.sexpr, escape))
+
+    def substr(self, pos, length=2**31 - 1):
+        out = ctypes.c_int64()
+        check(lib.b2_expr_substring(self.h, int(pos), int(length), ctypes.byref(out)))
+        return Expr(out.value, ("substr", self.sexpr, int(pos), int(length)))
+
+    def isin(self, values):
+        lits = [v if isinstance(v, Expr) else (strlit(v) if isinstance(v, (str, bytes)) else lit(v)) for v in values]
+        arr = (ctypes.c_int64 * max(len(lits), 1))(*[x.h.value for x in lits])
+        out = ctypes.c_int64()
+        check(lib.b2_expr_in(self.h, arr, len(lits), ctypes.byref(out)))
+        return Expr(out.value, ("in", self.sexpr, [x.sexpr for x in lits]))
     __hash__ = None
 
     def cast(self, dtype, precision=0, scale=0):
@@ -309,6 +342,23 @@ def lit(value, dtype=None, precision=0, scale=0):
     out = ctypes.c_int64()
     check(lib.b2_expr_literal(dtype, precision, scale, _ptr(buf), int(is_null), ctypes.byref(out)))
     return Expr(out.value, ("lit", value, (dtype, precision, scale)))
+
+
+def strlit(value):
+    """GpuLiteral(StringType); value: str / bytes / None"""
+    raw = None if value is None else (value.encode() if isinstance(value, str) else bytes(value))
+    out = ctypes.c_int64()
+    check(lib.b2_expr_string_literal(raw, len(raw) if raw else 0, int(raw is None), ctypes.byref(out)))
+    return Expr(out.value, ("lit", raw, (STRING, 0, 0)))
+
+
+def case_when(branches, otherwise=None):
+    """GpuCaseWhen: branches = [(condition Expr, value Expr)], otherwise = Expr or None (NULL)"""
+    conds = (ctypes.c_int64 * len(branches))(*[c.h.value for c, _ in branches])
+    vals = (ctypes.c_int64 * len(branches))(*[v.h.value for _, v in branches])
+    out = ctypes.c_int64()
+    check(lib.b2_expr_case_when(conds, vals, len(branches), otherwise.h if otherwise is not None else ctypes.c_int64(0), ctypes.byref(out)))
+    return Expr(out.value, ("case", [(c.sexpr, v.sexpr) for c, v in branches], otherwise.sexpr if otherwise is not None else None))
 
 
 def if_else(pred, a, b):
@@ -371,6 +421,19 @@ def filter(program, table):  # noqa: A001 - mirrors Table.filter
     out = ctypes.c_int64()
     check(lib.b2_filter(program.h, table.h, ctypes.byref(out)))
     return Table(out.value)
+
+
+def filter_select(program, table, keep_cols):
+    """GpuFilterExec under a column-pruning project, fused: only keep_cols are compacted"""
+    out = ctypes.c_int64()
+    check(lib.b2_filter_select(program.h, table.h, _i32s(keep_cols), len(keep_cols), ctypes.byref(out)))
+    return Table(out.value)
+
+
+def substring(column, pos, length=2**31 - 1):
+    out = ctypes.c_int64()
+    check(lib.b2_substring(column.h, int(pos), int(length), ctypes.byref(out)))
+    return Column(out.value)
 
 
 def filter_mask(table, mask):
@@ -572,6 +635,28 @@ class Comm:
     def exchange(self, partitioned_table, offsets):
         out = ctypes.c_int64()
         check(lib.b2_exchange(self.h, partitioned_table.h, _i32s(offsets), ctypes.byref(out)))
+        return Table(out.value)
+
+    def exchange_hash(self, table, key_cols, seed=42):
+        """fused hash partition + peer-store exchange; table may be None (no batch on this rank).  -> (Table|None, any_data)"""
+        out, anyd = ctypes.c_int64(), ctypes.c_int32()
+        check(lib.b2_exchange_hash(self.h, table.h if table is not None else ctypes.c_int64(0), _i32s(key_cols), len(key_cols), seed,
+                                   ctypes.byref(out), ctypes.byref(anyd)))
+        return (Table(out.value) if out.value else None), bool(anyd.value)
+
+    def fused_ready(self):
+        ok = ctypes.c_int32()
+        check(lib.b2_comm_fused_ready(self.h, ctypes.byref(ok)))
+        return bool(ok.value)
+
+    def stats(self):
+        out = (ctypes.c_int64 * 4)()
+        check(lib.b2_comm_stats(self.h, out))
+        return {"bytes_sent": out[0], "bytes_received": out[1], "calls": out[2], "arena_bytes": out[3]}
+
+    def broadcast(self, table, root):
+        out = ctypes.c_int64()
+        check(lib.b2_broadcast_table(self.h, table.h if table is not None else ctypes.c_int64(0), root, ctypes.byref(out)))
         return Table(out.value)
 
     def close(self):

@@ -26,6 +26,11 @@ class B2AggSpec(ctypes.Structure):
                 ("out_scale", ctypes.c_int32), ("out_precision", ctypes.c_int32)]
 
 
+class B2HostColumn(ctypes.Structure):
+    _fields_ = [("dtype", ctypes.c_int32), ("scale", ctypes.c_int32), ("rows", ctypes.c_int64), ("data", ctypes.c_void_p),
+                ("validity_bits", ctypes.c_void_p), ("offsets", ctypes.c_void_p)]
+
+
 class B2OrderByArg(ctypes.Structure):
     _fields_ = [("column", ctypes.c_int32), ("ascending", ctypes.c_int32), ("nulls_first", ctypes.c_int32)]
 

@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-    "-Xcudafe", "--diag_suppress=177", "-DB2_BUILD",
+    "-Xcudafe", "--diag_suppress=177", "-DB2_BUILD", "-split-compile", "0",
 ]
 
 
@@ -32,15 +32,30 @@ def _sources():
     return out
 
 
-def _deps_digest():
+_INC = None
+
+
+def _includes(path, seen):
+    """transitive closure of the quoted #include files of `path` (csrc/ and include/ only)"""
+    import re
+    if path in seen or not os.path.exists(path):
+        return
+    seen.add(path)
+    with open(path, "r", errors="replace") as fh:
+        for m in re.finditer(r'^\s*#\s*include\s+"([^"]+)"', fh.read(), flags=re.M):
+            _includes(os.path.normpath(os.path.join(os.path.dirname(path), m.group(1))), seen)
+
+
+def _deps_digest(src=None):
+    """digest of the headers `src` really includes (so touching vm.cuh does not rebuild join.cu) + the flags"""
+    seen = set()
+    _includes(src, seen)
+    seen.discard(src)
     h = hashlib.sha1()
-    for root, _, files in os.walk(CSRC):
-        for f in sorted(files):
-            if f.endswith((".cuh", ".h", ".hpp")):
-                with open(os.path.join(root, f), "rb") as fh:
-                    h.update(fh.read())
-    with open(os.path.join(HERE, "..", "include", "b200sql.h"), "rb") as fh:
-        h.update(fh.read())
+    for f in sorted(seen):
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
 
@@ -50,7 +65,7 @@ def _compile(src, digest, verbose):
     obj = os.path.join(OBJ, rel + ".o")
     stamp = obj + ".stamp"
     with open(src, "rb") as fh:
-        key = hashlib.sha1(fh.read() + digest.encode()).hexdigest()
+        key = hashlib.sha1(fh.read() + _deps_digest(src).encode() + digest.encode()).hexdigest()
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == key:
         return obj, False
     cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", src, "-o", obj]
@@ -69,7 +84,7 @@ def _compile(src, digest, verbose):
 def build_all(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    digest = _deps_digest() + ("force%d" % os.getpid() if force else "")
+    digest = "force%d" % os.getpid() if force else ""
     srcs = _sources()
     with concurrent.futures.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         res = list(ex.map(lambda s: _compile(s, digest, verbose), srcs))

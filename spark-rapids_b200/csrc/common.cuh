@@ -50,6 +50,7 @@ struct KernelTimer {  // scoped CUDA-event timer around a kernel launch; no-op u
   explicit KernelTimer(const char* name, cudaStream_t on = nullptr);
   ~KernelTimer();
 };
+bool profile_enabled();      // b2_profile_enable state
 cudaStream_t aux_stream();   // second per-thread stream for work that may overlap the main stream
 int sm_count();
 

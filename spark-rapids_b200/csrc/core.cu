@@ -81,6 +81,7 @@ KernelTimer::~KernelTimer() {
   g_prof_recs.push_back(r);
 }
 int sm_count() { return g_sms; }
+bool profile_enabled() { return g_prof.load(std::memory_order_relaxed); }
 
 static void ensure_init() {
   if (g_inited) return;

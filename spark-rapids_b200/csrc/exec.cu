@@ -26,6 +26,7 @@ Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullif
 Table* concat_tables(const std::vector<const Table*>& ts);
 Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const int* key_outs, int nkeys, const b2_agg_spec* specs, int naggs);
 Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
+Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, int nkeep);
 
 struct TableRef {  // owning reference
   Table* t = nullptr;
@@ -46,16 +47,36 @@ struct GpuExec {
   std::atomic<int> refs{1};
   std::vector<GpuExec*> children;
   int64_t num_output_rows = 0, num_output_batches = 0, op_time_ns = 0;
-  virtual ~GpuExec() { for (auto* c : children) c->release(); }
+  // device time of this node (CUDA events on the library stream around every next(), recorded while profiling is on):
+  // total includes the children pulled from inside next(); self = total - children  (opTime of GpuMetrics.scala:49-62)
+  struct Span { cudaEvent_t a, b; };
+  std::vector<Span> spans, child_spans;
+  virtual ~GpuExec() {
+    for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto* c : children) c->release();
+  }
   void release() { if (refs.fetch_sub(1) == 1) delete this; }
   void add_child(GpuExec* c) { c->refs.fetch_add(1); children.push_back(c); }
   virtual Table* do_next() = 0;  // nullptr when exhausted; returned table is owned by the caller
+  static GpuExec*& current() { static thread_local GpuExec* cur = nullptr; return cur; }
   Table* next() {
+    const bool prof = profile_enabled();
+    Span sp{nullptr, nullptr};
+    if (prof) { cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); cudaEventRecord(sp.a, stream()); }
+    GpuExec* parent = current();
+    struct Restore { GpuExec* p; ~Restore() { current() = p; } } restore{parent};
+    current() = this;
     auto t0 = std::chrono::steady_clock::now();
     Table* t = do_next();
     op_time_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    if (prof) { cudaEventRecord(sp.b, stream()); spans.push_back(sp); if (parent) parent->child_spans.push_back(sp); }
     if (t) { num_output_rows += t->rows; num_output_batches++; }
     return t;
+  }
+  static double span_ms(const std::vector<Span>& v) {
+    double ms = 0;
+    for (auto& sp : v) { float t = 0; cudaEventSynchronize(sp.b); if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ms += t; }
+    return ms;
   }
 };
 static GpuExec* exec_from(b2_handle h) {
@@ -91,13 +112,87 @@ struct GpuParquetScanExec : GpuExec {
 
 struct GpuFilterExec : GpuExec {
   b2_handle program;
+  std::vector<int32_t> keep;   // non-empty: a column-pruning GpuProjectExec above the filter, fused (only these are compacted)
   Table* do_next() override {
     TableRef in(children[0]->next());
     if (!in.t) return nullptr;
+    if (!keep.empty()) return filter_select(program_from(program), in.t, keep.data(), (int)keep.size());
     b2_handle out = 0;
     int rc = b2_filter(program, to_handle(in.t), &out);
     if (rc != B2_OK) throw Error(rc, b2_last_error());
     return from_handle_owned(out);
+  }
+};
+
+// HostColumnarToGpu (HostColumnarToGpu.scala; GpuRowToColumnarExec.scala:937-998 for the row source): host columnar batches
+// -> device batches.  The copy of batch k+1 runs on the copy stream while batch k is being consumed downstream
+// (the reference keeps host buffers in flight the same way: GpuMultiFileReader.scala).
+struct HostColumn { int32_t dtype, scale; int64_t rows; const void* data; const uint8_t* validity; const int32_t* offsets; };
+struct GpuHostBatchSource : GpuExec {
+  std::vector<std::vector<HostColumn>> batches;
+  size_t next_batch = 0;
+  struct InFlight { Table* t = nullptr; cudaEvent_t done = nullptr; };
+  std::deque<InFlight> flight;
+  cudaStream_t copy = nullptr;
+  int depth = 2;
+  ~GpuHostBatchSource() {
+    for (auto& f : flight) { if (f.done) { cudaEventSynchronize(f.done); cudaEventDestroy(f.done); } if (f.t) table_release(f.t); }
+    if (copy) cudaStreamDestroy(copy);
+  }
+  void issue() {
+    const auto& b = batches[next_batch++];
+    cudaStream_t s = stream();
+    if (!copy) CUDA_CHECK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    ColsGuard cols;
+    for (const HostColumn& h : b) {
+      std::unique_ptr<Column> c(new Column());
+      c->dtype = h.dtype; c->scale = h.scale; c->size = h.rows;
+      if (h.rows > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "host batch of more than 2^31-1 rows");
+      if (h.dtype == B2_STRING) {
+        c->offsets = DevBuf((size_t)(h.rows + 1) * 4);
+        c->chars_bytes = h.rows ? h.offsets[h.rows] : 0;
+        c->data = DevBuf((size_t)c->chars_bytes);
+      } else c->data = DevBuf((size_t)h.rows * dtype_width(h.dtype));
+      if (h.validity) { c->valid = DevBuf(validity_bytes(h.rows)); c->null_count = -1; }
+      cols.v.push_back(c.release());
+    }
+    // the buffers were allocated in compute-stream order: the copy stream may touch them only after that point
+    cudaEvent_t ready;
+    CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(ready, s));
+    CUDA_CHECK(cudaStreamWaitEvent(copy, ready, 0));
+    cudaEventDestroy(ready);
+    for (size_t i = 0; i < b.size(); i++) {
+      const HostColumn& h = b[i];
+      Column* c = cols.v[i];
+      if (h.dtype == B2_STRING) {
+        if (h.rows) CUDA_CHECK(cudaMemcpyAsync(c->offsets.p, h.offsets, (size_t)(h.rows + 1) * 4, cudaMemcpyHostToDevice, copy));
+        else CUDA_CHECK(cudaMemsetAsync(c->offsets.p, 0, 4, copy));
+        if (c->chars_bytes) CUDA_CHECK(cudaMemcpyAsync(c->data.p, h.data, (size_t)c->chars_bytes, cudaMemcpyHostToDevice, copy));
+      } else if (h.rows) {
+        CUDA_CHECK(cudaMemcpyAsync(c->data.p, h.data, (size_t)h.rows * dtype_width(h.dtype), cudaMemcpyHostToDevice, copy));
+      }
+      if (h.validity) {
+        CUDA_CHECK(cudaMemsetAsync(c->valid.p, 0, c->valid.bytes, copy));
+        CUDA_CHECK(cudaMemcpyAsync(c->valid.p, h.validity, (size_t)((h.rows + 7) / 8), cudaMemcpyHostToDevice, copy));
+      }
+      h2d_bytes_total += (h.dtype == B2_STRING ? (int64_t)(h.rows + 1) * 4 + c->chars_bytes : h.rows * dtype_width(h.dtype)) + (h.validity ? (h.rows + 7) / 8 : 0);
+    }
+    InFlight f;
+    f.t = new_table(cols.release());
+    CUDA_CHECK(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(f.done, copy));
+    flight.push_back(f);
+  }
+  int64_t h2d_bytes_total = 0;
+  Table* do_next() override {
+    while ((int)flight.size() < depth && next_batch < batches.size()) issue();
+    if (flight.empty()) return nullptr;
+    InFlight f = flight.front(); flight.pop_front();
+    CUDA_CHECK(cudaStreamWaitEvent(stream(), f.done, 0));   // the consumer's stream is ordered after the copy; the host does not block
+    cudaEventDestroy(f.done);
+    if (next_batch < batches.size() && (int)flight.size() < depth) issue();
+    return f.t;
   }
 };
 struct GpuProjectExec : GpuExec {
@@ -163,6 +258,8 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
   std::vector<int> stream_keys, build_keys;
   int kind = B2_JOIN_INNER;
   bool nulls_equal = false, built = false, full_done = false;
+  bool pruned = false;                       // a column-pruning GpuProjectExec above the join, fused into the gathers
+  std::vector<int> stream_out, build_out;    // pruned: the columns each side contributes (in this order)
   TableRef build_table;
   b2_handle ht = 0;
   ~GpuShuffledHashJoinExec() { if (ht) b2_join_hash_table_close(ht); }
@@ -206,9 +303,11 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
     if (rc != B2_OK) throw Error(rc, b2_last_error());
     ColGuard lmap(col_from(lm));
     ColGuard rmap(rm ? col_from(rm) : nullptr);
-    TableRef left(gather_table(s.t, lmap.c->data.as<int32_t>(), lmap.c->size, kind == B2_JOIN_FULL_OUTER, nullptr));
-    if (!rmap.c) return left.release();  // semi / anti: stream columns only
-    TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER || kind == B2_JOIN_FULL_OUTER, nullptr));
+    TableRef left(gather_table(s.t, lmap.c->data.as<int32_t>(), lmap.c->size, kind == B2_JOIN_FULL_OUTER, pruned ? &stream_out : nullptr));
+    if (!rmap.c || (pruned && build_out.empty())) return left.release();  // semi / anti (or nothing wanted from the build side): stream columns only
+    TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER || kind == B2_JOIN_FULL_OUTER,
+                                pruned ? &build_out : nullptr));
+    if (pruned && stream_out.empty()) return right.release();
     std::vector<Column*> cols;  // output = left columns ++ right columns (GpuHashJoin.scala:2451-2470)
     for (auto*& c : left.t->cols) { cols.push_back(c); c = nullptr; }
     for (auto*& c : right.t->cols) { cols.push_back(c); c = nullptr; }
@@ -275,30 +374,104 @@ struct GpuCoalesceBatches : GpuExec {
   }
 };
 
+extern "C" int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* key_cols, int32_t nkeys, int32_t seed, b2_handle* out_table, int32_t* any_data);
+extern "C" int b2_exchange_ex(b2_handle comm, b2_handle partitioned_table, const int32_t* offsets, b2_handle* out_table, int32_t* any_data);
+extern "C" int b2_comm_fused_ready(b2_handle comm, int32_t* ok);
+extern "C" int b2_comm_allmax(b2_handle comm, int32_t value, int32_t* out);
+extern "C" int b2_broadcast_table(b2_handle comm, b2_handle table, int32_t root, b2_handle* out_table);
+
+// GpuShuffleExchangeExec (GpuShuffleExchangeExecBase.scala:384-536).  Every call of the exchange is a collective, so the
+// node follows a termination protocol instead of stopping when ITS child is exhausted: a rank without a batch keeps
+// taking part (sending nothing) until no rank has data left — ranks with different batch counts, or with none at all,
+// cannot strand their peers (the reference's pull-based shuffle has no such constraint).
 struct GpuShuffleExchangeExec : GpuExec {
   std::vector<int32_t> key_cols;   // empty = SinglePartition (everything to rank 0)
   b2_handle comm = 0;
   int world = 1;
+  bool child_done = false, finished = false, probed = false, fused = false;
   Table* do_next() override {
-    TableRef in(children[0]->next());
-    if (!in.t) return nullptr;
-    std::vector<int32_t> offs(world + 1, 0);
-    TableRef part;
-    if (key_cols.empty()) {
-      in.t->refs.fetch_add(1);
-      part = TableRef(in.t);
-      for (int r = 1; r <= world; r++) offs[r] = (int32_t)in.t->rows;
-    } else {
+    if (finished) return nullptr;
+    if (world == 1 || !comm) {
+      TableRef in(children[0]->next());
+      if (!in.t) { finished = true; return nullptr; }
+      if (key_cols.empty()) return in.release();
+      std::vector<int32_t> offs(world + 1, 0);
       b2_handle out = 0;
       int rc = b2_hash_partition(to_handle(in.t), key_cols.data(), (int)key_cols.size(), 42, world, &out, offs.data());
       if (rc != B2_OK) throw Error(rc, b2_last_error());
-      part = TableRef(from_handle_owned(out));
+      return from_handle_owned(out);
     }
-    if (world == 1 || !comm) return part.release();
+    TableRef in;
+    if (!child_done) { in = TableRef(children[0]->next()); if (!in.t) child_done = true; }
+    if (!probed) {   // collective, once per node: can every rank store into every peer's arena, and is the schema fixed width?
+      int32_t ok = 0;
+      int rc = b2_comm_fused_ready(comm, &ok);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+      // a rank without a batch does not know the schema, so the ranks agree on "some batch carries STRING columns"
+      int32_t mine = 0, any_strings = 0;
+      if (in.t) for (auto* c : in.t->cols) if (c->dtype == B2_STRING) mine = 1;
+      rc = b2_comm_allmax(comm, mine, &any_strings);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+      has_strings = any_strings != 0;
+      fused = ok != 0; probed = true;
+    }
     b2_handle out = 0;
-    int rc = b2_exchange(comm, to_handle(part.t), offs.data(), &out);
-    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    int32_t any = 0;
+    if (fused && !has_strings) {
+      int rc = b2_exchange_hash(comm, in.t ? to_handle(in.t) : 0, key_cols.data(), (int)key_cols.size(), 42, &out, &any);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+    } else {
+      std::vector<int32_t> offs(world + 1, 0);
+      TableRef part;
+      if (in.t) {
+        if (key_cols.empty()) {
+          in.t->refs.fetch_add(1);
+          part = TableRef(in.t);
+          for (int r = 1; r <= world; r++) offs[r] = (int32_t)in.t->rows;
+        } else {
+          b2_handle ph = 0;
+          int rc = b2_hash_partition(to_handle(in.t), key_cols.data(), (int)key_cols.size(), 42, world, &ph, offs.data());
+          if (rc != B2_OK) throw Error(rc, b2_last_error());
+          part = TableRef(from_handle_owned(ph));
+        }
+      }
+      int rc = b2_exchange_ex(comm, part.t ? to_handle(part.t) : 0, part.t ? offs.data() : nullptr, &out, &any);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+    }
+    if (!any) { finished = true; return nullptr; }
     return from_handle_owned(out);
+  }
+  bool has_strings = false;   // the path (fused / NCCL) is a per-node property every rank agrees on at the first call
+};
+
+// GpuBroadcastExchangeExec (GpuBroadcastExchangeExec.scala:1-664): the child relation is collected once and every rank gets
+// the WHOLE relation.  SPMD form: each rank coalesces its slice and broadcasts it (ncclBroadcast per rank), the result is
+// the concatenation in rank order.  One batch out.
+struct GpuBroadcastExchangeExec : GpuExec {
+  b2_handle comm = 0;
+  int world = 1, rank = 0;
+  bool done = false;
+  std::vector<int> schema_dtype, schema_scale;   // needed when this rank's slice is empty
+  Table* do_next() override {
+    if (done) return nullptr;
+    done = true;
+    std::vector<TableRef> parts;
+    while (true) { TableRef b(children[0]->next()); if (!b.t) break; parts.emplace_back(b.release()); }
+    TableRef mine;
+    if (parts.size() == 1) mine = std::move(parts[0]);
+    else if (parts.size() > 1) { std::vector<const Table*> ts; for (auto& p : parts) ts.push_back(p.t); mine = TableRef(concat_tables(ts)); }
+    if (world == 1 || !comm) return mine.release();
+    if (!mine.t) throw Error(B2_ERR_UNSUPPORTED, "broadcast of a slice with no batches needs the schema (push an empty batch)");
+    std::vector<TableRef> got;
+    for (int r = 0; r < world; r++) {
+      b2_handle out = 0;
+      int rc = b2_broadcast_table(comm, r == rank ? to_handle(mine.t) : 0, r, &out);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+      got.emplace_back(from_handle_owned(out));
+    }
+    std::vector<const Table*> ts;
+    for (auto& g : got) ts.push_back(g.t);
+    return concat_tables(ts);
   }
 };
 
@@ -342,6 +515,33 @@ int b2_exec_filter(b2_handle child, b2_handle predicate_program, b2_handle* out)
   *out = to_handle(e);
   B2_CATCH
 }
+int b2_exec_filter_select(b2_handle child, b2_handle predicate_program, const int32_t* keep_cols, int32_t nkeep, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(nkeep >= 1, "filter: at least one output column");
+  auto* e = new GpuFilterExec();
+  e->add_child(exec_from(child)); e->program = predicate_program;
+  e->keep.assign(keep_cols, keep_cols + nkeep);
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_host_source(b2_handle* out) {
+  B2_TRY
+  *out = to_handle(new GpuHostBatchSource());
+  B2_CATCH
+}
+int b2_exec_host_source_push(b2_handle source, const b2_host_column* cols, int32_t ncols) {
+  B2_TRY
+  auto* s = dynamic_cast<GpuHostBatchSource*>(exec_from(source));
+  B2_CHECK(s, "not a host batch source");
+  B2_CHECK(ncols >= 1, "a batch needs columns");
+  std::vector<HostColumn> b;
+  for (int i = 0; i < ncols; i++) {
+    B2_CHECK(cols[i].rows == cols[0].rows, "host batch columns differ in length");
+    b.push_back({cols[i].dtype, cols[i].scale, cols[i].rows, cols[i].data, cols[i].validity_bits, cols[i].offsets});
+  }
+  s->batches.push_back(std::move(b));
+  B2_CATCH
+}
 int b2_exec_project(b2_handle child, b2_handle program, b2_handle* out) {
   B2_TRY
   auto* e = new GpuProjectExec();
@@ -367,6 +567,28 @@ int b2_exec_shuffled_hash_join(b2_handle stream_child, b2_handle build_child, co
   e->add_child(exec_from(stream_child)); e->add_child(exec_from(build_child));
   e->stream_keys.assign(stream_keys, stream_keys + nkeys); e->build_keys.assign(build_keys, build_keys + nkeys);
   e->kind = kind; e->nulls_equal = nulls_equal != 0;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_shuffled_hash_join_select(b2_handle stream_child, b2_handle build_child, const int32_t* stream_keys, const int32_t* build_keys, int32_t nkeys,
+                                      int32_t kind, int32_t nulls_equal, const int32_t* stream_out, int32_t nstream_out, const int32_t* build_out,
+                                      int32_t nbuild_out, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(nstream_out + nbuild_out >= 1, "join: at least one output column");
+  auto* e = new GpuShuffledHashJoinExec();
+  e->add_child(exec_from(stream_child)); e->add_child(exec_from(build_child));
+  e->stream_keys.assign(stream_keys, stream_keys + nkeys); e->build_keys.assign(build_keys, build_keys + nkeys);
+  e->kind = kind; e->nulls_equal = nulls_equal != 0;
+  e->pruned = true;
+  e->stream_out.assign(stream_out, stream_out + nstream_out); e->build_out.assign(build_out, build_out + nbuild_out);
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_broadcast_exchange(b2_handle child, b2_handle comm, int32_t rank, int32_t world, b2_handle* out) {
+  B2_TRY
+  auto* e = new GpuBroadcastExchangeExec();
+  e->add_child(exec_from(child));
+  e->comm = comm; e->rank = rank; e->world = world;
   *out = to_handle(e);
   B2_CATCH
 }
@@ -402,6 +624,13 @@ int b2_exec_metrics(b2_handle exec, int64_t* out3) {
   B2_TRY
   GpuExec* e = exec_from(exec);
   out3[0] = e->num_output_rows; out3[1] = e->num_output_batches; out3[2] = e->op_time_ns;
+  B2_CATCH
+}
+int b2_exec_device_time(b2_handle exec, double* out2) {
+  B2_TRY
+  GpuExec* e = exec_from(exec);
+  const double total = GpuExec::span_ms(e->spans), kids = GpuExec::span_ms(e->child_spans);
+  out2[0] = total - kids; out2[1] = total;
   B2_CATCH
 }
 int b2_exec_close(b2_handle exec) {

@@ -17,6 +17,8 @@ struct Expr {
   int column = -1;
   int64_t lit_lo = 0, lit_hi = 0;
   bool lit_null = false;
+  std::string str;       // STRING literal bytes (UTF-8)
+  int escape = '\\';     // LIKE escape character
   std::vector<Expr*> kids;
   ~Expr() {
     for (auto* k : kids)
@@ -68,6 +70,8 @@ struct Val {  // a compiled sub-expression
   int mt;
   int dtype, precision, scale;
   bool nullable;
+  bool win = false;          // STRING column seen through Substring(pos, len): only a string predicate can consume it
+  int64_t wpos = 0, wlen = 0;
 };
 
 struct Compiler {
@@ -115,7 +119,8 @@ struct Compiler {
   Val emit(int op, int mt, int mt2, int out_mt, bool out_nullable, int aux, const Val* a, const Val* b, const Val* c,
            int dtype, int precision, int scale) {
     for (const Val* v : {a, b, c})
-      if (v && v->dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "string expressions are not supported yet");
+      if (v && v->dtype == B2_STRING && !((op == V_ISNULL || op == V_ISNOTNULL) && v->o.kind == OK_COL && !v->win))
+        throw Error(B2_ERR_UNSUPPORTED, "string-valued expressions (only string predicates and IS [NOT] NULL are compiled)");
     VMInstr ins; memset(&ins, 0, sizeof(ins));
     ins.op = (uint8_t)op; ins.mt = (uint8_t)mt; ins.mt2 = (uint8_t)mt2; ins.aux = aux;
     ins.a = a ? a->o : none(); ins.b = b ? b->o : none(); ins.c = c ? c->o : none();
@@ -128,6 +133,30 @@ struct Compiler {
     prog->code.push_back(ins);
     Val v; v.o = none(); v.o.kind = OK_REG; v.o.idx = r; v.o.nullable = out_nullable;
     v.mt = out_mt; v.dtype = dtype; v.precision = precision; v.scale = scale; v.nullable = out_nullable;
+    return v;
+  }
+
+  int lit_used = 0;
+  int64_t intern(const std::string& bytes) {   // string literal -> offset in the program's pool
+    if (lit_used + (int)bytes.size() > VM_LIT_BYTES) throw Error(B2_ERR_UNSUPPORTED, "string literals of one program exceed 512 bytes");
+    const int off = lit_used;
+    memcpy(prog->hdr.lits + off, bytes.data(), bytes.size());
+    lit_used += (int)bytes.size();
+    return off;
+  }
+  Val emit_strpred(int kind, const Val& a, const Val& b, int escape) {
+    if (a.o.kind != OK_COL) throw Error(B2_ERR_UNSUPPORTED, "string predicate: the left side must be a STRING column");
+    if (b.o.kind != OK_COL && b.o.kind != OK_LIT) throw Error(B2_ERR_UNSUPPORTED, "string predicate: the right side must be a column or a literal");
+    if (b.win) throw Error(B2_ERR_UNSUPPORTED, "Substring on the right side of a string predicate");
+    VMInstr ins; memset(&ins, 0, sizeof(ins));
+    ins.op = V_STRPRED; ins.mt = MT_I8; ins.mt2 = b.o.kind == OK_LIT ? 1 : 0; ins.aux = kind | ((escape & 0xff) << 8);
+    ins.a = a.o; ins.b = b.o; ins.c = a.win ? lit(a.wpos, a.wlen, false) : none();
+    const bool nullable = a.nullable || b.nullable;
+    const int r = alloc_reg(MT_I8, nullable);
+    ins.dst = r; ins.dst_nullable = nullable;
+    prog->code.push_back(ins);
+    Val v; v.o = none(); v.o.kind = OK_REG; v.o.idx = r; v.o.nullable = nullable;
+    v.mt = MT_I8; v.dtype = B2_BOOL8; v.precision = 0; v.scale = 0; v.nullable = nullable;
     return v;
   }
 
@@ -217,6 +246,15 @@ struct Compiler {
       prog->col_dtype[e->column] = e->dtype;
       return v;
     }
+    if (e->op == -1 && e->dtype == B2_STRING) {  // string GpuLiteral: bytes go to the program's literal pool
+      Val v; v.o = lit(intern(e->str), (int64_t)e->str.size(), e->lit_null);
+      v.mt = MT_I8; v.dtype = B2_STRING; v.precision = 0; v.scale = 0; v.nullable = e->lit_null;
+      return v;
+    }
+    if (e->op == -1 && e->dtype < 0) {  // untyped NULL (CASE without ELSE): takes the type of its sibling in unify()
+      Val v; v.o = lit(0, 0, true); v.mt = MT_I8; v.dtype = -1; v.precision = 0; v.scale = 0; v.nullable = true;
+      return v;
+    }
     if (e->op == -1) {  // GpuLiteral
       Val v; v.o = lit(e->lit_lo, e->lit_hi, e->lit_null);
       v.mt = mt_of(e->dtype); v.dtype = e->dtype; v.precision = e->precision; v.scale = e->scale; v.nullable = e->lit_null;
@@ -285,6 +323,19 @@ struct Compiler {
         if (!is_float(a.dtype)) return a;
         return emit(V_NORM_NAN_ZERO, a.mt, a.mt, a.mt, a.nullable, 0, &a, nullptr, nullptr, a.dtype, 0, 0);
       }
+      case B2_OP_SUBSTRING: {   // stringFunctions.scala:524 GpuSubstring with literal pos / len
+        Val a = compile(e->kids[0]);
+        if (a.dtype != B2_STRING || a.o.kind != OK_COL || a.win) throw Error(B2_ERR_UNSUPPORTED, "Substring needs a plain STRING column");
+        a.win = true; a.wpos = e->lit_lo; a.wlen = e->lit_hi;
+        return a;
+      }
+      case B2_OP_STARTS_WITH: case B2_OP_ENDS_WITH: case B2_OP_CONTAINS: case B2_OP_LIKE: {
+        Val a = compile(e->kids[0]), b = compile(e->kids[1]);
+        // GpuBinaryExpressionArgsAnyScalar: the right side is a scalar (stringFunctions.scala:163,189,396,972)
+        if (a.dtype != B2_STRING || b.dtype != B2_STRING || b.o.kind != OK_LIT) throw Error(B2_ERR_UNSUPPORTED, "string predicate needs (STRING column, STRING literal)");
+        const int kind = e->op == B2_OP_STARTS_WITH ? SP_STARTS : e->op == B2_OP_ENDS_WITH ? SP_ENDS : e->op == B2_OP_CONTAINS ? SP_CONTAINS : SP_LIKE;
+        return emit_strpred(kind, a, b, e->escape);
+      }
       case B2_OP_YEAR: {
         Val a = compile(e->kids[0]);
         if (a.dtype != B2_DATE32) throw Error(B2_ERR_UNSUPPORTED, "YEAR needs a date");
@@ -295,7 +346,10 @@ struct Compiler {
   }
 
   void unify(Val& a, Val& b) {
-    if (a.dtype == B2_STRING || b.dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "string expressions are not supported yet");
+    if (a.dtype < 0 && b.dtype < 0) throw Error(B2_ERR_INVALID, "cannot type an expression whose branches are all untyped NULL");
+    if (a.dtype < 0) { a.dtype = b.dtype; a.precision = b.precision; a.scale = b.scale; a.mt = b.mt; return; }
+    if (b.dtype < 0) { b.dtype = a.dtype; b.precision = a.precision; b.scale = a.scale; b.mt = a.mt; return; }
+    if (a.dtype == B2_STRING || b.dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "string-valued expressions (only string predicates are compiled)");
     if (is_decimal(a.dtype) && is_decimal(b.dtype)) {
       int s = std::max(a.scale, b.scale);
       int p = std::max(a.precision - a.scale, b.precision - b.scale) + s;
@@ -308,6 +362,16 @@ struct Compiler {
 
   Val compile_compare(Expr* e) {
     Val a = compile(e->kids[0]), b = compile(e->kids[1]);
+    if (a.dtype == B2_STRING || b.dtype == B2_STRING) {   // predicates.scala:155-331 over strings: UTF8String byte order
+      if (a.dtype != b.dtype) throw Error(B2_ERR_INVALID, "comparison of a string with a non-string");
+      if (e->op == B2_OP_EQ_NULLSAFE) throw Error(B2_ERR_UNSUPPORTED, "<=> over strings");
+      int kind = SP_EQ + (e->op - B2_OP_EQ);
+      if (a.o.kind == OK_LIT && b.o.kind != OK_LIT) {
+        std::swap(a, b);
+        switch (kind) { case SP_LT: kind = SP_GT; break; case SP_LE: kind = SP_GE; break; case SP_GT: kind = SP_LT; break; case SP_GE: kind = SP_LE; break; }
+      }
+      return emit_strpred(kind, a, b, 0);
+    }
     unify(a, b);
     int op = V_EQ + (e->op - B2_OP_EQ);
     if (a.o.kind == OK_LIT && b.o.kind != OK_LIT) {  // keep the literal on the right
@@ -431,6 +495,9 @@ static Program* compile_program(const b2_handle* exprs, int n) {
   Compiler cc; cc.prog = prog.get();
   for (int i = 0; i < n; i++) {
     Val v = cc.compile(expr_from(exprs[i]));
+    if (v.win) throw Error(B2_ERR_UNSUPPORTED, "Substring as a projected output: use b2_substring on the column");
+    if (v.dtype < 0) throw Error(B2_ERR_INVALID, "untyped NULL output");
+    if (v.dtype == B2_STRING && v.o.kind != OK_COL) throw Error(B2_ERR_UNSUPPORTED, "string literal as a projected output");
     if (v.o.kind == OK_REG) cc.reg_pinned[v.o.idx] = true;  // outputs stay live
     if (i == 0) prog->hdr.npred = (int)prog->code.size();
     prog->hdr.outs[i] = v.o;
@@ -505,6 +572,70 @@ int b2_expr_cast(b2_handle child, int32_t dtype, int32_t precision, int32_t scal
   *out = to_handle(e);
   B2_CATCH
 }
+int b2_expr_string_literal(const char* utf8, int32_t len, int32_t is_null, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(len >= 0, "negative string length");
+  Expr* e = new Expr();
+  e->op = -1; e->dtype = B2_STRING; e->lit_null = is_null != 0; e->nullable = is_null != 0;
+  if (utf8 && len) e->str.assign(utf8, (size_t)len);
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_expr_like(b2_handle child, b2_handle pattern_literal, int32_t escape_char, b2_handle* out) {
+  B2_TRY
+  Expr* e = make_node(B2_OP_LIKE, {child, pattern_literal});
+  e->escape = escape_char;
+  *out = to_handle(e);
+  B2_CATCH
+}
+int b2_expr_substring(b2_handle child, int32_t pos, int32_t len, b2_handle* out) {
+  B2_TRY
+  Expr* e = make_node(B2_OP_SUBSTRING, {child});
+  e->lit_lo = pos; e->lit_hi = len;
+  *out = to_handle(e);
+  B2_CATCH
+}
+// GpuInSet / In over literals (GpuInSet.scala): Kleene OR of equalities — NULL input -> NULL, no match with a NULL in the
+// list -> NULL, exactly Spark's In
+int b2_expr_in(b2_handle child, const b2_handle* literals, int32_t n, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(n >= 0 && n <= 24, "IN list of 0..24 literals");
+  Expr* acc = nullptr;
+  for (int i = 0; i < n; i++) {
+    Expr* eq = make_node(B2_OP_EQ, {child, literals[i]});
+    if (!acc) acc = eq;
+    else {
+      std::unique_ptr<Expr> o(new Expr());
+      o->op = B2_OP_OR; o->kids.push_back(acc); o->kids.push_back(eq);   // takes over both references
+      acc = o.release();
+    }
+  }
+  if (!acc) {  // x IN () is false for non-null x, NULL for NULL x:  x IS NULL AND NULL  ->  (x <> x)
+    acc = make_node(B2_OP_NE, {child, child});
+  }
+  *out = to_handle(acc);
+  B2_CATCH
+}
+// GpuCaseWhen (conditionalExpressions.scala:322): the first branch whose condition is TRUE; NULL/false conditions fall
+// through; no ELSE = NULL.  Compiled as nested GpuIf (all VM ops are side-effect free outside ANSI mode).
+int b2_expr_case_when(const b2_handle* conds, const b2_handle* values, int32_t n, b2_handle else_value, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(n >= 1 && n <= 16, "CASE WHEN with 1..16 branches");
+  Expr* tail;
+  if (else_value) { tail = expr_from(else_value); tail->refs.fetch_add(1); }
+  else { tail = new Expr(); tail->op = -1; tail->dtype = -1; tail->lit_null = true; tail->nullable = true; }
+  for (int i = n - 1; i >= 0; i--) {
+    std::unique_ptr<Expr> f(new Expr());
+    f->op = B2_OP_IF;
+    Expr* c = expr_from(conds[i]); c->refs.fetch_add(1);
+    Expr* v = expr_from(values[i]); v->refs.fetch_add(1);
+    f->kids.push_back(c); f->kids.push_back(v); f->kids.push_back(tail);
+    tail = f.release();
+  }
+  *out = to_handle(tail);
+  B2_CATCH
+}
+
 int b2_expr_close(b2_handle h) {
   B2_TRY
   Expr* e = expr_from(h);

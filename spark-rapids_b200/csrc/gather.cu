@@ -236,6 +236,72 @@ Table* concat_tables(const std::vector<const Table*>& ts) {
   return new_table(outs.release());
 }
 
+// ---- GpuSubstring (stringFunctions.scala:524-620) with literal pos / len, materialised ------------------------------------------
+__device__ __forceinline__ int sub_utf8_len(uint8_t lead) { return lead < 0x80 ? 1 : ((lead >> 5) == 6 ? 2 : ((lead >> 4) == 14 ? 3 : ((lead >> 3) == 30 ? 4 : 1))); }
+// byte window [b0, b1) of string [p, p+n) for Spark's substringSQL(pos, len): code-point based, 1-based pos, negative pos
+// counts from the end; start = pos < 0 ? pos + nchars : (pos > 0 ? pos - 1 : 0), end = clamp(start + len, 0, INT_MAX)
+__device__ __forceinline__ void substring_window(const uint8_t* p, int n, int64_t pos, int64_t len, int& b0, int& b1) {
+  int nchars = 0;
+  for (int k = 0; k < n; k++) nchars += (p[k] & 0xc0) != 0x80;
+  int64_t start = pos < 0 ? pos + nchars : (pos > 0 ? pos - 1 : 0);
+  int64_t end = start + len;
+  if (end < 0) end = 0;
+  if (end > 0x7fffffffLL) end = 0x7fffffffLL;
+  if (start < 0) start = 0;
+  b0 = b1 = 0;
+  if (start >= end || start >= nchars) return;
+  int c = 0;
+  while (b0 < n && c < start) { b0 += sub_utf8_len(p[b0]); c++; }
+  b1 = b0;
+  while (b1 < n && c < end) { b1 += sub_utf8_len(p[b1]); c++; }
+  if (b1 > n) b1 = n;
+}
+__global__ void substring_sizes_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ chars, const uint32_t* __restrict__ valid, int64_t n,
+                                       int64_t pos, int64_t len, int32_t* __restrict__ sizes, int32_t* __restrict__ starts) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int b0 = 0, b1 = 0;
+    if (row_valid(valid, i)) substring_window(chars + offsets[i], offsets[i + 1] - offsets[i], pos, len, b0, b1);
+    sizes[i] = b1 - b0; starts[i] = offsets[i] + b0;
+  }
+}
+__global__ void substring_copy_kernel(const uint8_t* __restrict__ chars, const int32_t* __restrict__ starts, const int32_t* __restrict__ out_off, int64_t n,
+                                      uint8_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t o = out_off[i], l = out_off[i + 1] - o;
+    const uint8_t* s = chars + starts[i];
+    for (int k = 0; k < l; k++) out[o + k] = s[k];
+  }
+}
+Column* substring_column(const Column* ic, int64_t pos, int64_t len) {
+  if (ic->dtype != B2_STRING) throw Error(B2_ERR_INVALID, "substring needs a STRING column");
+  const int64_t n = ic->size;
+  std::unique_ptr<Column> oc(new Column());
+  oc->dtype = B2_STRING; oc->size = n;
+  oc->offsets = DevBuf((size_t)(n + 1) * 4);
+  if (ic->nullable()) {   // NULL in, NULL out (NullIntolerant)
+    oc->valid = DevBuf(validity_bytes(n)); oc->null_count = ic->null_count;
+    CUDA_CHECK(cudaMemcpyAsync(oc->valid.p, ic->valid.p, validity_bytes(n), cudaMemcpyDeviceToDevice, stream()));
+  }
+  if (n == 0) { CUDA_CHECK(cudaMemsetAsync(oc->offsets.p, 0, 4, stream())); oc->data = DevBuf(0); return oc.release(); }
+  DevBuf starts((size_t)n * 4);
+  substring_sizes_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(ic->offsets.as<int32_t>(), ic->data.as<uint8_t>(), ic->validity(), n, pos, len,
+                                                                 oc->offsets.as<int32_t>(), starts.as<int32_t>());
+  count_launch();
+  DevBuf sums = exclusive_scan<int32_t, int32_t>(oc->offsets.as<int32_t>(), oc->offsets.as<int32_t>(), n, true);
+  int64_t total = 0;
+  d2h(&total, sums.as<int64_t>() + (n + SCAN_TILE - 1) / SCAN_TILE, 1);
+  sync();
+  oc->chars_bytes = total;
+  oc->data = DevBuf((size_t)total);
+  if (total) {
+    substring_copy_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(ic->data.as<uint8_t>(), starts.as<int32_t>(), oc->offsets.as<int32_t>(), n, oc->data.as<uint8_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  sync();   // `starts` is freed on return
+  return oc.release();
+}
+
 Table* slice_table(const Table* t, int64_t start, int64_t end) {
   B2_CHECK(start >= 0 && end >= start && end <= t->rows, "slice out of range");
   int64_t n = end - start;
@@ -255,6 +321,12 @@ int b2_gather(b2_handle table, b2_handle int32_map, int32_t nullify_oob, b2_hand
   Column* m = col_from(int32_map);
   B2_CHECK(m->dtype == B2_INT32, "gather map must be INT32");
   *out_table = to_handle(gather_table(t, m->data.as<int32_t>(), m->size, nullify_oob != 0, nullptr));
+  B2_CATCH
+}
+
+int b2_substring(b2_handle string_column, int32_t pos, int32_t len, b2_handle* out_column) {
+  B2_TRY
+  *out_column = to_handle(substring_column(col_from(string_column), pos, len));
   B2_CATCH
 }
 

@@ -77,7 +77,7 @@ __global__ void join_probe_distinct_kernel(const __grid_constant__ KeyCols probe
   const int64_t nround = (n + 31) & ~(int64_t)31;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nround; r += (int64_t)gridDim.x * blockDim.x) {
     int32_t br = INT32_MIN;
-    if (r < n && (nulls_equal || !any_null_key(probe, r))) {
+    if (r < n && ((nulls_equal && !fast) || !any_null_key(probe, r))) {  // fast: the build side holds no NULL keys, so a NULL probe key matches nothing
       uint64_t kb = 0;
       uint32_t h;
       if (fast) { kb = pack_join_key(probe, r); h = hash_packed(kb); } else h = row_hash(probe, r);
@@ -116,7 +116,7 @@ __global__ void join_probe_kernel(const __grid_constant__ KeyCols probe, const _
     int32_t matches = 0;
     int64_t o = MODE == 1 ? offsets[r] : 0;
     const bool semi_like = kind == B2_JOIN_LEFT_SEMI || kind == B2_JOIN_LEFT_ANTI;
-    if (nulls_equal || !any_null_key(probe, r)) {
+    if ((nulls_equal && !fast) || !any_null_key(probe, r)) {  // fast: see join_probe_distinct_kernel
       uint64_t kb = 0;
       uint32_t h;
       if (fast) { kb = pack_join_key(probe, r); h = hash_packed(kb); } else h = row_hash(probe, r);

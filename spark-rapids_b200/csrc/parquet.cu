@@ -948,13 +948,21 @@ __global__ void __launch_bounds__(PQ_NT) values_kernel(const PageD* __restrict__
       // length-prefixed values: a sequential walk (dictionary pages normally carry the strings)
       if (threadIdx.x == 0) {
         const uint8_t* q = vals;
-        for (int k = 0; k < nvals && q + 4 <= pend; k++) {
+        int k = 0;
+        for (; k < nvals && q + 4 <= pend; k++) {
           uint32_t n; memcpy(&n, q, 4);
+          if (n > (uint32_t)(pend - (q + 4))) break;   // length runs past the page
           col.str_src[w.base + k] = (int64_t)reinterpret_cast<uintptr_t>(q + 4);
           col.str_len[w.base + k] = (int32_t)n;
           q += 4 + n;
         }
+        if (k < nvals) {   // truncated / corrupt page: flag it and leave the remaining rows as empty strings
+          atomicExch(errors, 5);
+          for (; k < nvals; k++) { col.str_src[w.base + k] = (int64_t)reinterpret_cast<uintptr_t>(vals); col.str_len[w.base + k] = 0; }
+        }
       }
+    } else if (vals > pend || (size_t)nvals * (size_t)src_width > (size_t)(pend - vals)) {
+      if (threadIdx.x == 0) atomicExch(errors, 5);   // fewer value bytes than the header promises
     } else {
       for (int k = threadIdx.x; k < nvals; k += PQ_NT) w.write_fixed(k, vals + (size_t)k * src_width);
     }
@@ -976,7 +984,8 @@ __global__ void __launch_bounds__(PQ_NT) values_kernel(const PageD* __restrict__
 
 // string dictionaries: walk the length-prefixed entries of each dictionary page once
 __global__ void dict_strings_kernel(const PageD* __restrict__ pages, const ChunkD* __restrict__ chunks, int nchunks, const uint8_t* __restrict__ file,
-                                    const uint8_t* __restrict__ scratch, int64_t* __restrict__ dict_src, int32_t* __restrict__ dict_len) {
+                                    const uint8_t* __restrict__ scratch, int64_t* __restrict__ dict_src, int32_t* __restrict__ dict_len,
+                                    int32_t* __restrict__ errors) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchunks) return;
   const ChunkD ch = chunks[c];
@@ -984,11 +993,17 @@ __global__ void dict_strings_kernel(const PageD* __restrict__ pages, const Chunk
   const PageD pg = pages[ch.dict_page];
   const uint8_t* q = page_ptr(pg, file, scratch);
   const uint8_t* end = q + pg.uncomp_size;
-  for (int k = 0; k < ch.dict_count && q + 4 <= end; k++) {
+  int k = 0;
+  for (; k < ch.dict_count && q + 4 <= end; k++) {
     uint32_t n; memcpy(&n, q, 4);
+    if (n > (uint32_t)(end - (q + 4))) break;   // entry runs past the dictionary page
     dict_src[ch.dict_str_off + k] = (int64_t)reinterpret_cast<uintptr_t>(q + 4);
     dict_len[ch.dict_str_off + k] = (int32_t)n;
     q += 4 + n;
+  }
+  if (k < ch.dict_count) {   // corrupt dictionary: the missing entries become empty strings, the decode reports an error
+    atomicExch(errors, 5);
+    for (; k < ch.dict_count; k++) { dict_src[ch.dict_str_off + k] = (int64_t)reinterpret_cast<uintptr_t>(end); dict_len[ch.dict_str_off + k] = 0; }
   }
 }
 
@@ -1173,7 +1188,12 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
         } else r.skip(t);
       }
       const int64_t payload = r.p - host;
+      // untrusted input: sizes and counts are zigzag varints and may decode negative (a negative csize would move
+      // `pos` backwards: endless loop / reads before the chunk)
+      if (csize < 0 || usize < 0 || nvals < 0 || v2_def_len < 0 || v2_rep_len < 0) throw Error(B2_ERR_INVALID, "parquet: negative size in a page header");
+      if ((int64_t)v2_def_len + v2_rep_len > usize) throw Error(B2_ERR_INVALID, "parquet: level bytes exceed the page");
       if (payload + csize > chunk_end) throw Error(B2_ERR_INVALID, "parquet: page runs past its chunk");
+      if (csize == 0 && (ptype == PG_DATA || ptype == PG_DATA_V2) && nvals > 0 && usize > 0) throw Error(B2_ERR_INVALID, "parquet: empty data page with values");
       if (ptype == PG_INDEX) { pos = payload + csize; continue; }
       PageD pg; memset(&pg, 0, sizeof(pg));
       pg.src_off = payload; pg.comp_size = csize; pg.uncomp_size = usize; pg.num_values = nvals; pg.encoding = enc; pg.kind = ptype;
@@ -1419,7 +1439,7 @@ Table* parquet_decode(const uint8_t* host, const uint8_t* dev_in, int64_t len, c
   DevBuf d_dict_src((size_t)std::max<int64_t>(dict_str_total, 1) * 8), d_dict_len((size_t)std::max<int64_t>(dict_str_total, 1) * 4);
   if (dict_str_total) {
     dict_strings_kernel<<<((int)chunks.size() + 63) / 64, 64, 0, s>>>(d_pages.as<PageD>(), d_chunks.as<ChunkD>(), (int)chunks.size(), d_file,
-                                                                       scratch.as<uint8_t>(), d_dict_src.as<int64_t>(), d_dict_len.as<int32_t>());
+                                                                       scratch.as<uint8_t>(), d_dict_src.as<int64_t>(), d_dict_len.as<int32_t>(), d_err.as<int32_t>());
     count_launch();
   }
   if (!todo_values.empty()) {

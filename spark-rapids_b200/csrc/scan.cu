@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(VM_NT, 4) project_kernel(const VMProgramHeader
     VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
     vm_run(tile_info(cx), code, 0, sh.hdr.ninstr);
     for (int o = 0; o < sh.hdr.nouts; o++) {
+      if (!outs.data[o]) continue;   // a bound reference: the input column itself is the output (refcount bump on the host)
       const int mt = sh.hdr.out_mt[o];
       Opnd op = resolve(cx, sh.hdr.outs[o], mt_width(mt));
       switch (mt_width(mt)) {
@@ -234,7 +235,7 @@ void check_program_inputs(const Program* p, const Table* t) {
 void fill_inputs(VMInputs& in, const Table* t) {
   memset(&in, 0, sizeof(in));
   int n = std::min<int>((int)t->cols.size(), VM_MAX_COLS);
-  for (int i = 0; i < n; i++) { in.data[i] = t->cols[i]->data.p; in.valid[i] = t->cols[i]->validity(); }
+  for (int i = 0; i < n; i++) { in.data[i] = t->cols[i]->data.p; in.valid[i] = t->cols[i]->validity(); in.offsets[i] = t->cols[i]->offsets.as<int32_t>(); }
 }
 
 template <typename K>
@@ -343,6 +344,18 @@ static Table* filter_impl(const Program* prog, const Table* pred_table, const Ta
 }  // namespace b2
 
 namespace b2 {
+// GpuFilterExec under a column-pruning GpuProjectExec, fused: the predicate sees the whole batch, only `keep` is compacted
+Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, int nkeep) {
+  Table view;
+  struct Unhook { Table& t; ~Unhook() { t.cols.clear(); } } unhook{view};  // the view does not own its columns
+  for (int k = 0; k < nkeep; k++) {
+    if (keep[k] < 0 || keep[k] >= (int)t->cols.size()) throw Error(B2_ERR_INVALID, "filter: output column out of range");
+    view.cols.push_back(t->cols[keep[k]]);
+  }
+  view.rows = t->rows;
+  return filter_impl(prog, t, &view);
+}
+
 // Table.filter(mask): order-preserving compaction of every column by a BOOL8 mask (NULL = drop)
 Table* filter_by_mask(const Table* t, Column* m) {
   B2_CHECK(m->dtype == B2_BOOL8, "filter mask must be BOOL8");
@@ -376,12 +389,24 @@ int b2_project(b2_handle program, b2_handle table, b2_handle* out_table) {
   VMInputs in; fill_inputs(in, t);
   OutCols oc; memset(&oc, 0, sizeof(oc));
   ColsGuard outs;
+  int computed = 0;
   for (int o = 0; o < prog->hdr.nouts; o++) {
+    const VMOperand& op = prog->hdr.outs[o];
+    if (op.kind == OK_COL) {
+      // GpuBoundReference.columnarEval: the output IS the input column, by refcount (basicPhysicalOperators.scala:117-119
+      // "no-op project just bumps refcounts"); also the only way a STRING column passes through a projection
+      Column* c = t->cols[op.idx];
+      col_incref(c);
+      outs.v.push_back(c);
+      continue;
+    }
+    if (prog->out_dtype[o] == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "computed string outputs (use b2_substring for Substring)");
     Column* c = new_column(prog->out_dtype[o], prog->out_scale[o], n, prog->out_nullable[o]);
     outs.v.push_back(c);
     oc.data[o] = c->data.p; oc.valid[o] = c->valid.as<uint32_t>();
+    computed++;
   }
-  if (n > 0) {
+  if (n > 0 && computed > 0) {
     int smem = prog->hdr.smem_bytes;
     set_dyn_smem(project_kernel, smem);
     KernelTimer kt_project_kernel("project_kernel");
@@ -397,6 +422,12 @@ int b2_filter(b2_handle predicate_program, b2_handle table, b2_handle* out_table
   B2_TRY
   Table* t = table_from(table);
   *out_table = to_handle(filter_impl(program_from(predicate_program), t, t));
+  B2_CATCH
+}
+
+int b2_filter_select(b2_handle predicate_program, b2_handle table, const int32_t* keep_cols, int32_t nkeep, b2_handle* out_table) {
+  B2_TRY
+  *out_table = to_handle(filter_select(program_from(predicate_program), table_from(table), keep_cols, nkeep));
   B2_CATCH
 }
 

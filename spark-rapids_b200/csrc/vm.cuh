@@ -47,8 +47,15 @@ enum VOP : uint8_t {
   V_NORM_NAN_ZERO,
   V_YEAR,
   V_MOV,
-  V_ANDCMP      // c AND (a <cmp> b), all operands non-null: aux = 3-bit truth mask over sign(a ? b) = {<, ==, >}
+  V_ANDCMP,     // c AND (a <cmp> b), all operands non-null: aux = 3-bit truth mask over sign(a ? b) = {<, ==, >}
+  V_STRPRED     // string predicate -> BOOL8.  a = STRING column, b = STRING column or pooled literal (mt2 = 1), c = optional
+                // substring window literal (lo = pos, hi = len; Spark 1-based substringSQL) applied to a;
+                // aux = kind (SP_*) | escape char << 8 (LIKE)
 };
+// stringFunctions.scala:163 GpuStartsWith, :189 GpuEndsWith, :396 GpuContains, :972 GpuLike; predicates.scala:155-331 on strings
+// (UTF8String.compareTo = unsigned byte order)
+enum SPK : int { SP_EQ = 0, SP_NE, SP_LT, SP_LE, SP_GT, SP_GE, SP_STARTS, SP_ENDS, SP_CONTAINS, SP_LIKE };
+constexpr int VM_LIT_BYTES = 512;   // pooled string literals of a program
 
 struct alignas(16) VMOperand {
   int64_t lo, hi;    // OK_LIT value (first so that 16-byte literal loads are aligned)
@@ -76,11 +83,13 @@ struct VMProgramHeader {
   VMReg regs[VM_MAX_REGS];
   VMOperand outs[VM_MAX_OUTS];
   uint8_t out_mt[VM_MAX_OUTS];
+  char lits[VM_LIT_BYTES];   // string literal pool (OK_LIT string operand: lo = offset, hi = length)
 };
 
 struct VMInputs {
   const void* data[VM_MAX_COLS];
   const uint32_t* valid[VM_MAX_COLS];
+  const int32_t* offsets[VM_MAX_COLS];   // STRING columns
 };
 
 // instruction with operands resolved once per CTA (shared memory): a row loop starts with two
@@ -348,7 +357,8 @@ __device__ __noinline__ void vm_arith(const TileInfo ti, const RInstr& ins) {
       else {
         if (y == (T)0) { v = false; return (T)0; }
         T r = (T)fmod((double)x, (double)y);
-        if (OP == V_PMOD && r != (T)0 && ((r < 0) != (y < 0))) r += y;
+        // Spark Pmod / cudf BinaryOp.PMOD (arithmetic.scala:1177): r = a % n; if (r < 0) (r + n) % n else r
+        if (OP == V_PMOD && r < (T)0) r = (T)fmod((double)(r + y), (double)y);
         return r;
       }
     } else {
@@ -360,7 +370,14 @@ __device__ __noinline__ void vm_arith(const TileInfo ti, const RInstr& ins) {
         if (y == (T)0) { v = false; return (T)0; }
         if (y == (T)-1) return (OP == V_DIV) ? (T)((U)0 - (U)x) : (T)0;
         if constexpr (OP == V_DIV) return x / y;
-        else { T r = x % y; if (OP == V_PMOD && r != 0 && ((r < 0) != (y < 0))) r += y; return r; }
+        else {
+          T r = x % y;
+          if (OP == V_PMOD && r < 0) {  // (r + n) % n with Java's wrap-around add in the operand type (byte/short add in int)
+            if constexpr (sizeof(T) < 4) r = (T)(((int)r + (int)y) % (int)y);
+            else { const T s = (T)((U)r + (U)y); r = (y == (T)-1) ? (T)0 : (T)(s % y); }
+          }
+          return r;
+        }
       }
     }
   });
@@ -698,6 +715,106 @@ static __device__ __noinline__ void vm_isnull(const TileInfo ti, const RInstr& i
   for (int j = 0; j < ti.K; j++) { VM_ROW_ACTIVE(j, i, g); if (act) dst_st<int8_t>(d, i, (int8_t)(opnd_valid(a, i, g) != want_null), true); }
 }
 
+
+// ---- string predicates -------------------------------------------------------------------------------------------
+// Strings never enter the register file: a predicate reads (offsets, chars) of its column operand straight from
+// global memory and leaves a BOOL8 register.  Literals sit in the program's pool (shared memory).
+__device__ __forceinline__ int utf8_len(uint8_t lead) { return lead < 0x80 ? 1 : ((lead >> 5) == 6 ? 2 : ((lead >> 4) == 14 ? 3 : ((lead >> 3) == 30 ? 4 : 1))); }
+// UTF8String.substringSQL(pos, len) as the reference restates it (stringFunctions.scala:540-600): code-point based,
+// start = pos < 0 ? pos + nchars : (pos > 0 ? pos - 1 : 0), end = clamp(start + len, 0, INT_MAX), start < 0 -> 0
+__device__ __forceinline__ void str_window(const uint8_t*& p, int& n, int64_t pos, int64_t len) {
+  int nchars = 0;
+  for (int k = 0; k < n; k++) nchars += (p[k] & 0xc0) != 0x80;
+  int64_t start = pos < 0 ? pos + nchars : (pos > 0 ? pos - 1 : 0);
+  int64_t end = start + len;
+  if (end < 0) end = 0;
+  if (end > 0x7fffffffLL) end = 0x7fffffffLL;
+  if (start < 0) start = 0;
+  if (start >= end || start >= nchars) { n = 0; return; }
+  int b0 = 0, c = 0;
+  while (b0 < n && c < start) { b0 += utf8_len(p[b0]); c++; }
+  int b1 = b0;
+  while (b1 < n && c < end) { b1 += utf8_len(p[b1]); c++; }
+  if (b1 > n) b1 = n;
+  p += b0; n = b1 - b0;
+}
+__device__ __forceinline__ int str_cmp(const uint8_t* a, int an, const uint8_t* b, int bn) {
+  const int m = an < bn ? an : bn;
+  for (int k = 0; k < m; k++) { const int d = (int)a[k] - (int)b[k]; if (d) return d; }
+  return an - bn;
+}
+__device__ __forceinline__ bool str_like(const uint8_t* s, int sn, const uint8_t* p, int pn, uint8_t esc) {
+  int si = 0, pi = 0, star_p = -1, star_s = 0;
+  while (si < sn) {
+    bool ok = false;
+    if (pi < pn) {
+      const uint8_t c = p[pi];
+      if (c == esc && pi + 1 < pn) { if (s[si] == p[pi + 1]) { si++; pi += 2; ok = true; } }
+      else if (c == '%') { star_p = ++pi; star_s = si; ok = true; }
+      else if (c == '_') { si += utf8_len(s[si]); pi++; ok = true; }
+      else if (c == s[si]) { si++; pi++; ok = true; }
+    }
+    if (ok) continue;
+    if (star_p < 0) return false;
+    pi = star_p; star_s += utf8_len(s[star_s]); si = star_s;
+  }
+  while (pi < pn && p[pi] == '%') pi++;
+  return pi == pn;
+}
+__device__ __forceinline__ bool str_pred(int kind, const uint8_t* a, int an, const uint8_t* b, int bn, uint8_t esc) {
+  switch (kind) {
+    case SP_EQ: return an == bn && str_cmp(a, an, b, bn) == 0;
+    case SP_NE: return !(an == bn && str_cmp(a, an, b, bn) == 0);
+    case SP_LT: return str_cmp(a, an, b, bn) < 0;
+    case SP_LE: return str_cmp(a, an, b, bn) <= 0;
+    case SP_GT: return str_cmp(a, an, b, bn) > 0;
+    case SP_GE: return str_cmp(a, an, b, bn) >= 0;
+    case SP_STARTS: return bn <= an && str_cmp(a, bn, b, bn) == 0;
+    case SP_ENDS: return bn <= an && str_cmp(a + (an - bn), bn, b, bn) == 0;
+    case SP_CONTAINS: {
+      if (bn == 0) return true;
+      for (int k = 0; k + bn <= an; k++) if (a[k] == b[0] && str_cmp(a + k, bn, b, bn) == 0) return true;
+      return false;
+    }
+    default: return str_like(a, an, b, bn, esc);
+  }
+}
+__device__ __forceinline__ const int32_t* ropnd_offsets(const ROpnd& o) {  // string column operand: the offsets pointer rides in (stride, tile_step)
+  const int32_t* p; memcpy(&p, &o.stride, sizeof(p)); return p;
+}
+static __device__ __noinline__ void vm_strpred(const TileInfo ti, const RInstr& ins) {
+  const uint8_t* achars = reinterpret_cast<const uint8_t*>(ins.a.base);
+  const int32_t* aoff = ropnd_offsets(ins.a);
+  const uint32_t* avalid = reinterpret_cast<const uint32_t*>(ins.a.vptr);
+  const bool b_lit = ins.mt2 == 1;
+  const uint8_t* bchars = reinterpret_cast<const uint8_t*>(ins.b.base);
+  const int32_t* boff = b_lit ? nullptr : ropnd_offsets(ins.b);
+  const uint32_t* bvalid = reinterpret_cast<const uint32_t*>(ins.b.vptr);
+  const int blit_len = b_lit ? ins.b.stride : 0;
+  const bool window = ins.c.base != nullptr;
+  int64_t wpos = 0, wlen = 0;
+  if (window) { wpos = reinterpret_cast<const int64_t*>(ins.c.base)[0]; wlen = reinterpret_cast<const int64_t*>(ins.c.base)[1]; }
+  const int kind = ins.aux & 0xff;
+  const uint8_t esc = (uint8_t)((ins.aux >> 8) & 0xff);
+  const Dst d = rdst(ins, 1);
+  for (int j = 0; j < ti.K; j++) {
+    VM_ROW_ACTIVE(j, i, g);
+    if (!act) continue;
+    bool v = (ins.a.vkind == 0 || (ins.a.vkind == 2 && bit_get(avalid, g))) && ins.b.vkind != 3;
+    if (!b_lit) v = v && (ins.b.vkind == 0 || (ins.b.vkind == 2 && bit_get(bvalid, g)));
+    bool r = false;
+    if (v) {
+      const int32_t a0 = aoff[g];
+      const uint8_t* ap = achars + a0; int an = aoff[g + 1] - a0;
+      if (window) str_window(ap, an, wpos, wlen);
+      const uint8_t* bp = bchars; int bn = blit_len;
+      if (!b_lit) { const int32_t b0 = boff[g]; bp = bchars + b0; bn = boff[g + 1] - b0; }
+      r = str_pred(kind, ap, an, bp, bn, esc);
+    }
+    dst_st<int8_t>(d, i, (int8_t)(r && v), v);
+  }
+}
+
 #define VM_TYPES_INT_FLOAT(fn, ...)                         \
   switch (ins.mt) {                                         \
     case MT_I8: fn<int8_t, ##__VA_ARGS__>(ti, ins); break;  \
@@ -760,6 +877,7 @@ static __device__ __noinline__ void vm_run(const TileInfo ti, const RInstr* __re
       case V_NORM_NAN_ZERO: if (ins.mt == MT_F32) vm_normnz<float>(ti, ins); else vm_normnz<double>(ti, ins); break;
       case V_YEAR: vm_year(ti, ins); break;
       case V_ANDCMP: VM_TYPES_ALL(vm_andcmp) break;
+      case V_STRPRED: vm_strpred(ti, ins); break;
       default: break;
     }
   }
@@ -803,6 +921,19 @@ static __device__ __forceinline__ const RInstr* vm_load_program(VMShared& sh, co
       if (g.op == V_AND || g.op == V_OR || g.op == V_NOT || (g.op == V_IF && j == 0)) width = 1;
       if (g.op == V_MULDEC && j == 1) width = mt_width(g.mt2);
       if (g.op == V_ANDCMP && j == 2) width = 1;   // the accumulated predicate
+      if (g.op == V_STRPRED) {   // string operands: see vm_strpred
+        q.base = nullptr; q.stride = 0; q.vkind = 0;
+        if (j == 2) { if (o.kind == OK_LIT) q.base = reinterpret_cast<const char*>(&o.lo); }
+        else if (o.kind == OK_COL) {
+          q.base = reinterpret_cast<const char*>(in.data[o.idx]); q.vptr = in.valid[o.idx];
+          q.vkind = (o.nullable && in.valid[o.idx]) ? 2 : 0;
+          const int32_t* offs = in.offsets[o.idx]; memcpy(&q.stride, &offs, sizeof(offs));
+        } else if (o.kind == OK_LIT) {
+          q.base = sh.hdr.lits + o.lo; q.stride = (int32_t)o.hi; q.vkind = o.lit_null ? 3 : 0;
+        }
+        *outs[j] = q;
+        continue;
+      }
       if (o.kind == OK_REG) {
         q.base = regs + (size_t)sh.hdr.regs[o.idx].off * tile_rows; q.stride = width;
         q.vkind = o.nullable ? 1 : 0; q.vptr = regs + (size_t)sh.hdr.regs[o.idx].voff * tile_rows;

@@ -41,6 +41,12 @@ class GpuExec:
         check(lib.b2_exec_metrics(self.h, out))
         return {"numOutputRows": out[0], "numOutputBatches": out[1], "opTime": out[2]}
 
+    def device_time(self):
+        """(self ms, total ms) of this node on the device while profiling was enabled"""
+        out = (ctypes.c_double * 2)()
+        check(lib.b2_exec_device_time(self.h, out))
+        return out[0], out[1]
+
 
 def _new(fn, *args, keep=()):
     out = ctypes.c_int64()
@@ -66,9 +72,43 @@ def GpuParquetScanExec(buffers, columns):
     return e
 
 
-def GpuFilterExec(condition, child):
-    prog = m.Program([condition])
+def GpuFilterExec(condition, child, output=None):
+    """output: column indexes a pruning GpuProjectExec above the filter keeps (fused: only those are compacted)"""
+    prog = condition if isinstance(condition, m.Program) else m.Program([condition])   # a Program: bound + compiled once per plan
+    if output is not None:
+        return _new(lib.b2_exec_filter_select, child.h, prog.h, m._i32s(output), len(output), keep=[prog, child])
     return _new(lib.b2_exec_filter, child.h, prog.h, keep=[prog, child])
+
+
+def host_columns(arrays):
+    """[(dtype, scale, numpy values | (chars, offsets), validity bits or None)] -> (ctypes array, keepalive)"""
+    arr = (m.B2HostColumn * len(arrays))()
+    keep = []
+    for i, (dtype, scale, data, valid) in enumerate(arrays):
+        arr[i].dtype, arr[i].scale = dtype, scale
+        if dtype == m.STRING:
+            chars, offsets = data
+            arr[i].rows = len(offsets) - 1
+            arr[i].data, arr[i].offsets = chars.ctypes.data, offsets.ctypes.data
+            keep += [chars, offsets]
+        else:
+            arr[i].rows = len(data) if dtype != m.DECIMAL128 else len(data)
+            arr[i].data = data.ctypes.data
+            keep.append(data)
+        if valid is not None:
+            arr[i].validity_bits = valid.ctypes.data
+            keep.append(valid)
+    return arr, keep
+
+
+def GpuHostBatchSource(batches):
+    """HostColumnarToGpu: batches = list of host column lists (see host_columns); buffers should be pinned"""
+    e = _new(lib.b2_exec_host_source)
+    for b in batches:
+        arr, keep = host_columns(b)
+        e._keep += keep
+        check(lib.b2_exec_host_source_push(e.h, arr, len(b)))
+    return e
 
 
 def GpuProjectExec(project_list, child):
@@ -82,13 +122,20 @@ def GpuHashAggregateExec(child, grouping, aggregates, pre_project=None, conditio
     if mode == "final":
         return _new(lib.b2_exec_hash_aggregate, child.h, ctypes.c_int64(0), 0, 1, m._i32s(grouping), len(grouping), m._agg_specs(aggregates),
                     len(aggregates), keep=[child])
-    exprs = ([condition] if condition is not None else []) + list(pre_project)
-    prog = m.Program(exprs)
+    if isinstance(pre_project, m.Program):    # compiled once per plan (output 0 is the fused condition when `condition` is truthy)
+        prog = pre_project
+    else:
+        prog = m.Program(([condition] if condition is not None else []) + list(pre_project))
     return _new(lib.b2_exec_hash_aggregate, child.h, prog.h, int(condition is not None), 0, m._i32s(grouping), len(grouping),
                 m._agg_specs(aggregates), len(aggregates), keep=[prog, child])
 
 
-def GpuShuffledHashJoinExec(stream_keys, build_keys, join_type, stream, build, nulls_equal=False):
+def GpuShuffledHashJoinExec(stream_keys, build_keys, join_type, stream, build, nulls_equal=False, stream_out=None, build_out=None):
+    """stream_out / build_out: columns a pruning GpuProjectExec above the join keeps (fused into the gathers)"""
+    if stream_out is not None or build_out is not None:
+        so, bo = list(stream_out or []), list(build_out or [])
+        return _new(lib.b2_exec_shuffled_hash_join_select, stream.h, build.h, m._i32s(stream_keys), m._i32s(build_keys), len(stream_keys), join_type,
+                    int(nulls_equal), m._i32s(so), len(so), m._i32s(bo), len(bo), keep=[stream, build])
     return _new(lib.b2_exec_shuffled_hash_join, stream.h, build.h, m._i32s(stream_keys), m._i32s(build_keys), len(stream_keys), join_type,
                 int(nulls_equal), keep=[stream, build])
 
@@ -108,3 +155,13 @@ def GpuCoalesceBatches(child, target_rows):
 def GpuShuffleExchangeExec(child, key_cols, comm=None, world=1):
     return _new(lib.b2_exec_shuffle_exchange, child.h, m._i32s(key_cols), len(key_cols), comm.h if comm else ctypes.c_int64(0), world,
                 keep=[child, comm])
+
+
+def GpuBroadcastExchangeExec(child, comm=None, rank=0, world=1):
+    """every rank gets the whole child relation (one batch); as the build child of a join: GpuBroadcastHashJoinExec"""
+    return _new(lib.b2_exec_broadcast_exchange, child.h, comm.h if comm else ctypes.c_int64(0), rank, world, keep=[child, comm])
+
+
+def GpuBroadcastHashJoinExec(stream_keys, build_keys, join_type, stream, build, comm=None, rank=0, world=1, **kw):
+    """GpuBroadcastHashJoinExecBase.scala: the build side is broadcast, the stream side stays where it is (no shuffle)"""
+    return GpuShuffledHashJoinExec(stream_keys, build_keys, join_type, stream, GpuBroadcastExchangeExec(build, comm, rank, world), **kw)

@@ -147,3 +147,49 @@ def test_full_outer_join_exec_multi_batch(b2):
             exp.append((None, None, int(k) if ok else None, int(v)))
     exp = sorted(exp, key=lambda r: tuple((x is None, x) for x in r))
     assert got == exp
+
+
+def _q3_small(b2, sf, host):
+    """the SF100 bench plan (bench.build_q3_plan) on a small instance of the same generator vs the numpy restatement"""
+    from spark_rapids_b200 import execs as E
+    import bench
+    chunks = bench.q3_host_chunks(sf, 0, 1)
+    progs = bench.q3_programs(b2)
+    if host:
+        hb = bench.q3_host_batches(b2, chunks)
+        src = {t: E.GpuHostBatchSource(hb[t]) for t in bench.Q3_SCHEMA}
+    else:
+        dev = bench.q3_device_batches(b2, chunks)
+        src = {t: E.GpuBatchSource(dev[t]) for t in bench.Q3_SCHEMA}
+    root, nodes = bench.build_q3_plan(b2, E, progs, src)
+    got = bench.q3_rows_of(root.collect())
+    exp = tpch.q3_expected(sf, 42, threads=4)
+    assert [(r[1], r[2]) for r in got] == [(r[1], r[2]) for r in exp]
+    assert sorted(got) == sorted(exp)
+    assert nodes["filter_lineitem"].metrics["numOutputBatches"] == 16 and nodes["join_lineitem_orders"].metrics["numOutputBatches"] == 16
+    return nodes
+
+
+def test_q3_bench_plan_small_resident(b2):
+    _q3_small(b2, 0.05, False)
+
+
+def test_q3_bench_plan_small_host_batches(b2):
+    """HostColumnarToGpu: the same plan fed from host column batches (pageable here; the bench pins them)"""
+    _q3_small(b2, 0.02, True)
+
+
+def test_join_exec_output_pruning(b2):
+    from spark_rapids_b200 import execs as E
+    rng = np.random.default_rng(21)
+    i64 = (O.INT64, 0, 0)
+    ns, nb = 5000, 800
+    stream = [O.OCol(rng.integers(0, 1000, ns).astype(np.int64), np.ones(ns, bool), i64), O.OCol(np.arange(ns, dtype=np.int64), np.ones(ns, bool), i64)]
+    build = [O.OCol(np.arange(nb, dtype=np.int64), np.ones(nb, bool), i64), O.OCol(np.arange(nb, dtype=np.int64) * 7, np.ones(nb, bool), i64)]
+    full = E.GpuShuffledHashJoinExec([0], [0], b2.JOIN_INNER, E.GpuBatchSource(batches(b2, stream, 3)), E.GpuBatchSource(batches(b2, build, 1))).collect()
+    pruned = E.GpuShuffledHashJoinExec([0], [0], b2.JOIN_INNER, E.GpuBatchSource(batches(b2, stream, 3)), E.GpuBatchSource(batches(b2, build, 1)),
+                                       stream_out=[1], build_out=[1]).collect()
+    assert sorted((r[1], r[3]) for r in full.to_rows()) == sorted(pruned.to_rows())
+    only_stream = E.GpuShuffledHashJoinExec([0], [0], b2.JOIN_INNER, E.GpuBatchSource(batches(b2, stream, 3)), E.GpuBatchSource(batches(b2, build, 1)),
+                                            stream_out=[1], build_out=[]).collect()
+    assert sorted(r[0] for r in only_stream.to_rows()) == sorted(r[1] for r in full.to_rows())

@@ -103,6 +103,23 @@ def test_join_multi_key_nulls_equal(b2):
             _check_join(b2, build, probe, kind, ne)
 
 
+def test_join_nulls_equal_packed_keys_nullable_probe(b2):
+    """<=> join whose build side has no NULLs (packed 8-byte key regime) probed with NULL keys: a NULL probe key must
+    match nothing, whatever bytes sit under the null (GpuHashJoin.scala:602-640)"""
+    rng = np.random.default_rng(31)
+    build = [gen(rng, (O.INT32, 0, 0), 1500, distinct=40, null_frac=0), gen(rng, (O.INT32, 0, 0), 1500, distinct=5, null_frac=0)]
+    probe = [gen(rng, (O.INT32, 0, 0), 3000, distinct=40, null_frac=0.3), gen(rng, (O.INT32, 0, 0), 3000, distinct=5, null_frac=0.3)]
+    for col in probe:   # the bytes under a NULL equal a real build key
+        col.values[~col.valid] = build[0].values[0]
+    for kind in (0, 1, 2, 3, 4):
+        _check_join(b2, build, probe, kind, True)
+    uniq = [O.OCol(np.arange(500, dtype=np.int64), np.ones(500, bool), (O.INT64, 0, 0))]   # distinct build side: single-pass probe
+    pr = [gen(rng, (O.INT64, 0, 0), 3000, distinct=700, null_frac=0.3)]
+    pr[0].values[~pr[0].valid] = 7
+    for kind in (0, 1, 2, 3, 4):
+        _check_join(b2, uniq, pr, kind, True)
+
+
 def test_join_empty_sides(b2):
     rng = np.random.default_rng(4)
     some, none = [gen(rng, (O.INT64, 0, 0), 100, distinct=10)], [gen(rng, (O.INT64, 0, 0), 0)]
