@@ -58,16 +58,36 @@ def q6_numpy(cols):
 #     and o_orderdate < date '1995-03-15' and l_shipdate > date '1995-03-15'
 #   group by l_orderkey, o_orderdate, o_shippriority order by revenue desc, o_orderdate limit 10
 # revenue is decimal(12,2) * decimal(13,2) = decimal(26,4), summed as decimal(36,4): unscaled value = price * (100 - disc).
-def q3_numpy(customer_chunks, orders_chunks, lineitem_chunks, date=None, segment=None, limit=10):
-    """exact integer restatement over the raw numpy columns, one chunk at a time (never holds a whole table).
+def _member_index(sorted_keys):
+    """-> f(keys) = (index into sorted_keys or -1): a direct-address table when the key range allows it, else binary search"""
+    import numpy as np
+    n = len(sorted_keys)
+    if n and sorted_keys[0] >= 0 and sorted_keys[-1] < (1 << 31):
+        lut = np.full(int(sorted_keys[-1]) + 2, -1, dtype=np.int32)
+        lut[sorted_keys] = np.arange(n, dtype=np.int32)
+        top = len(lut) - 1
+        return lambda k: lut[np.where((k >= 0) & (k < top), k, top)]
+    def f(k):
+        if n == 0:
+            return np.full(len(k), -1, dtype=np.int64)
+        pos = np.searchsorted(sorted_keys, k)
+        pos[pos >= n] = n - 1
+        return np.where(sorted_keys[pos] == k, pos, -1)
+    return f
+
+
+def q3_numpy(customer_chunks, orders_chunks, lineitem_chunks, date=None, segment=None, limit=10, threads=1):
+    """exact integer restatement over the raw numpy columns, one chunk at a time (never holds a whole table; the lineitem
+    chunks may be callables so that `threads` workers generate and reduce them in parallel).
     -> list of (l_orderkey, revenue_unscaled_dec36_4, o_orderdate, o_shippriority), ordered by revenue desc, o_orderdate asc,
     (then l_orderkey asc to make ties deterministic for the comparison)."""
     import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
     from benchdata import tpch as gen
     date = gen.Q3_DATE if date is None else date
     segment = gen.Q3_SEGMENT if segment is None else segment
     seg_code = gen.SEGMENTS.index(segment)
-    # customer: keys of the wanted segment (sorted unique array -> membership by binary search; no dense-key assumption)
+    # customer: keys of the wanted segment
     ckeys = []
     for c in customer_chunks:
         chars, offsets = c["c_mktsegment"]
@@ -81,49 +101,54 @@ def q3_numpy(customer_chunks, orders_chunks, lineitem_chunks, date=None, segment
             ckeys.append(c["c_custkey"][sel])
             assert (c["c_mktsegment_code"][sel] == seg_code).all()
     ckeys = np.sort(np.concatenate(ckeys)) if ckeys else np.zeros(0, np.int64)
+    cust_index = _member_index(ckeys)
     okeys, odate, oprio = [], [], []
     for o in orders_chunks:
-        m = o["o_orderdate"] < date
-        pos = np.searchsorted(ckeys, o["o_custkey"])
-        pos[pos >= len(ckeys)] = max(len(ckeys) - 1, 0)
-        m &= (ckeys[pos] == o["o_custkey"]) if len(ckeys) else False
+        m = (o["o_orderdate"] < date) & (cust_index(o["o_custkey"]) >= 0)
         okeys.append(o["o_orderkey"][m]); odate.append(o["o_orderdate"][m]); oprio.append(o["o_shippriority"][m])
     okeys = np.concatenate(okeys); odate = np.concatenate(odate); oprio = np.concatenate(oprio)
     order = np.argsort(okeys, kind="stable")
     okeys, odate, oprio = okeys[order], odate[order], oprio[order]
     assert len(okeys) == 0 or (np.diff(okeys) > 0).all(), "o_orderkey must be unique"
-    keys, revs = [], []
-    for li in lineitem_chunks:
-        m = li["l_shipdate"] > date
-        k = li["l_orderkey"][m]
-        pos = np.searchsorted(okeys, k)
-        pos[pos >= len(okeys)] = max(len(okeys) - 1, 0)
-        hit = (okeys[pos] == k) if len(okeys) else np.zeros(len(k), bool)
-        keys.append(pos[hit])     # index into the qualifying orders = group id
-        revs.append((li["l_extendedprice"][m][hit] * (100 - li["l_discount"][m][hit])).astype(np.int64))
-    gid = np.concatenate(keys); rev = np.concatenate(revs)
-    srt = np.argsort(gid, kind="stable")
-    gid, rev = gid[srt], rev[srt]
-    if len(gid) == 0:
+    if len(okeys) == 0:
         return []
-    starts = np.flatnonzero(np.concatenate(([True], gid[1:] != gid[:-1])))
-    sums = np.add.reduceat(rev, starts)            # int64, exact (<= 7 lines x 1.05e9 per group)
-    g = gid[starts]
-    top = np.lexsort((okeys[g], odate[g], -sums))[:limit]
-    return [(int(okeys[g[i]]), int(sums[i]), int(odate[g[i]]), int(oprio[g[i]])) for i in top]
+    order_index = _member_index(okeys)
+
+    def reduce_chunk(li):
+        li = li() if callable(li) else li
+        m = li["l_shipdate"] > date
+        gid = order_index(li["l_orderkey"][m])           # index into the qualifying orders = group id, -1 = no match
+        hit = gid >= 0
+        rev = li["l_extendedprice"][m][hit] * (100 - li["l_discount"][m][hit])
+        # per-group partial sums stay far below 2^53 (<= 7 lines x 1.05e9 per order), so float64 accumulation is exact
+        return np.bincount(gid[hit], weights=rev.astype(np.float64), minlength=len(okeys)), np.bincount(gid[hit], minlength=len(okeys))
+
+    sums = np.zeros(len(okeys), dtype=np.float64)
+    cnts = np.zeros(len(okeys), dtype=np.int64)
+    if threads > 1:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            for s_, c_ in ex.map(reduce_chunk, lineitem_chunks):
+                sums += s_; cnts += c_
+    else:
+        for li in lineitem_chunks:
+            s_, c_ = reduce_chunk(li)
+            sums += s_; cnts += c_
+    assert sums.max(initial=0) < 2.0**53
+    g = np.flatnonzero(cnts > 0)
+    isums = sums[g].astype(np.int64)
+    top = np.lexsort((okeys[g], odate[g], -isums))[:limit]
+    return [(int(okeys[g[i]]), int(isums[i]), int(odate[g[i]]), int(oprio[g[i]])) for i in top]
 
 
 def q3_expected(sf, seed=42, threads=8):
-    """q3_numpy over every chunk of the synthetic tables at scale factor sf (chunks generated on `threads` host threads)"""
+    """q3_numpy over every chunk of the synthetic tables at scale factor sf (chunks generated and reduced on `threads` host threads)"""
     from concurrent.futures import ThreadPoolExecutor
     from benchdata import tpch as gen
     with ThreadPoolExecutor(max_workers=threads) as ex:
         cust = list(ex.map(lambda i: gen.q3_chunk("customer", sf, i, seed), range(gen.Q3_CHUNKS["customer"])))
         orders = list(ex.map(lambda i: gen.q3_chunk("orders", sf, i, seed), range(gen.Q3_CHUNKS["orders"])))
-    def line():
-        for i in range(gen.Q3_CHUNKS["lineitem"]):
-            yield gen.q3_chunk("lineitem", sf, i, seed)
-    return q3_numpy(cust, orders, line())
+    line = [(lambda i=i: gen.q3_chunk("lineitem", sf, i, seed)) for i in range(gen.Q3_CHUNKS["lineitem"])]
+    return q3_numpy(cust, orders, line, threads=threads)
 
 
 def q3_cpu(customer, orders, lineitem, threads=None, date=None, segment=None, limit=10):

@@ -217,6 +217,122 @@ __global__ void __launch_bounds__(VM_NT, 4) filter_kernel(const VMProgramHeader*
   }
 }
 
+
+// ---- TMA-staged filter ---------------------------------------------------------------------------------------------------------
+// Same contract as filter_kernel<false>, different data movement: every fixed-width column the predicate reads or the
+// output keeps is brought into shared memory by TMA bulk copies (cp.async.bulk, one per column and tile, completion on an
+// mbarrier), double buffered, so the HBM stream of tile k+1 runs while tile k is evaluated and compacted.  The VM reads
+// its column operands from shared memory and the compaction takes the kept values from the same staged copy: each input
+// byte crosses HBM exactly once, in large bursts, and no thread waits on a global load.
+struct FilterStageCols {
+  int8_t slot[MAX_TABLE_COLS];   // kept column c -> staged slot (-1: not staged, read from global)
+};
+
+__global__ void __launch_bounds__(VM_NT, 3) filter_staged_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
+                                                                 const __grid_constant__ VMInputs in, const __grid_constant__ FilterCols fc,
+                                                                 const __grid_constant__ VMStage st, const __grid_constant__ FilterStageCols fs,
+                                                                 int64_t nrows, uint64_t* __restrict__ status, FilterWork* __restrict__ work) {
+  constexpr int NW = VM_NT / 32;
+  __shared__ VMShared sh;
+  __shared__ uint32_t s_counts[VM_MAX_K * NW];
+  __shared__ int64_t s_tile_excl;
+  __shared__ int64_t s_next;
+  __shared__ uint32_t s_tile_total;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  extern __shared__ __align__(128) char dyn[];
+  char* regs = dyn;
+  const int R = st.tile_rows;
+  const int64_t ntiles = (nrows + R - 1) / R;
+  // stage buffers follow the VM registers (bytes_per_row * R, rounded up to 128 B)
+  const int regs_bytes = (g_hdr->bytes_per_row * R + 127) & ~127;
+  char* stage = dyn + regs_bytes;
+  const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs, &st, stage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+    // tiles are claimed in launch order so that look-back only waits on tiles already owned by a running CTA
+    const int64_t t0 = (int64_t)atomicAdd(&work->tile_counter, 1ull);
+    s_next = t0;
+    if (t0 < ntiles) vm_stage_issue(st, stage, 0, t0, nrows, &s_bar[0]);
+  }
+  __syncthreads();
+  int64_t tile = s_next;
+  int buf = 0;
+  uint32_t phase[2] = {0, 0};
+  __syncthreads();
+  while (tile < ntiles) {
+    if (threadIdx.x == 0) {   // claim and prefetch the next tile into the other buffer (free since the end of the previous iteration)
+      const int64_t tn = (int64_t)atomicAdd(&work->tile_counter, 1ull);
+      s_next = tn;
+      if (tn < ntiles) vm_stage_issue(st, stage, buf ^ 1, tn, nrows, &s_bar[buf ^ 1]);
+    }
+    mbar_wait(&s_bar[buf], phase[buf]);   // this tile's columns have landed
+    phase[buf] ^= 1;
+    VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
+    cx.stage_off = buf * st.buf_bytes;
+    vm_run(tile_info(cx), code, 0, sh.hdr.ninstr);
+    const Opnd p = resolve(cx, sh.hdr.outs[0], 1);
+    const int K = cx.K;
+    uint32_t selmask = 0;
+    for (int j = 0; j < K; j++) {
+      const int i = threadIdx.x + j * VM_NT;
+      const int64_t g = cx.tile_base + i;
+      const bool sel = g < nrows && opnd_valid(p, i, g) && opnd_ld<int8_t>(p, i) != 0;
+      selmask |= (uint32_t)sel << j;
+      const uint32_t b = __ballot_sync(0xffffffffu, sel);
+      if (lane == 0) s_counts[j * NW + warp] = __popc(b);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int n = K * NW;
+      uint32_t c[4], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int e = lane * 4 + k; c[k] = e < n ? s_counts[e] : 0; sum += c[k]; }
+      uint32_t inc = sum;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      uint32_t run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int e = lane * 4 + k; if (e < n) s_counts[e] = run; run += c[k]; }
+      const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+      int64_t excl = lookback_exclusive(status, tile, total);
+      if (lane == 0) { s_tile_excl = excl; s_tile_total = total; }
+    }
+    __syncthreads();
+    const int64_t base = s_tile_excl;
+    const char* sbuf = stage + (size_t)buf * st.buf_bytes;
+    for (int j = 0; j < K; j++) {
+      const bool sel = (selmask >> j) & 1u;
+      const uint32_t b = __ballot_sync(0xffffffffu, sel);
+      if (!sel) continue;
+      const int i = threadIdx.x + j * VM_NT;
+      const int64_t g = cx.tile_base + i;
+      const int64_t pos = base + s_counts[j * NW + warp] + __popc(b & ((1u << lane) - 1u));
+      for (int c = 0; c < fc.ncols; c++) {
+        const int sl = fs.slot[c];
+        // staged: element i of the tile's copy in shared memory; else straight from global (row g)
+        const void* src = sl >= 0 ? (const void*)(sbuf + st.off[sl]) : fc.in[c];
+        const int64_t at = sl >= 0 ? (int64_t)i : g;
+        switch (fc.width[c]) {
+          case 1: compact_one<int8_t>(src, fc.out[c], at, pos); break;
+          case 2: compact_one<int16_t>(src, fc.out[c], at, pos); break;
+          case 4: compact_one<int32_t>(src, fc.out[c], at, pos); break;
+          case 8: compact_one<int64_t>(src, fc.out[c], at, pos); break;
+          case 16: compact_one<int4>(src, fc.out[c], at, pos); break;
+          default: break;  // strings go through the row-id map
+        }
+        if (fc.out_valid[c] && bit_get(fc.in_valid[c], g)) atomicOr(&fc.out_valid[c][pos >> 5], 1u << (pos & 31));
+      }
+      if (fc.row_ids) fc.row_ids[pos] = (int32_t)g;
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) work->total = (unsigned long long)(base + s_tile_total);
+    __syncthreads();   // every reader of this buffer is done: the next iteration may refill it
+    tile = s_next;
+    buf ^= 1;
+    __syncthreads();   // s_next is rewritten at the top of the next iteration
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -254,12 +370,51 @@ int vm_grid(int64_t nrows, int smem_bytes, int tile_rows) {
   return (int)std::max<int64_t>(1, std::min(ntiles, cap));
 }
 
+// plan the TMA staging of a filter: every fixed-width column the predicate references or the output keeps
+static bool plan_filter_stage(const Program* prog, const Table* pred_table, const FilterCols& fc, const Table* data, VMStage& st, FilterStageCols& fs) {
+  memset(&st, 0, sizeof(st));
+  memset(st.slot_of_col, -1, sizeof(st.slot_of_col));
+  memset(fs.slot, -1, sizeof(fs.slot));
+  if (getenv("B2_FILTER_NO_TMA")) return false;
+  int bytes_per_row = 0;
+  auto add = [&](const Column* c) -> int {
+    for (int k = 0; k < st.n; k++) if (st.src[k] == c->data.as<char>()) return k;
+    if (st.n >= VM_MAX_STAGED) return -1;
+    const int w = dtype_width(c->dtype);
+    st.width[st.n] = w; st.src[st.n] = c->data.as<char>(); bytes_per_row += w;
+    return st.n++;
+  };
+  for (int i = 0; i < prog->hdr.ncols && i < (int)pred_table->cols.size(); i++) {
+    if (prog->col_dtype[i] < 0 || prog->col_dtype[i] == B2_STRING) continue;   // unreferenced, or read in place by a string predicate
+    st.slot_of_col[i] = (int8_t)add(pred_table->cols[i]);
+  }
+  for (int c = 0; c < fc.ncols; c++) {
+    if (fc.width[c] == 0) continue;   // strings travel through the row-id map
+    fs.slot[c] = (int8_t)add(data->cols[c]);
+  }
+  if (st.n == 0 || bytes_per_row == 0) return false;
+  // tile: registers + two stage buffers within ~72 KB -> three CTAs per SM, each with a tile in flight
+  const int per_row = prog->hdr.bytes_per_row + 2 * bytes_per_row;
+  int k = (72 * 1024) / (per_row * VM_NT);
+  if (k > VM_MAX_K) k = VM_MAX_K;
+  if (k < 1) return false;                // rows too wide to stage: the direct kernel handles them
+  st.tile_rows = k * VM_NT;
+  int off = 0;
+  for (int i = 0; i < st.n; i++) { st.off[i] = off; off += st.width[i] * st.tile_rows; }
+  st.buf_bytes = (off + 127) & ~127;
+  return true;
+}
+
 // runs the fused filter; returns the selected-row count.  outputs sized for nrows.
-static int64_t run_filter(const Program* prog, const VMInputs& in, FilterCols& fc, int64_t nrows, bool count_only) {
+static int64_t run_filter(const Program* prog, const VMInputs& in, FilterCols& fc, int64_t nrows, bool count_only,
+                          const Table* pred_table = nullptr, const Table* data = nullptr) {
   if (nrows == 0) return 0;
-  int64_t ntiles = (nrows + prog->hdr.tile_rows - 1) / prog->hdr.tile_rows;
   DevBuf work(sizeof(FilterWork));
   CUDA_CHECK(cudaMemsetAsync(work.p, 0, sizeof(FilterWork), stream()));
+  VMStage st; FilterStageCols fs;
+  const bool staged = !count_only && pred_table && data && nrows >= (1 << 16) && plan_filter_stage(prog, pred_table, fc, data, st, fs);
+  const int tile_rows = staged ? st.tile_rows : prog->hdr.tile_rows;
+  int64_t ntiles = (nrows + tile_rows - 1) / tile_rows;
   DevBuf status;
   if (!count_only) {
     status = DevBuf((size_t)ntiles * 8);
@@ -267,7 +422,16 @@ static int64_t run_filter(const Program* prog, const VMInputs& in, FilterCols& f
   }
   int smem = prog->hdr.smem_bytes;
   int grid = vm_grid(nrows, smem, prog->hdr.tile_rows);
-  if (count_only) {
+  if (staged) {
+    const int regs_bytes = (prog->hdr.bytes_per_row * st.tile_rows + 127) & ~127;
+    smem = regs_bytes + 2 * st.buf_bytes;
+    CUDA_CHECK(cudaFuncSetAttribute(filter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int per_sm = std::max(1, std::min(3, (220 * 1024) / (smem + (int)sizeof(VMShared) + 2048)));
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm));
+    KernelTimer kt("filter_staged_kernel");
+    filter_staged_kernel<<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, fc, st, fs, nrows,
+                                                          status.as<uint64_t>(), work.as<FilterWork>());
+  } else if (count_only) {
     set_dyn_smem(filter_kernel<true>, smem);
     KernelTimer kt_filter_count_kernel("filter_count_kernel");
     filter_kernel<true><<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, fc,
@@ -311,7 +475,7 @@ static Table* filter_impl(const Program* prog, const Table* pred_table, const Ta
   }
   DevBuf row_ids;
   if (has_strings) { row_ids = DevBuf((size_t)std::max<int64_t>(n, 1) * 4); fc.row_ids = row_ids.as<int32_t>(); }
-  int64_t count = run_filter(prog, in, fc, n, false);
+  int64_t count = run_filter(prog, in, fc, n, false, pred_table, data);
   // shrink: keep the over-allocated buffers only when most rows survived
   for (int c = 0; c < fc.ncols; c++) {
     Column* oc = outs.v[c];

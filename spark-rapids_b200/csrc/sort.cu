@@ -328,25 +328,31 @@ static Table* top_n_select(const Table* t, const b2_order_by_arg* keys, int nkey
   if (n < (1 << 18) || limit <= 0 || limit > n / 16) return nullptr;
   SortPlan plan = make_sort_plan(t, keys, nkeys);
   DevBuf k0((size_t)n * 8);
-  build_chunk_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(plan, nullptr, n, 0, k0.as<uint64_t>());
   DevBuf hist(8 * 256 * 8);
-  CUDA_CHECK(cudaMemsetAsync(hist.p, 0, hist.bytes, stream()));
-  hist8_kernel<<<grid_for(n, 256 * 8), 256, 0, stream()>>>(k0.as<uint64_t>(), n, 8, hist.as<unsigned long long>());
-  CUDA_CHECK(cudaGetLastError());
-  count_launch(2);
-  std::vector<unsigned long long> h(8 * 256);
-  d2h(h.data(), hist.p, h.size());
-  sync();
+  const int nchunks = (plan.key_bytes + 7) / 8;
   uint64_t thr = 0;
   int64_t m = -1;
-  for (int d = 7; d >= 0 && m < 0; d--) {
-    int constant = -1;
-    for (int b = 0; b < 256; b++) if (h[d * 256 + b] == (unsigned long long)n) constant = b;
-    if (constant >= 0) { thr |= (uint64_t)constant << (8 * d); continue; }
-    int64_t cum = 0;
-    for (int b = 0; b < 256; b++) {
-      cum += (int64_t)h[d * 256 + b];
-      if (cum >= limit) { thr |= (uint64_t)b << (8 * d); if (d > 0) thr |= (1ull << (8 * d)) - 1; m = cum; break; }
+  // leading 8-byte chunks of the row key on which ALL rows agree cannot discriminate (e.g. the high half of a DECIMAL128
+  // revenue): the selection moves on to the next chunk, every row still being a candidate
+  for (int chunk = 0; chunk < nchunks && m < 0; chunk++) {
+    build_chunk_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(plan, nullptr, n, chunk, k0.as<uint64_t>());
+    CUDA_CHECK(cudaMemsetAsync(hist.p, 0, hist.bytes, stream()));
+    hist8_kernel<<<grid_for(n, 256 * 8), 256, 0, stream()>>>(k0.as<uint64_t>(), n, 8, hist.as<unsigned long long>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch(2);
+    std::vector<unsigned long long> h(8 * 256);
+    d2h(h.data(), hist.p, h.size());
+    sync();
+    thr = 0;
+    for (int d = 7; d >= 0 && m < 0; d--) {
+      int constant = -1;
+      for (int b = 0; b < 256; b++) if (h[d * 256 + b] == (unsigned long long)n) constant = b;
+      if (constant >= 0) { thr |= (uint64_t)constant << (8 * d); continue; }
+      int64_t cum = 0;
+      for (int b = 0; b < 256; b++) {
+        cum += (int64_t)h[d * 256 + b];
+        if (cum >= limit) { thr |= (uint64_t)b << (8 * d); if (d > 0) thr |= (1ull << (8 * d)) - 1; m = cum; break; }
+      }
     }
   }
   if (m < 0 || m > n / 4) return nullptr;   // all leading bytes equal, or one value dominates: sort everything

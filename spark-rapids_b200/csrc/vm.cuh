@@ -141,6 +141,7 @@ struct VMCtx {
   int K;              // rows per thread in this tile
   int tile_rows;
   uint32_t rowmask;   // bit j set = this thread's row j is wanted (post-predicate instructions)
+  int stage_off;      // staged input columns (TMA double buffer): byte offset of the buffer holding this tile
 };
 
 __device__ __forceinline__ Opnd resolve(const VMCtx& cx, const VMOperand& o, int width) {
@@ -211,13 +212,13 @@ template <> struct IsFloat<double> { static const bool v = true; };
 constexpr int VM_B = 4;  // the VM_LD*/VM_ST* expansions below are written for exactly 4
 // The context lives in the caller's frame (local memory) and every store through a register
 // pointer could alias it, so handlers copy what the row loops need into registers ONCE.
-struct TileInfo { int K; uint32_t rowmask; int64_t tile_base, nrows; int tile_rows; };
+struct TileInfo { int K; uint32_t rowmask; int64_t tile_base, nrows; int tile_rows; int stage_off; };
 __device__ __forceinline__ TileInfo tile_info(const VMCtx& cx) {
-  TileInfo t; t.K = cx.K; t.rowmask = cx.rowmask; t.tile_base = cx.tile_base; t.nrows = cx.nrows; t.tile_rows = cx.tile_rows; return t;
+  TileInfo t; t.K = cx.K; t.rowmask = cx.rowmask; t.tile_base = cx.tile_base; t.nrows = cx.nrows; t.tile_rows = cx.tile_rows; t.stage_off = cx.stage_off; return t;
 }
 __device__ __forceinline__ Opnd ropnd(const ROpnd& o, const TileInfo& ti) {
   Opnd r;
-  r.base = o.base + ti.tile_base * o.tile_step;
+  r.base = o.base + ti.tile_base * o.tile_step + (o.pad ? ti.stage_off : 0);   // pad = 1: a column staged in shared memory by TMA
   r.stride = o.stride; r.vkind = o.vkind;
   r.vbytes = reinterpret_cast<const uint8_t*>(o.vptr); r.vbits = reinterpret_cast<const uint32_t*>(o.vptr);
   return r;
@@ -887,9 +888,65 @@ static __device__ __noinline__ void vm_run(const TileInfo ti, const RInstr* __re
 __device__ __forceinline__ VMCtx vm_ctx(const VMProgramHeader* hdr, const VMInputs* in, char* smem, int64_t tile, int64_t nrows) {
   VMCtx cx;
   cx.hdr = hdr; cx.in = in; cx.smem = smem; cx.tile_rows = hdr->tile_rows; cx.K = hdr->tile_rows / VM_NT;
-  cx.tile_base = tile * (int64_t)hdr->tile_rows; cx.nrows = nrows; cx.rowmask = 0xffffffffu;
+  cx.tile_base = tile * (int64_t)hdr->tile_rows; cx.nrows = nrows; cx.rowmask = 0xffffffffu; cx.stage_off = 0;
   return cx;
 }
+
+// Input columns staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier, double buffered): the row loops of
+// the VM then touch shared memory only, and the HBM stream of tile k+1 overlaps the evaluation of tile k.
+constexpr int VM_MAX_STAGED = 24;
+struct VMStage {
+  int32_t n;                           // staged columns (0 = staging off)
+  int32_t tile_rows;                   // rows per tile of the staged kernel (overrides the program's own geometry)
+  int32_t buf_bytes;                   // bytes of ONE stage buffer (all staged columns of a tile)
+  int32_t pad;
+  int8_t slot_of_col[VM_MAX_COLS];     // table column -> staged slot, -1 = read from global
+  int32_t width[VM_MAX_STAGED];
+  int32_t off[VM_MAX_STAGED];          // byte offset of the column inside a stage buffer
+  const char* src[VM_MAX_STAGED];
+};
+
+// ---- TMA 1-D bulk copy + mbarrier (PTX; SASS: UBLKCP + SYNCS) -------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B2_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B2_MBAR_DONE;\n"
+      "bra B2_MBAR_WAIT;\n"
+      "B2_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one thread: start the copies of every staged column of tile `tile` into stage buffer `buf`
+__device__ __forceinline__ void vm_stage_issue(const VMStage& st, char* stage_base, int buf, int64_t tile, int64_t nrows, uint64_t* bar) {
+  const int64_t row0 = tile * (int64_t)st.tile_rows;
+  const int64_t rows = min((int64_t)st.tile_rows, nrows - row0);
+  uint32_t total = 0;
+  for (int k = 0; k < st.n; k++) total += (uint32_t)((rows * st.width[k] + 15) & ~15LL);
+  fence_proxy_async();    // the buffer was read through the generic proxy by the previous tile
+  mbar_expect_tx(bar, total);
+  for (int k = 0; k < st.n; k++) {
+    const uint32_t bytes = (uint32_t)((rows * st.width[k] + 15) & ~15LL);   // column buffers are padded to 64 B
+    tma_bulk_g2s(stage_base + (size_t)buf * st.buf_bytes + st.off[k], st.src[k] + row0 * st.width[k], bytes, bar);
+  }
+}
+#endif
 
 constexpr int VM_SMEM_CODE = 64;  // instructions per program (resolved form lives in shared memory)
 struct VMShared {
@@ -898,11 +955,16 @@ struct VMShared {
 };
 // cooperative load: header into shared memory, then one thread per instruction resolves its operands
 static __device__ __forceinline__ const RInstr* vm_load_program(VMShared& sh, const VMProgramHeader* g_hdr, const VMInstr* g_code,
-                                                                 const VMInputs& in, char* regs) {
+                                                                 const VMInputs& in, char* regs, const VMStage* stage = nullptr,
+                                                                 char* stage_base = nullptr) {
   const int* src = reinterpret_cast<const int*>(g_hdr);
   int* dst = reinterpret_cast<int*>(&sh.hdr);
   for (int k = threadIdx.x; k < (int)(sizeof(VMProgramHeader) / 4); k += blockDim.x) dst[k] = src[k];
   __syncthreads();
+  if (stage && stage->n > 0) {   // the staged kernel picks its own tile size (registers + two stage buffers per tile)
+    if (threadIdx.x == 0) { sh.hdr.tile_rows = stage->tile_rows; sh.hdr.smem_bytes = sh.hdr.bytes_per_row * stage->tile_rows; }
+    __syncthreads();
+  }
   const int n = sh.hdr.ninstr;
   const int tile_rows = sh.hdr.tile_rows;
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
@@ -940,6 +1002,9 @@ static __device__ __forceinline__ const RInstr* vm_load_program(VMShared& sh, co
       } else if (o.kind == OK_COL) {
         q.base = reinterpret_cast<const char*>(in.data[o.idx]); q.stride = width; q.tile_step = width;
         q.vptr = in.valid[o.idx]; q.vkind = (o.nullable && in.valid[o.idx]) ? 2 : 0;
+        if (stage && stage->n > 0 && stage->slot_of_col[o.idx] >= 0) {   // this column's tile sits in shared memory
+          q.base = stage_base + stage->off[stage->slot_of_col[o.idx]]; q.tile_step = 0; q.pad = 1;
+        }
       } else {
         q.base = reinterpret_cast<const char*>(&o.lo); q.stride = 0; q.vkind = o.lit_null ? 3 : 0;
       }

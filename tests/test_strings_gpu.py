@@ -99,8 +99,9 @@ def test_project_bound_reference_passes_through(b2):
     a, s = G.gen_column(rng, (O.INT64, 0, 0), n), str_col(rng, n)
     t = G.to_b2_table(b2, [a, s])
     ca, cs = G.b2_expr_col(b2, 0, a), G.b2_expr_col(b2, 1, s)
-    out = b2.project(b2.Program([cs, ca + 1, ca]), t)
+    one = b2.lit(1, b2.INT64)
+    out = b2.project(b2.Program([cs, ca + one, ca]), t)
     G.assert_col_equal(out.column(0), s)
-    G.assert_col_equal(out.column(1), O.eval_expr((ca + 1).sexpr, [a, s]))
+    G.assert_col_equal(out.column(1), O.eval_expr((ca + one).sexpr, [a, s]))
     G.assert_col_equal(out.column(2), a)
     assert out.column(0).info().data == t.column(1).info().data and out.column(2).info().data == t.column(0).info().data
