@@ -88,6 +88,25 @@ void* b2_get_stream(void);
 int b2_device_bytes_in_use(int64_t* out);
 int b2_set_alloc_limit(int64_t bytes);        /* test hook: RmmSpark.forceRetryOOM analogue */
 
+/* ---- (f4) memory pressure: spill store, semaphore, retry accounting ---------------------------------------------------------
+ * SpillableColumnarBatch (spill/SpillFramework.scala:49-150): a batch held across iterator next() calls is registered here;
+ * while nobody holds the table from b2_spillable_get the store may move it to host memory (on allocation failure, or on
+ * b2_spill) and brings it back on the next get.  Allocation failure = spill, then B2_ERR_OOM (GpuRetryOOM): the exec layer
+ * retries and, for joins and aggregates, splits the input batch and retries (RmmRapidsRetryIterator.scala:65-203). */
+int b2_spillable_create(b2_handle table, b2_handle* out_spillable);
+int b2_spillable_get(b2_handle spillable, b2_handle* out_table);     /* new reference; unspills when needed */
+int b2_spillable_is_spilled(b2_handle spillable, int32_t* out);
+int b2_spillable_close(b2_handle spillable);
+int b2_spill(int64_t want_bytes, int64_t* out_freed);
+/* out6: bytes in use, alloc limit, bytes spilled, bytes unspilled, retries, split-and-retries */
+int b2_memory_stats(int64_t* out6);
+/* GpuSemaphore (GpuSemaphore.scala:183-260): at most `permits` threads between acquire and release (0 = unlimited).
+ * b2_exec_next acquires for the calling thread; the task releases when it is done with the GPU. */
+int b2_semaphore_init(int32_t permits);
+int b2_semaphore_acquire(void);
+int b2_semaphore_release(void);
+int b2_semaphore_stats(int64_t* out3);   /* permits, holders, times a thread had to wait */
+
 /* ---- columns & tables (ai.rapids.cudf.ColumnVector / Table; GpuColumnVector.java:621-660) ------ */
 /* host -> device (HostColumnarToGpu.scala, RapidsHostColumnBuilder + tryBuild H2D) */
 int b2_column_from_host(int32_t dtype, int32_t scale, int64_t size, const void* data,
@@ -281,6 +300,14 @@ int b2_parquet_decode_row_groups(const uint8_t* host_buf, const uint8_t* dev_buf
                                  const char* const* column_names, int32_t ncols, int32_t rg_begin, int32_t rg_end,
                                  b2_handle* out_table);
 int b2_parquet_num_row_groups(const uint8_t* host_buf, int64_t len, int32_t* out_count);
+/* ai.rapids.cudf.ParquetChunkedReader (GpuParquetScan.scala:3403-3407, 3497-3498): decode the buffer in chunks whose decoded
+ * size stays under chunk_byte_limit (0 = no byte limit) and under 2^31-1 rows; a chunk is a run of whole row groups.
+ * host_buf must outlive the reader. */
+int b2_parquet_chunked_open(const uint8_t* host_buf, int64_t len, const char* const* column_names, int32_t ncols,
+                            int64_t chunk_byte_limit, b2_handle* out_reader);
+int b2_parquet_chunked_has_next(b2_handle reader, int32_t* out);
+int b2_parquet_chunked_next(b2_handle reader, b2_handle* out_table);
+int b2_parquet_chunked_close(b2_handle reader);
 
 /* byte accounting of this thread's last decode (roofline numerators of bench.py):
  * out[0] compressed bytes fed to the decompressor, out[1] bytes it produced, out[2] uncompressed
@@ -298,6 +325,15 @@ int b2_table_from_rows(const uint8_t* host_rows, int64_t nrows, const int32_t* d
 
 /* ---- a12: concatenate (GpuAggregateExec.scala:700-727; GpuCoalesceBatches.scala:43-108) -------- */
 int b2_concat(const b2_handle* tables, int32_t ntables, b2_handle* out_table);
+
+/* ---- (f1) shuffle wire format + coalesce on read (GpuColumnarBatchSerializer.scala:169-320, 385-470;
+ *      GpuShuffleCoalesceExec.scala:72-110, 371-475).  Format "B2T1" (serialize.cu): header, per-column descriptors, then
+ *      validity / offsets / data buffers padded to 64 bytes — the structure of JCudfSerialization's header + host buffer. */
+int b2_serialized_size(b2_handle table, int64_t row_start, int64_t row_end, int64_t* out_bytes);
+int b2_serialize_table(b2_handle table, int64_t row_start, int64_t row_end, uint8_t* host_out, int64_t capacity,
+                       int64_t* out_written);
+/* N serialised tables -> one device table: concatenated on the host, one upload per column buffer */
+int b2_deserialize_concat(const uint8_t* const* bufs, const int64_t* lens, int32_t nbufs, b2_handle* out_table);
 
 /* ---- (e) exchange: RapidsShuffleManager replaced by NCCL all-to-all over NVLink ---------------
  * (GpuShuffleExchangeExecBase.scala:384-536; RapidsShuffleInternalManagerBase.scala:1618, 1978) */

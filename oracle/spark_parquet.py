@@ -35,6 +35,11 @@ def arrow_to_ocol(col):
         dt, col = O.DATE32, col.cast(pa.int32())
     elif pa.types.is_timestamp(typ):
         dt, col = O.TIMESTAMP_US, col.cast(pa.timestamp("us")).cast(pa.int64())
+    elif pa.types.is_unsigned_integer(typ):   # cudf UINT* columns keep the stored bits; this library exposes the signed view of the same width
+        dt = {1: O.INT8, 2: O.INT16, 4: O.INT32, 8: O.INT64}[typ.bit_width // 8]
+        arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+        raw = np.array([0 if v is None else int(v) for v in arr.to_pylist()], dtype=np.uint64).astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[typ.bit_width // 8])
+        return O.OCol(raw.view(O._NP[dt]), valid, (dt, 0, 0))
     else:
         dt = m[typ]
     arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col

@@ -702,6 +702,128 @@ def parquet_decode_row_groups(buf, columns, rg_begin, rg_end, dev_ptr=None):
     return Table(out.value)
 
 
+# ---- (f4) memory pressure -------------------------------------------------------------------------------
+class Spillable:
+    """SpillableColumnarBatch: the store may move the batch to host memory while nobody holds the table from get()"""
+
+    def __init__(self, table):
+        out = ctypes.c_int64()
+        check(lib.b2_spillable_create(table.h, ctypes.byref(out)))
+        self.h = ctypes.c_int64(out.value)
+
+    def get(self):
+        out = ctypes.c_int64()
+        check(lib.b2_spillable_get(self.h, ctypes.byref(out)))
+        return Table(out.value)
+
+    @property
+    def spilled(self):
+        v = ctypes.c_int32()
+        check(lib.b2_spillable_is_spilled(self.h, ctypes.byref(v)))
+        return bool(v.value)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_spillable_close(self.h)
+            self.h = ctypes.c_int64(0)
+
+    __del__ = close
+
+
+def spill(want_bytes=2**62):
+    out = ctypes.c_int64()
+    check(lib.b2_spill(int(want_bytes), ctypes.byref(out)))
+    return out.value
+
+
+def memory_stats():
+    out = (ctypes.c_int64 * 6)()
+    check(lib.b2_memory_stats(out))
+    return {"in_use": out[0], "limit": out[1], "spilled_bytes": out[2], "unspilled_bytes": out[3], "retries": out[4], "splits": out[5]}
+
+
+def set_alloc_limit(nbytes):
+    check(lib.b2_set_alloc_limit(int(nbytes)))
+
+
+def device_bytes_in_use():
+    out = ctypes.c_int64()
+    check(lib.b2_device_bytes_in_use(ctypes.byref(out)))
+    return out.value
+
+
+def semaphore_init(permits):
+    check(lib.b2_semaphore_init(int(permits)))
+
+
+def semaphore_acquire():
+    check(lib.b2_semaphore_acquire())
+
+
+def semaphore_release():
+    check(lib.b2_semaphore_release())
+
+
+def semaphore_stats():
+    out = (ctypes.c_int64 * 3)()
+    check(lib.b2_semaphore_stats(out))
+    return {"permits": out[0], "holders": out[1], "waits": out[2]}
+
+
+# ---- (f1) shuffle wire format --------------------------------------------------------------------------
+def serialize_table(table, row_start=0, row_end=None):
+    """GpuColumnarBatchSerializer: rows [row_start, row_end) -> bytes (numpy uint8) in the B2T1 wire format"""
+    row_end = table.num_rows if row_end is None else row_end
+    n = ctypes.c_int64()
+    check(lib.b2_serialized_size(table.h, row_start, row_end, ctypes.byref(n)))
+    buf = np.zeros(n.value, dtype=np.uint8)
+    w = ctypes.c_int64()
+    check(lib.b2_serialize_table(table.h, row_start, row_end, _ptr(buf), buf.nbytes, ctypes.byref(w)))
+    return buf[:w.value]
+
+
+def deserialize_concat(buffers):
+    """GpuShuffleCoalesceExec: serialised tables -> one device Table (host concat, single upload)"""
+    arrs = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b) for b in buffers]
+    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    lens = (ctypes.c_int64 * len(arrs))(*[a.nbytes for a in arrs])
+    out = ctypes.c_int64()
+    check(lib.b2_deserialize_concat(ptrs, lens, len(arrs), ctypes.byref(out)))
+    return Table(out.value)
+
+
+class ParquetChunkedReader:
+    """ai.rapids.cudf.ParquetChunkedReader analogue: iterate tables of <= chunk_byte_limit decoded bytes"""
+
+    def __init__(self, buf, columns, chunk_byte_limit):
+        self.arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+        names = (ctypes.c_char_p * len(columns))(*[c.encode() for c in columns])
+        out = ctypes.c_int64()
+        check(lib.b2_parquet_chunked_open(_ptr(self.arr), self.arr.nbytes, names, len(columns), int(chunk_byte_limit), ctypes.byref(out)))
+        self.h = ctypes.c_int64(out.value)
+
+    def has_next(self):
+        v = ctypes.c_int32()
+        check(lib.b2_parquet_chunked_has_next(self.h, ctypes.byref(v)))
+        return bool(v.value)
+
+    def read_chunk(self):
+        out = ctypes.c_int64()
+        check(lib.b2_parquet_chunked_next(self.h, ctypes.byref(out)))
+        return Table(out.value)
+
+    def __iter__(self):
+        while self.has_next():
+            yield self.read_chunk()
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib.b2_parquet_chunked_close(self.h)
+            self.h = ctypes.c_int64(0)
+
+    __del__ = close
+
+
 # ---- profiling / raw buffers (bench.py) ---------------------------------------------------------------
 def profile_enable(on=True):
     check(lib.b2_profile_enable(int(on)))

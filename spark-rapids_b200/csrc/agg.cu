@@ -616,6 +616,58 @@ __device__ __forceinline__ i128 pow10_128(int e) {
   return r;
 }
 
+// finalise the accumulators of ONE group into row o of the output columns (shared by the hash-table and the radix paths)
+__device__ __forceinline__ void finalize_group(const AggPlan& plan, const uint64_t* __restrict__ gacc, const uint32_t* __restrict__ gnvalid, int64_t o,
+                                               const AggOut& out) {
+  for (int k = 0; k < plan.naggs; k++) {
+    const AggD& a = plan.aggs[k];
+    const uint64_t* acc = &gacc[a.limb_off];
+    bool valid = true;
+    if (a.track_valid) valid = gnvalid[a.valid_off] > 0;
+    switch (a.kind) {
+      case B2_AGG_COUNT: case B2_AGG_COUNT_ALL:
+        reinterpret_cast<int64_t*>(out.data[k])[o] = (int64_t)acc[0]; valid = true; break;
+      case B2_AGG_SUM:
+        if (a.is_float) {
+          double d = __longlong_as_double((long long)acc[0]);
+          if (out.out_dtype[k] == B2_FLOAT32) reinterpret_cast<float*>(out.data[k])[o] = (float)d;
+          else reinterpret_cast<double*>(out.data[k])[o] = d;
+        } else if (a.nlimbs == 1) {
+          reinterpret_cast<int64_t*>(out.data[k])[o] = (int64_t)acc[0];  // long sum wraps (aggregateFunctions.scala:1041-1104)
+        } else {
+          // exact 128/192-bit sum -> decimal; NULL when it needs more than out_precision digits
+          i128 v = (i128)(((u128)acc[1] << 64) | acc[0]);
+          bool fits = true;
+          if (a.nlimbs == 3) {
+            const int64_t ext = (int64_t)acc[2];
+            fits = (ext == 0 && (int64_t)acc[1] >= 0) || (ext == -1 && (int64_t)acc[1] < 0);
+          }
+          const i128 lim = pow10_128(out.out_precision[k]);
+          if (!fits || v >= lim || v <= -lim) valid = false;
+          if (out.out_dtype[k] == B2_DECIMAL128) reinterpret_cast<i128*>(out.data[k])[o] = valid ? v : (i128)0;
+          else reinterpret_cast<int64_t*>(out.data[k])[o] = valid ? (int64_t)v : 0;
+        }
+        break;
+      case B2_AGG_MIN: case B2_AGG_MAX: {
+        const uint64_t key = acc[0];
+        if (a.in_mt == MT_F32) reinterpret_cast<float*>(out.data[k])[o] = (float)unord_f64(key);
+        else if (a.in_mt == MT_F64) reinterpret_cast<double*>(out.data[k])[o] = unord_f64(key);
+        else {
+          const int64_t v = (int64_t)(key ^ 0x8000000000000000ull);
+          switch (a.in_mt) {
+            case MT_I8: reinterpret_cast<int8_t*>(out.data[k])[o] = (int8_t)v; break;
+            case MT_I16: reinterpret_cast<int16_t*>(out.data[k])[o] = (int16_t)v; break;
+            case MT_I32: reinterpret_cast<int32_t*>(out.data[k])[o] = (int32_t)v; break;
+            default: reinterpret_cast<int64_t*>(out.data[k])[o] = v; break;
+          }
+        }
+      } break;
+      default: break;
+    }
+    if (valid && out.valid[k]) atomicOr(&out.valid[k][o >> 5], 1u << (o & 31));
+  }
+}
+
 __global__ void finalize_kernel(GTable gt, const __grid_constant__ AggPlan plan, int64_t cap, const int32_t* __restrict__ pos,
                                 const __grid_constant__ AggOut out, int32_t* __restrict__ rep_rows) {
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < cap; s += (int64_t)gridDim.x * blockDim.x) {
@@ -623,53 +675,306 @@ __global__ void finalize_kernel(GTable gt, const __grid_constant__ AggPlan plan,
     if (row == SLOT_EMPTY) continue;
     const int32_t o = pos[s];
     rep_rows[o] = row;
-    for (int k = 0; k < plan.naggs; k++) {
-      const AggD& a = plan.aggs[k];
-      const uint64_t* acc = &gt.acc[s * plan.limbs + a.limb_off];
-      bool valid = true;
-      if (a.track_valid) valid = gt.nvalid[s * plan.nvalids + a.valid_off] > 0;
-      switch (a.kind) {
-        case B2_AGG_COUNT: case B2_AGG_COUNT_ALL:
-          reinterpret_cast<int64_t*>(out.data[k])[o] = (int64_t)acc[0]; valid = true; break;
-        case B2_AGG_SUM:
-          if (a.is_float) {
-            double d = __longlong_as_double((long long)acc[0]);
-            if (out.out_dtype[k] == B2_FLOAT32) reinterpret_cast<float*>(out.data[k])[o] = (float)d;
-            else reinterpret_cast<double*>(out.data[k])[o] = d;
-          } else if (a.nlimbs == 1) {
-            reinterpret_cast<int64_t*>(out.data[k])[o] = (int64_t)acc[0];  // long sum wraps (aggregateFunctions.scala:1041-1104)
-          } else {
-            // exact 128/192-bit sum -> decimal; NULL when it needs more than out_precision digits
-            i128 v = (i128)(((u128)acc[1] << 64) | acc[0]);
-            bool fits = true;
-            if (a.nlimbs == 3) {
-              const int64_t ext = (int64_t)acc[2];
-              fits = (ext == 0 && (int64_t)acc[1] >= 0) || (ext == -1 && (int64_t)acc[1] < 0);
-            }
-            const i128 lim = pow10_128(out.out_precision[k]);
-            if (!fits || v >= lim || v <= -lim) valid = false;
-            if (out.out_dtype[k] == B2_DECIMAL128) reinterpret_cast<i128*>(out.data[k])[o] = valid ? v : (i128)0;
-            else reinterpret_cast<int64_t*>(out.data[k])[o] = valid ? (int64_t)v : 0;
-          }
-          break;
-        case B2_AGG_MIN: case B2_AGG_MAX: {
-          const uint64_t key = acc[0];
-          if (a.in_mt == MT_F32) reinterpret_cast<float*>(out.data[k])[o] = (float)unord_f64(key);
-          else if (a.in_mt == MT_F64) reinterpret_cast<double*>(out.data[k])[o] = unord_f64(key);
-          else {
-            const int64_t v = (int64_t)(key ^ 0x8000000000000000ull);
-            switch (a.in_mt) {
-              case MT_I8: reinterpret_cast<int8_t*>(out.data[k])[o] = (int8_t)v; break;
-              case MT_I16: reinterpret_cast<int16_t*>(out.data[k])[o] = (int16_t)v; break;
-              case MT_I32: reinterpret_cast<int32_t*>(out.data[k])[o] = (int32_t)v; break;
-              default: reinterpret_cast<int64_t*>(out.data[k])[o] = v; break;
-            }
-          }
-        } break;
-        default: break;
+    finalize_group(plan, &gt.acc[s * plan.limbs], &gt.nvalid[s * plan.nvalids], o, out);
+  }
+}
+
+// ================================================================================================================================
+// Radix-partitioned group-by for high cardinalities (millions of groups: TPC-H q3's (l_orderkey, o_orderdate, o_shippriority)).
+// The global open-addressing table of the regime above pays several random HBM accesses per row and is sized for the worst
+// case (2 x rows slots).  Here the rows are first materialised (fused predicate + projection, keys packed into <= 16 bytes),
+// then radix-partitioned by key hash (one or two stable passes of hash.cu's tile-histogram scatter) into partitions of
+// ~1000 rows, and ONE persistent kernel aggregates each partition in a SHARED-MEMORY hash table: the partition's rows are
+// streamed into shared memory by TMA bulk copies (cp.async.bulk + mbarrier, double buffered) while the previous chunk is
+// being inserted; a finished partition's groups are appended to the compact group arrays and the table is reset.  No global
+// hash table exists, every row moves through HBM a fixed number of times, all probing happens in shared memory.
+// Reference it replaces: cudf hash groupby behind AggHelper.performGroupByAggregation (GpuAggregateExec.scala:562-585).
+constexpr int RG_MAX_VALS = 5;
+constexpr int RG_NT = 512;
+constexpr int RG_CHUNK = 1024;        // rows per staged chunk
+constexpr uint32_t RG_READY = 0x80000000u;
+struct RGVal { int32_t out_idx, in_mt, width, pad; };
+struct RGPlan {
+  int32_t nvals, has_k1, use_vbits, pad;
+  RGVal val[RG_MAX_VALS];
+  int32_t agg_val[AG_MAX_AGGS];     // aggregate -> value slot, -1 for COUNT(*)
+  int32_t key_shift[MAX_KEYS];      // bit offset of each key column inside the packed 128-bit key
+};
+struct RGRows {   // materialised rows, structure of arrays
+  uint32_t* h; uint64_t* k0; uint64_t* k1; char* v[RG_MAX_VALS]; uint32_t* vbits;
+};
+__device__ __forceinline__ uint64_t rg_hash(uint64_t k0, uint64_t k1) { return mix64(k0 ^ mix64(k1 ^ 0x9e3779b97f4a7c15ull)); }
+
+__global__ void __launch_bounds__(VM_NT, 4) radix_rows_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
+                                                              const __grid_constant__ VMInputs in, const __grid_constant__ AggPlan plan,
+                                                              const __grid_constant__ RGPlan rp, RGRows rows, int64_t nrows,
+                                                              unsigned long long* __restrict__ counter) {
+  __shared__ VMShared sh;
+  extern __shared__ __align__(16) char regs[];
+  const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs);
+  const int64_t ntiles = (nrows + sh.hdr.tile_rows - 1) / sh.hdr.tile_rows;
+  const int first_post = plan.has_pred ? sh.hdr.npred : 0;
+  const int lane = threadIdx.x & 31;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
+    uint32_t active_mask = 0;
+    if (plan.has_pred) {
+      vm_run(tile_info(cx), code, 0, first_post);
+      const Opnd pred = resolve(cx, sh.hdr.outs[0], 1);
+      for (int j = 0; j < cx.K; j++) {
+        const int i = threadIdx.x + j * VM_NT;
+        const int64_t g = cx.tile_base + i;
+        active_mask |= (uint32_t)(g < nrows && opnd_valid(pred, i, g) && opnd_ld<int8_t>(pred, i) != 0) << j;
       }
-      if (valid && out.valid[k]) atomicOr(&out.valid[k][o >> 5], 1u << (o & 31));
+    } else {
+      for (int j = 0; j < cx.K; j++) active_mask |= (uint32_t)(cx.tile_base + threadIdx.x + j * VM_NT < nrows) << j;
     }
+    vm_run(tile_info(cx), code, first_post, sh.hdr.ninstr);
+    Opnd ops[RG_MAX_VALS];
+    for (int s = 0; s < rp.nvals; s++) ops[s] = resolve(cx, sh.hdr.outs[rp.val[s].out_idx], mt_width(rp.val[s].in_mt));
+    for (int j = 0; j < cx.K; j++) {
+      const int i = threadIdx.x + j * VM_NT;
+      const int64_t g = cx.tile_base + i;
+      const bool active = (active_mask >> j) & 1u;
+      const uint32_t b = __ballot_sync(0xffffffffu, active);
+      if (b == 0) continue;
+      int64_t pos = g;
+      if (plan.has_pred) {   // compaction: order is irrelevant to an aggregation, one atomic per warp slice
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        pos = (int64_t)base + __popc(b & ((1u << lane) - 1u));
+      }
+      if (!active) continue;
+      u128 bits = 0;
+      for (int k = 0; k < plan.nkeys; k++) bits |= (u128)key_bits(plan.keys.c[k], g) << rp.key_shift[k];
+      const uint64_t k0 = (uint64_t)bits, k1 = (uint64_t)(bits >> 64);
+      rows.h[pos] = (uint32_t)(rg_hash(k0, k1) >> 32);
+      rows.k0[pos] = k0;
+      if (rp.has_k1) rows.k1[pos] = k1;
+      uint32_t vb = 0;
+      for (int s = 0; s < rp.nvals; s++) {
+        const bool valid = opnd_valid(ops[s], i, g);
+        vb |= (uint32_t)valid << s;
+        if (rp.val[s].width == 16) {
+          reinterpret_cast<i128*>(rows.v[s])[pos] = valid ? opnd_ld<i128>(ops[s], i) : (i128)0;
+        } else {
+          int64_t x = 0;
+          if (valid) switch (rp.val[s].in_mt) {
+            case MT_I8: x = opnd_ld<int8_t>(ops[s], i); break;
+            case MT_I16: x = opnd_ld<int16_t>(ops[s], i); break;
+            case MT_I32: x = opnd_ld<int32_t>(ops[s], i); break;
+            default: x = opnd_ld<int64_t>(ops[s], i); break;
+          }
+          reinterpret_cast<int64_t*>(rows.v[s])[pos] = x;
+        }
+      }
+      if (rp.use_vbits) rows.vbits[pos] = vb;
+    }
+  }
+}
+
+__global__ void rg_digit_kernel(const uint32_t* __restrict__ h, int64_t n, int shift, uint32_t mask, int32_t* __restrict__ pid) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) pid[i] = (int32_t)((h[i] >> shift) & mask);
+}
+// rows are sorted by q = h & (P - 1): off[q] = first row of partition q, off[P] = n
+__global__ void rg_offsets_kernel(const uint32_t* __restrict__ h, int64_t n, uint32_t pmask, int32_t* __restrict__ off) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = h[i] & pmask, qp = i ? (int64_t)(h[i - 1] & pmask) : -1;
+    for (int64_t x = qp + 1; x <= q; x++) off[x] = (int32_t)i;
+    if (i == n - 1) for (int64_t x = q + 1; x <= (int64_t)pmask + 1; x++) off[x] = (int32_t)n;
+  }
+}
+
+struct RGAgg {
+  RGRows rows;
+  const int32_t* off;
+  int32_t P, C;
+  int64_t m;
+  uint64_t* gk0; uint64_t* gk1; uint64_t* gacc; uint32_t* gnvalid;
+  unsigned long long* gcount;
+  int32_t* overflow;
+};
+
+__global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_constant__ AggPlan plan, const __grid_constant__ RGPlan rp, const __grid_constant__ RGAgg a) {
+  extern __shared__ __align__(128) char rg_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_scan[RG_NT / 32];
+  __shared__ unsigned long long s_base;
+  const int C = a.C;
+  // table: packed keys, accumulators, state (0 = empty, else (claiming stage index + 1) [| RG_READY once the key is published])
+  uint64_t* t_k0 = reinterpret_cast<uint64_t*>(rg_dyn);
+  uint64_t* t_k1 = t_k0 + C;
+  uint64_t* t_acc = t_k1 + (rp.has_k1 ? C : 0);
+  uint32_t* t_state = reinterpret_cast<uint32_t*>(t_acc + (size_t)C * plan.limbs);
+  uint32_t* t_nvalid = t_state + C;
+  char* stage0 = reinterpret_cast<char*>(((uintptr_t)(t_nvalid + (size_t)C * plan.nvalids) + 127) & ~(uintptr_t)127);
+  // one stage buffer: k0 | k1 | v[0..] | vbits, each CH rows (+ slack so that 16-byte rounded copies stay inside)
+  constexpr int CH = RG_CHUNK;
+  int soff_k1 = CH * 8 + 16, soff_v[RG_MAX_VALS], soff_vb, sbytes;
+  {
+    int o = soff_k1 + (rp.has_k1 ? CH * 8 + 16 : 0);
+    for (int s = 0; s < rp.nvals; s++) { soff_v[s] = o; o += CH * rp.val[s].width + 16; }
+    soff_vb = o; o += rp.use_vbits ? CH * 4 + 16 : 0;
+    sbytes = (o + 127) & ~127;
+  }
+  for (int s = threadIdx.x; s < C; s += RG_NT) {
+    t_state[s] = 0;
+    for (int k = 0; k < plan.naggs; k++)
+      for (int l = 0; l < plan.aggs[k].nlimbs; l++) t_acc[(size_t)s * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
+    for (int v = 0; v < plan.nvalids; v++) t_nvalid[(size_t)s * plan.nvalids + v] = 0;
+  }
+  // this CTA's partitions and the row stream that covers them (starts on a 4-row boundary: every array offset is 16-byte aligned)
+  const int pA = (int)((int64_t)a.P * blockIdx.x / gridDim.x), pB = (int)((int64_t)a.P * (blockIdx.x + 1) / gridDim.x);
+  const int64_t r_lo = a.off[pA], r_hi = a.off[pB];
+  const int64_t a0 = r_lo & ~(int64_t)3;
+  const int64_t nchunks = r_hi > r_lo ? (r_hi - a0 + CH - 1) / CH : 0;
+  auto issue = [&](int64_t c, int buf) {   // one thread: TMA copies of chunk c into stage buffer buf
+    const int64_t start = a0 + c * CH;
+    const int64_t rows = min((int64_t)CH, a.m - start);
+    char* sb = stage0 + (size_t)buf * sbytes;
+    uint32_t total = (uint32_t)((rows * 8 + 15) & ~15LL) * (rp.has_k1 ? 2 : 1);
+    for (int s = 0; s < rp.nvals; s++) total += (uint32_t)((rows * rp.val[s].width + 15) & ~15LL);
+    if (rp.use_vbits) total += (uint32_t)((rows * 4 + 15) & ~15LL);
+    fence_proxy_async();
+    mbar_expect_tx(&s_bar[buf], total);
+    tma_bulk_g2s(sb, a.rows.k0 + start, (uint32_t)((rows * 8 + 15) & ~15LL), &s_bar[buf]);
+    if (rp.has_k1) tma_bulk_g2s(sb + soff_k1, a.rows.k1 + start, (uint32_t)((rows * 8 + 15) & ~15LL), &s_bar[buf]);
+    for (int s = 0; s < rp.nvals; s++)
+      tma_bulk_g2s(sb + soff_v[s], a.rows.v[s] + start * rp.val[s].width, (uint32_t)((rows * rp.val[s].width + 15) & ~15LL), &s_bar[buf]);
+    if (rp.use_vbits) tma_bulk_g2s(sb + soff_vb, a.rows.vbits + start, (uint32_t)((rows * 4 + 15) & ~15LL), &s_bar[buf]);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+    if (nchunks > 0) issue(0, 0);
+  }
+  __syncthreads();
+  uint32_t phase[2] = {0, 0};
+  int p = pA;
+  int64_t cursor = r_lo;
+  const int per_thread = C / RG_NT;   // C is a multiple of RG_NT
+  for (int64_t c = 0; c < nchunks; c++) {
+    const int buf = (int)(c & 1);
+    if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1, buf ^ 1);
+    mbar_wait(&s_bar[buf], phase[buf]);
+    phase[buf] ^= 1;
+    const char* sb = stage0 + (size_t)buf * sbytes;
+    const uint64_t* s_k0 = reinterpret_cast<const uint64_t*>(sb);
+    const uint64_t* s_k1 = reinterpret_cast<const uint64_t*>(sb + soff_k1);
+    const uint32_t* s_vb = reinterpret_cast<const uint32_t*>(sb + soff_vb);
+    const int64_t cs = a0 + c * CH, ce = min(cs + CH, r_hi);
+    while (cursor < ce && p < pB) {
+      const int64_t pend = a.off[p + 1];
+      const int64_t hi = min(ce, pend);
+      for (int64_t r = cursor + threadIdx.x; r < hi; r += RG_NT) {
+        const int li = (int)(r - cs);
+        const uint64_t k0 = s_k0[li], k1 = rp.has_k1 ? s_k1[li] : 0;
+        uint32_t idx = (uint32_t)rg_hash(k0, k1) & (uint32_t)(C - 1);
+        int probes = 0;
+        bool found = false;
+        while (!found) {
+          uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t_state[idx]);
+          if (st == 0) {
+            const uint32_t old = atomicCAS(&t_state[idx], 0u, (uint32_t)(li + 1));
+            if (old == 0) {   // mine: publish the key, then the READY bit
+              t_k0[idx] = k0;
+              if (rp.has_k1) t_k1[idx] = k1;
+              __threadfence_block();
+              *reinterpret_cast<volatile uint32_t*>(&t_state[idx]) = (uint32_t)(li + 1) | RG_READY;
+              found = true;
+              break;
+            }
+            st = old;
+          }
+          bool same;
+          if (st & RG_READY) {
+            __threadfence_block();
+            same = *reinterpret_cast<volatile uint64_t*>(&t_k0[idx]) == k0 && (!rp.has_k1 || *reinterpret_cast<volatile uint64_t*>(&t_k1[idx]) == k1);
+          } else {   // claimed in this very chunk, key not visible yet: compare with the claiming row in the stage buffer
+            const int lj = (int)(st & ~RG_READY) - 1;
+            same = s_k0[lj] == k0 && (!rp.has_k1 || s_k1[lj] == k1);
+          }
+          if (same) { found = true; break; }
+          idx = (idx + 1) & (uint32_t)(C - 1);
+          if (++probes > C / 2) { atomicExch(a.overflow, 1); break; }
+        }
+        if (!found) continue;
+        const uint32_t vb = rp.use_vbits ? s_vb[li] : 0xffffffffu;
+        uint64_t* acc = t_acc + (size_t)idx * plan.limbs;
+        uint32_t* nv = t_nvalid + (size_t)idx * plan.nvalids;
+        for (int k = 0; k < plan.naggs; k++) {
+          const AggD& ag = plan.aggs[k];
+          const int vs = rp.agg_val[k];
+          const bool valid = vs < 0 || ((vb >> vs) & 1u);
+          if (!valid) continue;
+          if (ag.track_valid) atomicAdd(&nv[ag.valid_off], 1u);
+          if (ag.kind == B2_AGG_COUNT || ag.kind == B2_AGG_COUNT_ALL) { atomicAdd(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), 1ull); continue; }
+          uint64_t lo, hi;
+          if (rp.val[vs].width == 16) { const i128 x = reinterpret_cast<const i128*>(sb + soff_v[vs])[li]; lo = (uint64_t)x; hi = (uint64_t)(x >> 64); }
+          else { lo = (uint64_t)reinterpret_cast<const int64_t*>(sb + soff_v[vs])[li]; hi = (int64_t)lo < 0 ? ~0ull : 0ull; }
+          if (ag.kind == B2_AGG_SUM) acc_add_limbs(&acc[ag.limb_off], ag.nlimbs, lo, hi, (int64_t)hi < 0 ? ~0ull : 0ull);
+          else if (ag.kind == B2_AGG_MIN) atomicMin(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), (unsigned long long)ord_i64((int64_t)lo));
+          else if (ag.kind == B2_AGG_MAX) atomicMax(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), (unsigned long long)ord_i64((int64_t)lo));
+        }
+      }
+      cursor = hi;
+      if (hi < pend) break;   // the partition continues in the next chunk
+      // partition p is complete: append its groups to the compact group arrays and reset the table
+      __syncthreads();
+      {
+        uint32_t cnt = 0;
+        for (int q = 0; q < per_thread; q++) cnt += t_state[threadIdx.x * per_thread + q] != 0;
+        uint32_t inc = cnt;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+          uint32_t w = lane < RG_NT / 32 ? s_scan[lane] : 0, winc = w;
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+          if (lane < RG_NT / 32) s_scan[lane] = winc - w;
+          if (lane == 31) s_base = winc ? atomicAdd(a.gcount, (unsigned long long)winc) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long o = s_base + s_scan[warp] + (inc - cnt);
+        for (int q = 0; q < per_thread; q++) {
+          const int sl = threadIdx.x * per_thread + q;
+          if (t_state[sl] == 0) continue;
+          a.gk0[o] = t_k0[sl];
+          if (rp.has_k1) a.gk1[o] = t_k1[sl];
+          for (int l = 0; l < plan.limbs; l++) a.gacc[o * plan.limbs + l] = t_acc[(size_t)sl * plan.limbs + l];
+          for (int v = 0; v < plan.nvalids; v++) a.gnvalid[o * plan.nvalids + v] = t_nvalid[(size_t)sl * plan.nvalids + v];
+          o++;
+          t_state[sl] = 0;
+          for (int k = 0; k < plan.naggs; k++)
+            for (int l = 0; l < plan.aggs[k].nlimbs; l++) t_acc[(size_t)sl * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
+          for (int v = 0; v < plan.nvalids; v++) t_nvalid[(size_t)sl * plan.nvalids + v] = 0;
+        }
+      }
+      __syncthreads();
+      p++;
+    }
+    __syncthreads();   // every reader of this stage buffer is done before it is refilled
+  }
+}
+
+struct RGKeyOut { void* data[MAX_KEYS]; int32_t width[MAX_KEYS]; };
+__global__ void radix_finalize_kernel(const __grid_constant__ AggPlan plan, const __grid_constant__ RGPlan rp, int64_t ngroups, const uint64_t* __restrict__ gk0,
+                                      const uint64_t* __restrict__ gk1, const uint64_t* __restrict__ gacc, const uint32_t* __restrict__ gnvalid,
+                                      const __grid_constant__ AggOut out, const __grid_constant__ RGKeyOut ko) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < ngroups; o += (int64_t)gridDim.x * blockDim.x) {
+    const u128 bits = ((u128)(rp.has_k1 ? gk1[o] : 0ull) << 64) | gk0[o];
+    for (int k = 0; k < plan.nkeys; k++) {
+      const uint64_t v = (uint64_t)(bits >> rp.key_shift[k]);
+      switch (ko.width[k]) {
+        case 1: reinterpret_cast<uint8_t*>(ko.data[k])[o] = (uint8_t)v; break;
+        case 2: reinterpret_cast<uint16_t*>(ko.data[k])[o] = (uint16_t)v; break;
+        case 4: reinterpret_cast<uint32_t*>(ko.data[k])[o] = (uint32_t)v; break;
+        default: reinterpret_cast<uint64_t*>(ko.data[k])[o] = v; break;
+      }
+    }
+    finalize_group(plan, &gacc[o * plan.limbs], &gnvalid[o * plan.nvalids], o, out);
   }
 }
 
@@ -691,6 +996,164 @@ static int mt_of_dtype(int dtype) {
     case B2_FLOAT64: return MT_F64;
   }
   throw Error(B2_ERR_UNSUPPORTED, "aggregation over dtype " + std::to_string(dtype));
+}
+
+
+// result columns of the aggregates for `ngroups` groups
+static void make_agg_outputs(const AggPlan& plan, const Program* prog, const b2_agg_spec* specs, int naggs, int64_t ngroups, ColsGuard& outs, AggOut& ao) {
+  memset(&ao, 0, sizeof(ao));
+  for (int k = 0; k < naggs; k++) {
+    int odt = specs[k].out_dtype;
+    if (plan.aggs[k].kind == B2_AGG_COUNT || plan.aggs[k].kind == B2_AGG_COUNT_ALL) odt = B2_INT64;
+    if (plan.aggs[k].kind == B2_AGG_MIN || plan.aggs[k].kind == B2_AGG_MAX) odt = prog->out_dtype[plan.aggs[k].out_idx];
+    bool nullable = plan.aggs[k].track_valid || (plan.aggs[k].kind == B2_AGG_SUM && plan.aggs[k].nlimbs >= 2);
+    int oscale = (plan.aggs[k].kind == B2_AGG_MIN || plan.aggs[k].kind == B2_AGG_MAX) ? prog->out_scale[plan.aggs[k].out_idx] : specs[k].out_scale;
+    Column* c = new_column(odt, oscale, ngroups, nullable);
+    outs.v.push_back(c);
+    ao.data[k] = c->data.p; ao.valid[k] = c->valid.as<uint32_t>();
+    ao.out_dtype[k] = odt; ao.out_precision[k] = specs[k].out_precision;
+    if (c->valid.p) CUDA_CHECK(cudaMemsetAsync(c->valid.p, 0, c->valid.bytes, stream()));
+  }
+}
+
+// the radix-partitioned regime; nullptr = not applicable (or a partition overflowed its table): the caller falls back
+static Table* radix_groupby(const Program* prog, const Table* t, const AggPlan& plan, const b2_agg_spec* specs, const std::vector<int>& key_table_cols,
+                            const VMInputs& in) {
+  if (getenv("B2_AGG_NO_RADIX")) return nullptr;
+  const int64_t n = t->rows;
+  const int nkeys = plan.nkeys, naggs = plan.naggs;
+  RGPlan rp; memset(&rp, 0, sizeof(rp));
+  int kb = 0;
+  for (int k = 0; k < nkeys; k++) {
+    const KeyCol& c = plan.keys.c[k];
+    if (c.dtype == B2_STRING || c.width == 16 || c.valid) return nullptr;   // fixed-width NOT NULL keys, <= 16 bytes together
+    rp.key_shift[k] = 8 * kb; kb += c.width;
+  }
+  if (kb > 16 || kb == 0) return nullptr;
+  rp.has_k1 = kb > 8;
+  for (int k = 0; k < naggs; k++) {
+    const AggD& a = plan.aggs[k];
+    if (a.is_float) return nullptr;
+    if (a.kind != B2_AGG_SUM && a.kind != B2_AGG_COUNT && a.kind != B2_AGG_COUNT_ALL && a.kind != B2_AGG_MIN && a.kind != B2_AGG_MAX) return nullptr;
+    rp.agg_val[k] = -1;
+    if (a.out_idx < 0) continue;
+    int slot = -1;
+    for (int s2 = 0; s2 < rp.nvals; s2++) if (rp.val[s2].out_idx == a.out_idx) slot = s2;
+    if (slot < 0) {
+      if (rp.nvals >= RG_MAX_VALS) return nullptr;
+      slot = rp.nvals++;
+      rp.val[slot].out_idx = a.out_idx; rp.val[slot].in_mt = a.in_mt; rp.val[slot].width = a.in_mt == MT_I128 ? 16 : 8;
+      if (prog->out_nullable[a.out_idx]) rp.use_vbits = 1;
+    }
+    rp.agg_val[k] = slot;
+  }
+  const int ncols_moved = 2 + rp.has_k1 + rp.nvals + rp.use_vbits;
+  if (ncols_moved > PT_MAXC) return nullptr;
+  // shared-memory budget of the aggregation kernel: table of C slots + two stage buffers
+  const int slot_bytes = 8 + (rp.has_k1 ? 8 : 0) + plan.limbs * 8 + 4 + plan.nvalids * 4;
+  int sbytes = RG_CHUNK * 8 + 16 + (rp.has_k1 ? RG_CHUNK * 8 + 16 : 0) + (rp.use_vbits ? RG_CHUNK * 4 + 16 : 0);
+  for (int s2 = 0; s2 < rp.nvals; s2++) sbytes += RG_CHUNK * rp.val[s2].width + 16;
+  sbytes = (sbytes + 127) & ~127;
+  int C = 2048;
+  while (C >= 1024 && C * slot_bytes + 2 * sbytes + 512 > 200 * 1024) C >>= 1;
+  if (C < 1024) return nullptr;
+  const int agg_smem = C * slot_bytes + 2 * sbytes + 512;
+
+  // 1. materialise the (filtered, projected) rows
+  struct Side { DevBuf h, k0, k1, v[RG_MAX_VALS], vbits; };
+  Side A, B;
+  auto alloc_side = [&](Side& sd) {
+    sd.h = DevBuf((size_t)n * 4 + 64); sd.k0 = DevBuf((size_t)n * 8 + 64);
+    if (rp.has_k1) sd.k1 = DevBuf((size_t)n * 8 + 64);
+    for (int s2 = 0; s2 < rp.nvals; s2++) sd.v[s2] = DevBuf((size_t)n * rp.val[s2].width + 64);
+    if (rp.use_vbits) sd.vbits = DevBuf((size_t)n * 4 + 64);
+  };
+  auto rows_of = [&](Side& sd) {
+    RGRows r; memset(&r, 0, sizeof(r));
+    r.h = sd.h.as<uint32_t>(); r.k0 = sd.k0.as<uint64_t>(); r.k1 = sd.k1.as<uint64_t>(); r.vbits = sd.vbits.as<uint32_t>();
+    for (int s2 = 0; s2 < rp.nvals; s2++) r.v[s2] = sd.v[s2].as<char>();
+    return r;
+  };
+  alloc_side(A);
+  DevBuf counter(16);
+  CUDA_CHECK(cudaMemsetAsync(counter.p, 0, 16, stream()));
+  {
+    const int vm_smem = prog->hdr.smem_bytes;
+    if (vm_smem > 32 * 1024) CUDA_CHECK(cudaFuncSetAttribute(radix_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vm_smem));
+    KernelTimer kt("radix_rows_kernel");
+    radix_rows_kernel<<<vm_grid(n, vm_smem, prog->hdr.tile_rows), VM_NT, vm_smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, plan, rp,
+                                                                                                rows_of(A), n, counter.as<unsigned long long>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  int64_t m = n;
+  if (plan.has_pred) { unsigned long long hm = 0; d2h(&hm, counter.p, 1); sync(); m = (int64_t)hm; }
+  if (m == 0) return nullptr;
+  // 2. radix partition by key hash so that a partition's groups fit the shared-memory table at load <= ~0.4
+  int64_t P = 1;
+  while (P * (int64_t)(C * 2 / 5) < m && P < (1 << 20)) P <<= 1;
+  int lgP = 0; while ((1LL << lgP) < P) lgP++;
+  Side* cur = &A; Side* oth = &B;
+  if (P > 1) {
+    alloc_side(B);
+    DevBuf pid((size_t)m * 4);
+    const int npass = P <= 1024 ? 1 : 2;
+    const int lg1 = npass == 1 ? lgP : lgP / 2;
+    for (int pass = 0; pass < npass; pass++) {
+      const int shift = pass == 0 ? 0 : lg1, bits = pass == 0 ? lg1 : lgP - lg1;
+      rg_digit_kernel<<<grid_for(m, 256), 256, 0, stream()>>>(cur->h.as<uint32_t>(), m, shift, (1u << bits) - 1u, pid.as<int32_t>());
+      count_launch();
+      ScatterCols sc; memset(&sc, 0, sizeof(sc));
+      auto add = [&](DevBuf& i, DevBuf& o, int w) { sc.width[sc.n] = w; sc.in[sc.n] = i.p; sc.out[sc.n] = o.p; sc.n++; };
+      add(cur->h, oth->h, 4); add(cur->k0, oth->k0, 8);
+      if (rp.has_k1) add(cur->k1, oth->k1, 8);
+      for (int s2 = 0; s2 < rp.nvals; s2++) add(cur->v[s2], oth->v[s2], rp.val[s2].width);
+      if (rp.use_vbits) add(cur->vbits, oth->vbits, 4);
+      partition_scatter_arrays(pid.as<int32_t>(), m, 1 << bits, sc);
+      std::swap(cur, oth);
+    }
+  }
+  DevBuf off((size_t)(P + 1) * 4);
+  rg_offsets_kernel<<<grid_for(m, 256), 256, 0, stream()>>>(cur->h.as<uint32_t>(), m, (uint32_t)(P - 1), off.as<int32_t>());
+  count_launch();
+  // 3. aggregate every partition in shared memory
+  DevBuf gk0((size_t)m * 8), gk1(rp.has_k1 ? (size_t)m * 8 : 8), gacc((size_t)m * plan.limbs * 8), gnv((size_t)m * plan.nvalids * 4), ovf(4);
+  CUDA_CHECK(cudaMemsetAsync(ovf.p, 0, 4, stream()));
+  RGAgg ap; memset(&ap, 0, sizeof(ap));
+  ap.rows = rows_of(*cur); ap.off = off.as<int32_t>(); ap.P = (int32_t)P; ap.C = C; ap.m = m;
+  ap.gk0 = gk0.as<uint64_t>(); ap.gk1 = gk1.as<uint64_t>(); ap.gacc = gacc.as<uint64_t>(); ap.gnvalid = gnv.as<uint32_t>();
+  ap.gcount = counter.as<unsigned long long>() + 1; ap.overflow = ovf.as<int32_t>();
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(radix_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, agg_smem));
+    KernelTimer kt("radix_agg_kernel");
+    radix_agg_kernel<<<(int)std::min<int64_t>(P, sm_count()), RG_NT, agg_smem, stream()>>>(plan, rp, ap);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  unsigned long long hg = 0; int32_t hovf = 0;
+  d2h(&hg, counter.as<unsigned long long>() + 1, 1);
+  d2h(&hovf, ovf.p, 1);
+  sync();
+  if (hovf) return nullptr;   // pathological skew: the global-table regime takes over
+  const int64_t ngroups = (int64_t)hg;
+  // 4. unpack keys, finalise aggregates
+  ColsGuard outs;
+  RGKeyOut ko; memset(&ko, 0, sizeof(ko));
+  for (int k = 0; k < nkeys; k++) {
+    const Column* kc = t->cols[key_table_cols[k]];
+    Column* c = new_column(kc->dtype, kc->scale, ngroups, false);
+    outs.v.push_back(c);
+    ko.data[k] = c->data.p; ko.width[k] = dtype_width(kc->dtype);
+  }
+  AggOut ao;
+  make_agg_outputs(plan, prog, specs, naggs, ngroups, outs, ao);
+  if (ngroups) {
+    radix_finalize_kernel<<<grid_for(ngroups, 256), 256, 0, stream()>>>(plan, rp, ngroups, gk0.as<uint64_t>(), gk1.as<uint64_t>(), gacc.as<uint64_t>(), gnv.as<uint32_t>(), ao, ko);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  sync();   // the scratch arrays are freed on return
+  return new_table(outs.release());
 }
 
 // core: program outputs -> (keys, aggregates).  Key outputs must be plain input columns.
@@ -810,6 +1273,9 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
       sync();
       try_smem = h == 0;
     }
+    if (!try_smem) {   // many groups: radix-partitioned shared-memory aggregation (falls through when not applicable)
+      if (Table* r = radix_groupby(prog, t, plan, specs, key_table_cols, in)) return r;
+    }
   }
   // regime 1: shared-memory tables (always right for reductions; optimistic for group-by)
   if (try_smem) {
@@ -862,19 +1328,8 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
   d2h(&ngroups, pos.as<int32_t>() + cap, 1);
   sync();
   ColsGuard outs;
-  AggOut ao; memset(&ao, 0, sizeof(ao));
-  for (int k = 0; k < naggs; k++) {
-    int odt = specs[k].out_dtype;
-    if (plan.aggs[k].kind == B2_AGG_COUNT || plan.aggs[k].kind == B2_AGG_COUNT_ALL) odt = B2_INT64;
-    if (plan.aggs[k].kind == B2_AGG_MIN || plan.aggs[k].kind == B2_AGG_MAX) odt = prog->out_dtype[plan.aggs[k].out_idx];
-    bool nullable = plan.aggs[k].track_valid || (plan.aggs[k].kind == B2_AGG_SUM && plan.aggs[k].nlimbs >= 2);
-    int oscale = (plan.aggs[k].kind == B2_AGG_MIN || plan.aggs[k].kind == B2_AGG_MAX) ? prog->out_scale[plan.aggs[k].out_idx] : specs[k].out_scale;
-    Column* c = new_column(odt, oscale, ngroups, nullable);
-    outs.v.push_back(c);
-    ao.data[k] = c->data.p; ao.valid[k] = c->valid.as<uint32_t>();
-    ao.out_dtype[k] = odt; ao.out_precision[k] = specs[k].out_precision;
-    if (c->valid.p) CUDA_CHECK(cudaMemsetAsync(c->valid.p, 0, c->valid.bytes, stream()));
-  }
+  AggOut ao;
+  make_agg_outputs(plan, prog, specs, naggs, ngroups, outs, ao);
   DevBuf rep((size_t)std::max(ngroups, 1) * 4);
   finalize_kernel<<<grid_for(cap, 256), 256, 0, stream()>>>(gt, plan, cap, pos.as<int32_t>(), ao, rep.as<int32_t>());
   CUDA_CHECK(cudaGetLastError());

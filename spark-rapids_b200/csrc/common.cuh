@@ -51,6 +51,11 @@ struct KernelTimer {  // scoped CUDA-event timer around a kernel launch; no-op u
   ~KernelTimer();
 };
 bool profile_enabled();      // b2_profile_enable state
+int64_t spill_device(int64_t want_bytes);   // move spillable batches to the host (core.cu); returns device bytes released
+void note_retry();
+void note_split();
+void semaphore_acquire_if_necessary();      // GpuSemaphore.acquireIfNecessary
+void semaphore_release_if_necessary();
 cudaStream_t aux_stream();   // second per-thread stream for work that may overlap the main stream
 int sm_count();
 

@@ -3,6 +3,8 @@
 // (Rmm.initialize, ASYNC allocator mode), GpuColumnVector.java:621-660, HostColumnarToGpu.scala,
 // GpuColumnarToRowExec.scala:337-384 (copyToHost).
 #include <mutex>
+#include <condition_variable>
+#include <list>
 #include <algorithm>
 #include <unordered_map>
 #include <cstdio>
@@ -167,18 +169,25 @@ void h2d_bytes(void* dst, const void* src, size_t bytes) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+int64_t spill_device(int64_t want_bytes);   // below: the spill store
+
 void* dev_alloc(size_t bytes) {
   if (bytes == 0) bytes = 64;
   bytes = pad64(bytes);
   int64_t lim = g_limit.load();
-  if (lim > 0 && g_in_use.load() + (int64_t)bytes > lim)
-    throw Error(B2_ERR_OOM, "allocation of " + std::to_string(bytes) + " B exceeds the configured limit");
+  if (lim > 0 && g_in_use.load() + (int64_t)bytes > lim) {
+    // DeviceMemoryEventHandler.onAllocFailure (DeviceMemoryEventHandler.scala): spill first, fail with a retryable OOM if that was not enough
+    spill_device(g_in_use.load() + (int64_t)bytes - lim);
+    if (g_in_use.load() + (int64_t)bytes > lim)
+      throw Error(B2_ERR_OOM, "allocation of " + std::to_string(bytes) + " B exceeds the configured limit");
+  }
   void* p = nullptr;
   cudaStream_t s = stream();
   cudaError_t e = cudaMallocAsync(&p, bytes, s);
   if (e == cudaErrorMemoryAllocation) {
     cudaGetLastError();
-    // give outstanding frees a chance to land, then retry once (DeviceMemoryEventHandler analogue)
+    // give outstanding frees a chance to land and move spillable batches to the host, then retry once
+    spill_device((int64_t)bytes);
     cudaDeviceSynchronize();
     e = cudaMallocAsync(&p, bytes, s);
   }
@@ -201,6 +210,115 @@ void dev_free(void* p) {
   }
   g_in_use.fetch_sub((int64_t)bytes);
   cudaFreeAsync(p, stream());
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// (f4) memory pressure: spill store, semaphore, retry accounting.
+// Reference: spill/SpillFramework.scala:49-150 (SpillableColumnarBatch handles: anything held across iterator next() calls
+// may be moved to host memory at any time and is brought back on access), DeviceMemoryEventHandler (spill on allocation
+// failure, then GpuRetryOOM), GpuSemaphore.scala:183-260 (bounded number of tasks on the GPU), RmmRapidsRetryIterator.scala:
+// 65-203 (withRetry / split-and-retry: implemented in exec.cu above this store).
+struct HostColumn {
+  int dtype = 0, scale = 0; int64_t size = 0, null_count = 0, chars_bytes = 0;
+  std::vector<uint8_t> data, valid, offsets;
+};
+struct Spillable {
+  std::mutex mu;
+  Table* dev = nullptr;              // resident form (one reference held by the store)
+  std::vector<HostColumn> host;      // spilled form
+  int64_t bytes = 0;
+  uint64_t last_use = 0;
+};
+static std::mutex g_spill_mu;
+static std::list<Spillable*> g_spillables;
+static std::atomic<uint64_t> g_use_clock{1};
+static std::atomic<int64_t> g_spilled_bytes{0}, g_unspilled_bytes{0}, g_retries{0}, g_splits{0};
+void note_retry() { g_retries.fetch_add(1); }
+void note_split() { g_splits.fetch_add(1); }
+
+static int64_t table_bytes(const Table* t) {
+  int64_t b = 0;
+  for (auto* c : t->cols) b += (int64_t)c->data.bytes + (int64_t)c->valid.bytes + (int64_t)c->offsets.bytes;
+  return b;
+}
+static bool spill_one(Spillable* sp) {   // sp->mu held; true when device memory was released
+  if (!sp->dev || sp->dev->refs.load() != 1) return false;   // somebody is using the batch right now
+  for (auto* c : sp->dev->cols) if (c->refs.load() != 1) return false;
+  cudaStream_t s = stream();
+  sp->host.clear();
+  for (auto* c : sp->dev->cols) {
+    HostColumn h;
+    h.dtype = c->dtype; h.scale = c->scale; h.size = c->size; h.null_count = c->null_count; h.chars_bytes = c->chars_bytes;
+    const size_t db = c->dtype == B2_STRING ? (size_t)c->chars_bytes : (size_t)c->size * dtype_width(c->dtype);
+    h.data.resize(db);
+    if (db) CUDA_CHECK(cudaMemcpyAsync(h.data.data(), c->data.p, db, cudaMemcpyDeviceToHost, s));
+    if (c->valid.p) { h.valid.resize(validity_bytes(c->size)); CUDA_CHECK(cudaMemcpyAsync(h.valid.data(), c->valid.p, h.valid.size(), cudaMemcpyDeviceToHost, s)); }
+    if (c->dtype == B2_STRING) { h.offsets.resize((size_t)(c->size + 1) * 4); CUDA_CHECK(cudaMemcpyAsync(h.offsets.data(), c->offsets.p, h.offsets.size(), cudaMemcpyDeviceToHost, s)); }
+    sp->host.push_back(std::move(h));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  table_release(sp->dev);
+  sp->dev = nullptr;
+  g_spilled_bytes.fetch_add(sp->bytes);
+  return true;
+}
+// move least-recently-used spillable batches to the host until `want_bytes` of device memory were released
+int64_t spill_device(int64_t want_bytes) {
+  std::vector<Spillable*> order;
+  {
+    std::lock_guard<std::mutex> lk(g_spill_mu);
+    order.assign(g_spillables.begin(), g_spillables.end());
+  }
+  std::sort(order.begin(), order.end(), [](Spillable* a, Spillable* b) { return a->last_use < b->last_use; });
+  int64_t freed = 0;
+  for (auto* sp : order) {
+    if (freed >= want_bytes) break;
+    std::unique_lock<std::mutex> lk(sp->mu, std::try_to_lock);
+    if (!lk.owns_lock()) continue;
+    if (spill_one(sp)) freed += sp->bytes;
+  }
+  return freed;
+}
+static Table* unspill(Spillable* sp) {   // sp->mu held
+  ColsGuard cols;
+  cudaStream_t s = stream();
+  for (auto& h : sp->host) {
+    std::unique_ptr<Column> c(new Column());
+    c->dtype = h.dtype; c->scale = h.scale; c->size = h.size; c->null_count = h.null_count; c->chars_bytes = h.chars_bytes;
+    c->data = DevBuf(h.data.size());
+    if (!h.data.empty()) CUDA_CHECK(cudaMemcpyAsync(c->data.p, h.data.data(), h.data.size(), cudaMemcpyHostToDevice, s));
+    if (!h.valid.empty()) { c->valid = DevBuf(h.valid.size()); CUDA_CHECK(cudaMemcpyAsync(c->valid.p, h.valid.data(), h.valid.size(), cudaMemcpyHostToDevice, s)); }
+    if (!h.offsets.empty()) { c->offsets = DevBuf(h.offsets.size()); CUDA_CHECK(cudaMemcpyAsync(c->offsets.p, h.offsets.data(), h.offsets.size(), cudaMemcpyHostToDevice, s)); }
+    cols.v.push_back(c.release());
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  sp->host.clear(); sp->host.shrink_to_fit();
+  g_unspilled_bytes.fetch_add(sp->bytes);
+  return new_table(cols.release());
+}
+
+// GpuSemaphore: at most `permits` threads (tasks) between acquire and release; 0 = unlimited
+static std::mutex g_sem_mu;
+static std::condition_variable g_sem_cv;
+static int g_sem_permits = 0, g_sem_in_use = 0;
+static int64_t g_sem_waits = 0;
+static thread_local bool t_sem_held = false;
+void semaphore_acquire_if_necessary() {
+  if (t_sem_held) return;
+  std::unique_lock<std::mutex> lk(g_sem_mu);
+  if (g_sem_permits > 0) {
+    if (g_sem_in_use >= g_sem_permits) g_sem_waits++;
+    g_sem_cv.wait(lk, [] { return g_sem_permits <= 0 || g_sem_in_use < g_sem_permits; });
+  }
+  g_sem_in_use++;
+  t_sem_held = true;
+}
+void semaphore_release_if_necessary() {
+  if (!t_sem_held) return;
+  { std::lock_guard<std::mutex> lk(g_sem_mu); g_sem_in_use--; }
+  t_sem_held = false;
+  g_sem_cv.notify_one();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -580,6 +698,77 @@ int b2_upload_free(b2_handle upload) {
   cudaEventDestroy(u->done);
   delete u;
   B2_CATCH
+}
+
+
+// ---- (f4) spill store / semaphore / retry accounting ---------------------------------------------------------------------------
+int b2_spillable_create(b2_handle table, b2_handle* out) {
+  B2_TRY
+  Table* t = table_from(table);
+  std::unique_ptr<Spillable> sp(new Spillable());
+  t->refs.fetch_add(1);
+  for (auto* c : t->cols) finalize_nulls(c);
+  sp->dev = t; sp->bytes = table_bytes(t); sp->last_use = g_use_clock.fetch_add(1);
+  {
+    std::lock_guard<std::mutex> lk(g_spill_mu);
+    g_spillables.push_back(sp.get());
+  }
+  *out = to_handle(sp.release());
+  B2_CATCH
+}
+int b2_spillable_get(b2_handle h, b2_handle* out_table) {
+  B2_TRY
+  B2_CHECK(h, "null spillable handle");
+  Spillable* sp = reinterpret_cast<Spillable*>((intptr_t)h);
+  std::lock_guard<std::mutex> lk(sp->mu);
+  if (!sp->dev) sp->dev = unspill(sp);
+  sp->last_use = g_use_clock.fetch_add(1);
+  sp->dev->refs.fetch_add(1);
+  *out_table = to_handle(sp->dev);
+  B2_CATCH
+}
+int b2_spillable_is_spilled(b2_handle h, int32_t* out) {
+  B2_TRY
+  B2_CHECK(h, "null spillable handle");
+  Spillable* sp = reinterpret_cast<Spillable*>((intptr_t)h);
+  std::lock_guard<std::mutex> lk(sp->mu);
+  *out = sp->dev ? 0 : 1;
+  B2_CATCH
+}
+int b2_spillable_close(b2_handle h) {
+  B2_TRY
+  B2_CHECK(h, "null spillable handle");
+  Spillable* sp = reinterpret_cast<Spillable*>((intptr_t)h);
+  {
+    std::lock_guard<std::mutex> lk(g_spill_mu);
+    g_spillables.remove(sp);
+  }
+  { std::lock_guard<std::mutex> lk(sp->mu); if (sp->dev) table_release(sp->dev); sp->dev = nullptr; }
+  delete sp;
+  B2_CATCH
+}
+int b2_spill(int64_t want_bytes, int64_t* out_freed) {
+  B2_TRY
+  *out_freed = spill_device(want_bytes);
+  B2_CATCH
+}
+int b2_memory_stats(int64_t* out6) {
+  out6[0] = g_in_use.load(); out6[1] = g_limit.load(); out6[2] = g_spilled_bytes.load(); out6[3] = g_unspilled_bytes.load();
+  out6[4] = g_retries.load(); out6[5] = g_splits.load();
+  return B2_OK;
+}
+int b2_semaphore_init(int32_t permits) {
+  std::lock_guard<std::mutex> lk(g_sem_mu);
+  g_sem_permits = permits;
+  g_sem_cv.notify_all();
+  return B2_OK;
+}
+int b2_semaphore_acquire(void) { semaphore_acquire_if_necessary(); return B2_OK; }
+int b2_semaphore_release(void) { semaphore_release_if_necessary(); return B2_OK; }
+int b2_semaphore_stats(int64_t* out3) {
+  std::lock_guard<std::mutex> lk(g_sem_mu);
+  out3[0] = g_sem_permits; out3[1] = g_sem_in_use; out3[2] = g_sem_waits;
+  return B2_OK;
 }
 
 struct Event { cudaEvent_t ev; };

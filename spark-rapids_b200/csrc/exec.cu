@@ -28,6 +28,28 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
 Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
 Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, int nkeep);
 
+Table* slice_table(const Table* t, int64_t start, int64_t end);
+
+// RmmRapidsRetryIterator.withRetry (RmmRapidsRetryIterator.scala:65-203): an allocation failure first spills (core.cu does
+// that inside the allocator) and surfaces as B2_ERR_OOM = GpuRetryOOM; the operator then makes everything spillable leave
+// the device, waits for the stream and runs the attempt again.  After two retries the error is handed to the caller, which
+// for joins and aggregates splits the input batch in halves and retries each (GpuSplitAndRetryOOM semantics,
+// AbstractGpuJoinIterator.scala:235-250 for the join's 2^31 output limit).
+template <typename F>
+static auto with_retry(F&& attempt) -> decltype(attempt()) {
+  for (int n = 0;; n++) {
+    try {
+      return attempt();
+    } catch (const Error& e) {
+      if (e.code != B2_ERR_OOM || n >= 2) throw;
+      note_retry();
+      spill_device(INT64_MAX);
+      CUDA_CHECK(cudaStreamSynchronize(stream()));
+    }
+  }
+}
+static bool splittable(const Error& e) { return e.code == B2_ERR_OOM || e.code == B2_ERR_SIZE_OVERFLOW; }
+
 struct TableRef {  // owning reference
   Table* t = nullptr;
   TableRef() {}
@@ -231,6 +253,19 @@ struct GpuHashAggregateExec : GpuExec {
     std::unique_ptr<Program> p(make_passthrough_program(t, cols));
     return scan_aggregate(p.get(), false, t, key_outs.data(), (int)key_outs.size(), m.data(), (int)m.size());
   }
+  // first-pass aggregation of one input batch; when the device cannot hold it the batch is split in halves, each half
+  // yields its own partial (the merge pass combines them like any other pair of partials)
+  void first_pass(const Table* in, std::vector<TableRef>& partials, int depth) {
+    try {
+      partials.emplace_back(with_retry([&] { return scan_aggregate(program, has_pred, in, keys.data(), (int)keys.size(), aggs.data(), (int)aggs.size()); }));
+    } catch (const Error& e) {
+      if (!splittable(e) || in->rows < 2 || depth >= 12) throw;
+      note_split();
+      const int64_t mid = in->rows / 2;
+      { TableRef lo(slice_table(in, 0, mid)); first_pass(lo.t, partials, depth + 1); }
+      { TableRef hi(slice_table(in, mid, in->rows)); first_pass(hi.t, partials, depth + 1); }
+    }
+  }
   Table* do_next() override {
     if (done) return nullptr;
     done = true;
@@ -239,7 +274,7 @@ struct GpuHashAggregateExec : GpuExec {
       TableRef in(children[0]->next());
       if (!in.t) break;
       if (merge_mode) partials.emplace_back(in.release());   // inputs already are aggregation buffers
-      else partials.emplace_back(scan_aggregate(program, has_pred, in.t, keys.data(), (int)keys.size(), aggs.data(), (int)aggs.size()));
+      else first_pass(in.t, partials, 0);
     }
     if (partials.empty()) {
       // a keyless aggregate over no batches still emits its initial-value row (GpuAggregateExec.scala:1107-1126)
@@ -281,6 +316,7 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
     built = true;
   }
   Table* do_next() override {
+    if (!pending.empty()) { Table* out = pending.front().release(); pending.pop_front(); return out; }
     if (!built) build();
     TableRef s;
     if (kind == B2_JOIN_FULL_OUTER) {
@@ -297,13 +333,33 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
       s = TableRef(children[0]->next());
     }
     if (!s.t) return nullptr;
-    TableRef sk(select(s.t, stream_keys));
+    join_split(s.t, 0);
+    Table* out = pending.front().release();
+    pending.pop_front();
+    return out;
+  }
+  std::deque<TableRef> pending;   // outputs of a stream batch that had to be split (returned one per next())
+  // one stream batch -> output batch(es).  When the gather maps would pass 2^31-1 rows (B2_ERR_SIZE_OVERFLOW) or the device
+  // cannot hold the output (B2_ERR_OOM after retries) the stream batch is halved and each half joined on its own
+  void join_split(const Table* st, int depth) {
+    try {
+      pending.emplace_back(with_retry([&] { return join_batch(st); }));
+    } catch (const Error& e) {
+      if (!splittable(e) || st->rows < 2 || depth >= 12 || kind == B2_JOIN_FULL_OUTER) throw;
+      note_split();
+      const int64_t mid = st->rows / 2;
+      { TableRef lo(slice_table(st, 0, mid)); join_split(lo.t, depth + 1); }
+      { TableRef hi(slice_table(st, mid, st->rows)); join_split(hi.t, depth + 1); }
+    }
+  }
+  Table* join_batch(const Table* st) {
+    TableRef sk(select(st, stream_keys));
     b2_handle lm = 0, rm = 0;
     int rc = b2_join_probe(ht, to_handle(sk.t), kind, &lm, &rm);
     if (rc != B2_OK) throw Error(rc, b2_last_error());
     ColGuard lmap(col_from(lm));
     ColGuard rmap(rm ? col_from(rm) : nullptr);
-    TableRef left(gather_table(s.t, lmap.c->data.as<int32_t>(), lmap.c->size, kind == B2_JOIN_FULL_OUTER, pruned ? &stream_out : nullptr));
+    TableRef left(gather_table(st, lmap.c->data.as<int32_t>(), lmap.c->size, kind == B2_JOIN_FULL_OUTER, pruned ? &stream_out : nullptr));
     if (!rmap.c || (pruned && build_out.empty())) return left.release();  // semi / anti (or nothing wanted from the build side): stream columns only
     TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER || kind == B2_JOIN_FULL_OUTER,
                                 pruned ? &build_out : nullptr));
@@ -617,6 +673,7 @@ int b2_exec_shuffle_exchange(b2_handle child, const int32_t* key_cols, int32_t n
 }
 int b2_exec_next(b2_handle exec, b2_handle* out_table) {
   B2_TRY
+  semaphore_acquire_if_necessary();   // GpuSemaphore.acquireIfNecessary: the task enters the GPU at its first batch
   *out_table = to_handle(exec_from(exec)->next());
   B2_CATCH
 }

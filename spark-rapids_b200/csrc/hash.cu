@@ -48,14 +48,7 @@ Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullif
 // shared memory, 256 rows at a time in row order) and writes each fixed-width NOT NULL column straight to its final
 // place.  Reads are coalesced, writes are coalesced per run of equal ids.  Other columns (strings, nullable) go
 // through the gather map the same kernel can emit.  Replaces id->key expansion + radix pass + random-read gather.
-constexpr int PT_NT = 256, PT_STEPS = 16, PT_TILE = PT_NT * PT_STEPS, PT_MAXP = 1024, PT_MAXC = 8;
-struct ScatterCols {
-  int32_t n;
-  int32_t width[PT_MAXC];
-  const void* in[PT_MAXC];
-  void* out[PT_MAXC];
-};
-
+constexpr int PT_NT = 256, PT_STEPS = 16, PT_TILE = PT_NT * PT_STEPS, PT_MAXP = 1024;   // PT_MAXC, ScatterCols: prim.cuh
 __global__ void __launch_bounds__(PT_NT) part_tile_hist_kernel(const int32_t* __restrict__ pids, int64_t n, int32_t nparts, int64_t ntiles,
                                                                int32_t* __restrict__ tile_cnt) {
   __shared__ int32_t h[PT_MAXP];
@@ -160,6 +153,29 @@ static Table* partition_table_direct(const Table* t, const int32_t* d_pids, int3
     table_release(g);
   }
   return new_table(outs.release());
+}
+
+// raw-array form (radix group-by, agg.cu): stable scatter of up to PT_MAXC fixed-width arrays by partition id (< 1024)
+void partition_scatter_arrays(const int32_t* d_pids, int64_t n, int32_t nparts, const ScatterCols& sc) {
+  if (n == 0) return;
+  B2_CHECK(nparts >= 1 && nparts <= PT_MAXP, "partition_scatter_arrays: 1..1024 partitions");
+  const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
+  const int64_t cells = (int64_t)nparts * ntiles;
+  DevBuf cnt((size_t)(cells + 1) * 4);
+  {
+    KernelTimer kt("part_tile_hist_kernel");
+    part_tile_hist_kernel<<<(int)ntiles, PT_NT, 0, stream()>>>(d_pids, n, nparts, ntiles, cnt.as<int32_t>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  DevBuf sums = exclusive_scan<int32_t, int32_t>(cnt.as<int32_t>(), cnt.as<int32_t>(), cells, true);
+  {
+    KernelTimer kt("part_scatter_kernel");
+    part_scatter_kernel<<<(int)ntiles, PT_NT, 0, stream()>>>(d_pids, n, nparts, ntiles, cnt.as<int32_t>(), sc, nullptr);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  sync();   // cnt / sums are freed on return
 }
 
 // Table.partition: stable reorder so each partition is contiguous + partition start offsets

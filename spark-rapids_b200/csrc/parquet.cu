@@ -76,7 +76,7 @@ struct SchemaElem {
 };
 struct ChunkMeta {
   int type = -1, codec = 0;
-  int64_t num_values = 0, total_compressed = 0, data_page_offset = 0, dict_page_offset = -1;
+  int64_t num_values = 0, total_compressed = 0, total_uncompressed = 0, data_page_offset = 0, dict_page_offset = -1;
   std::vector<std::string> path;
 };
 struct RowGroupMeta { int64_t num_rows = 0; std::vector<ChunkMeta> chunks; };
@@ -153,6 +153,7 @@ static FileMeta parse_footer(const uint8_t* buf, int64_t len) {
                       case 3: { int np, pt; r.list_header(np, pt); for (int k = 0; k < np; k++) cm.path.push_back(r.str()); } break;
                       case 4: cm.codec = (int)r.zigzag(); break;
                       case 5: cm.num_values = r.zigzag(); break;
+                      case 6: cm.total_uncompressed = r.zigzag(); break;
                       case 7: cm.total_compressed = r.zigzag(); break;
                       case 9: cm.data_page_offset = r.zigzag(); break;
                       case 11: cm.dict_page_offset = r.zigzag(); break;
@@ -1536,6 +1537,66 @@ int b2_parquet_decode_row_groups(const uint8_t* host_buf, const uint8_t* dev_buf
   B2_TRY
   B2_CHECK(host_buf && len > 0 && ncols >= 1 && rg_begin >= 0 && rg_end >= rg_begin, "bad arguments");
   *out_table = to_handle(parquet_decode(host_buf, dev_buf, len, column_names, ncols, rg_begin, rg_end));
+  B2_CATCH
+}
+
+// ParquetChunkedReader (GpuParquetScan.scala:3403-3407, 3497-3498: `new ParquetChunkedReader(chunkSizeByteLimit, ...)`, then
+// hasNext / readChunk): the buffer is decoded in pieces whose decoded size stays under the limit (spark.rapids.sql.reader.
+// chunked + batchSizeBytes, RapidsConf.scala:660-668) and under the 2^31-1 row / char limits of a column.  The unit here is
+// the row group: a chunk is a run of consecutive row groups whose selected columns decode to <= limit bytes (always at
+// least one row group; a single row group larger than the limit is decoded whole).
+struct ParquetChunked {
+  const uint8_t* host; int64_t len;
+  std::vector<std::string> names;
+  std::vector<int64_t> rg_rows, rg_bytes;
+  int next_rg = 0;
+  int64_t limit = 0;
+};
+int b2_parquet_chunked_open(const uint8_t* host_buf, int64_t len, const char* const* column_names, int32_t ncols, int64_t chunk_byte_limit,
+                            b2_handle* out_reader) {
+  B2_TRY
+  B2_CHECK(host_buf && len > 0 && ncols >= 1, "bad arguments");
+  std::unique_ptr<ParquetChunked> r(new ParquetChunked());
+  r->host = host_buf; r->len = len; r->limit = chunk_byte_limit;
+  for (int i = 0; i < ncols; i++) r->names.push_back(column_names[i]);
+  FileMeta fm = parse_footer(host_buf, len);
+  for (auto& rg : fm.row_groups) {
+    int64_t bytes = 0;
+    for (auto& cm : rg.chunks)
+      for (auto& nm : r->names) if (!cm.path.empty() && cm.path[0] == nm) bytes += cm.total_uncompressed > 0 ? cm.total_uncompressed : cm.total_compressed;
+    r->rg_rows.push_back(rg.num_rows); r->rg_bytes.push_back(bytes);
+  }
+  *out_reader = to_handle(r.release());
+  B2_CATCH
+}
+int b2_parquet_chunked_has_next(b2_handle reader, int32_t* out) {
+  B2_TRY
+  B2_CHECK(reader, "null reader");
+  auto* r = reinterpret_cast<ParquetChunked*>((intptr_t)reader);
+  *out = r->next_rg < (int)r->rg_rows.size() ? 1 : 0;
+  B2_CATCH
+}
+int b2_parquet_chunked_next(b2_handle reader, b2_handle* out_table) {
+  B2_TRY
+  B2_CHECK(reader, "null reader");
+  auto* r = reinterpret_cast<ParquetChunked*>((intptr_t)reader);
+  B2_CHECK(r->next_rg < (int)r->rg_rows.size(), "chunked reader is exhausted");
+  int end = r->next_rg;
+  int64_t bytes = 0, rows = 0;
+  while (end < (int)r->rg_rows.size()) {
+    const bool first = end == r->next_rg;
+    if (!first && ((r->limit > 0 && bytes + r->rg_bytes[end] > r->limit) || rows + r->rg_rows[end] > 0x7fffffffLL)) break;
+    bytes += r->rg_bytes[end]; rows += r->rg_rows[end]; end++;
+  }
+  std::vector<const char*> cn;
+  for (auto& s : r->names) cn.push_back(s.c_str());
+  *out_table = to_handle(parquet_decode(r->host, nullptr, r->len, cn.data(), (int)cn.size(), r->next_rg, end));
+  r->next_rg = end;
+  B2_CATCH
+}
+int b2_parquet_chunked_close(b2_handle reader) {
+  B2_TRY
+  delete reinterpret_cast<ParquetChunked*>((intptr_t)reader);
   B2_CATCH
 }
 

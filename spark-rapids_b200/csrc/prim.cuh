@@ -6,6 +6,16 @@
 
 namespace b2 {
 
+// stable multi-array partition scatter (hash.cu): up to PT_MAXC fixed-width arrays moved by one kernel
+constexpr int PT_MAXC = 8;
+struct ScatterCols {
+  int32_t n;
+  int32_t width[PT_MAXC];
+  const void* in[PT_MAXC];
+  void* out[PT_MAXC];
+};
+void partition_scatter_arrays(const int32_t* d_pids, int64_t n, int32_t nparts, const ScatterCols& sc);
+
 #ifdef __CUDACC__
 constexpr int SCAN_NT = 256;
 constexpr int SCAN_ITEMS = 8;                      // items per thread

@@ -221,14 +221,16 @@ __global__ void __launch_bounds__(VM_NT, 4) filter_kernel(const VMProgramHeader*
 // ---- TMA-staged filter ---------------------------------------------------------------------------------------------------------
 // Same contract as filter_kernel<false>, different data movement: every fixed-width column the predicate reads or the
 // output keeps is brought into shared memory by TMA bulk copies (cp.async.bulk, one per column and tile, completion on an
-// mbarrier), double buffered, so the HBM stream of tile k+1 runs while tile k is evaluated and compacted.  The VM reads
-// its column operands from shared memory and the compaction takes the kept values from the same staged copy: each input
-// byte crosses HBM exactly once, in large bursts, and no thread waits on a global load.
+// mbarrier).  The whole tile is requested in one go (maximum memory-level parallelism, no load instruction in any row
+// loop), the VM reads its column operands from shared memory and the compaction takes the kept values from the same
+// staged copy: each input byte crosses HBM exactly once, in large bursts.  Overlap comes from the 3-4 resident CTAs per
+// SM being in different phases; a CTA never holds a claimed tile it has not started (a prefetched-but-unstarted tile
+// would stall every later tile's look-back for a whole tile time — measured: 2x slower than the direct kernel).
 struct FilterStageCols {
   int8_t slot[MAX_TABLE_COLS];   // kept column c -> staged slot (-1: not staged, read from global)
 };
 
-__global__ void __launch_bounds__(VM_NT, 3) filter_staged_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
+__global__ void __launch_bounds__(VM_NT, 4) filter_staged_kernel(const VMProgramHeader* __restrict__ g_hdr, const VMInstr* __restrict__ g_code,
                                                                  const __grid_constant__ VMInputs in, const __grid_constant__ FilterCols fc,
                                                                  const __grid_constant__ VMStage st, const __grid_constant__ FilterStageCols fs,
                                                                  int64_t nrows, uint64_t* __restrict__ status, FilterWork* __restrict__ work) {
@@ -236,41 +238,34 @@ __global__ void __launch_bounds__(VM_NT, 3) filter_staged_kernel(const VMProgram
   __shared__ VMShared sh;
   __shared__ uint32_t s_counts[VM_MAX_K * NW];
   __shared__ int64_t s_tile_excl;
-  __shared__ int64_t s_next;
+  __shared__ int64_t s_tile;
   __shared__ uint32_t s_tile_total;
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_bar;
   extern __shared__ __align__(128) char dyn[];
   char* regs = dyn;
   const int R = st.tile_rows;
   const int64_t ntiles = (nrows + R - 1) / R;
-  // stage buffers follow the VM registers (bytes_per_row * R, rounded up to 128 B)
+  // the stage buffer follows the VM registers (bytes_per_row * R, rounded up to 128 B)
   const int regs_bytes = (g_hdr->bytes_per_row * R + 127) & ~127;
   char* stage = dyn + regs_bytes;
   const RInstr* code = vm_load_program(sh, g_hdr, g_code, in, regs, &st, stage);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
-    mbar_fence_init();
-    // tiles are claimed in launch order so that look-back only waits on tiles already owned by a running CTA
-    const int64_t t0 = (int64_t)atomicAdd(&work->tile_counter, 1ull);
-    s_next = t0;
-    if (t0 < ntiles) vm_stage_issue(st, stage, 0, t0, nrows, &s_bar[0]);
-  }
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
   __syncthreads();
-  int64_t tile = s_next;
-  int buf = 0;
-  uint32_t phase[2] = {0, 0};
-  __syncthreads();
-  while (tile < ntiles) {
-    if (threadIdx.x == 0) {   // claim and prefetch the next tile into the other buffer (free since the end of the previous iteration)
-      const int64_t tn = (int64_t)atomicAdd(&work->tile_counter, 1ull);
-      s_next = tn;
-      if (tn < ntiles) vm_stage_issue(st, stage, buf ^ 1, tn, nrows, &s_bar[buf ^ 1]);
+  uint32_t phase = 0;
+  while (true) {
+    if (threadIdx.x == 0) {
+      // tiles are claimed in launch order so that look-back only waits on tiles already being processed
+      const int64_t t = (int64_t)atomicAdd(&work->tile_counter, 1ull);
+      s_tile = t;
+      if (t < ntiles) vm_stage_issue(st, stage, 0, t, nrows, &s_bar);
     }
-    mbar_wait(&s_bar[buf], phase[buf]);   // this tile's columns have landed
-    phase[buf] ^= 1;
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= ntiles) break;
+    mbar_wait(&s_bar, phase);   // this tile's columns have landed
+    phase ^= 1;
     VMCtx cx = vm_ctx(&sh.hdr, &in, regs, tile, nrows);
-    cx.stage_off = buf * st.buf_bytes;
     vm_run(tile_info(cx), code, 0, sh.hdr.ninstr);
     const Opnd p = resolve(cx, sh.hdr.outs[0], 1);
     const int K = cx.K;
@@ -300,7 +295,6 @@ __global__ void __launch_bounds__(VM_NT, 3) filter_staged_kernel(const VMProgram
     }
     __syncthreads();
     const int64_t base = s_tile_excl;
-    const char* sbuf = stage + (size_t)buf * st.buf_bytes;
     for (int j = 0; j < K; j++) {
       const bool sel = (selmask >> j) & 1u;
       const uint32_t b = __ballot_sync(0xffffffffu, sel);
@@ -311,7 +305,7 @@ __global__ void __launch_bounds__(VM_NT, 3) filter_staged_kernel(const VMProgram
       for (int c = 0; c < fc.ncols; c++) {
         const int sl = fs.slot[c];
         // staged: element i of the tile's copy in shared memory; else straight from global (row g)
-        const void* src = sl >= 0 ? (const void*)(sbuf + st.off[sl]) : fc.in[c];
+        const void* src = sl >= 0 ? (const void*)(stage + st.off[sl]) : fc.in[c];
         const int64_t at = sl >= 0 ? (int64_t)i : g;
         switch (fc.width[c]) {
           case 1: compact_one<int8_t>(src, fc.out[c], at, pos); break;
@@ -326,10 +320,7 @@ __global__ void __launch_bounds__(VM_NT, 3) filter_staged_kernel(const VMProgram
       if (fc.row_ids) fc.row_ids[pos] = (int32_t)g;
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) work->total = (unsigned long long)(base + s_tile_total);
-    __syncthreads();   // every reader of this buffer is done: the next iteration may refill it
-    tile = s_next;
-    buf ^= 1;
-    __syncthreads();   // s_next is rewritten at the top of the next iteration
+    __syncthreads();   // every reader of the stage buffer is done: the next tile may overwrite it (and s_tile)
   }
 }
 
@@ -393,9 +384,9 @@ static bool plan_filter_stage(const Program* prog, const Table* pred_table, cons
     fs.slot[c] = (int8_t)add(data->cols[c]);
   }
   if (st.n == 0 || bytes_per_row == 0) return false;
-  // tile: registers + two stage buffers within ~72 KB -> three CTAs per SM, each with a tile in flight
-  const int per_row = prog->hdr.bytes_per_row + 2 * bytes_per_row;
-  int k = (72 * 1024) / (per_row * VM_NT);
+  // tile: registers + the stage buffer within ~42 KB -> four CTAs per SM, each requesting a whole tile at once
+  const int per_row = prog->hdr.bytes_per_row + bytes_per_row;
+  int k = (42 * 1024) / (per_row * VM_NT);
   if (k > VM_MAX_K) k = VM_MAX_K;
   if (k < 1) return false;                // rows too wide to stage: the direct kernel handles them
   st.tile_rows = k * VM_NT;
@@ -424,9 +415,9 @@ static int64_t run_filter(const Program* prog, const VMInputs& in, FilterCols& f
   int grid = vm_grid(nrows, smem, prog->hdr.tile_rows);
   if (staged) {
     const int regs_bytes = (prog->hdr.bytes_per_row * st.tile_rows + 127) & ~127;
-    smem = regs_bytes + 2 * st.buf_bytes;
+    smem = regs_bytes + st.buf_bytes;
     CUDA_CHECK(cudaFuncSetAttribute(filter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int per_sm = std::max(1, std::min(3, (220 * 1024) / (smem + (int)sizeof(VMShared) + 2048)));
+    const int per_sm = std::max(1, std::min(4, (224 * 1024) / (smem + (int)sizeof(VMShared) + 2048)));
     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm));
     KernelTimer kt("filter_staged_kernel");
     filter_staged_kernel<<<grid, VM_NT, smem, stream()>>>(prog->d_hdr.as<VMProgramHeader>(), prog->d_code.as<VMInstr>(), in, fc, st, fs, nrows,

@@ -34,6 +34,16 @@ FILES = {
     "single_nan.parquet": ["mycol"],
     "nan_in_stats.parquet": ["x"],
 }
+# the reference's own Scala/pytest fixtures (tests/src/test/resources): Spark-written decimals as INT32/INT64 and as legacy
+# FIXED_LEN_BYTE_ARRAY, timestamp/date columns, a 10-row-group file its split tests read, an unsigned 64-bit column
+SRC2 = "/root/reference/tests/src/test/resources"
+FILES2 = {
+    "decimal-test.parquet": ["c_0", "c_1", "c_2", "c_3", "c_4", "c_5"],
+    "decimal-test-legacy.parquet": ["c_0", "c_1", "c_2", "c_3", "c_4", "c_5"],
+    "timestamp-date-test.parquet": ["time", "date"],
+    "file-splits.parquet": ["loan_id", "orig_channel", "orig_interest_rate", "orig_upb", "orig_date", "dti", "zip", "seller_id"],
+    "test_unsigned64.parquet": ["simple_uint64"],
+}
 # DELTA_BINARY_PACKED: the integer columns of the corpus' delta files (selected by their encoding); these files come
 # with the corpus' own *_expect.csv goldens, which the generator checks pyarrow against before trusting it
 DELTA_FILES = ["delta_binary_packed.parquet", "delta_encoding_required_column.parquet", "delta_encoding_optional_column.parquet"]
@@ -80,8 +90,12 @@ def main():
     files = dict(FILES)
     for name in DELTA_FILES:
         files[name] = delta_int_columns(os.path.join(SRC, name))
+    srcdir = {name: SRC for name in files}
+    for name, cols in FILES2.items():
+        files["spark_rapids_tests/" + name] = cols
+        srcdir["spark_rapids_tests/" + name] = SRC2
     for name, cols in files.items():
-        path = os.path.join(SRC, name)
+        path = os.path.join(srcdir[name], os.path.basename(name))
         raw = open(path, "rb").read()
         tbl = pq.read_table(path, columns=cols)
         if name in DELTA_FILES:
@@ -94,6 +108,8 @@ def main():
                 vals = [None if v is None else int(v) for v in col.cast(pa.int32()).to_pylist()]
             elif pa.types.is_timestamp(typ):
                 vals = [None if v is None else int(v) for v in col.cast(pa.timestamp("us")).cast(pa.int64()).to_pylist()]
+            elif pa.types.is_uint64(typ):   # cudf UINT64 is delivered as the same 64 bits; the library's INT64 view is two's complement
+                vals = [None if v is None else (int(v) - (1 << 64) if int(v) >= (1 << 63) else int(v)) for v in col.to_pylist()]
             else:
                 vals = [norm(v, typ) for v in col.to_pylist()]
             expect[c] = {"type": str(typ), "values": vals}

@@ -216,3 +216,37 @@ def test_delta_binary_packed_generated(b2, opts, nulls):
     exp = P.read_parquet(raw, names)
     for i in range(len(names)):
         G.assert_col_equal(t.column(i), exp[i])
+
+
+def test_parquet_chunked_reader_row_group_chunks(b2):
+    """ParquetChunkedReader: the reference's 10-row-group fixture (tests/src/test/resources/file-splits.parquet) read under
+    byte limits -> same rows in the same order as one whole-buffer decode, chunk boundaries on row groups"""
+    entry = GOLDEN["spark_rapids_tests/file-splits.parquet"]
+    raw = base64.b64decode(entry["b64"])
+    cols = entry["columns"]
+    whole = b2.parquet_decode(raw, cols).to_rows()
+    assert b2.parquet_num_row_groups(raw) == 10
+    for limit, min_chunks in [(0, 1), (1, 10), (40_000, 2), (10**9, 1)]:
+        rd = b2.ParquetChunkedReader(raw, cols, limit)
+        rows, nchunks = [], 0
+        for t in rd:
+            rows += t.to_rows(); nchunks += 1
+        rd.close()
+        assert rows == whole, limit
+        assert nchunks >= min_chunks and (limit != 1 or nchunks == 10) and (limit not in (0, 10**9) or nchunks == 1), (limit, nchunks)
+
+
+def test_parquet_corrupt_page_header_is_rejected(b2):
+    """untrusted input: negative sizes / truncated values in a page header must raise, not hang or read out of bounds"""
+    rng = np.random.default_rng(12)
+    tbl = pa.table({"a": pa.array(rng.integers(0, 1000, 5000), type=pa.int64()), "s": pa.array(["x%d" % i for i in range(5000)])})
+    raw = bytearray(_write(tbl, compression="NONE", use_dictionary=False))
+    good = b2.parquet_decode(bytes(raw), ["a", "s"])
+    assert good.num_rows == 5000
+    # truncate the file body while keeping the footer: pages then run past their chunk / promise more values than they hold
+    md = pq.ParquetFile(io.BytesIO(bytes(raw))).metadata
+    off = md.row_group(0).column(0).data_page_offset
+    bad = bytearray(raw)
+    bad[off + 2: off + 6] = b"\xff\xff\xff\x0f"   # uncompressed/compressed size varints become huge / negative
+    with pytest.raises(b2.B2Error):
+        b2.parquet_decode(bytes(bad), ["a", "s"])
