@@ -198,6 +198,8 @@ int b2_filter(b2_handle predicate_program, b2_handle table, b2_handle* out_table
 /* GpuFilterExec under a column-pruning GpuProjectExec, fused: only keep_cols (in that order) are compacted */
 int b2_filter_select(b2_handle predicate_program, b2_handle table, const int32_t* keep_cols, int32_t nkeep,
                      b2_handle* out_table);
+/* selection vector of a filter: the INT32 row ids (ascending) of the rows that pass, nothing is compacted */
+int b2_filter_row_ids(b2_handle predicate_program, b2_handle table, b2_handle* out_int32_ids);
 /* count-only path, basicPhysicalOperators.scala:1161-1169 */
 int b2_filter_count(b2_handle predicate_program, b2_handle table, int64_t* out_count);
 
@@ -252,6 +254,11 @@ int b2_join_hash_table_close(b2_handle ht);
  * matched build rows itself, as GpuHashJoin.scala's HashFullJoinIterator does). */
 int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind,
                   b2_handle* out_left_map, b2_handle* out_right_map);
+/* late materialisation: `selection` = INT32 row ids (ascending) of the stream rows that take part, e.g. the rows a
+ * GpuFilterExec directly below the join keeps (b2_filter_row_ids); the left map carries ORIGINAL row ids, so the payload is
+ * gathered from the unfiltered batch and the filtered copy is never written.  selection = 0: plain b2_join_probe. */
+int b2_join_probe_sel(b2_handle ht, b2_handle probe_keys_table, b2_handle selection, int32_t kind,
+                      b2_handle* out_left_map, b2_handle* out_right_map);
 /* Table.gather(map, OutOfBoundsPolicy): out-of-range index -> null row when nullify != 0 */
 int b2_gather(b2_handle table, b2_handle int32_map, int32_t nullify_oob, b2_handle* out_table);
 
@@ -354,6 +361,10 @@ int b2_exchange_ex(b2_handle comm, b2_handle partitioned_table, const int32_t* o
  * (GpuShuffleExchangeExecBase.scala:384-536, GpuHashPartitioningBase.scala:36-54, GpuPartitioning.scala:66-99) */
 int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* key_cols, int32_t nkeys, int32_t seed,
                      b2_handle* out_table, int32_t* any_data);
+/* same through a selection vector (see b2_join_probe_sel): only rows `selection` names are sent, and only columns out_cols
+ * (a filter + column pruning directly below the exchange, fused into the scatter) */
+int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, const int32_t* out_cols, int32_t nout,
+                         const int32_t* key_cols, int32_t nkeys, int32_t seed, b2_handle* out_table, int32_t* any_data);
 int b2_comm_fused_ready(b2_handle comm, int32_t* ok);        /* collective: peer arenas mapped on every rank? */
 int b2_comm_allmax(b2_handle comm, int32_t value, int32_t* out);   /* collective max of one int per rank */
 /* out4: payload bytes sent to / received from OTHER ranks so far, exchange calls, arena bytes (0 = NCCL path) */

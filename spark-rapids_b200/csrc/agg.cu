@@ -1097,10 +1097,9 @@ static Table* radix_groupby(const Program* prog, const Table* t, const AggPlan& 
   if (P > 1) {
     alloc_side(B);
     DevBuf pid((size_t)m * 4);
-    const int npass = P <= 1024 ? 1 : 2;
-    const int lg1 = npass == 1 ? lgP : lgP / 2;
-    for (int pass = 0; pass < npass; pass++) {
-      const int shift = pass == 0 ? 0 : lg1, bits = pass == 0 ? lg1 : lgP - lg1;
+    // LSD passes of at most 8 bits each (the <= 256-way scatter is the fast one), stable, so the final order is by h & (P - 1)
+    for (int shift = 0; shift < lgP;) {
+      const int bits = std::min(8, lgP - shift);
       rg_digit_kernel<<<grid_for(m, 256), 256, 0, stream()>>>(cur->h.as<uint32_t>(), m, shift, (1u << bits) - 1u, pid.as<int32_t>());
       count_launch();
       ScatterCols sc; memset(&sc, 0, sizeof(sc));
@@ -1111,6 +1110,7 @@ static Table* radix_groupby(const Program* prog, const Table* t, const AggPlan& 
       if (rp.use_vbits) add(cur->vbits, oth->vbits, 4);
       partition_scatter_arrays(pid.as<int32_t>(), m, 1 << bits, sc);
       std::swap(cur, oth);
+      shift += bits;
     }
   }
   DevBuf off((size_t)(P + 1) * 4);

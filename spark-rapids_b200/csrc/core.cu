@@ -219,14 +219,14 @@ void dev_free(void* p) {
 // may be moved to host memory at any time and is brought back on access), DeviceMemoryEventHandler (spill on allocation
 // failure, then GpuRetryOOM), GpuSemaphore.scala:183-260 (bounded number of tasks on the GPU), RmmRapidsRetryIterator.scala:
 // 65-203 (withRetry / split-and-retry: implemented in exec.cu above this store).
-struct HostColumn {
+struct SpilledColumn {   // (distinct name: exec.cu has its own HostColumn; two layouts under one name would be an ODR violation)
   int dtype = 0, scale = 0; int64_t size = 0, null_count = 0, chars_bytes = 0;
   std::vector<uint8_t> data, valid, offsets;
 };
 struct Spillable {
   std::mutex mu;
   Table* dev = nullptr;              // resident form (one reference held by the store)
-  std::vector<HostColumn> host;      // spilled form
+  std::vector<SpilledColumn> host;      // spilled form
   int64_t bytes = 0;
   uint64_t last_use = 0;
 };
@@ -248,7 +248,7 @@ static bool spill_one(Spillable* sp) {   // sp->mu held; true when device memory
   cudaStream_t s = stream();
   sp->host.clear();
   for (auto* c : sp->dev->cols) {
-    HostColumn h;
+    SpilledColumn h;
     h.dtype = c->dtype; h.scale = c->scale; h.size = c->size; h.null_count = c->null_count; h.chars_bytes = c->chars_bytes;
     const size_t db = c->dtype == B2_STRING ? (size_t)c->chars_bytes : (size_t)c->size * dtype_width(c->dtype);
     h.data.resize(db);

@@ -183,6 +183,7 @@ struct XPlan {
   int64_t val_off[XMAX_COLS];     // byte offset of its validity bytes inside a region
   const void* in[XMAX_COLS];
   const uint32_t* in_valid[XMAX_COLS];   // null = this column ships no validity
+  const int32_t* sel;                    // selection vector (row ids into the batch) or null: late materialisation of a filter below
 };
 
 template <typename T>
@@ -192,7 +193,7 @@ __device__ __forceinline__ void xs_move_column(const XPlan& pl, int c, const T* 
 #pragma unroll
   for (int j = 0; j < XS_STEPS; j++) {
     const int64_t i = tile_base + (int64_t)j * XS_NT + threadIdx.x;
-    if (i < n) stage[lpos[j]] = in[i];
+    if (i < n) stage[lpos[j]] = in[pl.sel ? (int64_t)pl.sel[i] : i];
   }
   __syncthreads();
   // ... then stream each destination's run out with consecutive lanes on consecutive addresses (full NVLink packets)
@@ -229,7 +230,8 @@ __global__ void __launch_bounds__(XS_NT) xchg_scatter_kernel(const __grid_consta
         if (pl.single) p = 0;
         else {
           uint32_t h = seed;
-          for (int c = 0; c < keys.n; c++) h = murmur_col(keys.c[c], i, h);
+          const int64_t src = pl.sel ? (int64_t)pl.sel[i] : i;
+          for (int c = 0; c < keys.n; c++) h = murmur_col(keys.c[c], src, h);
           int32_t v = (int32_t)h % pl.W; if (v < 0) v += pl.W;
           p = v;
         }
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(XS_NT) xchg_scatter_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < XS_STEPS; j++) {
           const int64_t i = tile_base + (int64_t)j * XS_NT + threadIdx.x;
-          if (i < n) stage[lpos[j]] = (uint8_t)bit_get(pl.in_valid[c], i);
+          if (i < n) stage[lpos[j]] = (uint8_t)bit_get(pl.in_valid[c], pl.sel ? (int64_t)pl.sel[i] : i);
         }
         __syncthreads();
         for (int k = threadIdx.x; k < tile_n; k += XS_NT) {
@@ -432,22 +434,49 @@ int b2_comm_stats(b2_handle h, int64_t* out4) {
 // copy-out of call k.
 int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* key_cols, int32_t nkeys, int32_t seed,
                      b2_handle* out_table, int32_t* any_data) {
+  return b2_exchange_hash_sel(comm, table, 0, nullptr, 0, key_cols, nkeys, seed, out_table, any_data);
+}
+
+// key_cols index the columns of `table` (the unpruned batch); out_cols (nout > 0) are the columns that travel
+int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, const int32_t* out_cols, int32_t nout,
+                         const int32_t* key_cols, int32_t nkeys, int32_t seed, b2_handle* out_table, int32_t* any_data) {
   B2_TRY
   Comm* c = comm_from(comm);
   const int W = c->world, me = c->rank;
-  Table* t = table ? table_from(table) : nullptr;
+  Table* full = table ? table_from(table) : nullptr;
+  // the travelling columns as a (non-owning) view; keys are read from the full batch
+  Table view;
+  struct Unhook { Table& t; ~Unhook() { t.cols.clear(); } } unhook{view};
+  Table* t = full;
+  if (full && nout > 0) {
+    for (int i = 0; i < nout; i++) {
+      B2_CHECK(out_cols[i] >= 0 && out_cols[i] < (int)full->cols.size(), "exchange: output column out of range");
+      view.cols.push_back(full->cols[out_cols[i]]);
+    }
+    view.rows = full->rows;
+    t = &view;
+  }
+  const int32_t* sel = nullptr;
+  int64_t nsend = t ? t->rows : 0;
+  if (selection) {
+    Column* sc = col_from(selection);
+    B2_CHECK(sc->dtype == B2_INT32 && full, "selection vector must be INT32 over a batch");
+    sel = sc->data.as<int32_t>(); nsend = sc->size;
+  }
   cudaStream_t s = stream();
   *out_table = 0; *any_data = 0;
   if (t) {
     B2_CHECK((int)t->cols.size() >= 1 && (int)t->cols.size() <= XMAX_COLS, "fused exchange: 1..32 columns");
     for (auto* col : t->cols) if (col->dtype == B2_STRING) throw Error(B2_ERR_UNSUPPORTED, "fused exchange: STRING columns take the NCCL path (b2_exchange)");
-    c->schema_dtype.clear(); c->schema_scale.clear();
-    for (auto* col : t->cols) { c->schema_dtype.push_back(col->dtype); c->schema_scale.push_back(col->scale); }
   }
+  // the schema travels in the header of every rank that has a batch; a rank without one adopts it from a peer (a communicator
+  // serves many exchange nodes with different schemas, so nothing is remembered between calls)
+  c->schema_dtype.clear(); c->schema_scale.clear();
+  if (t) for (auto* col : t->cols) { c->schema_dtype.push_back(col->dtype); c->schema_scale.push_back(col->scale); }
   { int32_t ok = 0; int rc = b2_comm_fused_ready(comm, &ok); if (rc != B2_OK) return rc; }
   if (!c->arena_ok) throw Error(B2_ERR_UNSUPPORTED, "fused exchange: peer arenas could not be mapped (no NVLink P2P / IPC between the ranks)");
   KeyCols keys; memset(&keys, 0, sizeof(keys));
-  if (t && nkeys > 0) keys = key_cols_of(t, key_cols, nkeys);
+  if (full && nkeys > 0) keys = key_cols_of(full, key_cols, nkeys);
   XHeader hdr; memset(&hdr, 0, sizeof(hdr));
   hdr.has_data = t ? 1 : 0;
   hdr.ncols = (int)c->schema_dtype.size();
@@ -462,8 +491,9 @@ int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* key_cols, i
     c->epoch++;
     L = region_layout(c->arena_bytes, W, widths);
     h2d_bytes(c->d_hdr, &hdr, sizeof(hdr));
-    if (t && t->rows > 0) {
+    if (t && nsend > 0) {
       XPlan pl; memset(&pl, 0, sizeof(pl));
+      pl.sel = sel;
       pl.W = W; pl.me = me; pl.ncols = hdr.ncols; pl.single = nkeys == 0 ? 1 : 0;
       pl.cap = L.cap; pl.region_bytes = L.region_bytes;
       for (int r = 0; r < W; r++) pl.arena[r] = c->arena_peer[parity][r];
@@ -475,11 +505,11 @@ int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* key_cols, i
       }
       const int smem = XS_TILE * maxw;
       if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(xchg_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      const int64_t ntiles = (t->rows + XS_TILE - 1) / XS_TILE;
+      const int64_t ntiles = (nsend + XS_TILE - 1) / XS_TILE;
       const int per_sm = std::max(1, std::min(8, (200 * 1024) / (smem + 1024)));
       const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
       KernelTimer kt("xchg_scatter_kernel");
-      xchg_scatter_kernel<<<grid, XS_NT, smem, s>>>(keys, pl, t->rows, (uint32_t)seed, c->d_hdr->counts);
+      xchg_scatter_kernel<<<grid, XS_NT, smem, s>>>(keys, pl, nsend, (uint32_t)seed, c->d_hdr->counts);
       CUDA_CHECK(cudaGetLastError());
       count_launch();
     }
@@ -530,6 +560,7 @@ int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* key_cols, i
   if (!anyd) return B2_OK;
   if (hdr.ncols == 0) throw Error(B2_ERR_INVALID, "exchange: no rank knows the schema");
   int64_t out_rows = 0;
+  for (int r = 0; r < W; r++) if (!all[r].has_data) for (int d = 0; d < W; d++) all[r].counts[d] = 0;   // a rank without a batch stored nothing
   for (int r = 0; r < W; r++) out_rows += (int64_t)all[r].counts[me];
   if (out_rows > 0x7fffffffLL) throw Error(B2_ERR_SIZE_OVERFLOW, "exchange result exceeds 2^31-1 rows");
   uint32_t any_null = 0;
@@ -580,12 +611,9 @@ int b2_exchange_ex(b2_handle comm, b2_handle partitioned_table, const int32_t* o
   Table* t = partitioned_table ? table_from(partitioned_table) : nullptr;
   std::vector<int32_t> zero_offs(W + 1, 0);
   const bool mine = t != nullptr;
-  if (t) {
-    c->schema_dtype.clear(); c->schema_scale.clear();
-    for (auto* col : t->cols) { c->schema_dtype.push_back(col->dtype); c->schema_scale.push_back(col->scale); }
-  } else {
-    offsets = zero_offs.data();
-  }
+  c->schema_dtype.clear(); c->schema_scale.clear();   // nothing is remembered between calls: see b2_exchange_hash
+  if (t) for (auto* col : t->cols) { c->schema_dtype.push_back(col->dtype); c->schema_scale.push_back(col->scale); }
+  else offsets = zero_offs.data();
   // round 0: who has data, and the schema for ranks that never saw a batch
   XHeader hdr; memset(&hdr, 0, sizeof(hdr));
   hdr.has_data = mine ? 1 : 0;

@@ -27,6 +27,7 @@ Table* concat_tables(const std::vector<const Table*>& ts);
 Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const int* key_outs, int nkeys, const b2_agg_spec* specs, int naggs);
 Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
 Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, int nkeep);
+Column* filter_row_ids(const Program* prog, const Table* t);
 
 Table* slice_table(const Table* t, int64_t start, int64_t end);
 
@@ -94,6 +95,15 @@ struct GpuExec {
     if (prof) { cudaEventRecord(sp.b, stream()); spans.push_back(sp); if (parent) parent->child_spans.push_back(sp); }
     if (t) { num_output_rows += t->rows; num_output_batches++; }
     return t;
+  }
+  // run f() as if node `who` had done it (an operator fused into this one keeps its own line in the metrics)
+  template <typename F>
+  auto run_as(GpuExec* who, F&& f) -> decltype(f()) {
+    if (!profile_enabled()) return f();
+    Span sp{nullptr, nullptr};
+    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); cudaEventRecord(sp.a, stream());
+    struct Done { Span& sp; GpuExec* who; GpuExec* me; ~Done() { cudaEventRecord(sp.b, stream()); who->spans.push_back(sp); me->child_spans.push_back(sp); } } done{sp, who, this};
+    return f();
   }
   static double span_ms(const std::vector<Span>& v) {
     double ms = 0;
@@ -315,9 +325,60 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
     if (rc != B2_OK) throw Error(rc, b2_last_error());
     built = true;
   }
+  // A GpuFilterExec directly below the stream side is fused by late materialisation: the filter yields a selection vector
+  // (row ids), the probe reads the keys through it and emits ORIGINAL row ids, the payload is gathered from the unfiltered
+  // batch — the filtered copy of the stream side (TPC-H q3: 7.8 GB per pass over lineitem) is never written or re-read.
+  GpuFilterExec* fused = nullptr;
+  bool fusion_checked = false;
+  int raw_col(int filter_out_col) const { return fused->keep.empty() ? filter_out_col : fused->keep[filter_out_col]; }
+  Table* fused_next() {
+    TableRef raw(fused->children[0]->next());
+    if (!raw.t) return nullptr;
+    ColGuard sel(run_as(fused, [&] { return filter_row_ids(program_from(fused->program), raw.t); }));
+    fused->num_output_rows += sel.c->size; fused->num_output_batches++;
+    std::vector<int> keys, left_cols;
+    for (int k : stream_keys) keys.push_back(raw_col(k));
+    if (pruned) for (int c : stream_out) left_cols.push_back(raw_col(c));
+    else { const int n = fused->keep.empty() ? (int)raw.t->cols.size() : (int)fused->keep.size(); for (int c = 0; c < n; c++) left_cols.push_back(raw_col(c)); }
+    try {
+      return with_retry([&]() -> Table* {
+        TableRef sk(select(raw.t, keys));
+        b2_handle lm = 0, rm = 0;
+        int rc = b2_join_probe_sel(ht, to_handle(sk.t), to_handle(sel.c), kind, &lm, &rm);
+        if (rc != B2_OK) throw Error(rc, b2_last_error());
+        ColGuard lmap(col_from(lm));
+        ColGuard rmap(rm ? col_from(rm) : nullptr);
+        TableRef left(gather_table(raw.t, lmap.c->data.as<int32_t>(), lmap.c->size, false, &left_cols));
+        if (!rmap.c || (pruned && build_out.empty())) return left.release();
+        TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER, pruned ? &build_out : nullptr));
+        if (pruned && stream_out.empty()) return right.release();
+        std::vector<Column*> cols;
+        for (auto*& c : left.t->cols) { cols.push_back(c); c = nullptr; }
+        for (auto*& c : right.t->cols) { cols.push_back(c); c = nullptr; }
+        left.t->cols.clear(); right.t->cols.clear();
+        return new_table(std::move(cols));
+      });
+    } catch (const Error& e) {
+      if (!splittable(e)) throw;
+      // memory pressure / 2^31 limit: materialise the filter output after all and take the split-and-retry path
+      std::vector<int> fcols;
+      const int n = fused->keep.empty() ? (int)raw.t->cols.size() : (int)fused->keep.size();
+      for (int c = 0; c < n; c++) fcols.push_back(raw_col(c));
+      TableRef ft(gather_table(raw.t, sel.c->data.as<int32_t>(), sel.c->size, false, &fcols));
+      join_split(ft.t, 0);
+      Table* out = pending.front().release();
+      pending.pop_front();
+      return out;
+    }
+  }
   Table* do_next() override {
     if (!pending.empty()) { Table* out = pending.front().release(); pending.pop_front(); return out; }
     if (!built) build();
+    if (!fusion_checked) {
+      fusion_checked = true;
+      if (kind != B2_JOIN_FULL_OUTER && !getenv("B2_NO_FILTER_FUSION")) fused = dynamic_cast<GpuFilterExec*>(children[0]);
+    }
+    if (fused) return fused_next();
     TableRef s;
     if (kind == B2_JOIN_FULL_OUTER) {
       // the unmatched build rows can only be emitted once every stream row has been seen: the stream side is
@@ -434,6 +495,8 @@ extern "C" int b2_exchange_hash(b2_handle comm, b2_handle table, const int32_t* 
 extern "C" int b2_exchange_ex(b2_handle comm, b2_handle partitioned_table, const int32_t* offsets, b2_handle* out_table, int32_t* any_data);
 extern "C" int b2_comm_fused_ready(b2_handle comm, int32_t* ok);
 extern "C" int b2_comm_allmax(b2_handle comm, int32_t value, int32_t* out);
+extern "C" int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, const int32_t* out_cols, int32_t nout, const int32_t* key_cols,
+                                    int32_t nkeys, int32_t seed, b2_handle* out_table, int32_t* any_data);
 extern "C" int b2_broadcast_table(b2_handle comm, b2_handle table, int32_t root, b2_handle* out_table);
 
 // GpuShuffleExchangeExec (GpuShuffleExchangeExecBase.scala:384-536).  Every call of the exchange is a collective, so the
@@ -457,15 +520,24 @@ struct GpuShuffleExchangeExec : GpuExec {
       if (rc != B2_OK) throw Error(rc, b2_last_error());
       return from_handle_owned(out);
     }
+    // a GpuFilterExec (with its column pruning) directly below is fused into the scatter: see GpuShuffledHashJoinExec::fused
+    GpuFilterExec* ff = getenv("B2_NO_FILTER_FUSION") ? nullptr : dynamic_cast<GpuFilterExec*>(children[0]);
+    GpuExec* src = ff ? ff->children[0] : children[0];
     TableRef in;
-    if (!child_done) { in = TableRef(children[0]->next()); if (!in.t) child_done = true; }
+    if (!child_done) { in = TableRef(src->next()); if (!in.t) child_done = true; }
+    std::vector<int32_t> out_cols;     // the columns that travel (indices into the batch pulled from src)
+    if (ff && in.t) {
+      if (ff->keep.empty()) for (int c = 0; c < (int)in.t->cols.size(); c++) out_cols.push_back(c);
+      else out_cols = ff->keep;
+    }
     if (!probed) {   // collective, once per node: can every rank store into every peer's arena, and is the schema fixed width?
       int32_t ok = 0;
       int rc = b2_comm_fused_ready(comm, &ok);
       if (rc != B2_OK) throw Error(rc, b2_last_error());
       // a rank without a batch does not know the schema, so the ranks agree on "some batch carries STRING columns"
       int32_t mine = 0, any_strings = 0;
-      if (in.t) for (auto* c : in.t->cols) if (c->dtype == B2_STRING) mine = 1;
+      if (in.t && !ff) for (auto* c : in.t->cols) if (c->dtype == B2_STRING) mine = 1;
+      if (in.t && ff) for (int c : out_cols) if (in.t->cols[c]->dtype == B2_STRING) mine = 1;
       rc = b2_comm_allmax(comm, mine, &any_strings);
       if (rc != B2_OK) throw Error(rc, b2_last_error());
       has_strings = any_strings != 0;
@@ -473,10 +545,24 @@ struct GpuShuffleExchangeExec : GpuExec {
     }
     b2_handle out = 0;
     int32_t any = 0;
-    if (fused && !has_strings) {
+    if (fused && !has_strings && ff) {
+      ColGuard sel(in.t ? run_as(ff, [&] { return filter_row_ids(program_from(ff->program), in.t); }) : nullptr);
+      if (in.t) { ff->num_output_rows += sel.c->size; ff->num_output_batches++; }
+      std::vector<int32_t> keys;   // key_cols index the filter's output columns
+      for (int32_t k : key_cols) keys.push_back(ff->keep.empty() ? k : ff->keep[k]);
+      int rc = b2_exchange_hash_sel(comm, in.t ? to_handle(in.t) : 0, sel.c ? to_handle(sel.c) : 0, out_cols.data(), (int)out_cols.size(), keys.data(),
+                                    (int)keys.size(), 42, &out, &any);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+    } else if (fused && !has_strings) {
       int rc = b2_exchange_hash(comm, in.t ? to_handle(in.t) : 0, key_cols.data(), (int)key_cols.size(), 42, &out, &any);
       if (rc != B2_OK) throw Error(rc, b2_last_error());
     } else {
+      if (ff && in.t) {   // NCCL path: the filter runs unfused
+        TableRef f(ff->keep.empty() ? nullptr : filter_select(program_from(ff->program), in.t, ff->keep.data(), (int)ff->keep.size()));
+        if (!f.t) { b2_handle fh = 0; int rc = b2_filter(ff->program, to_handle(in.t), &fh); if (rc != B2_OK) throw Error(rc, b2_last_error()); f = TableRef(from_handle_owned(fh)); }
+        ff->num_output_rows += f.t->rows; ff->num_output_batches++;
+        in = std::move(f);
+      }
       std::vector<int32_t> offs(world + 1, 0);
       TableRef part;
       if (in.t) {

@@ -12,6 +12,7 @@
 #include "prim.cuh"
 #include "rowops.cuh"
 #include "murmur.cuh"
+#include <algorithm>
 
 namespace b2 {
 
@@ -108,6 +109,101 @@ __global__ void __launch_bounds__(PT_NT) part_scatter_kernel(const int32_t* __re
   }
 }
 
+
+// Stable multi-array scatter for <= 256 partitions, the workhorse of the radix group-by passes.  Ranks are computed like the
+// radix sort's scatter (sort.cu): each warp owns 512 consecutive rows and ranks them 32 at a time with match_any against
+// per-warp running counts (no block barrier inside the loop), one cross-warp scan gives every row its position in the
+// tile's partition-sorted order.  Each array is then staged through shared memory in that order, so a partition's run
+// leaves the SM as consecutive addresses (full sectors) instead of one scattered 8-byte store per row.
+constexpr int PS_WARPS = PT_NT / 32, PS_WARP_ITEMS = PT_TILE / PS_WARPS;
+template <typename T>
+__device__ __forceinline__ void ps_move(const T* __restrict__ in, T* __restrict__ out, T* stage, const uint16_t* lpos, int64_t wbase, int64_t n, int tile_n,
+                                        const uint8_t* s_owner, const int32_t* s_start, const int32_t* s_gbase) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < PT_STEPS; r++) {
+    const int64_t i = wbase + r * 32 + lane;
+    if (i < n) stage[lpos[r]] = in[i];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < tile_n; k += PT_NT) {
+    const int p = s_owner[k];
+    out[s_gbase[p] + (k - s_start[p])] = stage[k];
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(PT_NT) part_scatter2_kernel(const int32_t* __restrict__ pids, int64_t n, int32_t nparts, int64_t ntiles,
+                                                              const int32_t* __restrict__ base, const __grid_constant__ ScatterCols sc) {
+  extern __shared__ __align__(16) char ps_stage[];    // PT_TILE x widest array
+  __shared__ uint32_t s_wh[PS_WARPS][256];
+  __shared__ int32_t s_start[257], s_gbase[256];
+  __shared__ uint8_t s_owner[PT_TILE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tile = blockIdx.x;
+  const int tile_n = (int)min((int64_t)PT_TILE, n - tile * PT_TILE);
+  for (int k = threadIdx.x; k < PS_WARPS * 256; k += PT_NT) (&s_wh[0][0])[k] = 0;
+  __syncthreads();
+  const int64_t wbase = tile * PT_TILE + (int64_t)warp * PS_WARP_ITEMS;
+  uint8_t pid[PT_STEPS];
+  uint16_t lpos[PT_STEPS];
+#pragma unroll
+  for (int r = 0; r < PT_STEPS; r++) {
+    const int64_t i = wbase + r * 32 + lane;
+    const bool in = i < n;
+    const uint32_t d = in ? (uint32_t)pids[i] : 256u + lane;   // out-of-range lanes match nobody
+    const uint32_t m = __match_any_sync(0xffffffffu, d);
+    const uint32_t before = __popc(m & ((1u << lane) - 1u));
+    uint32_t prev = 0;
+    if (in) prev = s_wh[warp][d];
+    __syncwarp();
+    if (in && before == 0) s_wh[warp][d] = prev + __popc(m);
+    __syncwarp();
+    pid[r] = (uint8_t)d;
+    lpos[r] = (uint16_t)(prev + before);
+  }
+  __syncthreads();
+  {  // partition d = threadIdx.x: exclusive offsets of the warps inside the partition's run, run length, global base
+    const int d = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < PS_WARPS; w++) { const uint32_t c = s_wh[w][d]; s_wh[w][d] = run; run += c; }
+    s_start[d + 1] = (int32_t)run;     // counts for now
+    s_gbase[d] = d < nparts ? base[(int64_t)d * ntiles + tile] : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {   // exclusive scan of the 256 run lengths (8 per lane)
+    int32_t c[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { c[k] = s_start[lane * 8 + k + 1]; sum += c[k]; }
+    int32_t inc = sum;
+    for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    int32_t runx = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s_start[lane * 8 + k] = runx; runx += c[k]; }
+    if (lane == 31) s_start[256] = runx;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < PT_STEPS; r++) {
+    const int64_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      const int p = pid[r];
+      lpos[r] = (uint16_t)(s_start[p] + s_wh[warp][p] + lpos[r]);
+      s_owner[lpos[r]] = (uint8_t)p;
+    }
+  }
+  __syncthreads();
+  for (int c = 0; c < sc.n; c++) {
+    switch (sc.width[c]) {
+      case 1: ps_move<uint8_t>((const uint8_t*)sc.in[c], (uint8_t*)sc.out[c], (uint8_t*)ps_stage, lpos, wbase, n, tile_n, s_owner, s_start, s_gbase); break;
+      case 2: ps_move<uint16_t>((const uint16_t*)sc.in[c], (uint16_t*)sc.out[c], (uint16_t*)ps_stage, lpos, wbase, n, tile_n, s_owner, s_start, s_gbase); break;
+      case 4: ps_move<uint32_t>((const uint32_t*)sc.in[c], (uint32_t*)sc.out[c], (uint32_t*)ps_stage, lpos, wbase, n, tile_n, s_owner, s_start, s_gbase); break;
+      case 8: ps_move<uint64_t>((const uint64_t*)sc.in[c], (uint64_t*)sc.out[c], (uint64_t*)ps_stage, lpos, wbase, n, tile_n, s_owner, s_start, s_gbase); break;
+      default: ps_move<uint4>((const uint4*)sc.in[c], (uint4*)sc.out[c], (uint4*)ps_stage, lpos, wbase, n, tile_n, s_owner, s_start, s_gbase); break;
+    }
+  }
+}
+
 static Table* partition_table_direct(const Table* t, const int32_t* d_pids, int32_t nparts, int32_t* offsets_out) {
   const int64_t n = t->rows;
   const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
@@ -169,7 +265,16 @@ void partition_scatter_arrays(const int32_t* d_pids, int64_t n, int32_t nparts, 
     count_launch();
   }
   DevBuf sums = exclusive_scan<int32_t, int32_t>(cnt.as<int32_t>(), cnt.as<int32_t>(), cells, true);
-  {
+  if (nparts <= 256) {
+    int maxw = 1;
+    for (int c = 0; c < sc.n; c++) maxw = std::max(maxw, sc.width[c]);
+    const int smem = PT_TILE * maxw;
+    if (smem > 32 * 1024) CUDA_CHECK(cudaFuncSetAttribute(part_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KernelTimer kt("part_scatter2_kernel");
+    part_scatter2_kernel<<<(int)ntiles, PT_NT, smem, stream()>>>(d_pids, n, nparts, ntiles, cnt.as<int32_t>(), sc);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  } else {
     KernelTimer kt("part_scatter_kernel");
     part_scatter_kernel<<<(int)ntiles, PT_NT, 0, stream()>>>(d_pids, n, nparts, ntiles, cnt.as<int32_t>(), sc, nullptr);
     CUDA_CHECK(cudaGetLastError());

@@ -93,12 +93,16 @@ __device__ __forceinline__ uint64_t join_entry(const uint64_t* __restrict__ slot
 __global__ void join_probe_distinct_kernel(const __grid_constant__ KeyCols probe, const __grid_constant__ KeyCols build, int64_t n,
                                            const uint64_t* __restrict__ slots, uint32_t mask, bool nulls_equal,
                                            bool fast, int kind, unsigned long long* __restrict__ total, int32_t* __restrict__ left_map,
-                                           int32_t* __restrict__ right_map, const unsigned long long* __restrict__ bloom, uint32_t bloom_mask) {
+                                           int32_t* __restrict__ right_map, const unsigned long long* __restrict__ bloom, uint32_t bloom_mask,
+                                           const int32_t* __restrict__ sel) {
   const int lane = threadIdx.x & 31;
   const int64_t nround = (n + 31) & ~(int64_t)31;
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nround; r += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t rr = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; rr < nround; rr += (int64_t)gridDim.x * blockDim.x) {
     int32_t br = INT32_MIN;
-    if (r < n && ((nulls_equal && !fast) || !any_null_key(probe, r))) {  // fast: the build side holds no NULL keys, so a NULL probe key matches nothing
+    // selection vector: probe row rr of the (virtual) filtered batch is row sel[rr] of the batch itself; the left map then
+    // carries ORIGINAL row ids, so the payload gather reads the unfiltered batch and no filtered copy ever exists
+    const int64_t r = (rr < n && sel) ? (int64_t)sel[rr] : rr;
+    if (rr < n && ((nulls_equal && !fast) || !any_null_key(probe, r))) {  // fast: the build side holds no NULL keys, so a NULL probe key matches nothing
       uint64_t kb = 0;
       uint32_t h;
       if (fast) { kb = pack_join_key(probe, r); h = hash_packed(kb); } else h = row_hash(probe, r);
@@ -116,7 +120,7 @@ __global__ void join_probe_distinct_kernel(const __grid_constant__ KeyCols probe
       }
     }
     if (kind == B2_JOIN_LEFT_OUTER) {
-      if (r < n) { left_map[r] = (int32_t)r; right_map[r] = br; }
+      if (rr < n) { left_map[rr] = (int32_t)r; right_map[rr] = br; }
     } else {
       const bool hit = br != INT32_MIN;
       const uint32_t b = __ballot_sync(0xffffffffu, hit);
@@ -134,10 +138,11 @@ __global__ void join_probe_kernel(const __grid_constant__ KeyCols probe, const _
                                   const uint64_t* __restrict__ slots, uint32_t mask, bool nulls_equal,
                                   bool fast, int kind, int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
                                   int32_t* __restrict__ left_map, int32_t* __restrict__ right_map,
-                                  const unsigned long long* __restrict__ bloom, uint32_t bloom_mask) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+                                  const unsigned long long* __restrict__ bloom, uint32_t bloom_mask, const int32_t* __restrict__ sel) {
+  for (int64_t rr = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; rr < n; rr += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = sel ? (int64_t)sel[rr] : rr;   // see join_probe_distinct_kernel
     int32_t matches = 0;
-    int64_t o = MODE == 1 ? offsets[r] : 0;
+    int64_t o = MODE == 1 ? offsets[rr] : 0;
     const bool semi_like = kind == B2_JOIN_LEFT_SEMI || kind == B2_JOIN_LEFT_ANTI;
     if ((nulls_equal && !fast) || !any_null_key(probe, r)) {  // fast: see join_probe_distinct_kernel
       uint64_t kb = 0;
@@ -167,7 +172,7 @@ __global__ void join_probe_kernel(const __grid_constant__ KeyCols probe, const _
       case B2_JOIN_LEFT_SEMI: emit = matches > 0 ? 1 : 0; break;
       default: emit = matches > 0 ? 0 : 1; break;  // LEFT_ANTI
     }
-    if (MODE == 0) counts[r] = emit;
+    if (MODE == 0) counts[rr] = emit;
     else {
       if (semi_like) { if (emit) left_map[o] = (int32_t)r; }
       else if (kind == B2_JOIN_LEFT_OUTER && matches == 0) { left_map[o] = (int32_t)r; right_map[o] = INT32_MIN; }
@@ -255,9 +260,23 @@ int b2_join_hash_table_close(b2_handle ht) {
 }
 
 int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_handle* out_left_map, b2_handle* out_right_map) {
+  return b2_join_probe_sel(ht, probe_keys_table, 0, kind, out_left_map, out_right_map);
+}
+
+// probe through a selection vector: `selection` (INT32 row ids into probe_keys_table, ascending, e.g. from b2_filter_row_ids)
+// names the stream rows that take part; the left gather map carries ORIGINAL row ids of probe_keys_table's batch
+int b2_join_probe_sel(b2_handle ht, b2_handle probe_keys_table, b2_handle selection, int32_t kind, b2_handle* out_left_map, b2_handle* out_right_map) {
   B2_TRY
   JoinTable* jt = jt_from(ht);
   Table* pt = table_from(probe_keys_table);
+  const int32_t* sel = nullptr;
+  int64_t nsel = 0;
+  if (selection) {
+    Column* sc = col_from(selection);
+    B2_CHECK(sc->dtype == B2_INT32, "selection vector must be INT32");
+    B2_CHECK(kind != B2_JOIN_FULL_OUTER, "full outer join through a selection vector");
+    sel = sc->data.as<int32_t>(); nsel = sc->size;
+  }
   B2_CHECK(pt->cols.size() == jt->keys->cols.size(), "probe and build key counts differ");
   for (size_t i = 0; i < pt->cols.size(); i++)
     B2_CHECK(pt->cols[i]->dtype == jt->keys->cols[i]->dtype, "probe and build key dtypes differ");
@@ -265,7 +284,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
     // left outer maps, then one extra row (left = out of bounds -> NULLs) per build row that nothing matched
     B2_CHECK(out_right_map != nullptr, "a full outer join needs both gather maps");
     b2_handle hl = 0, hr = 0;
-    int rc = b2_join_probe(ht, probe_keys_table, B2_JOIN_LEFT_OUTER, &hl, &hr);
+    int rc = b2_join_probe_sel(ht, probe_keys_table, 0, B2_JOIN_LEFT_OUTER, &hl, &hr);
     if (rc != B2_OK) return rc;
     ColGuard lo(col_from(hl)), ro(col_from(hr));
     const int64_t m = lo.c->size, nb = jt->keys->rows;
@@ -297,7 +316,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
     return B2_OK;
   }
   B2_CHECK(kind >= B2_JOIN_INNER && kind <= B2_JOIN_LEFT_ANTI, "bad join kind");
-  const int64_t n = pt->rows;
+  const int64_t n = sel ? nsel : pt->rows;
   const bool semi_like = kind == B2_JOIN_LEFT_SEMI || kind == B2_JOIN_LEFT_ANTI;
   KeyCols pk = key_cols_of(pt, jt->key_idx.data(), (int)jt->key_idx.size());
   KeyCols bk = key_cols_of(jt->keys, jt->key_idx.data(), (int)jt->key_idx.size());
@@ -311,7 +330,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
       KernelTimer kt("join_probe_distinct_kernel");
       join_probe_distinct_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1),
                                                                           jt->nulls_equal, jt->fast, kind, tot.as<unsigned long long>(),
-                                                                          lm.c->data.as<int32_t>(), rm.c->data.as<int32_t>(), jt->bloom.as<unsigned long long>(), jt->bloom_mask);
+                                                                          lm.c->data.as<int32_t>(), rm.c->data.as<int32_t>(), jt->bloom.as<unsigned long long>(), jt->bloom_mask, sel);
       CUDA_CHECK(cudaGetLastError());
       count_launch();
       if (kind == B2_JOIN_INNER) { unsigned long long h = 0; d2h(&h, tot.p, 1); sync(); matched = (int64_t)h; }
@@ -326,7 +345,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
   if (n) {
     KernelTimer kt_join_probe_count_kernel("join_probe_count_kernel");
     join_probe_kernel<0><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, jt->fast, kind,
-                                                                  counts.as<int32_t>(), nullptr, nullptr, nullptr, jt->bloom.as<unsigned long long>(), jt->bloom_mask);
+                                                                  counts.as<int32_t>(), nullptr, nullptr, nullptr, jt->bloom.as<unsigned long long>(), jt->bloom_mask, sel);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
     exclusive_scan<int32_t, int64_t>(counts.as<int32_t>(), offsets.as<int64_t>(), n, true);
@@ -342,7 +361,7 @@ int b2_join_probe(b2_handle ht, b2_handle probe_keys_table, int32_t kind, b2_han
     KernelTimer kt_join_probe_write_kernel("join_probe_write_kernel");
     join_probe_kernel<1><<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1), jt->nulls_equal, jt->fast, kind,
                                                                   nullptr, offsets.as<int64_t>(), lm.c->data.as<int32_t>(),
-                                                                  semi_like ? nullptr : rm.c->data.as<int32_t>(), jt->bloom.as<unsigned long long>(), jt->bloom_mask);
+                                                                  semi_like ? nullptr : rm.c->data.as<int32_t>(), jt->bloom.as<unsigned long long>(), jt->bloom_mask, sel);
     CUDA_CHECK(cudaGetLastError());
     count_launch();
   }

@@ -511,6 +511,21 @@ Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, i
   return filter_impl(prog, t, &view);
 }
 
+// selection vector: the row ids that pass the predicate, in order, and nothing else (late materialisation: a join probe or
+// an exchange scatter directly above the filter reads the batch through it instead of through a compacted copy)
+Column* filter_row_ids(const Program* prog, const Table* t) {
+  check_program_inputs(prog, t);
+  B2_CHECK(prog->hdr.nouts >= 1 && prog->out_dtype[0] == B2_BOOL8, "filter predicate must be a single BOOL8 expression");
+  const int64_t n = t->rows;
+  VMInputs in; fill_inputs(in, t);
+  FilterCols fc; memset(&fc, 0, sizeof(fc));
+  ColGuard ids(new_column(B2_INT32, 0, n, false));
+  fc.row_ids = ids.c->data.as<int32_t>();
+  Table none;   // no payload columns: only the predicate's inputs are staged
+  ids.c->size = run_filter(prog, in, fc, n, false, t, &none);
+  return ids.release();
+}
+
 // Table.filter(mask): order-preserving compaction of every column by a BOOL8 mask (NULL = drop)
 Table* filter_by_mask(const Table* t, Column* m) {
   B2_CHECK(m->dtype == B2_BOOL8, "filter mask must be BOOL8");
@@ -583,6 +598,12 @@ int b2_filter(b2_handle predicate_program, b2_handle table, b2_handle* out_table
 int b2_filter_select(b2_handle predicate_program, b2_handle table, const int32_t* keep_cols, int32_t nkeep, b2_handle* out_table) {
   B2_TRY
   *out_table = to_handle(filter_select(program_from(predicate_program), table_from(table), keep_cols, nkeep));
+  B2_CATCH
+}
+
+int b2_filter_row_ids(b2_handle predicate_program, b2_handle table, b2_handle* out_int32_ids) {
+  B2_TRY
+  *out_int32_ids = to_handle(filter_row_ids(program_from(predicate_program), table_from(table)));
   B2_CATCH
 }
 

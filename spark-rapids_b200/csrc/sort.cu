@@ -315,6 +315,20 @@ Table* gather_table(const Table* t, const int32_t* d_map, int64_t n, bool nullif
 Table* concat_tables(const std::vector<const Table*>& ts);
 Table* filter_by_mask(const Table* t, Column* m);
 
+// histogram of digit (key >> shift) & 255 over the rows whose key agrees with `pval` on the bits of `pmask`
+__global__ void __launch_bounds__(256) hist_prefix_kernel(const uint64_t* __restrict__ keys, int64_t n, uint64_t pmask, uint64_t pval, int shift,
+                                                          unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    if ((k & pmask) == pval) atomicAdd(&s_h[(k >> shift) & 255], 1u);
+  }
+  __syncthreads();
+  if (s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_h[threadIdx.x]);
+}
+
 __global__ void topn_mask_kernel(const uint64_t* __restrict__ keys, int64_t n, uint64_t thr, int8_t* __restrict__ mask) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mask[i] = keys[i] <= thr;
 }
@@ -344,15 +358,34 @@ static Table* top_n_select(const Table* t, const b2_order_by_arg* keys, int nkey
     d2h(h.data(), hist.p, h.size());
     sync();
     thr = 0;
-    for (int d = 7; d >= 0 && m < 0; d--) {
+    int d = 7;
+    for (; d >= 0; d--) {   // leading digits of this chunk on which all rows agree
       int constant = -1;
       for (int b = 0; b < 256; b++) if (h[d * 256 + b] == (unsigned long long)n) constant = b;
-      if (constant >= 0) { thr |= (uint64_t)constant << (8 * d); continue; }
-      int64_t cum = 0;
-      for (int b = 0; b < 256; b++) {
-        cum += (int64_t)h[d * 256 + b];
-        if (cum >= limit) { thr |= (uint64_t)b << (8 * d); if (d > 0) thr |= (1ull << (8 * d)) - 1; m = cum; break; }
-      }
+      if (constant < 0) break;
+      thr |= (uint64_t)constant << (8 * d);
+    }
+    if (d < 0) continue;   // the whole chunk is constant: the next chunk decides
+    // radix select from the first varying digit down: each round histograms the next digit of the rows that still tie with
+    // the prefix, keeps the bucket in which the limit-th smallest key lies and stops once few rows share the prefix
+    int64_t k = limit, below = 0;
+    uint64_t pmask = d == 7 ? 0 : ~((1ull << (8 * (d + 1))) - 1);
+    uint64_t pval = thr;
+    std::vector<unsigned long long> hd(h.begin() + d * 256, h.begin() + (d + 1) * 256);
+    while (true) {
+      int64_t cum = 0; int b = 0;
+      for (; b < 256; b++) { if (cum + (int64_t)hd[b] >= k) break; cum += (int64_t)hd[b]; }
+      below += cum; k -= cum;
+      pval |= (uint64_t)b << (8 * d); pmask |= 0xffull << (8 * d);
+      const int64_t tied = (int64_t)hd[b];
+      if (d == 0 || tied <= 8192) { thr = pval | (d > 0 ? (1ull << (8 * d)) - 1 : 0); m = below + tied; break; }
+      d--;
+      CUDA_CHECK(cudaMemsetAsync(hist.p, 0, 256 * 8, stream()));
+      hist_prefix_kernel<<<grid_for(n, 256 * 8), 256, 0, stream()>>>(k0.as<uint64_t>(), n, pmask, pval, 8 * d, hist.as<unsigned long long>());
+      CUDA_CHECK(cudaGetLastError());
+      count_launch();
+      d2h(hd.data(), hist.p, 256);
+      sync();
     }
   }
   if (m < 0 || m > n / 4) return nullptr;   // all leading bytes equal, or one value dominates: sort everything

@@ -48,3 +48,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_jni_shim_compiles_and_binds_only_declared_entry_points():
+    """jni/b2_jni.c is real source: it must pass a syntax check (against the stub jni.h when no JDK is present) and every
+    b2_* function it calls must be declared in include/b200sql.h"""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", os.path.join(root, "jni"), "check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    src = open(os.path.join(root, "jni", "b2_jni.c")).read()
+    called = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", src)) - {"b2_throw"}
+    from spark_rapids_b200 import parse_header
+    declared = set(parse_header())
+    assert called <= declared, sorted(called - declared)
+    natives = re.findall(r"JNICALL\s+(Java_[A-Za-z0-9_]+)", src)
+    assert len(natives) >= 18 and len(set(natives)) == len(natives)

@@ -276,3 +276,37 @@ def test_full_outer_join_then_gather(b2):
         G.assert_col_equal(gl.column(0), el[0])
         G.assert_col_equal(gr.column(0), er[0])
         G.assert_col_equal(gr.column(1), er[1])
+
+
+def test_join_probe_through_selection_vector(b2):
+    """late materialisation: filter row ids + probe through them == filter, then probe; the left map holds ORIGINAL row ids"""
+    import ctypes
+    rng = np.random.default_rng(41)
+    nb, ns = 3000, 20000
+    build = [gen(rng, (O.INT64, 0, 0), nb, distinct=4000, null_frac=0.02)]
+    key = gen(rng, (O.INT64, 0, 0), ns, distinct=5000, null_frac=0.05)
+    flt = gen(rng, (O.INT32, 0, 0), ns, distinct=10, null_frac=0.1)
+    st = G.to_b2_table(b2, [key, flt])
+    pred = G.b2_expr_col(b2, 1, flt) < b2.lit(4, b2.INT32)
+    prog = b2.Program([pred])
+    ids = ctypes.c_int64()
+    b2.check(b2.lib.b2_filter_row_ids(prog.h, st.h, ctypes.byref(ids)))
+    sel = b2.Column(ids.value)
+    keep = O.eval_expr(pred.sexpr, [key, flt])
+    mask = keep.valid & (keep.values != 0)
+    assert sel.to_pylist() == [int(i) for i in np.flatnonzero(mask)]
+    ht = b2.JoinHashTable(G.to_b2_table(b2, build))
+    keys_only = b2.Table.from_columns([st.column(0)])
+    for kind in (0, 1, 2, 3):
+        lm, rm = ctypes.c_int64(), ctypes.c_int64()
+        b2.check(b2.lib.b2_join_probe_sel(ht.h, keys_only.h, sel.h, kind, ctypes.byref(lm), ctypes.byref(rm)))
+        glm = b2.Column(lm.value).to_pylist()
+        grm = b2.Column(rm.value).to_pylist() if rm.value else None
+        fkey = O.OCol(key.values[mask], key.valid[mask], key.typ)
+        elm, erm = R.hash_join(build, [fkey], kind)
+        orig = np.flatnonzero(mask)
+        elm = [int(orig[i]) for i in elm]
+        if grm is None:
+            assert glm == elm
+        else:
+            assert sorted(zip(glm, grm)) == sorted(zip(elm, erm))
