@@ -394,6 +394,9 @@ int b2_exec_filter(b2_handle child, b2_handle predicate_program, b2_handle* out)
 /* GpuProjectExec(column pruning) over GpuFilterExec, fused: only keep_cols are compacted */
 int b2_exec_filter_select(b2_handle child, b2_handle predicate_program, const int32_t* keep_cols, int32_t nkeep, b2_handle* out);
 int b2_exec_project(b2_handle child, b2_handle program, b2_handle* out);                       /* GpuProjectExec :755-884 */
+/* GpuExpandExec (GpuExpandExec.scala): each batch projected once per projection list, results stacked (GROUPING SETS,
+ * several COUNT(DISTINCT)); all projection programs must produce the same output types */
+int b2_exec_expand(b2_handle child, const b2_handle* projection_programs, int32_t nprojections, b2_handle* out);
 /* GpuHashAggregateExec (GpuAggregateExec.scala:1942-2085).  merge_mode 0: update aggregates over the
  * program's outputs (Partial/Complete); 1: input batches are aggregation buffers, keys leading (Final) */
 int b2_exec_hash_aggregate(b2_handle child, b2_handle program, int32_t has_predicate, int32_t merge_mode,
@@ -406,6 +409,10 @@ int b2_exec_shuffled_hash_join_select(b2_handle stream_child, b2_handle build_ch
                                       const int32_t* build_keys, int32_t nkeys, int32_t kind, int32_t nulls_equal,
                                       const int32_t* stream_out, int32_t nstream_out, const int32_t* build_out,
                                       int32_t nbuild_out, b2_handle* out);
+/* mixed join: an extra non-equi condition (BOOL8 program bound over [stream columns ++ build columns]) decides which
+ * equi-matched pairs survive — Table.mixed{Inner,Left,LeftSemi,LeftAnti}JoinGatherMap(s) (GpuHashJoin.scala:335-600),
+ * ConditionalHashJoinIterator (:1556).  Inner / left outer / left semi / left anti. */
+int b2_exec_join_set_condition(b2_handle join, b2_handle condition_program);
 /* GpuBroadcastExchangeExec (GpuBroadcastExchangeExec.scala): every rank gets the whole child relation, one batch.  Used as
  * the build child of a join it makes GpuBroadcastHashJoinExec (GpuBroadcastHashJoinExecBase.scala:1-203). */
 int b2_exec_broadcast_exchange(b2_handle child, b2_handle comm, int32_t rank, int32_t world, b2_handle* out);

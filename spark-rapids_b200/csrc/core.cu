@@ -191,7 +191,7 @@ void* dev_alloc(size_t bytes) {
     cudaDeviceSynchronize();
     e = cudaMallocAsync(&p, bytes, s);
   }
-  if (e != cudaSuccess) cuda_check(e, "cudaMallocAsync", __FILE__, __LINE__);
+  if (e != cudaSuccess) cuda_check(e, ("cudaMallocAsync of " + std::to_string(bytes) + " B with " + std::to_string(g_in_use.load()) + " B in use").c_str(), __FILE__, __LINE__);
   g_in_use.fetch_add((int64_t)bytes);
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -307,16 +307,16 @@ static thread_local bool t_sem_held = false;
 void semaphore_acquire_if_necessary() {
   if (t_sem_held) return;
   std::unique_lock<std::mutex> lk(g_sem_mu);
-  if (g_sem_permits > 0) {
-    if (g_sem_in_use >= g_sem_permits) g_sem_waits++;
-    g_sem_cv.wait(lk, [] { return g_sem_permits <= 0 || g_sem_in_use < g_sem_permits; });
-  }
+  if (g_sem_permits <= 0) return;   // unlimited: nothing to account for
+  if (g_sem_in_use >= g_sem_permits) g_sem_waits++;
+  g_sem_cv.wait(lk, [] { return g_sem_permits <= 0 || g_sem_in_use < g_sem_permits; });
+  if (g_sem_permits <= 0) return;   // the limit was lifted while waiting
   g_sem_in_use++;
   t_sem_held = true;
 }
 void semaphore_release_if_necessary() {
   if (!t_sem_held) return;
-  { std::lock_guard<std::mutex> lk(g_sem_mu); g_sem_in_use--; }
+  { std::lock_guard<std::mutex> lk(g_sem_mu); if (g_sem_in_use > 0) g_sem_in_use--; }
   t_sem_held = false;
   g_sem_cv.notify_one();
 }
@@ -760,6 +760,7 @@ int b2_memory_stats(int64_t* out6) {
 int b2_semaphore_init(int32_t permits) {
   std::lock_guard<std::mutex> lk(g_sem_mu);
   g_sem_permits = permits;
+  if (permits <= 0) g_sem_in_use = 0;
   g_sem_cv.notify_all();
   return B2_OK;
 }

@@ -393,7 +393,7 @@ int b2_comm_fused_ready(b2_handle h, int32_t* ok) {
     c->arena_tried = true;
     size_t mb = 1024;
     if (const char* e = getenv("B2_EXCHANGE_ARENA_MB")) mb = (size_t)std::max(1, atoi(e));
-    if (c->world > 1 && !getenv("B2_EXCHANGE_NO_FUSED")) arena_setup(c, mb << 20);
+    if (!getenv("B2_EXCHANGE_NO_FUSED")) arena_setup(c, mb << 20);   // a world of one stores into its own arena (probe / single-GPU plans)
   }
   *ok = c->arena_ok ? 1 : 0;
   B2_CATCH

@@ -28,6 +28,8 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
 Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
 Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, int nkeep);
 Column* filter_row_ids(const Program* prog, const Table* t);
+Table* filter_by_mask(const Table* t, Column* m);
+Column* rows_with_passing_pair(const Column* left_map, const Column* pass, int64_t stream_rows, bool invert);
 
 Table* slice_table(const Table* t, int64_t start, int64_t end);
 
@@ -239,6 +241,27 @@ struct GpuProjectExec : GpuExec {
   }
 };
 
+// GpuExpandExec (GpuExpandExec.scala): every input batch is projected once per projection list and the results are stacked —
+// the plan Spark uses for GROUPING SETS / ROLLUP / several COUNT(DISTINCT).  Output rows = rows x projections, projection-major.
+struct GpuExpandExec : GpuExec {
+  std::vector<b2_handle> projections;
+  Table* do_next() override {
+    TableRef in(children[0]->next());
+    if (!in.t) return nullptr;
+    std::vector<TableRef> parts;
+    for (b2_handle p : projections) {
+      b2_handle out = 0;
+      int rc = b2_project(p, to_handle(in.t), &out);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+      parts.emplace_back(from_handle_owned(out));
+    }
+    if (parts.size() == 1) return parts[0].release();
+    std::vector<const Table*> ts;
+    for (auto& p : parts) ts.push_back(p.t);
+    return concat_tables(ts);
+  }
+};
+
 // aggregate modes as in Spark: Partial/Complete run the update aggregates on raw input, Final merges
 // partial buffers (SUM of sums, SUM of counts, MIN of mins, MAX of maxes)
 struct GpuHashAggregateExec : GpuExec {
@@ -303,6 +326,9 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
   std::vector<int> stream_keys, build_keys;
   int kind = B2_JOIN_INNER;
   bool nulls_equal = false, built = false, full_done = false;
+  // mixed join (GpuHashJoin.scala:335-530 mixed*JoinGatherMaps, :1556 ConditionalHashJoinIterator): an extra non-equi
+  // condition, bound over [stream columns ++ build columns], decides which equi-matched pairs survive
+  b2_handle condition = 0;
   bool pruned = false;                       // a column-pruning GpuProjectExec above the join, fused into the gathers
   std::vector<int> stream_out, build_out;    // pruned: the columns each side contributes (in this order)
   TableRef build_table;
@@ -365,18 +391,16 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
       const int n = fused->keep.empty() ? (int)raw.t->cols.size() : (int)fused->keep.size();
       for (int c = 0; c < n; c++) fcols.push_back(raw_col(c));
       TableRef ft(gather_table(raw.t, sel.c->data.as<int32_t>(), sel.c->size, false, &fcols));
-      join_split(ft.t, 0);
-      Table* out = pending.front().release();
-      pending.pop_front();
-      return out;
+      todo.emplace_back(std::move(ft), 0);
+      return drain_todo();
     }
   }
   Table* do_next() override {
-    if (!pending.empty()) { Table* out = pending.front().release(); pending.pop_front(); return out; }
+    if (!todo.empty()) return drain_todo();
     if (!built) build();
     if (!fusion_checked) {
       fusion_checked = true;
-      if (kind != B2_JOIN_FULL_OUTER && !getenv("B2_NO_FILTER_FUSION")) fused = dynamic_cast<GpuFilterExec*>(children[0]);
+      if (kind != B2_JOIN_FULL_OUTER && !condition && !getenv("B2_NO_FILTER_FUSION")) fused = dynamic_cast<GpuFilterExec*>(children[0]);
     }
     if (fused) return fused_next();
     TableRef s;
@@ -394,26 +418,103 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
       s = TableRef(children[0]->next());
     }
     if (!s.t) return nullptr;
-    join_split(s.t, 0);
-    Table* out = pending.front().release();
-    pending.pop_front();
-    return out;
+    todo.emplace_back(std::move(s), 0);
+    return drain_todo();
   }
-  std::deque<TableRef> pending;   // outputs of a stream batch that had to be split (returned one per next())
+  // stream slices waiting to be joined (a batch that had to be split leaves its halves here; one output per next())
+  std::deque<std::pair<TableRef, int>> todo;
   // one stream batch -> output batch(es).  When the gather maps would pass 2^31-1 rows (B2_ERR_SIZE_OVERFLOW) or the device
-  // cannot hold the output (B2_ERR_OOM after retries) the stream batch is halved and each half joined on its own
-  void join_split(const Table* st, int depth) {
-    try {
-      pending.emplace_back(with_retry([&] { return join_batch(st); }));
-    } catch (const Error& e) {
-      if (!splittable(e) || st->rows < 2 || depth >= 12 || kind == B2_JOIN_FULL_OUTER) throw;
-      note_split();
-      const int64_t mid = st->rows / 2;
-      { TableRef lo(slice_table(st, 0, mid)); join_split(lo.t, depth + 1); }
-      { TableRef hi(slice_table(st, mid, st->rows)); join_split(hi.t, depth + 1); }
+  // cannot hold the output (B2_ERR_OOM after retries) the stream batch is halved and each half joined on its own — lazily,
+  // so that at most one output batch exists at a time (GpuSplitAndRetryOOM, AbstractGpuJoinIterator.scala:235-250)
+  Table* drain_todo() {
+    while (!todo.empty()) {
+      TableRef st = std::move(todo.front().first);
+      const int depth = todo.front().second;
+      todo.pop_front();
+      try {
+        return with_retry([&] { return join_batch(st.t); });
+      } catch (const Error& e) {
+        if (!splittable(e) || st.t->rows < 2 || depth >= 16 || kind == B2_JOIN_FULL_OUTER) throw;
+        note_split();
+        const int64_t mid = st.t->rows / 2;
+        TableRef lo, hi;
+        // the halves replace the batch: the batch itself is released before they are made, so the split needs no extra room
+        {
+          std::vector<int> all;
+          for (int c = 0; c < (int)st.t->cols.size(); c++) all.push_back(c);
+          lo = TableRef(slice_table(st.t, 0, mid));
+          hi = TableRef(slice_table(st.t, mid, st.t->rows));
+        }
+        st.reset();
+        todo.emplace_front(std::move(hi), depth + 1);
+        todo.emplace_front(std::move(lo), depth + 1);
+      }
     }
+    return nullptr;
+  }
+  static Table* concat_cols(Table* a, Table* b) {   // steals the columns of both
+    std::vector<Column*> cols;
+    for (auto*& c : a->cols) { cols.push_back(c); c = nullptr; }
+    for (auto*& c : b->cols) { cols.push_back(c); c = nullptr; }
+    a->cols.clear(); b->cols.clear();
+    return new_table(std::move(cols));
+  }
+  Table* prune_pairs(const Table* pairs, int nstream) {   // [stream ++ build] -> the output columns of the node
+    std::vector<Column*> cols;
+    auto take = [&](int i) { col_incref(pairs->cols[i]); cols.push_back(pairs->cols[i]); };
+    if (pruned) { for (int c : stream_out) take(c); for (int c : build_out) take(nstream + c); }
+    else for (int i = 0; i < (int)pairs->cols.size(); i++) take(i);
+    return new_table(std::move(cols));
+  }
+  // equi-join pairs -> condition over the pair rows -> per join type
+  Table* join_batch_conditional(const Table* st) {
+    if (kind == B2_JOIN_FULL_OUTER) throw Error(B2_ERR_UNSUPPORTED, "full outer join with a non-equi condition");
+    TableRef sk(select(st, stream_keys));
+    b2_handle lm = 0, rm = 0;
+    int rc = b2_join_probe(ht, to_handle(sk.t), B2_JOIN_INNER, &lm, &rm);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    ColGuard lmap(col_from(lm)), rmap(col_from(rm));
+    const int nstream = (int)st->cols.size();
+    TableRef left(gather_table(st, lmap.c->data.as<int32_t>(), lmap.c->size, false, nullptr));
+    TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, false, nullptr));
+    TableRef pairs(concat_cols(left.t, right.t));
+    b2_handle ph = 0;
+    rc = b2_project(condition, to_handle(pairs.t), &ph);
+    if (rc != B2_OK) throw Error(rc, b2_last_error());
+    TableRef pt(from_handle_owned(ph));
+    Column* pass = pt.t->cols[0];
+    if (pass->dtype != B2_BOOL8) throw Error(B2_ERR_INVALID, "join condition must be BOOL8");
+    auto stream_side = [&](const Table* t) {   // semi / anti output: the node's stream columns
+      std::vector<Column*> cols;
+      if (pruned) for (int c : stream_out) { col_incref(t->cols[c]); cols.push_back(t->cols[c]); }
+      else for (auto* c : t->cols) { col_incref(c); cols.push_back(c); }
+      return new_table(std::move(cols));
+    };
+    if (kind == B2_JOIN_INNER) {
+      TableRef out(prune_pairs(pairs.t, nstream));
+      return filter_by_mask(out.t, pass);
+    }
+    if (kind == B2_JOIN_LEFT_SEMI || kind == B2_JOIN_LEFT_ANTI) {
+      ColGuard flags(rows_with_passing_pair(lmap.c, pass, st->rows, kind == B2_JOIN_LEFT_ANTI));
+      TableRef side(stream_side(st));
+      return filter_by_mask(side.t, flags.c);
+    }
+    // LEFT OUTER: the passing pairs, then every stream row without one, NULL on the build side
+    TableRef pruned_pairs(prune_pairs(pairs.t, nstream));
+    TableRef matched(filter_by_mask(pruned_pairs.t, pass));
+    ColGuard lonely(rows_with_passing_pair(lmap.c, pass, st->rows, true));
+    TableRef lonely_stream(filter_by_mask(st, lonely.c));
+    ColGuard oob(new_column(B2_INT32, 0, lonely_stream.t->rows, false));
+    if (lonely_stream.t->rows) CUDA_CHECK(cudaMemsetAsync(oob.c->data.p, 0x80, (size_t)lonely_stream.t->rows * 4, stream()));   // 0x80808080 < 0: out of bounds -> NULL row
+    TableRef nulls(gather_table(build_table.t, oob.c->data.as<int32_t>(), lonely_stream.t->rows, true, nullptr));
+    TableRef lonely_pairs(concat_cols(lonely_stream.t, nulls.t));
+    TableRef lonely_out(prune_pairs(lonely_pairs.t, nstream));
+    // nullability must agree for the concatenation: concat_tables merges validity
+    std::vector<const Table*> ts{matched.t, lonely_out.t};
+    return concat_tables(ts);
   }
   Table* join_batch(const Table* st) {
+    if (condition) return join_batch_conditional(st);
     TableRef sk(select(st, stream_keys));
     b2_handle lm = 0, rm = 0;
     int rc = b2_join_probe(ht, to_handle(sk.t), kind, &lm, &rm);
@@ -434,12 +535,14 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
 };
 
 DevBuf sort_order(const Table* t, const b2_order_by_arg* keys, int nkeys);
+Table* top_n_table(const Table* t, const b2_order_by_arg* keys, int nkeys, int64_t limit);
 struct GpuSortExec : GpuExec {
   std::vector<b2_order_by_arg> order;
   bool global = true;   // false: sort each batch (SortEachBatch); true: full sort of the partition
   int64_t limit = -1;   // >= 0: GpuTopN
   bool done = false;
   Table* sorted(const Table* t, int64_t n) {
+    if (n >= 0) return top_n_table(t, order.data(), (int)order.size(), n);   // GpuTopN: radix select, then a sort of the candidates
     DevBuf perm = sort_order(t, order.data(), (int)order.size());
     return gather_table(t, perm.as<int32_t>(), n < 0 ? t->rows : std::min<int64_t>(n, t->rows), false, nullptr);
   }
@@ -684,6 +787,15 @@ int b2_exec_host_source_push(b2_handle source, const b2_host_column* cols, int32
   s->batches.push_back(std::move(b));
   B2_CATCH
 }
+int b2_exec_expand(b2_handle child, const b2_handle* projection_programs, int32_t nprojections, b2_handle* out) {
+  B2_TRY
+  B2_CHECK(nprojections >= 1, "expand needs at least one projection");
+  auto* e = new GpuExpandExec();
+  e->add_child(exec_from(child));
+  e->projections.assign(projection_programs, projection_programs + nprojections);
+  *out = to_handle(e);
+  B2_CATCH
+}
 int b2_exec_project(b2_handle child, b2_handle program, b2_handle* out) {
   B2_TRY
   auto* e = new GpuProjectExec();
@@ -724,6 +836,13 @@ int b2_exec_shuffled_hash_join_select(b2_handle stream_child, b2_handle build_ch
   e->pruned = true;
   e->stream_out.assign(stream_out, stream_out + nstream_out); e->build_out.assign(build_out, build_out + nbuild_out);
   *out = to_handle(e);
+  B2_CATCH
+}
+int b2_exec_join_set_condition(b2_handle join, b2_handle condition_program) {
+  B2_TRY
+  auto* j = dynamic_cast<GpuShuffledHashJoinExec*>(exec_from(join));
+  B2_CHECK(j, "not a hash join node");
+  j->condition = condition_program;
   B2_CATCH
 }
 int b2_exec_broadcast_exchange(b2_handle child, b2_handle comm, int32_t rank, int32_t world, b2_handle* out) {

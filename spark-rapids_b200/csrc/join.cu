@@ -196,6 +196,30 @@ __global__ void append_unmatched_kernel(const uint8_t* __restrict__ matched, con
     if (!matched[i]) { left_map[base + pos[i]] = INT32_MIN; right_map[base + pos[i]] = (int32_t)i; }
 }
 
+// ---- mixed (conditional) joins: which stream rows own at least one pair that passes the join condition ------------------------
+__global__ void mark_passing_kernel(const int32_t* __restrict__ left_map, const int8_t* __restrict__ pass, const uint32_t* __restrict__ pass_valid, int64_t n,
+                                    int8_t* __restrict__ flags) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (pass[i] && row_valid(pass_valid, i)) flags[left_map[i]] = 1;
+}
+__global__ void invert_flags_kernel(int8_t* __restrict__ flags, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) flags[i] = flags[i] ? 0 : 1;
+}
+// BOOL8 column over the stream rows: 1 where some (stream row, build row) pair of the equi-join passed the condition
+// (invert: 1 where none did)
+Column* rows_with_passing_pair(const Column* left_map, const Column* pass, int64_t stream_rows, bool invert) {
+  ColGuard flags(new_column(B2_BOOL8, 0, stream_rows, false));
+  if (stream_rows) CUDA_CHECK(cudaMemsetAsync(flags.c->data.p, 0, (size_t)stream_rows, stream()));
+  if (left_map->size) {
+    mark_passing_kernel<<<grid_for(left_map->size, 256), 256, 0, stream()>>>(left_map->data.as<int32_t>(), pass->data.as<int8_t>(), pass->validity(), left_map->size,
+                                                                              flags.c->data.as<int8_t>());
+    count_launch();
+  }
+  if (invert && stream_rows) { invert_flags_kernel<<<grid_for(stream_rows, 256), 256, 0, stream()>>>(flags.c->data.as<int8_t>(), stream_rows); count_launch(); }
+  CUDA_CHECK(cudaGetLastError());
+  return flags.release();
+}
+
 static JoinTable* jt_from(b2_handle h) {
   if (!h) throw Error(B2_ERR_INVALID, "null hash table handle");
   return reinterpret_cast<JoinTable*>((intptr_t)h);

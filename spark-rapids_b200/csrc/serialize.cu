@@ -14,6 +14,7 @@
 //   padding to 64, then for every column: validity (LSB-first bits, absent when null_count == 0) | offsets (int32,
 //   rebased to 0, STRING only) | data — each padded to a multiple of 64 bytes.
 #include <algorithm>
+#include <deque>
 #include "common.cuh"
 
 namespace b2 {
@@ -126,7 +127,7 @@ int b2_deserialize_concat(const uint8_t* const* bufs, const int64_t* lens, int32
   for (int b = 0; b < nbufs; b++) cur[b] = pad64i((int64_t)sizeof(SerHeader) + (int64_t)ncols * (int64_t)sizeof(SerCol));
   ColsGuard outs;
   cudaStream_t s = stream();
-  std::vector<std::vector<uint8_t>> staging;   // host concatenations stay alive until the copies are done
+  std::deque<std::vector<uint8_t>> staging;   // host concatenations stay alive until the copies are done (deque: references stay valid)
   for (int i = 0; i < ncols; i++) {
     const int dtype = cs[0][i].dtype;
     int64_t nulls = 0, chars = 0;

@@ -400,6 +400,13 @@ static Table* top_n_select(const Table* t, const b2_order_by_arg* keys, int nkey
 }
 
 
+// GpuTopN (limit.scala:234-330): the first `limit` rows of the sorted batch — radix select when it pays, else a full sort
+Table* top_n_table(const Table* t, const b2_order_by_arg* keys, int nkeys, int64_t limit) {
+  if (Table* sel = top_n_select(t, keys, nkeys, limit)) return sel;
+  DevBuf perm = sort_order(t, keys, nkeys);
+  return gather_table(t, perm.as<int32_t>(), std::min<int64_t>(limit, t->rows), false, nullptr);
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -428,9 +435,7 @@ int b2_top_n(b2_handle table, const b2_order_by_arg* keys, int32_t nkeys, int64_
   // GpuTopN (limit.scala:234-330): the first n rows of the sorted batch
   Table* t = table_from(table);
   B2_CHECK(n >= 0, "negative limit");
-  if (Table* sel = top_n_select(t, keys, nkeys, n)) { *out_table = to_handle(sel); return B2_OK; }
-  DevBuf perm = sort_order(t, keys, nkeys);
-  *out_table = to_handle(gather_table(t, perm.as<int32_t>(), std::min<int64_t>(n, t->rows), false, nullptr));
+  *out_table = to_handle(top_n_table(t, keys, nkeys, n));
   B2_CATCH
 }
 

@@ -116,6 +116,13 @@ def GpuProjectExec(project_list, child):
     return _new(lib.b2_exec_project, child.h, prog.h, keep=[prog, child])
 
 
+def GpuExpandExec(projections, child):
+    """projections: list of expression lists (same output types); output = every batch projected by each, stacked"""
+    progs = [p if isinstance(p, m.Program) else m.Program(p) for p in projections]
+    arr = (ctypes.c_int64 * len(progs))(*[p.h.value for p in progs])
+    return _new(lib.b2_exec_expand, child.h, arr, len(progs), keep=progs + [child])
+
+
 def GpuHashAggregateExec(child, grouping, aggregates, pre_project=None, condition=None, mode="partial"):
     """mode 'partial'/'complete': update aggregates over `pre_project` expressions (with `condition`
     fused in as the child filter); 'final': merge aggregation buffers whose keys lead the input."""
@@ -130,8 +137,18 @@ def GpuHashAggregateExec(child, grouping, aggregates, pre_project=None, conditio
                 m._agg_specs(aggregates), len(aggregates), keep=[prog, child])
 
 
-def GpuShuffledHashJoinExec(stream_keys, build_keys, join_type, stream, build, nulls_equal=False, stream_out=None, build_out=None):
-    """stream_out / build_out: columns a pruning GpuProjectExec above the join keeps (fused into the gathers)"""
+def GpuShuffledHashJoinExec(stream_keys, build_keys, join_type, stream, build, nulls_equal=False, stream_out=None, build_out=None, condition=None):
+    """stream_out / build_out: columns a pruning GpuProjectExec above the join keeps (fused into the gathers);
+    condition: non-equi join condition (Expr / Program) bound over [stream columns ++ build columns] (mixed join)"""
+    e = _hash_join(stream_keys, build_keys, join_type, stream, build, nulls_equal, stream_out, build_out)
+    if condition is not None:
+        prog = condition if isinstance(condition, m.Program) else m.Program([condition])
+        check(lib.b2_exec_join_set_condition(e.h, prog.h))
+        e._keep.append(prog)
+    return e
+
+
+def _hash_join(stream_keys, build_keys, join_type, stream, build, nulls_equal, stream_out, build_out):
     if stream_out is not None or build_out is not None:
         so, bo = list(stream_out or []), list(build_out or [])
         return _new(lib.b2_exec_shuffled_hash_join_select, stream.h, build.h, m._i32s(stream_keys), m._i32s(build_keys), len(stream_keys), join_type,

@@ -193,3 +193,60 @@ def test_join_exec_output_pruning(b2):
     only_stream = E.GpuShuffledHashJoinExec([0], [0], b2.JOIN_INNER, E.GpuBatchSource(batches(b2, stream, 3)), E.GpuBatchSource(batches(b2, build, 1)),
                                             stream_out=[1], build_out=[]).collect()
     assert sorted(r[0] for r in only_stream.to_rows()) == sorted(r[1] for r in full.to_rows())
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_mixed_join_condition(b2, kind):
+    """Table.mixed*JoinGatherMaps (GpuHashJoin.scala:335-600): equi keys + a non-equi condition over both sides
+    (TPC-H q21 shape: l2.l_orderkey = l1.l_orderkey AND l2.l_suppkey <> l1.l_suppkey), vs a nested-loop restatement"""
+    from spark_rapids_b200 import execs as E
+    rng = np.random.default_rng(50 + kind)
+    i64 = (O.INT64, 0, 0)
+    ns, nb = 4000, 1500
+    stream = [O.OCol(rng.integers(0, 600, ns).astype(np.int64), rng.random(ns) > 0.03, i64), O.OCol(rng.integers(0, 8, ns).astype(np.int64), np.ones(ns, bool), i64),
+              O.OCol(np.arange(ns, dtype=np.int64), np.ones(ns, bool), i64)]
+    build = [O.OCol(rng.integers(0, 600, nb).astype(np.int64), rng.random(nb) > 0.03, i64), O.OCol(rng.integers(0, 8, nb).astype(np.int64), rng.random(nb) > 0.1, i64)]
+    cond = b2.col(1, b2.INT64) != b2.col(4, b2.INT64)          # stream.supp <> build.supp (pair columns: 3 stream ++ 2 build)
+    j = E.GpuShuffledHashJoinExec([0], [0], kind, E.GpuBatchSource(batches(b2, stream, 3)), E.GpuBatchSource(batches(b2, build, 2)), condition=cond)
+    out = j.collect()
+    got = out.to_rows() if out is not None else []
+    exp = []
+    bk = {}
+    for k, s, ok, sok in zip(build[0].values, build[1].values, build[0].valid, build[1].valid):
+        if ok:
+            bk.setdefault(int(k), []).append((int(k), int(s) if sok else None))
+    for k, s, i, ok in zip(stream[0].values, stream[1].values, stream[2].values, stream[0].valid):
+        srow = (int(k) if ok else None, int(s), int(i))
+        hits = [b for b in bk.get(int(k), [])] if ok else []
+        passing = [b for b in hits if b[1] is not None and b[1] != int(s)]     # NULL <> x is NULL -> not a match
+        if kind == 0:
+            exp += [srow + b for b in passing]
+        elif kind == 1:
+            exp += [srow + b for b in passing] if passing else [srow + (None, None)]
+        elif kind == 2 and passing:
+            exp.append(srow)
+        elif kind == 3 and not passing:
+            exp.append(srow)
+    key = lambda r: tuple((x is None, x) for x in r)
+    assert sorted(got, key=key) == sorted(exp, key=key)
+
+
+def test_expand_exec_two_count_distincts(b2):
+    """GpuExpandExec: the plan shape of `select count(distinct a), count(distinct b)`: expand to (a, NULL, 1) / (NULL, b, 2),
+    group by (a, b, gid), then count per gid"""
+    from spark_rapids_b200 import execs as E
+    rng = np.random.default_rng(31)
+    i64, i32 = (O.INT64, 0, 0), (O.INT32, 0, 0)
+    n = 5000
+    a, b = G.gen_column(rng, i64, n, distinct=37, null_frac=0.1), G.gen_column(rng, i64, n, distinct=91, null_frac=0.05)
+    ca, cb = G.b2_expr_col(b2, 0, a), G.b2_expr_col(b2, 1, b)
+    null64 = b2.lit(None, b2.INT64)
+    ex = E.GpuExpandExec([[ca, null64, b2.lit(1, b2.INT32)], [null64, cb, b2.lit(2, b2.INT32)]], E.GpuBatchSource(batches(b2, [a, b], 3)))
+    rows = [r for t in ex for r in t.to_rows()]
+    assert len(rows) == 2 * n
+    exp = [(x, None, 1) for x in a.to_pylist()] + [(None, y, 2) for y in b.to_pylist()]
+    key = lambda r: tuple((x is None, x) for x in r)
+    assert sorted(rows, key=key) == sorted(exp, key=key)
+    da = len({x for x in a.to_pylist() if x is not None}); db = len({y for y in b.to_pylist() if y is not None})
+    distinct = {r for r in rows}
+    assert sum(1 for r in distinct if r[2] == 1 and r[0] is not None) == da and sum(1 for r in distinct if r[2] == 2 and r[1] is not None) == db

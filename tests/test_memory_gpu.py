@@ -91,15 +91,24 @@ def test_join_exec_splits_and_retries_under_memory_pressure(b2, limits):
     del ref
     b2.sync()
     s0 = b2.memory_stats()
-    # the whole stream batch needs ~2 x 4 MiB of maps + 4 x 4 MiB of gathered columns; leave room for about half of that
-    b2.set_alloc_limit(b2.device_bytes_in_use() + (14 << 20))
+    # the whole stream batch needs 2 x 2 MiB of maps + 4 x 4 MiB of gathered columns = 20 MiB at its peak; 14 MiB force a split
+    # (each half peaks at 10 MiB + its 4 MiB slice; the consumer drops every output batch before asking for the next)
+    b2.set_alloc_limit(b2.device_bytes_in_use() + (15 << 20))
     j = E.GpuShuffledHashJoinExec([0], [0], b2.JOIN_INNER, E.GpuBatchSource([st]), E.GpuBatchSource([bt]))
-    outs = list(j)
+    got, nout = [], 0
+    while True:
+        t = j.next()
+        if t is None:
+            break
+        b2.set_alloc_limit(0)           # reading the batch back needs no device memory, but keep the limit out of the way
+        got += t.to_rows(); nout += 1
+        del t
+        b2.sync()
+        b2.set_alloc_limit(b2.device_bytes_in_use() + (15 << 20))
     b2.set_alloc_limit(0)
     s1 = b2.memory_stats()
-    assert s1["splits"] > s0["splits"] and len(outs) >= 2, (s0, s1, len(outs))
-    got = sorted(r for t in outs for r in t.to_rows())
-    assert got == exp
+    assert s1["splits"] > s0["splits"] and nout >= 2, (s0, s1, nout)
+    assert sorted(got) == exp
 
 
 def test_semaphore_bounds_concurrent_tasks(b2, limits):

@@ -226,7 +226,7 @@ def test_parquet_chunked_reader_row_group_chunks(b2):
     cols = entry["columns"]
     whole = b2.parquet_decode(raw, cols).to_rows()
     assert b2.parquet_num_row_groups(raw) == 10
-    for limit, min_chunks in [(0, 1), (1, 10), (40_000, 2), (10**9, 1)]:
+    for limit, min_chunks in [(0, 1), (1, 10), (5_000, 2), (10**9, 1)]:
         rd = b2.ParquetChunkedReader(raw, cols, limit)
         rows, nchunks = [], 0
         for t in rd:
