@@ -40,6 +40,7 @@ SF10_ROWS = 59_986_052
 COLS = ["l_shipdate", "l_discount", "l_quantity", "l_extendedprice"]
 CACHE = os.environ.get("B2_BENCH_CACHE", "/tmp/b2_bench_cache")
 NVLINK_GBS = 900.0   # NVLink 5 per direction per GPU (SURVEY §8d exchange roofline)
+Q3_WORKLOAD = "TPC-H SF%g q3 (3 filters, customer JOIN orders JOIN lineitem, group-by (l_orderkey, o_orderdate, o_shippriority), top-10)"
 
 
 def hbm_peak():
@@ -238,7 +239,7 @@ def run_reference(args, rank, world):
         for _ in range(args.steps):
             res = tpch.q6_cpu(raw, cores)
         dt = time.perf_counter() - t0
-        rows, name, cfg = args.rows, "tpch_q6_rows_per_sec", {"workload": "TPC-H SF10 q6 (scan+filter+agg), Parquet source, CPU plan", "rows": args.rows, "result": res}
+        rows, name, cfg = args.rows, "tpch_q6_rows_per_sec", {"workload": "TPC-H SF10 q6 (scan+filter+agg), Parquet source (snappy, dictionary, INT64 decimals)", "rows": args.rows, "result": res}
         sample = "full %d-row partition per step; pyarrow %d threads (CPU restatement, NOT Spark)" % (rows, cores)
     else:
         from benchdata import tpch as gen
@@ -255,7 +256,7 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t0
         args.steps = steps
         name = "tpch_q3_rows_per_sec"
-        cfg = {"workload": "TPC-H SF100 q3 (3-way hash join + group-by + top-10), CPU plan on the SF%g sample of the same generator" % sf,
+        cfg = {"workload": Q3_WORKLOAD % args.sf, "sf": args.sf, "cpu_plan": "pyarrow Acero on all host cores over the SF%g instance of the same generator (bounded sample)" % sf,
                "sample_sf": sf, "lineitem_rows_per_step": rows, "result_top1": res[0] if res else None}
         sample = "SF%g instance of the synthetic q3 tables (%d lineitem rows) per step, columns cached in host memory; pyarrow Acero on %d threads " \
                  "(CPU restatement, NOT Spark)" % (sf, rows, cores)
@@ -504,7 +505,7 @@ def bench_q3(ctx):
     line = {"metric": "tpch_q3_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "query_sec": ms / args.steps / 1000, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int64/decimal128", "data": "synthetic",
-            "config": {"workload": "TPC-H SF%g q3 (3 filters, customer JOIN orders JOIN lineitem, group-by (l_orderkey, o_orderdate, o_shippriority), top-10)" % sf,
+            "config": {"workload": Q3_WORKLOAD % sf,
                        "sf": sf, "rows": rows_all, "input_bytes_per_gpu": int(in_bytes), "batches_per_gpu": {t: len(chunks[t]) for t in chunks},
                        "l2": "inputs larger than L2 (%.1f GB of input columns per GPU per step)" % (in_bytes / 1e9),
                        "result_top1": res[0] if res else None, "datagen_s": gen_s,

@@ -35,9 +35,9 @@ for path in args:
                     pass
         stalls = {}
         for i, h in enumerate(hdr):
-            if h.startswith("smsp__average_warp") and "issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
                 try:
-                    stalls[h.split("issue_stalled_")[1].split("_per_warp")[0]] = float(r[i])
+                    stalls[h.split("issue_stalled_")[1].split("_per_issue")[0]] = float(r[i])
                 except ValueError:
                     pass
         top = sorted(stalls.items(), key=lambda kv: -kv[1])[:6]
@@ -58,12 +58,12 @@ for path in args:
                      "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"), "warp_instructions": val("smsp__inst_executed.sum"),
                      "registers_per_thread": val("launch__registers_per_thread"), "grid": val("launch__grid_size"), "block": val("launch__block_size"),
                      "smem_dynamic": val("launch__shared_mem_per_block_dynamic"), "smem_static": val("launch__shared_mem_per_block_static"),
-                     "top_stalls_pct_of_warp_active": top, "source": path}
+                     "top_stalls_cycles_per_issue": top, "source": path}
         e = out[name]
         print("%s\n  duration %.3f ms (cold-cache, under ncu)  DRAM read %.1f MB + write %.1f MB = %.1f MB  -> %.0f GB/s (%.1f %% of peak)  L2 %.1f %% of peak, hit rate %.1f %%"
               % (name, dur, e["dram_read_bytes"] / 1e6, e["dram_write_bytes"] / 1e6, traffic / 1e6, e["dram_GBps"] or 0, e["dram_pct_of_peak"], e["l2_pct_of_peak"], e["l2_hit_rate_pct"]))
         print("  grid %d x %d threads, %d regs/thread, smem %d + %d B; warps active %.1f %%, issue slots busy %.1f %%, %.3g warp instructions"
               % (e["grid"], e["block"], e["registers_per_thread"], e["smem_dynamic"], e["smem_static"], e["warps_active_pct"], e["issue_active_pct"], e["warp_instructions"]))
-        print("  stalls (%% of active warp cycles): " + ", ".join("%s %.1f" % kv for kv in top))
+        print("  stalls (warp cycles stalled per issued instruction): " + ", ".join("%s %.2f" % kv for kv in top))
 if jpath:
     json.dump(out, open(jpath, "w"), indent=1)

@@ -196,18 +196,32 @@ __device__ __forceinline__ void xs_move_column(const XPlan& pl, int c, const T* 
     if (i < n) stage[lpos[j]] = in[pl.sel ? (int64_t)pl.sel[i] : i];
   }
   __syncthreads();
-  // ... then stream each destination's run out with consecutive lanes on consecutive addresses (full NVLink packets)
-  for (int k = threadIdx.x; k < tile_n; k += XS_NT) {
+  // ... then stream each destination's run out with consecutive lanes on consecutive addresses.  Elements are moved 16 bytes
+  // at a time wherever a whole vector belongs to one destination and lands 16-byte aligned there (runs are long, so nearly
+  // always): 512 contiguous bytes per warp store, the shape NVLink carries at full rate
+  constexpr int V = sizeof(T) >= 16 ? 1 : 16 / (int)sizeof(T);
+  for (int k0 = threadIdx.x * V; k0 < tile_n; k0 += XS_NT * V) {
     int p = 0;
-    while (p + 1 < pl.W && k >= s_start[p + 1]) p++;
-    const long long dest = s_base[p] + (k - s_start[p]);
-    if (dest < pl.cap) reinterpret_cast<T*>(pl.arena[p] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c])[dest] = stage[k];
+    while (p + 1 < pl.W && k0 >= s_start[p + 1]) p++;
+    const long long dest = s_base[p] + (k0 - s_start[p]);
+    T* out = reinterpret_cast<T*>(pl.arena[p] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c]);
+    const bool whole = V > 1 && k0 + V <= tile_n && k0 + V <= s_start[p + 1] && (dest % V) == 0 && dest + V <= pl.cap;
+    if (whole) {
+      *reinterpret_cast<uint4*>(out + dest) = *reinterpret_cast<const uint4*>(stage + k0);
+    } else {
+      for (int k = k0; k < k0 + V && k < tile_n; k++) {
+        int q = p;
+        while (q + 1 < pl.W && k >= s_start[q + 1]) q++;
+        const long long d = s_base[q] + (k - s_start[q]);
+        if (d < pl.cap) reinterpret_cast<T*>(pl.arena[q] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c])[d] = stage[k];
+      }
+    }
   }
   __syncthreads();
   (void)pid;
 }
 
-__global__ void __launch_bounds__(XS_NT) xchg_scatter_kernel(const __grid_constant__ KeyCols keys, const __grid_constant__ XPlan pl, int64_t n, uint32_t seed,
+__global__ void __launch_bounds__(XS_NT, 5) xchg_scatter_kernel(const __grid_constant__ KeyCols keys, const __grid_constant__ XPlan pl, int64_t n, uint32_t seed,
                                                              unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) char stage_raw[];   // XS_TILE * widest column
   __shared__ int s_cnt[XMAX_W], s_start[XMAX_W + 1], s_cur[XMAX_W];

@@ -126,13 +126,20 @@ __device__ __forceinline__ void ps_move(const T* __restrict__ in, T* __restrict_
     if (i < n) stage[lpos[r]] = in[i];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < tile_n; k += PT_NT) {
-    const int p = s_owner[k];
-    out[s_gbase[p] + (k - s_start[p])] = stage[k];
+  // 16 bytes per store wherever a whole vector belongs to one partition and lands aligned (runs average 16+ rows)
+  constexpr int V = sizeof(T) >= 16 ? 1 : 16 / (int)sizeof(T);
+  for (int k0 = threadIdx.x * V; k0 < tile_n; k0 += PT_NT * V) {
+    const int p = s_owner[k0];
+    const int64_t dest = (int64_t)s_gbase[p] + (k0 - s_start[p]);
+    if (V > 1 && k0 + V <= tile_n && s_owner[k0 + V - 1] == p && (dest % V) == 0) {
+      *reinterpret_cast<uint4*>(out + dest) = *reinterpret_cast<const uint4*>(stage + k0);
+    } else {
+      for (int k = k0; k < k0 + V && k < tile_n; k++) { const int q = s_owner[k]; out[s_gbase[q] + (k - s_start[q])] = stage[k]; }
+    }
   }
   __syncthreads();
 }
-__global__ void __launch_bounds__(PT_NT) part_scatter2_kernel(const int32_t* __restrict__ pids, int64_t n, int32_t nparts, int64_t ntiles,
+__global__ void __launch_bounds__(PT_NT, 4) part_scatter2_kernel(const int32_t* __restrict__ pids, int64_t n, int32_t nparts, int64_t ntiles,
                                                               const int32_t* __restrict__ base, const __grid_constant__ ScatterCols sc) {
   extern __shared__ __align__(16) char ps_stage[];    // PT_TILE x widest array
   __shared__ uint32_t s_wh[PS_WARPS][256];
