@@ -299,6 +299,21 @@ __global__ void __launch_bounds__(XS_NT, 5) xchg_scatter_kernel(const __grid_con
   }
 }
 
+// receiver side: all (source region, column) segments of one exchange call copied out of the arena by ONE kernel
+// (W x ncols cudaMemcpyAsync calls would cost more in launch latency than in bytes at W = 8)
+struct CopySeg { const char* src; char* dst; int64_t bytes; };
+__global__ void xchg_copy_out_kernel(const CopySeg* __restrict__ segs, int nsegs) {
+  for (int sgi = blockIdx.y; sgi < nsegs; sgi += gridDim.y) {
+    const CopySeg sg = segs[sgi];
+    const uintptr_t a = (uintptr_t)sg.src | (uintptr_t)sg.dst | (uintptr_t)sg.bytes;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    if ((a & 15) == 0) { for (int64_t i = t0; i < sg.bytes / 16; i += step) reinterpret_cast<uint4*>(sg.dst)[i] = reinterpret_cast<const uint4*>(sg.src)[i]; }
+    else if ((a & 7) == 0) { for (int64_t i = t0; i < sg.bytes / 8; i += step) reinterpret_cast<uint64_t*>(sg.dst)[i] = reinterpret_cast<const uint64_t*>(sg.src)[i]; }
+    else if ((a & 3) == 0) { for (int64_t i = t0; i < sg.bytes / 4; i += step) reinterpret_cast<uint32_t*>(sg.dst)[i] = reinterpret_cast<const uint32_t*>(sg.src)[i]; }
+    else { for (int64_t i = t0; i < sg.bytes; i += step) sg.dst[i] = sg.src[i]; }
+  }
+}
+
 // receiver side: validity bytes of one source region -> bits at an arbitrary row offset of the output mask (pre-zeroed)
 __global__ void bytes_to_bits_at_kernel(const uint8_t* __restrict__ in, int64_t n, uint32_t* __restrict__ bits, int64_t start) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -590,14 +605,16 @@ int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, c
   }
   {
     KernelTimer kt("xchg_copy_out");
-    int64_t row = 0;
+    std::vector<CopySeg> segs;
+    int64_t row = 0, biggest = 0;
     for (int r = 0; r < W; r++) {
       const int64_t cnt = (int64_t)all[r].counts[me];
       if (!cnt) continue;
       const char* region = c->arena_local[parity] + (int64_t)r * L.region_bytes;
       for (int i = 0; i < hdr.ncols; i++) {
         Column* oc = outs.v[i];
-        CUDA_CHECK(cudaMemcpyAsync(oc->data.as<char>() + row * widths[i], region + L.col_off[i], (size_t)cnt * widths[i], cudaMemcpyDeviceToDevice, s));
+        segs.push_back({region + L.col_off[i], oc->data.as<char>() + row * widths[i], cnt * widths[i]});
+        biggest = std::max(biggest, cnt * widths[i]);
         if (oc->valid.p) {
           const uint8_t* vb = ((all[r].nullable_mask >> i) & 1u) ? reinterpret_cast<const uint8_t*>(region + L.val_off[i]) : nullptr;
           bytes_to_bits_at_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(vb, cnt, oc->valid.as<uint32_t>(), row);
@@ -605,6 +622,16 @@ int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, c
         }
       }
       row += cnt;
+    }
+    if (!segs.empty()) {
+      DevBuf d_segs(segs.size() * sizeof(CopySeg));
+      h2d_bytes(d_segs.p, segs.data(), segs.size() * sizeof(CopySeg));
+      const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((biggest / 16 + 255) / 256, (int64_t)sm_count() * 4));
+      const int gy = (int)std::min<size_t>(segs.size(), 64);
+      xchg_copy_out_kernel<<<dim3(gx, gy), 256, 0, s>>>(d_segs.as<CopySeg>(), (int)segs.size());
+      count_launch();
+      CUDA_CHECK(cudaGetLastError());
+      // d_segs is stream-ordered: freed after the kernel
     }
     CUDA_CHECK(cudaGetLastError());
   }

@@ -513,10 +513,13 @@ Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, i
 
 // selection vector: the row ids that pass the predicate, in order, and nothing else (late materialisation: a join probe or
 // an exchange scatter directly above the filter reads the batch through it instead of through a compacted copy)
+bool simple_filter_row_ids(const Program* prog, const Table* t, Column** out);   // simplefilter.cu
 Column* filter_row_ids(const Program* prog, const Table* t) {
   check_program_inputs(prog, t);
   B2_CHECK(prog->hdr.nouts >= 1 && prog->out_dtype[0] == B2_BOOL8, "filter predicate must be a single BOOL8 expression");
   const int64_t n = t->rows;
+  Column* fast = nullptr;
+  if (simple_filter_row_ids(prog, t, &fast)) return fast;   // conjunction of column-vs-literal comparisons: no VM
   VMInputs in; fill_inputs(in, t);
   FilterCols fc; memset(&fc, 0, sizeof(fc));
   ColGuard ids(new_column(B2_INT32, 0, n, false));

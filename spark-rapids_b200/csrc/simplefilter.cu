@@ -1,0 +1,167 @@
+// simplefilter.cu — fast path of GpuFilter's selection vector (basicPhysicalOperators.scala:1148-1224) for the commonest
+// predicate shape: a conjunction of comparisons between NOT NULL fixed-width integer columns (ints, dates, timestamps,
+// DECIMAL32/64) and literals — date ranges, key bounds, flags (TPC-H q3: o_orderdate < d, l_shipdate > d; q6's five terms).
+// The general path interprets the predicate in the expression VM (vm.cuh) one 4096-row tile at a time; here the compiled
+// program is pattern-matched on the host and a specialised kernel streams the columns with 16-byte loads, 16 consecutive
+// rows per thread, keeps the per-thread result as a bit mask and writes the selected row ids in order (single pass:
+// block scan + decoupled look-back across tiles).  Anything that does not match the shape returns false and takes the VM.
+#include "prim.cuh"
+#include "vm.cuh"
+
+namespace b2 {
+
+constexpr int SF_NT = 256, SF_ROWS = 16, SF_TILE = SF_NT * SF_ROWS, SF_MAX_TERMS = 8;
+struct SimpleTerm { const void* col; int32_t width; int32_t truth; int64_t lit; };   // truth: bit0 '<', bit1 '==', bit2 '>'
+struct SimplePred { int32_t n; int32_t pad; SimpleTerm t[SF_MAX_TERMS]; };
+struct SimpleWork { unsigned long long tile_counter, total; };
+
+constexpr uint64_t SLB_AGG = 1ull << 62, SLB_PREFIX = 2ull << 62, SLB_MASK = (1ull << 62) - 1;
+__device__ __forceinline__ uint64_t sf_ld(const uint64_t* p) { uint64_t v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void sf_st(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+// decoupled look-back over per-tile counts (same protocol as scan.cu); called by warp 0
+__device__ __forceinline__ int64_t sf_lookback(uint64_t* status, int64_t tile, uint32_t count) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) { if (lane == 0) { __threadfence(); sf_st(&status[0], SLB_PREFIX | count); } return 0; }
+  if (lane == 0) { __threadfence(); sf_st(&status[tile], SLB_AGG | count); }
+  int64_t excl = 0, look = tile - 1;
+  while (true) {
+    const int64_t idx = look - lane;
+    uint64_t v;
+    if (idx >= 0) { do { v = sf_ld(&status[idx]); } while ((v >> 62) == 0); } else v = SLB_PREFIX;
+    const uint32_t is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+    const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
+    int64_t contrib = (lane <= first) ? (int64_t)(v & SLB_MASK) : 0;
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    excl += contrib;
+    if (is_prefix) break;
+    look -= 32;
+  }
+  if (lane == 0) { __threadfence(); sf_st(&status[tile], SLB_PREFIX | (uint64_t)(excl + count)); }
+  return excl;
+}
+
+// 16 consecutive values of a column as signed 64-bit, through 16-byte loads (row0 is a multiple of 16: every access is aligned)
+template <typename T>
+__device__ __forceinline__ void sf_load16(const void* col, int64_t row0, int64_t v[SF_ROWS]) {
+  constexpr int PER = 16 / (int)sizeof(T);
+  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(col) + row0);
+#pragma unroll
+  for (int q = 0; q < SF_ROWS / PER; q++) {
+    const uint4 w = __ldg(p + q);
+    const T* e = reinterpret_cast<const T*>(&w);
+#pragma unroll
+    for (int k = 0; k < PER; k++) v[q * PER + k] = (int64_t)e[k];
+  }
+}
+
+__global__ void __launch_bounds__(SF_NT) simple_filter_ids_kernel(const __grid_constant__ SimplePred sp, int64_t n, int32_t* __restrict__ ids,
+                                                                  uint64_t* __restrict__ status, SimpleWork* __restrict__ work) {
+  __shared__ uint32_t s_w[SF_NT / 32];
+  __shared__ int64_t s_tile, s_excl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ntiles = (n + SF_TILE - 1) / SF_TILE;
+  while (true) {
+    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(&work->tile_counter, 1ull);   // tiles in launch order: look-back never waits on an unstarted tile
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= ntiles) break;
+    const int64_t row0 = tile * SF_TILE + (int64_t)threadIdx.x * SF_ROWS;
+    uint32_t m = 0;
+    if (row0 < n) {
+      m = row0 + SF_ROWS <= n ? 0xffffu : (0xffffu >> (SF_ROWS - (int)(n - row0)));   // the last rows of the column
+      for (int k = 0; k < sp.n; k++) {
+        const SimpleTerm t = sp.t[k];
+        int64_t v[SF_ROWS];
+        // columns are padded to 64 B, so the 16-byte loads of a partial last group stay inside the allocation
+        switch (t.width) {
+          case 1: sf_load16<int8_t>(t.col, row0, v); break;
+          case 2: sf_load16<int16_t>(t.col, row0, v); break;
+          case 4: sf_load16<int32_t>(t.col, row0, v); break;
+          default: sf_load16<int64_t>(t.col, row0, v); break;
+        }
+        uint32_t tm = 0;
+#pragma unroll
+        for (int j = 0; j < SF_ROWS; j++) {
+          const int c = v[j] < t.lit ? 1 : (v[j] == t.lit ? 2 : 4);
+          tm |= (uint32_t)((t.truth & c) != 0) << j;
+        }
+        m &= tm;
+      }
+    }
+    const uint32_t cnt = __popc(m);
+    uint32_t inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < SF_NT / 32 ? s_w[lane] : 0, winc = w;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += x; }
+      if (lane < SF_NT / 32) s_w[lane] = winc - w;
+      const uint32_t total = __shfl_sync(0xffffffffu, winc, 31);
+      const int64_t excl = sf_lookback(status, tile, total);
+      if (lane == 0) { s_excl = excl; if (tile == ntiles - 1) work->total = (unsigned long long)(excl + total); }
+    }
+    __syncthreads();
+    int64_t pos = s_excl + s_w[warp] + (inc - cnt);
+    for (uint32_t mm = m; mm; mm &= mm - 1) ids[pos++] = (int32_t)(row0 + (__ffs(mm) - 1));
+    __syncthreads();   // s_tile / s_w are rewritten by the next iteration
+  }
+}
+
+// pattern match: output 0 = c0 AND c1 AND ... with c_i = (NOT NULL fixed-width integer column) <cmp> (non-null literal)
+static bool simple_pred_of(const Program* prog, const Table* t, SimplePred& sp) {
+  memset(&sp, 0, sizeof(sp));
+  const int n = prog->hdr.ninstr;
+  if (prog->hdr.nouts != 1 || n < 1 || n > SF_MAX_TERMS || (int)prog->code.size() != n) return false;
+  static const int truth_of[6] = {2, 5, 1, 3, 4, 6};   // EQ NE LT LE GT GE over {<, ==, >}
+  int prev_dst = -1;
+  for (int i = 0; i < n; i++) {
+    const VMInstr& ins = prog->code[i];
+    int truth;
+    if (i == 0) { if (ins.op < V_EQ || ins.op > V_GE || ins.dst_nullable) return false; truth = truth_of[ins.op - V_EQ]; }
+    else { if (ins.op != V_ANDCMP || ins.c.kind != OK_REG || ins.c.idx != prev_dst) return false; truth = ins.aux; }
+    if (ins.mt != MT_I8 && ins.mt != MT_I16 && ins.mt != MT_I32 && ins.mt != MT_I64) return false;
+    if (ins.a.kind != OK_COL || ins.b.kind != OK_LIT || ins.b.lit_null) return false;
+    if (ins.a.idx < 0 || ins.a.idx >= (int)t->cols.size()) return false;
+    const Column* c = t->cols[ins.a.idx];
+    if (c->nullable() || c->dtype == B2_STRING || c->dtype == B2_BOOL8 || is_float(c->dtype) || dtype_width(c->dtype) != mt_width(ins.mt)) return false;
+    sp.t[i].col = c->data.p; sp.t[i].width = mt_width(ins.mt); sp.t[i].truth = truth;
+    // literals are stored sign-extended to 64 bits (b2_expr_literal); narrower machine types compare on their own width
+    int64_t lit = ins.b.lo;
+    switch (ins.mt) { case MT_I8: lit = (int8_t)lit; break; case MT_I16: lit = (int16_t)lit; break; case MT_I32: lit = (int32_t)lit; break; default: break; }
+    sp.t[i].lit = lit;
+    prev_dst = ins.dst;
+  }
+  const VMOperand& out = prog->hdr.outs[0];
+  if (out.kind != OK_REG || out.idx != prev_dst) return false;
+  sp.n = n;
+  return true;
+}
+
+// the selection vector of `prog` over `t` through the specialised kernel; false = the predicate is not of the simple shape
+bool simple_filter_row_ids(const Program* prog, const Table* t, Column** out) {
+  if (getenv("B2_FILTER_NO_SIMPLE")) return false;
+  SimplePred sp;
+  const int64_t n = t->rows;
+  if (n < (1 << 16) || !simple_pred_of(prog, t, sp)) return false;
+  ColGuard ids(new_column(B2_INT32, 0, n, false));
+  const int64_t ntiles = (n + SF_TILE - 1) / SF_TILE;
+  DevBuf work(sizeof(SimpleWork)), status((size_t)ntiles * 8);
+  CUDA_CHECK(cudaMemsetAsync(work.p, 0, sizeof(SimpleWork), stream()));
+  CUDA_CHECK(cudaMemsetAsync(status.p, 0, (size_t)ntiles * 8, stream()));
+  {
+    KernelTimer kt("simple_filter_ids_kernel");
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * 8);
+    simple_filter_ids_kernel<<<grid, SF_NT, 0, stream()>>>(sp, n, ids.c->data.as<int32_t>(), status.as<uint64_t>(), work.as<SimpleWork>());
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  SimpleWork hw;
+  d2h(&hw, work.p, 1);
+  sync();
+  ids.c->size = (int64_t)hw.total;
+  *out = ids.release();
+  return true;
+}
+
+}  // namespace b2

@@ -63,6 +63,61 @@ dist.destroy_process_group()
 '''
 
 
+Q3_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+import bench                                    # the product bench's host-side sharding (q3_host_chunks / q3_chunks_of_rank)
+from benchdata import tpch as gen
+from oracle import spark_cpu as O, spark_hash as H, tpch as T
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sf = 0.002
+chunks = bench.q3_host_chunks(sf, rank, world)   # this rank's 1/world of every table, as bench.py shards it
+def cat(table, col):
+    parts = [c[col] for c in chunks[table]]
+    return np.concatenate(parts) if parts else np.zeros(0, np.int64)
+def exchange(cols, key):                         # GpuShuffleExchangeExec: Spark Murmur3 pmod world on `key`, all-to-all
+    kc = O.OCol(cols[key].astype(np.int64), np.ones(len(cols[key]), bool), (O.INT64, 0, 0))
+    pid = H.partition_ids([kc], world) if len(cols[key]) else np.zeros(0, np.int32)
+    send = [{k: v[pid == r] for k, v in cols.items()} for r in range(world)]
+    got = []
+    for r in range(world):
+        lst = [None]
+        dist.scatter_object_list(lst, send if rank == r else None, src=r)
+        got.append(lst[0])
+    return {k: np.concatenate([g[k] for g in got]) for k in cols}
+# filters (each rank on its own slice)
+ck = []
+for c in chunks["customer"]:
+    ck.append(c["c_custkey"][c["c_mktsegment_code"] == gen.SEGMENTS.index(gen.Q3_SEGMENT)])
+cust = exchange({"c_custkey": np.concatenate(ck) if ck else np.zeros(0, np.int64)}, "c_custkey")
+om = cat("orders", "o_orderdate") < gen.Q3_DATE
+orders = exchange({k: cat("orders", k)[om] for k in ("o_orderkey", "o_custkey", "o_orderdate", "o_shippriority")}, "o_custkey")
+hit = np.isin(orders["o_custkey"], cust["c_custkey"])           # co-partitioned: the join is local
+j1 = exchange({k: orders[k][hit] for k in ("o_orderkey", "o_orderdate", "o_shippriority")}, "o_orderkey")
+lm = cat("lineitem", "l_shipdate") > gen.Q3_DATE
+line = exchange({k: cat("lineitem", k)[lm] for k in ("l_orderkey", "l_extendedprice", "l_discount")}, "l_orderkey")
+info = {int(k): (int(d), int(p)) for k, d, p in zip(j1["o_orderkey"], j1["o_orderdate"], j1["o_shippriority"])}
+rev = {}
+for k, p, d in zip(line["l_orderkey"], line["l_extendedprice"], line["l_discount"]):
+    if int(k) in info:
+        rev[int(k)] = rev.get(int(k), 0) + int(p) * (100 - int(d))
+local = sorted(((k, v) + info[k] for k, v in rev.items()), key=lambda r: (-r[1], r[2], r[0]))[:10]   # GpuTopN per rank
+alltop = [None] * world
+dist.gather_object(local, alltop if rank == 0 else None, dst=0)                                       # SinglePartition exchange
+if rank == 0:
+    final = sorted([r for t in alltop for r in t], key=lambda r: (-r[1], r[2], r[0]))[:10]
+    assert final == T.q3_expected(sf, 42, threads=2), (final,)
+    owned = [set(gen.q3_chunks_of_rank("lineitem", r, world)) for r in range(world)]
+    assert set().union(*owned) == set(range(gen.Q3_CHUNKS["lineitem"])) and sum(len(o) for o in owned) == gen.Q3_CHUNKS["lineitem"]
+    print("Q3_DIST_OK", final[0])
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
 def _torchrun(args, script_args=(), timeout=300):
     return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                            "--master-port", "29531"] + list(args) + list(script_args), capture_output=True, text=True, timeout=timeout, cwd=ROOT)
@@ -76,8 +131,18 @@ def test_partial_exchange_final_protocol_world2(tmp_path):
     assert "DIST_OK" in r.stdout
 
 
+def test_q3_strong_scaled_plan_protocol_world2(tmp_path):
+    """the bench's strong-scaled q3 (its own host-side sharding: bench.q3_host_chunks) with the exchanges emulated over gloo:
+    filters on each rank's slice, Murmur3 exchanges on the join keys, local joins, local top-10, final top-10 == numpy q3"""
+    script = tmp_path / "q3_worker.py"
+    script.write_text(Q3_WORKER % {"root": ROOT})
+    r = _torchrun([str(script)])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "Q3_DIST_OK" in r.stdout
+
+
 def test_reference_arm_under_torchrun_prints_once():
-    env_rows = ["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--rows", "200000"]
+    env_rows = ["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--ref-sf", "0.1"]
     r = _torchrun([os.path.join(ROOT, "bench.py")], env_rows)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]

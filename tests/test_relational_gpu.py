@@ -310,3 +310,42 @@ def test_join_probe_through_selection_vector(b2):
             assert glm == elm
         else:
             assert sorted(zip(glm, grm)) == sorted(zip(elm, erm))
+
+
+@pytest.mark.parametrize("n", [65536, 65536 + 1, 200_003, 1_000_000 + 15])
+def test_simple_predicate_row_ids_fast_path(b2, n, monkeypatch):
+    """conjunctions of NOT NULL integer column vs literal comparisons take the specialised kernel (simplefilter.cu); its row ids
+    equal the VM's and the numpy restatement for every width, every comparison and a ragged last tile"""
+    import ctypes
+    rng = np.random.default_rng(n)
+    cols = {
+        "i8": (rng.integers(-100, 100, n).astype(np.int8), b2.INT8),
+        "i16": (rng.integers(-3000, 3000, n).astype(np.int16), b2.INT16),
+        "i32": (rng.integers(-2**31, 2**31 - 1, n).astype(np.int32), b2.INT32),
+        "i64": (rng.integers(-2**62, 2**62, n).astype(np.int64), b2.INT64),
+        "date": (rng.integers(8000, 11000, n).astype(np.int32), b2.DATE32),
+    }
+    names = list(cols)
+    t = b2.Table.from_columns([b2.Column.from_numpy(cols[k][0], dtype=cols[k][1]) if cols[k][1] == b2.DATE32 else b2.Column.from_numpy(cols[k][0]) for k in names])
+    c = {k: b2.col(i, cols[k][1], nullable=False) for i, k in enumerate(names)}
+    v = {k: cols[k][0] for k in names}
+    cases = [
+        (c["date"] < b2.lit(9204, b2.DATE32), v["date"] < 9204),
+        ((c["date"] >= b2.lit(8500, b2.DATE32)) & (c["date"] < b2.lit(10000, b2.DATE32)) & (c["i8"] > b2.lit(-5, b2.INT8)) & (c["i16"] != b2.lit(7, b2.INT16)),
+         (v["date"] >= 8500) & (v["date"] < 10000) & (v["i8"] > -5) & (v["i16"] != 7)),
+        ((c["i64"] <= b2.lit(1 << 40, b2.INT64)) & (c["i32"] > b2.lit(-12345, b2.INT32)), (v["i64"] <= (1 << 40)) & (v["i32"] > -12345)),
+        ((c["i8"] == b2.lit(3, b2.INT8)) & (c["i64"] >= b2.lit(-(1 << 61), b2.INT64)), (v["i8"] == 3) & (v["i64"] >= -(1 << 61))),
+        (c["i32"] > b2.lit(2**31 - 1, b2.INT32), np.zeros(n, bool)),
+    ]
+    for pred, mask in cases:
+        prog = b2.Program([pred])
+        got = []
+        for env in (None, "1"):
+            if env: monkeypatch.setenv("B2_FILTER_NO_SIMPLE", env)
+            else: monkeypatch.delenv("B2_FILTER_NO_SIMPLE", raising=False)
+            ids = ctypes.c_int64()
+            b2.check(b2.lib.b2_filter_row_ids(prog.h, t.h, ctypes.byref(ids)))
+            got.append(b2.Column(ids.value).to_numpy()[0])
+        want = np.flatnonzero(mask).astype(np.int32)
+        assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
+    monkeypatch.delenv("B2_FILTER_NO_SIMPLE", raising=False)
