@@ -404,6 +404,9 @@ __device__ __forceinline__ int32_t smem_find_slot(const AggPlan& plan, int64_t g
   const bool packed = plan.fast_keys && pack_keys(plan.keys, g, kb, kn);
   uint32_t idx = (packed ? (uint32_t)mix64(kb ^ ((uint64_t)kn << 56) ^ 0x9e3779b97f4a7c15ull) : row_hash(plan.keys, g)) & (SLOTS - 1);
   int probes = 0;
+  // a table this full is abandoned at once: walking long probe chains (row compares through global memory for unpacked
+  // keys) only to overflow a few rows later made the 256 K-row cardinality probe of TPC-H q3 cost 1.8 ms
+  if (*reinterpret_cast<volatile uint32_t*>(s_nocc) > (uint32_t)(SLOTS - SLOTS / 8)) { atomicExch(overflow, 1); return -1; }
   while (true) {
     int32_t cur = s_slots[idx];
     if (cur == SLOT_EMPTY) {
@@ -799,8 +802,7 @@ struct RGAgg {
 __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_constant__ AggPlan plan, const __grid_constant__ RGPlan rp, const __grid_constant__ RGAgg a) {
   extern __shared__ __align__(128) char rg_dyn[];
   __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ uint32_t s_scan[RG_NT / 32];
-  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_nused[2];
   const int C = a.C;
   // table: packed keys, accumulators, state (0 = empty, else (claiming stage index + 1) [| RG_READY once the key is published])
   uint64_t* t_k0 = reinterpret_cast<uint64_t*>(rg_dyn);
@@ -808,7 +810,8 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
   uint64_t* t_acc = t_k1 + (rp.has_k1 ? C : 0);
   uint32_t* t_state = reinterpret_cast<uint32_t*>(t_acc + (size_t)C * plan.limbs);
   uint32_t* t_nvalid = t_state + C;
-  char* stage0 = reinterpret_cast<char*>(((uintptr_t)(t_nvalid + (size_t)C * plan.nvalids) + 127) & ~(uintptr_t)127);
+  uint16_t* t_used = reinterpret_cast<uint16_t*>(t_nvalid + (size_t)C * plan.nvalids);   // slots claimed by the current partition
+  char* stage0 = reinterpret_cast<char*>(((uintptr_t)(t_used + C) + 127) & ~(uintptr_t)127);
   // one stage buffer: k0 | k1 | v[0..] | vbits, each CH rows (+ slack so that 16-byte rounded copies stay inside)
   constexpr int CH = RG_CHUNK;
   int soff_k1 = CH * 8 + 16, soff_v[RG_MAX_VALS], soff_vb, sbytes;
@@ -845,6 +848,7 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
     if (rp.use_vbits) tma_bulk_g2s(sb + soff_vb, a.rows.vbits + start, (uint32_t)((rows * 4 + 15) & ~15LL), &s_bar[buf]);
   };
   if (threadIdx.x == 0) {
+    s_nused[0] = 0; s_nused[1] = 0;
     mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
     mbar_fence_init();
     if (nchunks > 0) issue(0, 0);
@@ -853,7 +857,7 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
   uint32_t phase[2] = {0, 0};
   int p = pA;
   int64_t cursor = r_lo;
-  const int per_thread = C / RG_NT;   // C is a multiple of RG_NT
+  int nflushed = 0;
   for (int64_t c = 0; c < nchunks; c++) {
     const int buf = (int)(c & 1);
     if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1, buf ^ 1);
@@ -882,6 +886,7 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
               if (rp.has_k1) t_k1[idx] = k1;
               __threadfence_block();
               *reinterpret_cast<volatile uint32_t*>(&t_state[idx]) = (uint32_t)(li + 1) | RG_READY;
+              t_used[atomicAdd(&s_nused[nflushed & 1], 1u)] = (uint16_t)idx;
               found = true;
               break;
             }
@@ -920,37 +925,32 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
       }
       cursor = hi;
       if (hi < pend) break;   // the partition continues in the next chunk
-      // partition p is complete: append its groups to the compact group arrays and reset the table
+      // partition p is complete: append its groups to the compact group arrays and reset their slots.  Claimed slots were
+      // logged in t_used, so the flush touches the partition's groups only (not all C slots) and needs no block scan: each
+      // warp reserves output space for its 32 entries with one atomic.
       __syncthreads();
       {
-        uint32_t cnt = 0;
-        for (int q = 0; q < per_thread; q++) cnt += t_state[threadIdx.x * per_thread + q] != 0;
-        uint32_t inc = cnt;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) s_scan[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-          uint32_t w = lane < RG_NT / 32 ? s_scan[lane] : 0, winc = w;
-          for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-          if (lane < RG_NT / 32) s_scan[lane] = winc - w;
-          if (lane == 31) s_base = winc ? atomicAdd(a.gcount, (unsigned long long)winc) : 0ull;
-        }
-        __syncthreads();
-        unsigned long long o = s_base + s_scan[warp] + (inc - cnt);
-        for (int q = 0; q < per_thread; q++) {
-          const int sl = threadIdx.x * per_thread + q;
-          if (t_state[sl] == 0) continue;
+        const int par = nflushed & 1;
+        const uint32_t nu = s_nused[par];
+        if (threadIdx.x == 0) s_nused[par ^ 1] = 0;   // the next partition logs into the other counter
+        const int lane = threadIdx.x & 31;
+        for (uint32_t u0 = threadIdx.x & ~31u; u0 < nu; u0 += RG_NT) {
+          const uint32_t cnt = min(32u, nu - u0);
+          unsigned long long o = 0;
+          if (lane == 0) o = atomicAdd(a.gcount, (unsigned long long)cnt);
+          o = __shfl_sync(0xffffffffu, o, 0) + lane;
+          if ((uint32_t)lane >= cnt) continue;
+          const int sl = t_used[u0 + lane];
           a.gk0[o] = t_k0[sl];
           if (rp.has_k1) a.gk1[o] = t_k1[sl];
           for (int l = 0; l < plan.limbs; l++) a.gacc[o * plan.limbs + l] = t_acc[(size_t)sl * plan.limbs + l];
           for (int v = 0; v < plan.nvalids; v++) a.gnvalid[o * plan.nvalids + v] = t_nvalid[(size_t)sl * plan.nvalids + v];
-          o++;
           t_state[sl] = 0;
           for (int k = 0; k < plan.naggs; k++)
             for (int l = 0; l < plan.aggs[k].nlimbs; l++) t_acc[(size_t)sl * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
           for (int v = 0; v < plan.nvalids; v++) t_nvalid[(size_t)sl * plan.nvalids + v] = 0;
         }
+        nflushed++;
       }
       __syncthreads();
       p++;
@@ -1050,7 +1050,7 @@ static Table* radix_groupby(const Program* prog, const Table* t, const AggPlan& 
   const int ncols_moved = 2 + rp.has_k1 + rp.nvals + rp.use_vbits;
   if (ncols_moved > PT_MAXC) return nullptr;
   // shared-memory budget of the aggregation kernel: table of C slots + two stage buffers
-  const int slot_bytes = 8 + (rp.has_k1 ? 8 : 0) + plan.limbs * 8 + 4 + plan.nvalids * 4;
+  const int slot_bytes = 8 + (rp.has_k1 ? 8 : 0) + plan.limbs * 8 + 4 + plan.nvalids * 4 + 2;   // + the claimed-slot log
   int sbytes = RG_CHUNK * 8 + 16 + (rp.has_k1 ? RG_CHUNK * 8 + 16 : 0) + (rp.use_vbits ? RG_CHUNK * 4 + 16 : 0);
   for (int s2 = 0; s2 < rp.nvals; s2++) sbytes += RG_CHUNK * rp.val[s2].width + 16;
   sbytes = (sbytes + 127) & ~127;

@@ -30,6 +30,7 @@
 #include <nccl.h>
 #include <algorithm>
 #include <mutex>
+#include "pack16.cuh"
 #include "prim.cuh"
 #include "rowops.cuh"
 #include "murmur.cuh"
@@ -187,7 +188,7 @@ struct XPlan {
 };
 
 template <typename T>
-__device__ __forceinline__ void xs_move_column(const XPlan& pl, int c, const T* __restrict__ in, T* stage, const uint16_t* lpos, const uint8_t* pid,
+__device__ __forceinline__ void xs_move_column(const XPlan& pl, int c_idx, const T* __restrict__ in, T* stage, const uint16_t* lpos, const uint8_t* pid,
                                                int64_t tile_base, int64_t n, int tile_n, const int* s_start, const long long* s_base) {
   // scatter the tile's values into destination order in shared memory ...
 #pragma unroll
@@ -196,25 +197,38 @@ __device__ __forceinline__ void xs_move_column(const XPlan& pl, int c, const T* 
     if (i < n) stage[lpos[j]] = in[pl.sel ? (int64_t)pl.sel[i] : i];
   }
   __syncthreads();
-  // ... then stream each destination's run out with consecutive lanes on consecutive addresses.  Elements are moved 16 bytes
-  // at a time wherever a whole vector belongs to one destination and lands 16-byte aligned there (runs are long, so nearly
-  // always): 512 contiguous bytes per warp store, the shape NVLink carries at full rate
+  // ... then stream each destination's run out.  Every store that can be is a 16-byte store to a 16-byte aligned address of
+  // the destination region (512 contiguous bytes per warp store, the shape NVLink carries at full rate): the vector slot
+  // anchored at stage index k0 is shifted back by the run's misalignment dest(k0) % V, reads V elements from shared memory
+  // and writes one aligned vector; only the elements whose aligned vector crosses the run's ends (< 2V per destination and
+  // tile) leave one by one.  Rows past the region's capacity are dropped here and counted by the caller (grow + retry).
   constexpr int V = sizeof(T) >= 16 ? 1 : 16 / (int)sizeof(T);
   for (int k0 = threadIdx.x * V; k0 < tile_n; k0 += XS_NT * V) {
     int p = 0;
     while (p + 1 < pl.W && k0 >= s_start[p + 1]) p++;
-    const long long dest = s_base[p] + (k0 - s_start[p]);
-    T* out = reinterpret_cast<T*>(pl.arena[p] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c]);
-    const bool whole = V > 1 && k0 + V <= tile_n && k0 + V <= s_start[p + 1] && (dest % V) == 0 && dest + V <= pl.cap;
-    if (whole) {
-      *reinterpret_cast<uint4*>(out + dest) = *reinterpret_cast<const uint4*>(stage + k0);
-    } else {
-      for (int k = k0; k < k0 + V && k < tile_n; k++) {
-        int q = p;
-        while (q + 1 < pl.W && k >= s_start[q + 1]) q++;
-        const long long d = s_base[q] + (k - s_start[q]);
-        if (d < pl.cap) reinterpret_cast<T*>(pl.arena[q] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c])[d] = stage[k];
+    {
+      const long long c = s_base[p] - s_start[p];                       // dest(k) = k + c inside run p
+      const long long room = pl.cap - s_base[p];                        // rows of this run that still fit the region
+      const int end = (int)min((long long)s_start[p + 1], (long long)s_start[p] + max(room, 0LL));
+      const int kk = k0 - (int)((k0 + c) % V);
+      T* out = reinterpret_cast<T*>(pl.arena[p] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c_idx]);
+      if (V == 1) { if (k0 < end) out[k0 + c] = stage[k0]; continue; }
+      if (kk >= s_start[p] && kk + V <= end) {
+        *reinterpret_cast<uint4*>(out + (kk + c)) = pack16<T>(stage + kk);
       }
+    }
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+      const int e = k0 + i;
+      if (e >= tile_n) break;
+      int q = p;
+      while (q + 1 < pl.W && e >= s_start[q + 1]) q++;
+      const long long c = s_base[q] - s_start[q];
+      const long long room = pl.cap - s_base[q];
+      const int end = (int)min((long long)s_start[q + 1], (long long)s_start[q] + max(room, 0LL));
+      const int kk = e - (int)((e + c) % V);
+      if (e < end && !(kk >= s_start[q] && kk + V <= end))
+        reinterpret_cast<T*>(pl.arena[q] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c_idx])[e + c] = stage[e];
     }
   }
   __syncthreads();

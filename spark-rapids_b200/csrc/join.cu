@@ -132,19 +132,28 @@ __global__ void __launch_bounds__(256) join_probe_distinct_kernel(const __grid_c
         live[j] = live[j] && (w[j] & bits) == bits;
       }
     }
+    // first slot of every surviving row: PI independent (DRAM-latency) loads in flight before any of them is looked at.
+    // A per-row "load, compare, walk" loop serialised them: although only ~10 % of the q3 rows pass the filter, some lane of
+    // the warp does in nearly every one of the PI rounds, so each round paid a full memory latency on its own.
+    uint64_t e0[PI], ek0[PI];
+#pragma unroll
+    for (int j = 0; j < PI; j++) {
+      e0[j] = JSLOT_EMPTY; ek0[j] = 0;
+      if (live[j]) e0[j] = join_entry(slots, h[j] & mask, fast, ek0[j]);
+    }
 #pragma unroll
     for (int j = 0; j < PI; j++) {
       if (!live[j]) continue;
       uint32_t idx = h[j] & mask;
+      uint64_t e = e0[j], ek = ek0[j];
       while (true) {
-        uint64_t ek;
-        const uint64_t e = join_entry(slots, idx, fast, ek);
         if (e == JSLOT_EMPTY) break;
         if ((uint32_t)(e >> 32) == h[j]) {
           const bool eq = fast ? (ek == kb[j]) : rows_equal(probe, src[j], build, (int32_t)(uint32_t)e, nulls_equal);
           if (eq) { br[j] = (int32_t)(uint32_t)e; break; }
         }
         idx = (idx + 1) & mask;
+        e = join_entry(slots, idx, fast, ek);
       }
     }
     if (kind == B2_JOIN_LEFT_OUTER) {
@@ -169,6 +178,41 @@ __global__ void __launch_bounds__(256) join_probe_distinct_kernel(const __grid_c
     }
   }
 }
+
+// Keeps a region (the Bloom filter) in the persisting part of L2 while probe kernels stream the probe columns past it
+// (cudaStreamAttributeAccessPolicyWindow); off unless B2_JOIN_BLOOM_PERSIST is set.
+struct L2Persist {
+  bool on = false;
+  L2Persist(void* p, size_t bytes) {
+    static const bool enabled = getenv("B2_JOIN_BLOOM_PERSIST") != nullptr;
+    if (!enabled || !p || !bytes) return;
+    static size_t max_window = 0, carve = 0;
+    static bool init = false;
+    if (!init) {
+      init = true;
+      int dev = 0; cudaGetDevice(&dev);
+      cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev);
+      carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)48 << 20);
+      max_window = (size_t)prop.accessPolicyMaxWindowSize;
+      if (carve) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    }
+    if (!carve || !max_window) return;
+    cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
+    a.accessPolicyWindow.base_ptr = p;
+    a.accessPolicyWindow.num_bytes = std::min(bytes, max_window);
+    a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)a.accessPolicyWindow.num_bytes);
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    on = cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess;
+    if (!on) cudaGetLastError();
+  }
+  ~L2Persist() {
+    if (!on) return;
+    cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
+    a.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &a);
+  }
+};
 
 // MODE 0: count matches per probe row; MODE 1: write pairs at offsets
 template <int MODE>
@@ -289,8 +333,12 @@ int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* ou
   jt->slots = DevBuf((size_t)cap * (jt->fast ? 16 : 8));
   CUDA_CHECK(cudaMemsetAsync(jt->slots.p, 0xff, jt->slots.bytes, stream()));
   if (t->rows >= (1 << 18) && !getenv("B2_JOIN_NO_BLOOM")) {   // smaller tables are L2 resident themselves
+    // bits per key: fewer bits = more false positives (each costs one DRAM-latency slot read) but a filter that stays in
+    // L2 next to the streamed probe columns.  ncu (profiles/r2_*): a 32 MB filter was evicted by the probe stream
+    // (60 % L2 miss rate); see DESIGN.md section 9 for the sweep
+    static const int bits_per_key = getenv("B2_JOIN_BLOOM_BITS") ? std::max(2, atoi(getenv("B2_JOIN_BLOOM_BITS"))) : 16;
     int64_t words = 1 << 15;
-    while (words < t->rows / 4 && words < (8 << 20)) words <<= 1;   // ~16 bits per key, at most 64 MB
+    while (words * 64 < t->rows * bits_per_key && words < (8 << 20)) words <<= 1;   // at most 64 MB
     if (words * 64 >= t->rows * 6) {                                // below ~6 bits per key the filter stops paying
       jt->bloom = DevBuf((size_t)words * 8);
       jt->bloom_mask = (uint32_t)(words - 1);
@@ -389,6 +437,7 @@ int b2_join_probe_sel(b2_handle ht, b2_handle probe_keys_table, b2_handle select
     if (n) {
       DevBuf tot(8);
       CUDA_CHECK(cudaMemsetAsync(tot.p, 0, 8, stream()));
+      L2Persist keep(jt->bloom.p, jt->bloom.bytes);
       KernelTimer kt("join_probe_distinct_kernel");
       join_probe_distinct_kernel<<<grid_for(n, 256), 256, 0, stream()>>>(pk, bk, n, jt->slots.as<uint64_t>(), (uint32_t)(jt->cap - 1),
                                                                           jt->nulls_equal, jt->fast, kind, tot.as<unsigned long long>(),

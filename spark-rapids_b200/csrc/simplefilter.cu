@@ -2,9 +2,9 @@
 // predicate shape: a conjunction of comparisons between NOT NULL fixed-width integer columns (ints, dates, timestamps,
 // DECIMAL32/64) and literals — date ranges, key bounds, flags (TPC-H q3: o_orderdate < d, l_shipdate > d; q6's five terms).
 // The general path interprets the predicate in the expression VM (vm.cuh) one 4096-row tile at a time; here the compiled
-// program is pattern-matched on the host and a specialised kernel streams the columns with 16-byte loads, 16 consecutive
-// rows per thread, keeps the per-thread result as a bit mask and writes the selected row ids in order (single pass:
-// block scan + decoupled look-back across tiles).  Anything that does not match the shape returns false and takes the VM.
+// program is pattern-matched on the host and a specialised kernel streams the columns with 16-byte loads (consecutive lanes
+// on consecutive vectors), keeps the tile's result as a bit mask in shared memory and writes the selected row ids in order,
+// coalesced, through a shared-memory stage (single pass: block scan + decoupled look-back across tiles).  Anything that does not match the shape returns false and takes the VM.
 #include "prim.cuh"
 #include "vm.cuh"
 
@@ -40,24 +40,38 @@ __device__ __forceinline__ int64_t sf_lookback(uint64_t* status, int64_t tile, u
   return excl;
 }
 
-// 16 consecutive values of a column as signed 64-bit, through 16-byte loads (row0 is a multiple of 16: every access is aligned)
+// One term over one tile: every thread tests 16-byte vectors of the column, consecutive lanes on consecutive vectors (each
+// warp load covers 512 contiguous bytes), and clears the bits of the failing rows in the tile's shared bit mask.
 template <typename T>
-__device__ __forceinline__ void sf_load16(const void* col, int64_t row0, int64_t v[SF_ROWS]) {
-  constexpr int PER = 16 / (int)sizeof(T);
-  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(col) + row0);
-#pragma unroll
-  for (int q = 0; q < SF_ROWS / PER; q++) {
-    const uint4 w = __ldg(p + q);
+__device__ __forceinline__ void sf_term(const SimpleTerm& t, int64_t tile_row0, int tile_n, uint32_t* s_mask) {
+  constexpr int PER = 16 / (int)sizeof(T);                 // rows per vector
+  constexpr int NVEC = SF_TILE / PER;                      // vectors per tile
+  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(t.col) + tile_row0);   // tile_row0 is a multiple of 4096
+  const T lit = (T)t.lit;
+#pragma unroll 4
+  for (int v = threadIdx.x; v < NVEC; v += SF_NT) {
+    const int r0 = v * PER;
+    if (r0 >= tile_n) break;          // columns are padded to 64 B: a partial last vector is readable, its extra bits are masked below
+    const uint4 w = __ldg(p + v);
     const T* e = reinterpret_cast<const T*>(&w);
+    uint32_t pass = 0;
 #pragma unroll
-    for (int k = 0; k < PER; k++) v[q * PER + k] = (int64_t)e[k];
+    for (int k = 0; k < PER; k++) {
+      const int c = e[k] < lit ? 1 : (e[k] == lit ? 2 : 4);
+      pass |= (uint32_t)((t.truth & c) != 0) << k;
+    }
+    const uint32_t fail = ~pass & (PER == 32 ? 0xffffffffu : ((1u << PER) - 1u));
+    if (fail) atomicAnd(&s_mask[r0 >> 5], ~(fail << (r0 & 31)));
   }
 }
 
 __global__ void __launch_bounds__(SF_NT) simple_filter_ids_kernel(const __grid_constant__ SimplePred sp, int64_t n, int32_t* __restrict__ ids,
                                                                   uint64_t* __restrict__ status, SimpleWork* __restrict__ work) {
+  __shared__ uint32_t s_mask[SF_TILE / 32];     // bit r: row r of the tile passes every term so far
+  __shared__ int32_t s_ids[SF_TILE];            // the tile's selected row ids in order, then written out coalesced
   __shared__ uint32_t s_w[SF_NT / 32];
   __shared__ int64_t s_tile, s_excl;
+  __shared__ uint32_t s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ntiles = (n + SF_TILE - 1) / SF_TILE;
   while (true) {
@@ -65,46 +79,53 @@ __global__ void __launch_bounds__(SF_NT) simple_filter_ids_kernel(const __grid_c
     __syncthreads();
     const int64_t tile = s_tile;
     if (tile >= ntiles) break;
-    const int64_t row0 = tile * SF_TILE + (int64_t)threadIdx.x * SF_ROWS;
-    uint32_t m = 0;
-    if (row0 < n) {
-      m = row0 + SF_ROWS <= n ? 0xffffu : (0xffffu >> (SF_ROWS - (int)(n - row0)));   // the last rows of the column
-      for (int k = 0; k < sp.n; k++) {
-        const SimpleTerm t = sp.t[k];
-        int64_t v[SF_ROWS];
-        // columns are padded to 64 B, so the 16-byte loads of a partial last group stay inside the allocation
-        switch (t.width) {
-          case 1: sf_load16<int8_t>(t.col, row0, v); break;
-          case 2: sf_load16<int16_t>(t.col, row0, v); break;
-          case 4: sf_load16<int32_t>(t.col, row0, v); break;
-          default: sf_load16<int64_t>(t.col, row0, v); break;
-        }
-        uint32_t tm = 0;
-#pragma unroll
-        for (int j = 0; j < SF_ROWS; j++) {
-          const int c = v[j] < t.lit ? 1 : (v[j] == t.lit ? 2 : 4);
-          tm |= (uint32_t)((t.truth & c) != 0) << j;
-        }
-        m &= tm;
+    const int64_t tile_row0 = tile * SF_TILE;
+    const int tile_n = (int)min((int64_t)SF_TILE, n - tile_row0);
+    if (threadIdx.x < SF_TILE / 32) {
+      const int lo = threadIdx.x * 32;
+      s_mask[threadIdx.x] = tile_n >= lo + 32 ? 0xffffffffu : (tile_n > lo ? (1u << (tile_n - lo)) - 1u : 0u);
+    }
+    __syncthreads();
+    for (int k = 0; k < sp.n; k++) {
+      const SimpleTerm& t = sp.t[k];
+      switch (t.width) {
+        case 1: sf_term<int8_t>(t, tile_row0, tile_n, s_mask); break;
+        case 2: sf_term<int16_t>(t, tile_row0, tile_n, s_mask); break;
+        case 4: sf_term<int32_t>(t, tile_row0, tile_n, s_mask); break;
+        default: sf_term<int64_t>(t, tile_row0, tile_n, s_mask); break;
       }
     }
+    __syncthreads();
+    // thread t owns rows 16 t .. 16 t + 15 of the tile
+    const uint32_t m = (s_mask[threadIdx.x >> 1] >> ((threadIdx.x & 1) * 16)) & 0xffffu;
     const uint32_t cnt = __popc(m);
     uint32_t inc = cnt;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
     if (lane == 31) s_w[warp] = inc;
     __syncthreads();
+    uint32_t total = 0;
     if (warp == 0) {
       uint32_t w = lane < SF_NT / 32 ? s_w[lane] : 0, winc = w;
       for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += x; }
+      total = __shfl_sync(0xffffffffu, winc, 31);
       if (lane < SF_NT / 32) s_w[lane] = winc - w;
-      const uint32_t total = __shfl_sync(0xffffffffu, winc, 31);
+      if (lane == 0) s_total = total;
+    }
+    __syncthreads();
+    if (warp == 0) {   // the look-back of warp 0 overlaps the other warps' staging
       const int64_t excl = sf_lookback(status, tile, total);
       if (lane == 0) { s_excl = excl; if (tile == ntiles - 1) work->total = (unsigned long long)(excl + total); }
     }
+    {
+      uint32_t pos = s_w[warp] + (inc - cnt);
+      const int32_t r0 = (int32_t)(tile_row0 + threadIdx.x * SF_ROWS);
+      for (uint32_t mm = m; mm; mm &= mm - 1) s_ids[pos++] = r0 + (__ffs(mm) - 1);
+    }
     __syncthreads();
-    int64_t pos = s_excl + s_w[warp] + (inc - cnt);
-    for (uint32_t mm = m; mm; mm &= mm - 1) ids[pos++] = (int32_t)(row0 + (__ffs(mm) - 1));
-    __syncthreads();   // s_tile / s_w are rewritten by the next iteration
+    const int64_t excl = s_excl;
+    total = s_total;
+    for (uint32_t i = threadIdx.x; i < total; i += SF_NT) ids[excl + i] = s_ids[i];
+    // the next iteration's first barrier orders these reads of s_ids / s_w before they are rewritten
   }
 }
 
