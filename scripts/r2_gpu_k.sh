@@ -1,0 +1,28 @@
+#!/bin/bash
+# pass J: tests + q3 SF100 bench + quick ncu of the kernels changed since pass I
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2k_pytest.txt 2>&1; echo "--- pytest rc=$?"; tail -4 gpurun_out/r2k_pytest.txt
+timeout 600 python bench.py --steps 5 --extra-q6 0 --cpu-baseline 0 --check 1 > gpurun_out/r2k_base.json 2> gpurun_out/r2k_base.err; echo "--- base rc=$?"; tail -2 gpurun_out/r2k_base.err
+python - <<'PY'
+import json
+f = "r2k_base"
+try:
+    d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
+    print(f, round(d["value"] / 1e9, 3), "G rows/s", round(d["ms_per_step"], 2), "ms; e2e", round(d["e2e"]["ms_per_step"], 1), d["config"].get("checked"))
+    for o in d["operators"]: print("  op", o["name"], round(o["ms_per_step"], 3))
+    for k in d["kernels"][:14]: print("  k", k["name"], round(k["ms_per_step"], 3), round(k["launches_per_step"], 1))
+except Exception as e:
+    print(f, "ERR", e)
+PY
+BENCH="python bench.py --steps 1 --warmup 3 --cpu-baseline 0 --check 0 --extra-q6 0"
+for K in join_probe_distinct1_kernel simple_filter_ids_kernel; do
+  SKIP=30; case $K in radix_agg_kernel) SKIP=3;; part_scatter2_kernel) SKIP=6;; esac
+  timeout 600 ncu --set full --clock-control none -k regex:$K -s $SKIP -c 1 -o gpurun_out/r2k_ncu_$K -f $BENCH > gpurun_out/r2k_ncu_$K.log 2>&1
+  echo "--- $K rc=$?"
+  if [ -f gpurun_out/r2k_ncu_$K.ncu-rep ]; then
+    ncu -i gpurun_out/r2k_ncu_$K.ncu-rep --page raw --csv > gpurun_out/r2k_ncu_${K}_raw.csv 2>/dev/null
+    rm gpurun_out/r2k_ncu_$K.ncu-rep
+  fi
+done
+python scripts/ncu_summarize.py gpurun_out/r2k_ncu_*_raw.csv

@@ -10,7 +10,7 @@
 
 namespace b2 {
 
-constexpr int SF_NT = 256, SF_ROWS = 16, SF_TILE = SF_NT * SF_ROWS, SF_MAX_TERMS = 8;
+constexpr int SF_NT = 256, SF_WARPS = SF_NT / 32, SF_TILE = 32768, SF_WORDS = SF_TILE / 32, SF_WWORDS = SF_WORDS / SF_WARPS, SF_MAX_TERMS = 8;
 struct SimpleTerm { const void* col; int32_t width; int32_t truth; int64_t lit; };   // truth: bit0 '<', bit1 '==', bit2 '>'
 struct SimplePred { int32_t n; int32_t pad; SimpleTerm t[SF_MAX_TERMS]; };
 struct SimpleWork { unsigned long long tile_counter, total; };
@@ -18,40 +18,47 @@ struct SimpleWork { unsigned long long tile_counter, total; };
 constexpr uint64_t SLB_AGG = 1ull << 62, SLB_PREFIX = 2ull << 62, SLB_MASK = (1ull << 62) - 1;
 __device__ __forceinline__ uint64_t sf_ld(const uint64_t* p) { uint64_t v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void sf_st(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-// decoupled look-back over per-tile counts (same protocol as scan.cu); called by warp 0
-__device__ __forceinline__ int64_t sf_lookback(uint64_t* status, int64_t tile, uint32_t count) {
-  const int lane = threadIdx.x & 31;
-  if (tile == 0) { if (lane == 0) { __threadfence(); sf_st(&status[0], SLB_PREFIX | count); } return 0; }
-  if (lane == 0) { __threadfence(); sf_st(&status[tile], SLB_AGG | count); }
+
+// Decoupled look-back over the per-tile counts, by the WHOLE CTA: 256 predecessors are inspected per step.  The tiles of a
+// launch are uniform, so they finish counting at about the same time and nobody's prefix is ready: a warp-wide window
+// (32 per step, scan.cu) made every tile walk ~all running tiles one L2 round trip at a time; this walks them 256 at a time.
+// Called by every thread; returns the exclusive prefix of `tile` and publishes its inclusive prefix.
+__device__ __forceinline__ int64_t sf_block_lookback(uint64_t* status, int64_t tile, uint32_t count, int64_t* s_sum, int* s_has) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (tile == 0) { if (threadIdx.x == 0) { __threadfence(); sf_st(&status[0], SLB_PREFIX | count); } return 0; }
+  if (threadIdx.x == 0) { __threadfence(); sf_st(&status[tile], SLB_AGG | count); }
   int64_t excl = 0, look = tile - 1;
   while (true) {
-    const int64_t idx = look - lane;
+    const int64_t idx = look - threadIdx.x;
     uint64_t v;
     if (idx >= 0) { do { v = sf_ld(&status[idx]); } while ((v >> 62) == 0); } else v = SLB_PREFIX;
     const uint32_t is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
     const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
     int64_t contrib = (lane <= first) ? (int64_t)(v & SLB_MASK) : 0;
     for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-    excl += contrib;
-    if (is_prefix) break;
-    look -= 32;
+    if (lane == 0) { s_sum[warp] = contrib; s_has[warp] = is_prefix != 0; }
+    __syncthreads();
+    bool done = false;
+    for (int w = 0; w < SF_WARPS && !done; w++) { excl += s_sum[w]; done = s_has[w] != 0; }   // warp 0 holds the nearest predecessors
+    __syncthreads();
+    if (done) break;
+    look -= SF_NT;
   }
-  if (lane == 0) { __threadfence(); sf_st(&status[tile], SLB_PREFIX | (uint64_t)(excl + count)); }
+  if (threadIdx.x == 0) { __threadfence(); sf_st(&status[tile], SLB_PREFIX | (uint64_t)(excl + count)); }
   return excl;
 }
 
 // One term over one tile: every thread tests 16-byte vectors of the column, consecutive lanes on consecutive vectors (each
-// warp load covers 512 contiguous bytes), and clears the bits of the failing rows in the tile's shared bit mask.
+// warp load covers 512 contiguous bytes; no barrier inside, 4 loads in flight per thread), and clears the bits of the failing
+// rows in the tile's shared bit mask.
 template <typename T>
 __device__ __forceinline__ void sf_term(const SimpleTerm& t, int64_t tile_row0, int tile_n, uint32_t* s_mask) {
   constexpr int PER = 16 / (int)sizeof(T);                 // rows per vector
-  constexpr int NVEC = SF_TILE / PER;                      // vectors per tile
-  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(t.col) + tile_row0);   // tile_row0 is a multiple of 4096
+  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(t.col) + tile_row0);   // tile_row0 is a multiple of 32768
+  const int nvec = (tile_n + PER - 1) / PER;               // columns are padded to 64 B: a partial last vector is readable, its extra bits are already 0 in the mask
   const T lit = (T)t.lit;
 #pragma unroll 4
-  for (int v = threadIdx.x; v < NVEC; v += SF_NT) {
-    const int r0 = v * PER;
-    if (r0 >= tile_n) break;          // columns are padded to 64 B: a partial last vector is readable, its extra bits are masked below
+  for (int v = threadIdx.x; v < nvec; v += SF_NT) {
     const uint4 w = __ldg(p + v);
     const T* e = reinterpret_cast<const T*>(&w);
     uint32_t pass = 0;
@@ -60,18 +67,19 @@ __device__ __forceinline__ void sf_term(const SimpleTerm& t, int64_t tile_row0, 
       const int c = e[k] < lit ? 1 : (e[k] == lit ? 2 : 4);
       pass |= (uint32_t)((t.truth & c) != 0) << k;
     }
-    const uint32_t fail = ~pass & (PER == 32 ? 0xffffffffu : ((1u << PER) - 1u));
+    const uint32_t fail = ~pass & ((1u << PER) - 1u);
+    const int r0 = v * PER;
     if (fail) atomicAnd(&s_mask[r0 >> 5], ~(fail << (r0 & 31)));
   }
 }
 
 __global__ void __launch_bounds__(SF_NT) simple_filter_ids_kernel(const __grid_constant__ SimplePred sp, int64_t n, int32_t* __restrict__ ids,
                                                                   uint64_t* __restrict__ status, SimpleWork* __restrict__ work) {
-  __shared__ uint32_t s_mask[SF_TILE / 32];     // bit r: row r of the tile passes every term so far
-  __shared__ int32_t s_ids[SF_TILE];            // the tile's selected row ids in order, then written out coalesced
-  __shared__ uint32_t s_w[SF_NT / 32];
-  __shared__ int64_t s_tile, s_excl;
-  __shared__ uint32_t s_total;
+  __shared__ uint32_t s_mask[SF_WORDS];              // bit r: row r of the tile passes every term
+  __shared__ int32_t s_stage[SF_WARPS][1024];        // per warp: the selected ids of 1024 rows, then written out coalesced
+  __shared__ uint32_t s_wtot[SF_WARPS];
+  __shared__ int64_t s_tile, s_sum[SF_WARPS];
+  __shared__ int s_has[SF_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ntiles = (n + SF_TILE - 1) / SF_TILE;
   while (true) {
@@ -81,9 +89,9 @@ __global__ void __launch_bounds__(SF_NT) simple_filter_ids_kernel(const __grid_c
     if (tile >= ntiles) break;
     const int64_t tile_row0 = tile * SF_TILE;
     const int tile_n = (int)min((int64_t)SF_TILE, n - tile_row0);
-    if (threadIdx.x < SF_TILE / 32) {
-      const int lo = threadIdx.x * 32;
-      s_mask[threadIdx.x] = tile_n >= lo + 32 ? 0xffffffffu : (tile_n > lo ? (1u << (tile_n - lo)) - 1u : 0u);
+    for (int i = threadIdx.x; i < SF_WORDS; i += SF_NT) {
+      const int lo = i * 32;
+      s_mask[i] = tile_n >= lo + 32 ? 0xffffffffu : (tile_n > lo ? (1u << (tile_n - lo)) - 1u : 0u);
     }
     __syncthreads();
     for (int k = 0; k < sp.n; k++) {
@@ -96,36 +104,39 @@ __global__ void __launch_bounds__(SF_NT) simple_filter_ids_kernel(const __grid_c
       }
     }
     __syncthreads();
-    // thread t owns rows 16 t .. 16 t + 15 of the tile
-    const uint32_t m = (s_mask[threadIdx.x >> 1] >> ((threadIdx.x & 1) * 16)) & 0xffffu;
-    const uint32_t cnt = __popc(m);
-    uint32_t inc = cnt;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    uint32_t total = 0;
-    if (warp == 0) {
-      uint32_t w = lane < SF_NT / 32 ? s_w[lane] : 0, winc = w;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += x; }
-      total = __shfl_sync(0xffffffffu, winc, 31);
-      if (lane < SF_NT / 32) s_w[lane] = winc - w;
-      if (lane == 0) s_total = total;
-    }
-    __syncthreads();
-    if (warp == 0) {   // the look-back of warp 0 overlaps the other warps' staging
-      const int64_t excl = sf_lookback(status, tile, total);
-      if (lane == 0) { s_excl = excl; if (tile == ntiles - 1) work->total = (unsigned long long)(excl + total); }
-    }
+    // warp w owns mask words [w * 128, (w + 1) * 128) = rows [w * 4096, (w + 1) * 4096) of the tile
     {
-      uint32_t pos = s_w[warp] + (inc - cnt);
-      const int32_t r0 = (int32_t)(tile_row0 + threadIdx.x * SF_ROWS);
-      for (uint32_t mm = m; mm; mm &= mm - 1) s_ids[pos++] = r0 + (__ffs(mm) - 1);
+      uint32_t c = 0;
+#pragma unroll
+      for (int i = 0; i < SF_WWORDS / 32; i++) c += __popc(s_mask[warp * SF_WWORDS + i * 32 + lane]);
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) s_wtot[warp] = c;
     }
     __syncthreads();
-    const int64_t excl = s_excl;
-    total = s_total;
-    for (uint32_t i = threadIdx.x; i < total; i += SF_NT) ids[excl + i] = s_ids[i];
-    // the next iteration's first barrier orders these reads of s_ids / s_w before they are rewritten
+    uint32_t total = 0, before = 0;
+#pragma unroll
+    for (int w = 0; w < SF_WARPS; w++) { if (w < warp) before += s_wtot[w]; total += s_wtot[w]; }
+    const int64_t excl = sf_block_lookback(status, tile, total, s_sum, s_has);
+    if (threadIdx.x == 0 && tile == ntiles - 1) work->total = (unsigned long long)(excl + total);
+    // ids of the warp's rows, 1024 rows at a time: positions by a warp scan of the word popcounts, staged in shared memory,
+    // written out with consecutive lanes on consecutive ids (no block barrier in this phase)
+    int64_t out = excl + before;
+    for (int r = 0; r < SF_WWORDS / 32; r++) {
+      const int word = warp * SF_WWORDS + r * 32 + lane;
+      const uint32_t m = s_mask[word];
+      const uint32_t cnt = __popc(m);
+      uint32_t inc = cnt;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+      const uint32_t rtot = __shfl_sync(0xffffffffu, inc, 31);
+      uint32_t pos = inc - cnt;
+      const int32_t r0 = (int32_t)(tile_row0 + (int64_t)word * 32);
+      for (uint32_t mm = m; mm; mm &= mm - 1) s_stage[warp][pos++] = r0 + (__ffs(mm) - 1);
+      __syncwarp();
+      for (uint32_t i = lane; i < rtot; i += 32) ids[out + i] = s_stage[warp][i];
+      out += rtot;
+      __syncwarp();
+    }
+    __syncthreads();   // s_mask / s_wtot / s_tile are rewritten by the next tile
   }
 }
 
@@ -146,6 +157,7 @@ static bool simple_pred_of(const Program* prog, const Table* t, SimplePred& sp) 
     if (ins.a.idx < 0 || ins.a.idx >= (int)t->cols.size()) return false;
     const Column* c = t->cols[ins.a.idx];
     if (c->nullable() || c->dtype == B2_STRING || c->dtype == B2_BOOL8 || is_float(c->dtype) || dtype_width(c->dtype) != mt_width(ins.mt)) return false;
+    if ((uintptr_t)c->data.p & 15) return false;   // 16-byte vector loads
     sp.t[i].col = c->data.p; sp.t[i].width = mt_width(ins.mt); sp.t[i].truth = truth;
     // literals are stored sign-extended to 64 bits (b2_expr_literal); narrower machine types compare on their own width
     int64_t lit = ins.b.lo;
@@ -172,7 +184,7 @@ bool simple_filter_row_ids(const Program* prog, const Table* t, Column** out) {
   CUDA_CHECK(cudaMemsetAsync(status.p, 0, (size_t)ntiles * 8, stream()));
   {
     KernelTimer kt("simple_filter_ids_kernel");
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * 8);
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * 5);
     simple_filter_ids_kernel<<<grid, SF_NT, 0, stream()>>>(sp, n, ids.c->data.as<int32_t>(), status.as<uint64_t>(), work.as<SimpleWork>());
     CUDA_CHECK(cudaGetLastError());
     count_launch();
