@@ -187,69 +187,76 @@ struct XPlan {
   const int32_t* sel;                    // selection vector (row ids into the batch) or null: late materialisation of a filter below
 };
 
-template <typename T>
-__device__ __forceinline__ void xs_move_column(const XPlan& pl, int c_idx, const T* __restrict__ in, T* stage, const uint16_t* lpos, const uint8_t* pid,
-                                               int64_t tile_base, int64_t n, int tile_n, const int* s_start, const long long* s_base) {
-  // scatter the tile's values into destination order in shared memory ...
+// per-tile geometry of the destination runs (shared memory): stage rows [start, start_next) belong to destination p in
+// destination order; rows [start, end) fit the (me -> p) region; destination row = stage row + c
+struct XRuns {
+  int start[XMAX_W + 1];
+  int end[XMAX_W];
+  long long c[XMAX_W];
+};
+
+// one column of one tile: the values are scattered into destination order in shared memory, then every destination's run is
+// streamed out.  Every store that can be is a 16-byte store to a 16-byte aligned address of the destination region (512
+// contiguous bytes per warp store, the shape NVLink carries at full rate): the run is cut at the destination's vector
+// boundaries, a vector reads its V (in general unaligned) elements from shared memory, and only the < V rows in front of the
+// first and behind the last whole vector leave one by one.  Rows past the region's capacity are dropped here and counted by
+// the caller (grow + retry).  VALID: the source is a validity bit mask, shipped as one byte per row.
+template <typename T, bool VALID>
+__device__ __forceinline__ void xs_move_column(const XPlan& pl, int64_t off_bytes, const void* __restrict__ in, T* stage, const uint16_t* lpos,
+                                               int64_t tile_base, int64_t n, const XRuns& rn) {
 #pragma unroll
   for (int j = 0; j < XS_STEPS; j++) {
     const int64_t i = tile_base + (int64_t)j * XS_NT + threadIdx.x;
-    if (i < n) stage[lpos[j]] = in[pl.sel ? (int64_t)pl.sel[i] : i];
+    if (i < n) {
+      const int64_t src = pl.sel ? (int64_t)pl.sel[i] : i;
+      if constexpr (VALID) stage[lpos[j]] = (T)bit_get(reinterpret_cast<const uint32_t*>(in), src);
+      else stage[lpos[j]] = reinterpret_cast<const T*>(in)[src];
+    }
   }
   __syncthreads();
-  // ... then stream each destination's run out.  Every store that can be is a 16-byte store to a 16-byte aligned address of
-  // the destination region (512 contiguous bytes per warp store, the shape NVLink carries at full rate): the vector slot
-  // anchored at stage index k0 is shifted back by the run's misalignment dest(k0) % V, reads V elements from shared memory
-  // and writes one aligned vector; only the elements whose aligned vector crosses the run's ends (< 2V per destination and
-  // tile) leave one by one.  Rows past the region's capacity are dropped here and counted by the caller (grow + retry).
   constexpr int V = sizeof(T) >= 16 ? 1 : 16 / (int)sizeof(T);
-  for (int k0 = threadIdx.x * V; k0 < tile_n; k0 += XS_NT * V) {
-    int p = 0;
-    while (p + 1 < pl.W && k0 >= s_start[p + 1]) p++;
-    {
-      const long long c = s_base[p] - s_start[p];                       // dest(k) = k + c inside run p
-      const long long room = pl.cap - s_base[p];                        // rows of this run that still fit the region
-      const int end = (int)min((long long)s_start[p + 1], (long long)s_start[p] + max(room, 0LL));
-      const int kk = k0 - (int)((k0 + c) % V);
-      T* out = reinterpret_cast<T*>(pl.arena[p] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c_idx]);
-      if (V == 1) { if (k0 < end) out[k0 + c] = stage[k0]; continue; }
-      if (kk >= s_start[p] && kk + V <= end) {
-        *reinterpret_cast<uint4*>(out + (kk + c)) = pack16<T>(stage + kk);
-      }
+  for (int p = 0; p < pl.W; p++) {
+    const int st = rn.start[p], en = rn.end[p];
+    if (en <= st) continue;
+    const long long c = rn.c[p];
+    T* out = reinterpret_cast<T*>(pl.arena[p] + (int64_t)pl.me * pl.region_bytes + off_bytes) + c;   // out[k] = destination of stage row k
+    if (V == 1) { for (int k = st + threadIdx.x; k < en; k += XS_NT) out[k] = stage[k]; continue; }
+    const int head = min(en - st, (V - (int)((st + c) & (V - 1))) & (V - 1));
+    const int vlo = st + head;
+    const int nvec = (en - vlo) / V;
+    for (int v = threadIdx.x; v < nvec; v += XS_NT) {
+      const int kk = vlo + v * V;
+      *reinterpret_cast<uint4*>(out + kk) = pack16<T>(stage + kk);
     }
-#pragma unroll
-    for (int i = 0; i < V; i++) {
-      const int e = k0 + i;
-      if (e >= tile_n) break;
-      int q = p;
-      while (q + 1 < pl.W && e >= s_start[q + 1]) q++;
-      const long long c = s_base[q] - s_start[q];
-      const long long room = pl.cap - s_base[q];
-      const int end = (int)min((long long)s_start[q + 1], (long long)s_start[q] + max(room, 0LL));
-      const int kk = e - (int)((e + c) % V);
-      if (e < end && !(kk >= s_start[q] && kk + V <= end))
-        reinterpret_cast<T*>(pl.arena[q] + (int64_t)pl.me * pl.region_bytes + pl.col_off[c_idx])[e + c] = stage[e];
-    }
+    const int vhi = vlo + nvec * V;
+    const int nb = head + (en - vhi);   // < 2 V <= 32 rows
+    if ((int)threadIdx.x < nb) { const int k = (int)threadIdx.x < head ? st + threadIdx.x : vhi + ((int)threadIdx.x - head); out[k] = stage[k]; }
   }
   __syncthreads();
-  (void)pid;
 }
 
-__global__ void __launch_bounds__(XS_NT, 5) xchg_scatter_kernel(const __grid_constant__ KeyCols keys, const __grid_constant__ XPlan pl, int64_t n, uint32_t seed,
+// KM: how a row's destination is computed.  0 = generic (any key columns, NULLs), 1 = ONE 64-bit integer-like key column without
+// NULLs (INT64 / TIMESTAMP / DECIMAL64: Spark hashes the raw long), 2 = ONE INT32 / DATE32 column without NULLs.
+template <int KM>
+__global__ void __launch_bounds__(XS_NT, 4) xchg_scatter_kernel(const __grid_constant__ KeyCols keys, const __grid_constant__ XPlan pl, int64_t n, uint32_t seed,
                                                              unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) char stage_raw[];   // XS_TILE * widest column
-  __shared__ int s_cnt[XMAX_W], s_start[XMAX_W + 1], s_cur[XMAX_W];
-  __shared__ long long s_base[XMAX_W];
-  const int lane = threadIdx.x & 31;
+  __shared__ int s_wcnt[XS_NT / 32][XMAX_W];          // rows of (warp, destination); then the warp's offset inside the destination's run
+  __shared__ int s_cnt[XMAX_W];
+  __shared__ long long s_gbase[XMAX_W];
+  __shared__ XRuns rn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
   const int64_t ntiles = (n + XS_TILE - 1) / XS_TILE;
+  const bool pow2 = (pl.W & (pl.W - 1)) == 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t tile_base = tile * XS_TILE;
-    const int tile_n = (int)min((int64_t)XS_TILE, n - tile_base);
-    if (threadIdx.x < XMAX_W) { s_cnt[threadIdx.x] = 0; s_cur[threadIdx.x] = 0; }
+    for (int k = threadIdx.x; k < (XS_NT / 32) * XMAX_W; k += XS_NT) (&s_wcnt[0][0])[k] = 0;
     __syncthreads();
     uint8_t pid[XS_STEPS];
     uint16_t lpos[XS_STEPS];
-    // destination of every row (Spark Murmur3 over the key columns, pmod world) + per-destination tile counts
+    // destination of every row (Spark Murmur3 over the key columns, pmod world) and its rank among the warp's rows for that
+    // destination: one match_any per 32 rows, running counts per (warp, destination) — no atomics, deterministic order
 #pragma unroll
     for (int j = 0; j < XS_STEPS; j++) {
       const int64_t i = tile_base + (int64_t)j * XS_NT + threadIdx.x;
@@ -257,58 +264,61 @@ __global__ void __launch_bounds__(XS_NT, 5) xchg_scatter_kernel(const __grid_con
       if (i < n) {
         if (pl.single) p = 0;
         else {
-          uint32_t h = seed;
           const int64_t src = pl.sel ? (int64_t)pl.sel[i] : i;
-          for (int c = 0; c < keys.n; c++) h = murmur_col(keys.c[c], src, h);
-          int32_t v = (int32_t)h % pl.W; if (v < 0) v += pl.W;
-          p = v;
+          uint32_t h = seed;
+          if (KM == 1) h = hash_long(reinterpret_cast<const uint64_t*>(keys.c[0].data)[src], seed);
+          else if (KM == 2) h = hash_int(reinterpret_cast<const uint32_t*>(keys.c[0].data)[src], seed);
+          else for (int c = 0; c < keys.n; c++) h = murmur_col(keys.c[c], src, h);
+          if (pow2) p = (int)(h & (uint32_t)(pl.W - 1));   // pmod of a two's complement int by a power of two
+          else { int32_t v = (int32_t)h % pl.W; if (v < 0) v += pl.W; p = v; }
         }
       }
-      pid[j] = (uint8_t)p;
       const uint32_t m = __match_any_sync(0xffffffffu, p);
-      if (p >= 0 && lane == __ffs(m) - 1) atomicAdd(&s_cnt[p], __popc(m));
+      const int leader = __ffs(m) - 1;
+      int first = 0;
+      if (p >= 0 && lane == leader) { first = s_wcnt[warp][p]; s_wcnt[warp][p] = first + __popc(m); }
+      first = __shfl_sync(0xffffffffu, first, leader);
+      __syncwarp();
+      pid[j] = (uint8_t)p;
+      lpos[j] = (uint16_t)(first + __popc(m & lt));
     }
     __syncthreads();
-    if (threadIdx.x < pl.W) {   // reserve my range in every destination's (me -> dst) region: one atomic per tile and destination
-      const int cnt = s_cnt[threadIdx.x];
-      s_base[threadIdx.x] = cnt ? (long long)atomicAdd(&counters[threadIdx.x], (unsigned long long)cnt) : 0;
+    if (threadIdx.x < pl.W) {   // offsets of the warps inside the destination's run; one reservation per tile and destination
+      const int p = threadIdx.x;
+      int run = 0;
+#pragma unroll
+      for (int w = 0; w < XS_NT / 32; w++) { const int c = s_wcnt[w][p]; s_wcnt[w][p] = run; run += c; }
+      s_cnt[p] = run;
+      s_gbase[p] = run ? (long long)atomicAdd(&counters[p], (unsigned long long)run) : 0;
     }
-    if (threadIdx.x == 0) { int run = 0; for (int p = 0; p < pl.W; p++) { s_start[p] = run; run += s_cnt[p]; } s_start[pl.W] = run; }
     __syncthreads();
-    // position of every row inside the tile's destination-sorted order (warp-aggregated cursor bumps)
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int p = 0; p < pl.W; p++) {
+        const long long room = pl.cap - s_gbase[p];
+        rn.start[p] = run;
+        rn.end[p] = run + (int)max(0LL, min(room, (long long)s_cnt[p]));
+        rn.c[p] = s_gbase[p] - run;
+        run += s_cnt[p];
+      }
+      rn.start[pl.W] = run;
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < XS_STEPS; j++) {
-      const int p = pid[j] == 0xff ? -1 : (int)pid[j];
-      const uint32_t m = __match_any_sync(0xffffffffu, p);
-      int first = 0;
-      if (p >= 0 && lane == __ffs(m) - 1) first = atomicAdd(&s_cur[p], __popc(m));
-      first = __shfl_sync(0xffffffffu, first, __ffs(m) - 1);
-      lpos[j] = (uint16_t)(p >= 0 ? s_start[p] + first + __popc(m & ((1u << lane) - 1u)) : 0);
+      const int p = pid[j];
+      lpos[j] = (uint16_t)(p != 0xff ? rn.start[p] + s_wcnt[warp][p] + lpos[j] : 0);
     }
     for (int c = 0; c < pl.ncols; c++) {
       switch (pl.width[c]) {
-        case 1: xs_move_column<uint8_t>(pl, c, (const uint8_t*)pl.in[c], (uint8_t*)stage_raw, lpos, pid, tile_base, n, tile_n, s_start, s_base); break;
-        case 2: xs_move_column<uint16_t>(pl, c, (const uint16_t*)pl.in[c], (uint16_t*)stage_raw, lpos, pid, tile_base, n, tile_n, s_start, s_base); break;
-        case 4: xs_move_column<uint32_t>(pl, c, (const uint32_t*)pl.in[c], (uint32_t*)stage_raw, lpos, pid, tile_base, n, tile_n, s_start, s_base); break;
-        case 8: xs_move_column<uint64_t>(pl, c, (const uint64_t*)pl.in[c], (uint64_t*)stage_raw, lpos, pid, tile_base, n, tile_n, s_start, s_base); break;
-        default: xs_move_column<uint4>(pl, c, (const uint4*)pl.in[c], (uint4*)stage_raw, lpos, pid, tile_base, n, tile_n, s_start, s_base); break;
+        case 1: xs_move_column<uint8_t, false>(pl, pl.col_off[c], pl.in[c], (uint8_t*)stage_raw, lpos, tile_base, n, rn); break;
+        case 2: xs_move_column<uint16_t, false>(pl, pl.col_off[c], pl.in[c], (uint16_t*)stage_raw, lpos, tile_base, n, rn); break;
+        case 4: xs_move_column<uint32_t, false>(pl, pl.col_off[c], pl.in[c], (uint32_t*)stage_raw, lpos, tile_base, n, rn); break;
+        case 8: xs_move_column<uint64_t, false>(pl, pl.col_off[c], pl.in[c], (uint64_t*)stage_raw, lpos, tile_base, n, rn); break;
+        default: xs_move_column<uint4, false>(pl, pl.col_off[c], pl.in[c], (uint4*)stage_raw, lpos, tile_base, n, rn); break;
       }
-      if (pl.in_valid[c]) {   // validity as one byte per row (only for columns that carry NULLs here)
-        uint8_t* stage = (uint8_t*)stage_raw;
-#pragma unroll
-        for (int j = 0; j < XS_STEPS; j++) {
-          const int64_t i = tile_base + (int64_t)j * XS_NT + threadIdx.x;
-          if (i < n) stage[lpos[j]] = (uint8_t)bit_get(pl.in_valid[c], pl.sel ? (int64_t)pl.sel[i] : i);
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < tile_n; k += XS_NT) {
-          int p = 0;
-          while (p + 1 < pl.W && k >= s_start[p + 1]) p++;
-          const long long dest = s_base[p] + (k - s_start[p]);
-          if (dest < pl.cap) reinterpret_cast<uint8_t*>(pl.arena[p] + (int64_t)pl.me * pl.region_bytes + pl.val_off[c])[dest] = stage[k];
-        }
-        __syncthreads();
-      }
+      // validity as one byte per row (only for columns that carry NULLs here)
+      if (pl.in_valid[c]) xs_move_column<uint8_t, true>(pl, pl.val_off[c], pl.in_valid[c], (uint8_t*)stage_raw, lpos, tile_base, n, rn);
     }
   }
 }
@@ -547,12 +557,20 @@ int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, c
         maxw = std::max(maxw, widths[i]);
       }
       const int smem = XS_TILE * maxw;
-      if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(xchg_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      // key mode: one integer key column without NULLs (every TPC-H join key) skips the generic per-row type dispatch
+      int km = 0;
+      if (keys.n == 1 && !keys.c[0].valid) {
+        const int dt = keys.c[0].dtype;
+        if (dt == B2_INT64 || dt == B2_TIMESTAMP_US || dt == B2_DECIMAL64) km = 1;
+        else if (dt == B2_INT32 || dt == B2_DATE32) km = 2;
+      }
+      auto kern = km == 1 ? xchg_scatter_kernel<1> : (km == 2 ? xchg_scatter_kernel<2> : xchg_scatter_kernel<0>);
+      if (smem > 40 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       const int64_t ntiles = (nsend + XS_TILE - 1) / XS_TILE;
-      const int per_sm = std::max(1, std::min(8, (200 * 1024) / (smem + 1024)));
+      const int per_sm = std::max(1, std::min(8, (200 * 1024) / (smem + 2048)));
       const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
       KernelTimer kt("xchg_scatter_kernel");
-      xchg_scatter_kernel<<<grid, XS_NT, smem, s>>>(keys, pl, nsend, (uint32_t)seed, c->d_hdr->counts);
+      kern<<<grid, XS_NT, smem, s>>>(keys, pl, nsend, (uint32_t)seed, c->d_hdr->counts);
       CUDA_CHECK(cudaGetLastError());
       count_launch();
     }
