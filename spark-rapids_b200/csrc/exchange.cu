@@ -204,14 +204,30 @@ struct XRuns {
 template <typename T, bool VALID>
 __device__ __forceinline__ void xs_move_column(const XPlan& pl, int64_t off_bytes, const void* __restrict__ in, T* stage, const uint16_t* lpos,
                                                int64_t tile_base, int64_t n, const XRuns& rn) {
+  // loads in explicit batches: all of a batch's (dependent: selection vector -> value) loads are in flight before the first
+  // shared-memory store waits for one.  (Left to the compiler under a register cap, the 16 fully unrolled steps became 16
+  // serial load -> store round trips: ncu put 60 % of the kernel's stall samples on the STS / first use of the loaded value.)
+  // The batch loop itself is NOT unrolled and the stage positions live in shared memory, which keeps the kernel small enough
+  // to hold a batch in registers without spilling.
+  constexpr int XB = sizeof(T) >= 16 ? 4 : 8;
+#pragma unroll 1
+  for (int j0 = 0; j0 < XS_STEPS; j0 += XB) {
+    int64_t src[XB];
+    T v[XB];
 #pragma unroll
-  for (int j = 0; j < XS_STEPS; j++) {
-    const int64_t i = tile_base + (int64_t)j * XS_NT + threadIdx.x;
-    if (i < n) {
-      const int64_t src = pl.sel ? (int64_t)pl.sel[i] : i;
-      if constexpr (VALID) stage[lpos[j]] = (T)bit_get(reinterpret_cast<const uint32_t*>(in), src);
-      else stage[lpos[j]] = reinterpret_cast<const T*>(in)[src];
+    for (int b = 0; b < XB; b++) {
+      const int64_t i = tile_base + (int64_t)(j0 + b) * XS_NT + threadIdx.x;
+      src[b] = i < n ? (pl.sel ? (int64_t)pl.sel[i] : i) : -1;
     }
+#pragma unroll
+    for (int b = 0; b < XB; b++) {
+      if (src[b] >= 0) {
+        if constexpr (VALID) v[b] = (T)bit_get(reinterpret_cast<const uint32_t*>(in), src[b]);
+        else v[b] = reinterpret_cast<const T*>(in)[src[b]];
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < XB; b++) if (src[b] >= 0) stage[lpos[(j0 + b) * XS_NT + threadIdx.x]] = v[b];
   }
   __syncthreads();
   constexpr int V = sizeof(T) >= 16 ? 1 : 16 / (int)sizeof(T);
@@ -238,12 +254,14 @@ __device__ __forceinline__ void xs_move_column(const XPlan& pl, int64_t off_byte
 // KM: how a row's destination is computed.  0 = generic (any key columns, NULLs), 1 = ONE 64-bit integer-like key column without
 // NULLs (INT64 / TIMESTAMP / DECIMAL64: Spark hashes the raw long), 2 = ONE INT32 / DATE32 column without NULLs.
 template <int KM>
-__global__ void __launch_bounds__(XS_NT, 4) xchg_scatter_kernel(const __grid_constant__ KeyCols keys, const __grid_constant__ XPlan pl, int64_t n, uint32_t seed,
+__global__ void __launch_bounds__(XS_NT, 3) xchg_scatter_kernel(const __grid_constant__ KeyCols keys, const __grid_constant__ XPlan pl, int64_t n, uint32_t seed,
                                                              unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) char stage_raw[];   // XS_TILE * widest column
   __shared__ int s_wcnt[XS_NT / 32][XMAX_W];          // rows of (warp, destination); then the warp's offset inside the destination's run
   __shared__ int s_cnt[XMAX_W];
   __shared__ long long s_gbase[XMAX_W];
+  __shared__ uint16_t s_lpos[XS_TILE];   // rank among the warp's rows for the destination, then the stage position
+  __shared__ uint8_t s_pid[XS_TILE];
   __shared__ XRuns rn;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -253,34 +271,56 @@ __global__ void __launch_bounds__(XS_NT, 4) xchg_scatter_kernel(const __grid_con
     const int64_t tile_base = tile * XS_TILE;
     for (int k = threadIdx.x; k < (XS_NT / 32) * XMAX_W; k += XS_NT) (&s_wcnt[0][0])[k] = 0;
     __syncthreads();
-    uint8_t pid[XS_STEPS];
-    uint16_t lpos[XS_STEPS];
     // destination of every row (Spark Murmur3 over the key columns, pmod world) and its rank among the warp's rows for that
-    // destination: one match_any per 32 rows, running counts per (warp, destination) — no atomics, deterministic order
+    // destination: one match_any per 32 rows, running counts per (warp, destination) — no atomics, deterministic order.
+    // Batches of XH rows per thread: XH selection-vector loads, then XH key loads in flight at once.
+    constexpr int XH = 8;
+#pragma unroll 1
+    for (int j0 = 0; j0 < XS_STEPS; j0 += XH) {
+      int64_t src[XH];
+      uint32_t h[XH];
 #pragma unroll
-    for (int j = 0; j < XS_STEPS; j++) {
-      const int64_t i = tile_base + (int64_t)j * XS_NT + threadIdx.x;
-      int p = -1;
-      if (i < n) {
-        if (pl.single) p = 0;
-        else {
-          const int64_t src = pl.sel ? (int64_t)pl.sel[i] : i;
-          uint32_t h = seed;
-          if (KM == 1) h = hash_long(reinterpret_cast<const uint64_t*>(keys.c[0].data)[src], seed);
-          else if (KM == 2) h = hash_int(reinterpret_cast<const uint32_t*>(keys.c[0].data)[src], seed);
-          else for (int c = 0; c < keys.n; c++) h = murmur_col(keys.c[c], src, h);
-          if (pow2) p = (int)(h & (uint32_t)(pl.W - 1));   // pmod of a two's complement int by a power of two
-          else { int32_t v = (int32_t)h % pl.W; if (v < 0) v += pl.W; p = v; }
+      for (int b = 0; b < XH; b++) {
+        const int64_t i = tile_base + (int64_t)(j0 + b) * XS_NT + threadIdx.x;
+        src[b] = i < n ? (pl.sel ? (int64_t)pl.sel[i] : i) : -1;
+      }
+      if (KM == 1) {
+        uint64_t kv[XH];
+#pragma unroll
+        for (int b = 0; b < XH; b++) kv[b] = src[b] >= 0 ? reinterpret_cast<const uint64_t*>(keys.c[0].data)[src[b]] : 0ull;
+#pragma unroll
+        for (int b = 0; b < XH; b++) h[b] = hash_long(kv[b], seed);
+      } else if (KM == 2) {
+        uint32_t kv[XH];
+#pragma unroll
+        for (int b = 0; b < XH; b++) kv[b] = src[b] >= 0 ? reinterpret_cast<const uint32_t*>(keys.c[0].data)[src[b]] : 0u;
+#pragma unroll
+        for (int b = 0; b < XH; b++) h[b] = hash_int(kv[b], seed);
+      } else {
+#pragma unroll
+        for (int b = 0; b < XH; b++) {
+          h[b] = seed;
+          if (src[b] >= 0 && !pl.single) for (int c = 0; c < keys.n; c++) h[b] = murmur_col(keys.c[c], src[b], h[b]);
         }
       }
-      const uint32_t m = __match_any_sync(0xffffffffu, p);
-      const int leader = __ffs(m) - 1;
-      int first = 0;
-      if (p >= 0 && lane == leader) { first = s_wcnt[warp][p]; s_wcnt[warp][p] = first + __popc(m); }
-      first = __shfl_sync(0xffffffffu, first, leader);
-      __syncwarp();
-      pid[j] = (uint8_t)p;
-      lpos[j] = (uint16_t)(first + __popc(m & lt));
+#pragma unroll
+      for (int b = 0; b < XH; b++) {
+        int p = -1;
+        if (src[b] >= 0) {
+          if (pl.single) p = 0;
+          else if (pow2) p = (int)(h[b] & (uint32_t)(pl.W - 1));   // pmod of a two's complement int by a power of two
+          else { int32_t v = (int32_t)h[b] % pl.W; if (v < 0) v += pl.W; p = v; }
+        }
+        const uint32_t m = __match_any_sync(0xffffffffu, p);
+        const int leader = __ffs(m) - 1;
+        int first = 0;
+        if (p >= 0 && lane == leader) { first = s_wcnt[warp][p]; s_wcnt[warp][p] = first + __popc(m); }
+        first = __shfl_sync(0xffffffffu, first, leader);
+        __syncwarp();
+        const int li = (j0 + b) * XS_NT + threadIdx.x;
+        s_pid[li] = (uint8_t)p;
+        s_lpos[li] = (uint16_t)(first + __popc(m & lt));
+      }
     }
     __syncthreads();
     if (threadIdx.x < pl.W) {   // offsets of the warps inside the destination's run; one reservation per tile and destination
@@ -304,21 +344,20 @@ __global__ void __launch_bounds__(XS_NT, 4) xchg_scatter_kernel(const __grid_con
       rn.start[pl.W] = run;
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < XS_STEPS; j++) {
-      const int p = pid[j];
-      lpos[j] = (uint16_t)(p != 0xff ? rn.start[p] + s_wcnt[warp][p] + lpos[j] : 0);
+    for (int li = threadIdx.x; li < XS_TILE; li += XS_NT) {   // same thread as above: no barrier needed for its own entries
+      const int p = s_pid[li];
+      if (p != 0xff) s_lpos[li] = (uint16_t)(rn.start[p] + s_wcnt[warp][p] + s_lpos[li]);
     }
     for (int c = 0; c < pl.ncols; c++) {
       switch (pl.width[c]) {
-        case 1: xs_move_column<uint8_t, false>(pl, pl.col_off[c], pl.in[c], (uint8_t*)stage_raw, lpos, tile_base, n, rn); break;
-        case 2: xs_move_column<uint16_t, false>(pl, pl.col_off[c], pl.in[c], (uint16_t*)stage_raw, lpos, tile_base, n, rn); break;
-        case 4: xs_move_column<uint32_t, false>(pl, pl.col_off[c], pl.in[c], (uint32_t*)stage_raw, lpos, tile_base, n, rn); break;
-        case 8: xs_move_column<uint64_t, false>(pl, pl.col_off[c], pl.in[c], (uint64_t*)stage_raw, lpos, tile_base, n, rn); break;
-        default: xs_move_column<uint4, false>(pl, pl.col_off[c], pl.in[c], (uint4*)stage_raw, lpos, tile_base, n, rn); break;
+        case 1: xs_move_column<uint8_t, false>(pl, pl.col_off[c], pl.in[c], (uint8_t*)stage_raw, s_lpos, tile_base, n, rn); break;
+        case 2: xs_move_column<uint16_t, false>(pl, pl.col_off[c], pl.in[c], (uint16_t*)stage_raw, s_lpos, tile_base, n, rn); break;
+        case 4: xs_move_column<uint32_t, false>(pl, pl.col_off[c], pl.in[c], (uint32_t*)stage_raw, s_lpos, tile_base, n, rn); break;
+        case 8: xs_move_column<uint64_t, false>(pl, pl.col_off[c], pl.in[c], (uint64_t*)stage_raw, s_lpos, tile_base, n, rn); break;
+        default: xs_move_column<uint4, false>(pl, pl.col_off[c], pl.in[c], (uint4*)stage_raw, s_lpos, tile_base, n, rn); break;
       }
       // validity as one byte per row (only for columns that carry NULLs here)
-      if (pl.in_valid[c]) xs_move_column<uint8_t, true>(pl, pl.val_off[c], pl.in_valid[c], (uint8_t*)stage_raw, lpos, tile_base, n, rn);
+      if (pl.in_valid[c]) xs_move_column<uint8_t, true>(pl, pl.val_off[c], pl.in_valid[c], (uint8_t*)stage_raw, s_lpos, tile_base, n, rn);
     }
   }
 }
@@ -567,7 +606,7 @@ int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, c
       auto kern = km == 1 ? xchg_scatter_kernel<1> : (km == 2 ? xchg_scatter_kernel<2> : xchg_scatter_kernel<0>);
       if (smem > 40 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       const int64_t ntiles = (nsend + XS_TILE - 1) / XS_TILE;
-      const int per_sm = std::max(1, std::min(8, (200 * 1024) / (smem + 2048)));
+      const int per_sm = std::max(1, std::min(3, (200 * 1024) / (smem + 2048)));
       const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
       KernelTimer kt("xchg_scatter_kernel");
       kern<<<grid, XS_NT, smem, s>>>(keys, pl, nsend, (uint32_t)seed, c->d_hdr->counts);
