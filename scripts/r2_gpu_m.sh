@@ -15,11 +15,6 @@ try:
 except Exception as e:
     print(f, "ERR", e)
 PY
-timeout 300 python scripts/xchg_local_probe.py > gpurun_out/r2m_xchg_local.txt 2>&1; tail -6 gpurun_out/r2m_xchg_local.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:xchg_scatter_kernel -s 3 -c 1 -o gpurun_out/r2m_ncu_xchg_scatter_kernel -f python scripts/xchg_local_probe.py > gpurun_out/r2m_ncu_xchg.log 2>&1
-ncu -i gpurun_out/r2m_ncu_xchg_scatter_kernel.ncu-rep --page raw --csv > gpurun_out/r2m_ncu_xchg_scatter_kernel_raw.csv 2>/dev/null
-ncu -i gpurun_out/r2m_ncu_xchg_scatter_kernel.ncu-rep --page source --csv > gpurun_out/r2m_ncu_xchg_scatter_kernel_source.csv 2>/dev/null
-rm -f gpurun_out/r2m_ncu_xchg_scatter_kernel.ncu-rep
 BENCH="python bench.py --steps 1 --warmup 3 --cpu-baseline 0 --check 0 --extra-q6 0"
 for K in radix_agg_kernel; do
   timeout 600 ncu --set full --clock-control none -k regex:$K -s 3 -c 1 -o gpurun_out/r2m_ncu_$K -f $BENCH > gpurun_out/r2m_ncu_$K.log 2>&1

@@ -810,10 +810,8 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
   uint64_t* t_acc = t_k1 + (rp.has_k1 ? C : 0);
   uint32_t* t_state = reinterpret_cast<uint32_t*>(t_acc + (size_t)C * plan.limbs);
   uint32_t* t_nvalid = t_state + C;
-  // two logs of claimed slots (slot, claiming row): the current one and the one the open partition's groups are re-logged into
-  uint32_t* t_urow = t_nvalid + (size_t)C * plan.nvalids;
-  uint16_t* t_used = reinterpret_cast<uint16_t*>(t_urow + 2 * (size_t)C);
-  char* stage0 = reinterpret_cast<char*>(((uintptr_t)(t_used + 2 * (size_t)C) + 127) & ~(uintptr_t)127);
+  uint16_t* t_used = reinterpret_cast<uint16_t*>(t_nvalid + (size_t)C * plan.nvalids);   // log of the claimed slots
+  char* stage0 = reinterpret_cast<char*>(((uintptr_t)(t_used + C) + 127) & ~(uintptr_t)127);
   // one stage buffer: k0 | k1 | v[0..] | vbits, each CH rows (+ slack so that 16-byte rounded copies stay inside)
   constexpr int CH = RG_CHUNK;
   int soff_k1 = CH * 8 + 16, soff_v[RG_MAX_VALS], soff_vb, sbytes;
@@ -857,15 +855,43 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
   }
   __syncthreads();
   uint32_t phase[2] = {0, 0};
-  int p = pA;           // first partition of this CTA that is not known to be complete
-  int nb = 0;           // which claimed-slot log is current
+  int p = pA;
+  uint32_t nu = 0;      // claimed slots (= groups alive in the table), block-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
+  // every logged group -> the compact group arrays, every logged slot reset: the table is EMPTY afterwards.  Only called at a
+  // partition boundary (all rows of every group in the table have been seen).  A partial flush is not possible with linear
+  // probing: resetting some slots breaks the probe chains of the groups that stay.
+  auto flush_all = [&]() {
+    __syncthreads();
+    const uint32_t n_used = s_nused[0];
+    for (uint32_t u0 = threadIdx.x & ~31u; u0 < n_used; u0 += RG_NT) {
+      const uint32_t u = u0 + lane;
+      const bool valid = u < n_used;
+      const int sl = valid ? t_used[u] : 0;
+      const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+      unsigned long long o = 0;
+      if (lane == 0) o = atomicAdd(a.gcount, (unsigned long long)__popc(bal));
+      o = __shfl_sync(0xffffffffu, o, 0) + __popc(bal & lt);
+      if (valid) {
+        a.gk0[o] = t_k0[sl];
+        if (rp.has_k1) a.gk1[o] = t_k1[sl];
+        for (int l = 0; l < plan.limbs; l++) a.gacc[o * plan.limbs + l] = t_acc[(size_t)sl * plan.limbs + l];
+        for (int v = 0; v < plan.nvalids; v++) a.gnvalid[o * plan.nvalids + v] = t_nvalid[(size_t)sl * plan.nvalids + v];
+        t_state[sl] = 0;
+        for (int k = 0; k < plan.naggs; k++)
+          for (int l = 0; l < plan.aggs[k].nlimbs; l++) t_acc[(size_t)sl * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
+        for (int v = 0; v < plan.nvalids; v++) t_nvalid[(size_t)sl * plan.nvalids + v] = 0;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_nused[0] = 0;
+    __syncthreads();
+  };
   // A chunk's rows are aggregated all at once, whatever partitions they belong to (different partitions are just different
-  // keys to the table); the partition order of the rows only bounds how many groups are alive at a time.  Groups leave when
-  // the log of claimed slots has grown past C/4: every logged group whose partition is complete (claiming row in front of
-  // the still open partition) is appended to the compact group arrays and its slot reset; the open partition's groups are
-  // re-logged.  One barrier per chunk + two per flush, instead of four per partition (~480 rows) before.
+  // keys to the table); the partition order of the rows only bounds how many groups are alive at a time.  When the log of
+  // claimed slots has grown past C/4 the chunk is cut at the next partition boundary and the table flushed there.  Two
+  // barriers per chunk + three per flush, instead of four per partition (~480 rows) before.
   for (int64_t c = 0; c < nchunks; c++) {
     const int buf = (int)(c & 1);
     if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1, buf ^ 1);
@@ -877,99 +903,77 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
     const uint32_t* s_vb = reinterpret_cast<const uint32_t*>(sb + soff_vb);
     const int64_t cs = a0 + c * CH;
     const int64_t lo = max(cs, r_lo), hi = min(cs + CH, r_hi);
-    uint16_t* u_slot = t_used + (size_t)nb * C;
-    uint32_t* u_row = t_urow + (size_t)nb * C;
-    for (int64_t r = lo + threadIdx.x; r < hi; r += RG_NT) {
-      const int li = (int)(r - cs);
-      const uint64_t k0 = s_k0[li], k1 = rp.has_k1 ? s_k1[li] : 0;
-      uint32_t idx = (uint32_t)rg_hash(k0, k1) & (uint32_t)(C - 1);
-      int probes = 0;
-      bool found = false;
-      while (!found) {
-        uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t_state[idx]);
-        if (st == 0) {
-          const uint32_t old = atomicCAS(&t_state[idx], 0u, (uint32_t)(li + 1));
-          if (old == 0) {   // mine: publish the key, then the READY bit
-            t_k0[idx] = k0;
-            if (rp.has_k1) t_k1[idx] = k1;
+    auto aggregate_rows = [&](int64_t from, int64_t to) {
+      for (int64_t r = from + threadIdx.x; r < to; r += RG_NT) {
+        const int li = (int)(r - cs);
+        const uint64_t k0 = s_k0[li], k1 = rp.has_k1 ? s_k1[li] : 0;
+        uint32_t idx = (uint32_t)rg_hash(k0, k1) & (uint32_t)(C - 1);
+        int probes = 0;
+        bool found = false;
+        while (!found) {
+          uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t_state[idx]);
+          if (st == 0) {
+            const uint32_t old = atomicCAS(&t_state[idx], 0u, (uint32_t)(li + 1));
+            if (old == 0) {   // mine: publish the key, then the READY bit
+              t_k0[idx] = k0;
+              if (rp.has_k1) t_k1[idx] = k1;
+              __threadfence_block();
+              *reinterpret_cast<volatile uint32_t*>(&t_state[idx]) = (uint32_t)(li + 1) | RG_READY;
+              t_used[atomicAdd(&s_nused[0], 1u)] = (uint16_t)idx;
+              found = true;
+              break;
+            }
+            st = old;
+          }
+          bool same;
+          if (st & RG_READY) {
             __threadfence_block();
-            *reinterpret_cast<volatile uint32_t*>(&t_state[idx]) = (uint32_t)(li + 1) | RG_READY;
-            const uint32_t u = atomicAdd(&s_nused[nb], 1u);
-            u_slot[u] = (uint16_t)idx; u_row[u] = (uint32_t)r;
-            found = true;
-            break;
+            same = *reinterpret_cast<volatile uint64_t*>(&t_k0[idx]) == k0 && (!rp.has_k1 || *reinterpret_cast<volatile uint64_t*>(&t_k1[idx]) == k1);
+          } else {   // claimed in this very segment, key not visible yet: compare with the claiming row in the stage buffer
+            const int lj = (int)(st & ~RG_READY) - 1;
+            same = s_k0[lj] == k0 && (!rp.has_k1 || s_k1[lj] == k1);
           }
-          st = old;
+          if (same) { found = true; break; }
+          idx = (idx + 1) & (uint32_t)(C - 1);
+          if (++probes > C / 2) { atomicExch(a.overflow, 1); break; }
         }
-        bool same;
-        if (st & RG_READY) {
-          __threadfence_block();
-          same = *reinterpret_cast<volatile uint64_t*>(&t_k0[idx]) == k0 && (!rp.has_k1 || *reinterpret_cast<volatile uint64_t*>(&t_k1[idx]) == k1);
-        } else {   // claimed in this very chunk, key not visible yet: compare with the claiming row in the stage buffer
-          const int lj = (int)(st & ~RG_READY) - 1;
-          same = s_k0[lj] == k0 && (!rp.has_k1 || s_k1[lj] == k1);
+        if (!found) continue;
+        const uint32_t vb = rp.use_vbits ? s_vb[li] : 0xffffffffu;
+        uint64_t* acc = t_acc + (size_t)idx * plan.limbs;
+        uint32_t* nv = t_nvalid + (size_t)idx * plan.nvalids;
+        for (int k = 0; k < plan.naggs; k++) {
+          const AggD& ag = plan.aggs[k];
+          const int vs = rp.agg_val[k];
+          const bool valid = vs < 0 || ((vb >> vs) & 1u);
+          if (!valid) continue;
+          if (ag.track_valid) atomicAdd(&nv[ag.valid_off], 1u);
+          if (ag.kind == B2_AGG_COUNT || ag.kind == B2_AGG_COUNT_ALL) { atomicAdd(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), 1ull); continue; }
+          uint64_t lo64, hi64;
+          if (rp.val[vs].width == 16) { const i128 x = reinterpret_cast<const i128*>(sb + soff_v[vs])[li]; lo64 = (uint64_t)x; hi64 = (uint64_t)(x >> 64); }
+          else { lo64 = (uint64_t)reinterpret_cast<const int64_t*>(sb + soff_v[vs])[li]; hi64 = (int64_t)lo64 < 0 ? ~0ull : 0ull; }
+          if (ag.kind == B2_AGG_SUM) acc_add_limbs(&acc[ag.limb_off], ag.nlimbs, lo64, hi64, (int64_t)hi64 < 0 ? ~0ull : 0ull);
+          else if (ag.kind == B2_AGG_MIN) atomicMin(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), (unsigned long long)ord_i64((int64_t)lo64));
+          else if (ag.kind == B2_AGG_MAX) atomicMax(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), (unsigned long long)ord_i64((int64_t)lo64));
         }
-        if (same) { found = true; break; }
-        idx = (idx + 1) & (uint32_t)(C - 1);
-        if (++probes > C / 2) { atomicExch(a.overflow, 1); break; }
       }
-      if (!found) continue;
-      const uint32_t vb = rp.use_vbits ? s_vb[li] : 0xffffffffu;
-      uint64_t* acc = t_acc + (size_t)idx * plan.limbs;
-      uint32_t* nv = t_nvalid + (size_t)idx * plan.nvalids;
-      for (int k = 0; k < plan.naggs; k++) {
-        const AggD& ag = plan.aggs[k];
-        const int vs = rp.agg_val[k];
-        const bool valid = vs < 0 || ((vb >> vs) & 1u);
-        if (!valid) continue;
-        if (ag.track_valid) atomicAdd(&nv[ag.valid_off], 1u);
-        if (ag.kind == B2_AGG_COUNT || ag.kind == B2_AGG_COUNT_ALL) { atomicAdd(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), 1ull); continue; }
-        uint64_t lo64, hi64;
-        if (rp.val[vs].width == 16) { const i128 x = reinterpret_cast<const i128*>(sb + soff_v[vs])[li]; lo64 = (uint64_t)x; hi64 = (uint64_t)(x >> 64); }
-        else { lo64 = (uint64_t)reinterpret_cast<const int64_t*>(sb + soff_v[vs])[li]; hi64 = (int64_t)lo64 < 0 ? ~0ull : 0ull; }
-        if (ag.kind == B2_AGG_SUM) acc_add_limbs(&acc[ag.limb_off], ag.nlimbs, lo64, hi64, (int64_t)hi64 < 0 ? ~0ull : 0ull);
-        else if (ag.kind == B2_AGG_MIN) atomicMin(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), (unsigned long long)ord_i64((int64_t)lo64));
-        else if (ag.kind == B2_AGG_MAX) atomicMax(reinterpret_cast<unsigned long long*>(&acc[ag.limb_off]), (unsigned long long)ord_i64((int64_t)lo64));
+    };
+    int64_t from = lo;
+    if (nu >= (uint32_t)(C / 4)) {
+      while (p < pB && (int64_t)a.off[p + 1] <= lo) p++;   // a.off[p] <= lo < a.off[p + 1]
+      if (p < pB) {
+        const int64_t bnd = (int64_t)a.off[p] == lo ? lo : (int64_t)a.off[p + 1];   // the first partition boundary at or after lo
+        if (bnd <= hi) {
+          aggregate_rows(lo, bnd);
+          flush_all();
+          from = bnd;
+        }
       }
     }
-    if (threadIdx.x == 0) s_nused[nb ^ 1] = 0;
+    aggregate_rows(from, hi);
+    if (c + 1 == nchunks) flush_all();
     __syncthreads();   // the chunk is aggregated: every key is published, the stage buffer may be refilled
-    const bool last = c + 1 == nchunks;
-    const uint32_t nu = s_nused[nb];
-    if (last || nu >= (uint32_t)(C / 4)) {
-      while (p < pB && (int64_t)a.off[p + 1] <= hi) p++;
-      // rows from keep_from on belong to the partition that continues in the next chunk: its groups stay in the table
-      const int64_t keep_from = (!last && p < pB) ? (int64_t)a.off[p] : INT64_MAX;
-      uint16_t* k_slot = t_used + (size_t)(nb ^ 1) * C;
-      uint32_t* k_row = t_urow + (size_t)(nb ^ 1) * C;
-      for (uint32_t u0 = threadIdx.x & ~31u; u0 < nu; u0 += RG_NT) {
-        const uint32_t u = u0 + lane;
-        const bool valid = u < nu;
-        const int sl = valid ? u_slot[u] : 0;
-        const uint32_t row = valid ? u_row[u] : 0;
-        const bool keep = valid && (int64_t)row >= keep_from;
-        const bool emit = valid && !keep;
-        const uint32_t bal = __ballot_sync(0xffffffffu, emit);
-        if (bal) {
-          unsigned long long o = 0;
-          if (lane == 0) o = atomicAdd(a.gcount, (unsigned long long)__popc(bal));
-          o = __shfl_sync(0xffffffffu, o, 0) + __popc(bal & lt);
-          if (emit) {
-            a.gk0[o] = t_k0[sl];
-            if (rp.has_k1) a.gk1[o] = t_k1[sl];
-            for (int l = 0; l < plan.limbs; l++) a.gacc[o * plan.limbs + l] = t_acc[(size_t)sl * plan.limbs + l];
-            for (int v = 0; v < plan.nvalids; v++) a.gnvalid[o * plan.nvalids + v] = t_nvalid[(size_t)sl * plan.nvalids + v];
-            t_state[sl] = 0;
-            for (int k = 0; k < plan.naggs; k++)
-              for (int l = 0; l < plan.aggs[k].nlimbs; l++) t_acc[(size_t)sl * plan.limbs + plan.aggs[k].limb_off + l] = init_limb(plan.aggs[k]);
-            for (int v = 0; v < plan.nvalids; v++) t_nvalid[(size_t)sl * plan.nvalids + v] = 0;
-          }
-        }
-        if (keep) { const uint32_t q = atomicAdd(&s_nused[nb ^ 1], 1u); k_slot[q] = (uint16_t)sl; k_row[q] = row; }
-      }
-      __syncthreads();
-      nb ^= 1;
-    }
+    nu = s_nused[0];
+    __syncthreads();   // nobody claims a slot of the next chunk before everybody has read the count
   }
 }
 
@@ -1064,7 +1068,7 @@ static Table* radix_groupby(const Program* prog, const Table* t, const AggPlan& 
   const int ncols_moved = 2 + rp.has_k1 + rp.nvals + rp.use_vbits;
   if (ncols_moved > PT_MAXC) return nullptr;
   // shared-memory budget of the aggregation kernel: table of C slots + two stage buffers
-  const int slot_bytes = 8 + (rp.has_k1 ? 8 : 0) + plan.limbs * 8 + 4 + plan.nvalids * 4 + 12;   // + two claimed-slot logs (slot u16, row u32)
+  const int slot_bytes = 8 + (rp.has_k1 ? 8 : 0) + plan.limbs * 8 + 4 + plan.nvalids * 4 + 2;   // + the claimed-slot log
   int sbytes = RG_CHUNK * 8 + 16 + (rp.has_k1 ? RG_CHUNK * 8 + 16 : 0) + (rp.use_vbits ? RG_CHUNK * 4 + 16 : 0);
   for (int s2 = 0; s2 < rp.nvals; s2++) sbytes += RG_CHUNK * rp.val[s2].width + 16;
   sbytes = (sbytes + 127) & ~127;

@@ -96,6 +96,29 @@ def test_groupby_full_size(b2, big):
     assert int(out.column(3).to_numpy()[0].max()) == int(key.max())
 
 
+@pytest.mark.parametrize("n,ngroups", [(3_000_000, 1_200_000), (20_000_000, 7_000_003)])
+def test_groupby_high_cardinality_radix_regime(b2, n, ngroups):
+    """millions of groups: the radix-partitioned shared-memory regime (partitions cut across chunks, tables flushed at
+    partition boundaries).  Sums / counts per key equal np.bincount; run twice: the result does not depend on scheduling"""
+    rng = np.random.default_rng(n)
+    k0 = rng.integers(0, ngroups, n, dtype=np.int64)
+    k1 = (k0 % 2557).astype(np.int32)                   # functionally dependent second key (q3's o_orderdate shape)
+    val = rng.integers(1, 10_000_000, n, dtype=np.int64)
+    t = b2.Table.from_columns([b2.Column.from_numpy(k0), b2.Column.from_numpy(k1), b2.Column.from_numpy(val)])
+    want_sum = np.bincount(k0, weights=val, minlength=ngroups).astype(np.int64)     # < 2^53: exact
+    want_cnt = np.bincount(k0, minlength=ngroups)
+    present = np.flatnonzero(want_cnt)
+    for _ in range(2):
+        out = b2.groupby(t, [0, 1], [(b2.AGG_SUM, 2, b2.INT64, 0, 0), (b2.AGG_COUNT_ALL, 2, b2.INT64, 0, 0)])
+        assert out.num_rows == len(present)
+        g = out.column(0).to_numpy()[0]
+        o = np.argsort(g)
+        assert np.array_equal(g[o], present)
+        assert np.array_equal(out.column(1).to_numpy()[0][o], (present % 2557).astype(np.int32))
+        assert np.array_equal(out.column(2).to_numpy()[0][o], want_sum[present])
+        assert np.array_equal(out.column(3).to_numpy()[0][o], want_cnt[present])
+
+
 def test_sort_full_size(b2, big):
     key, val, grp, t = big
     n = 30_000_000                                                      # 2 x 12-byte key/value buffers of the radix sort per row
