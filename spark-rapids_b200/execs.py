@@ -12,7 +12,7 @@ class GpuExec:
         self._keep = list(keep)  # programs / children / host buffers that must outlive the node
 
     def __del__(self):
-        if getattr(self, "h", None) is not None and self.h.value:
+        if getattr(self, "h", None) is not None and self.h.value and lib is not None:   # lib is None during interpreter shutdown
             lib.b2_exec_close(self.h)
             self.h = ctypes.c_int64(0)
 
