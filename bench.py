@@ -54,13 +54,58 @@ def hbm_peak():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region.  NVML in a thread (a query costs microseconds, so even a 40 ms
+    region at N = 8 gets dozens of samples; one is taken synchronously at start and one at stop); `nvidia-smi -lms` (first
+    sample after ~50 ms) only when the NVML binding is missing."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu):
-        self.gpu, self.proc = gpu, None
+        self.gpu, self.proc, self.nv, self.h = gpu, None, None, None
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.thread, self.stop_flag = None, False
+
+    def _nvml_sample(self):
+        nv, h = self.nv, self.h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for bit, name in self.BITS.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        import time as _t
+        while not self.stop_flag:
+            try:
+                self._nvml_sample()
+            except Exception:
+                return
+            _t.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            try:
+                import torch
+                u = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + u if not u.startswith("GPU-") else u).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nv, self.h = nv, h
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nvml_sample()
+            import threading
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -68,6 +113,16 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1)
+            try:
+                self._nvml_sample()
+            except Exception:
+                pass
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,7 +145,7 @@ class ClockSampler:
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -475,6 +530,13 @@ def bench_q3(ctx):
         "filter_kernel": alg["filter_customer"] + alg["filter_orders"] + alg["filter_lineitem"],
         "join_build_kernel": (b1 + b2) * (K + 4 + K),
         "join_probe_distinct_kernel": (s1 + s2) * K + (m1 + m2) * 8,
+        "join_probe_distinct1_kernel": (s1 + s2) * K + (m1 + m2) * 8,      # S*k read + M*8 maps written
+        # selection vectors: the predicate column (DATE32) read + 4 B per selected row written
+        "simple_filter_ids_kernel": (rows_in("orders") + rows_in("lineitem")) * 4 + (r["filter_orders"] + r["filter_lineitem"]) * 4,
+        "filter_staged_kernel": alg["filter_customer"],
+        "radix_rows_kernel": m2 * (32 + 28),                                 # join output row in, packed (hash, key, value) row out
+        "part_scatter2_kernel": 2 * m2 * 28 * 2,                             # two 8-bit passes, each reads and writes 28 B per row
+        "radix_agg_kernel": alg["aggregate"],
         "gather_fixed_kernel": m1 * (4 + 2 * 16) + m2 * (4 + 2 * 24) + m2 * (4 + 2 * 8) + g * (4 + 2 * 16),
         "aggregate_global_kernel": alg["aggregate"], "aggregate_smem_kernel": alg["aggregate"],
         "xchg_scatter_kernel": (r.get("filter_customer", 0) * 8 + r.get("filter_orders", 0) * 24 + m1 * 16 + r.get("filter_lineitem", 0) * 24) * 2,

@@ -694,7 +694,7 @@ __global__ void finalize_kernel(GTable gt, const __grid_constant__ AggPlan plan,
 // Reference it replaces: cudf hash groupby behind AggHelper.performGroupByAggregation (GpuAggregateExec.scala:562-585).
 constexpr int RG_MAX_VALS = 5;
 constexpr int RG_NT = 512;
-constexpr int RG_CHUNK = 1024;        // rows per staged chunk
+constexpr int RG_CHUNK = 1024;        // rows per staged chunk (<= 4 x RG_NT: see `claimed` in radix_agg_kernel)
 constexpr uint32_t RG_READY = 0x80000000u;
 struct RGVal { int32_t out_idx, in_mt, width, pad; };
 struct RGPlan {
@@ -832,20 +832,33 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
   const int64_t r_lo = a.off[pA], r_hi = a.off[pB];
   const int64_t a0 = r_lo & ~(int64_t)3;
   const int64_t nchunks = r_hi > r_lo ? (r_hi - a0 + CH - 1) / CH : 0;
+  // the arrays a chunk is made of (base pointer, element width, offset inside a stage buffer): built once, so that the thread
+  // that issues the TMA copies runs a short rolled loop (the inlined, unrolled form was ~600 instructions per chunk on the
+  // critical path of warp 0)
+  __shared__ const char* s_abase[RG_MAX_VALS + 3];
+  __shared__ int s_awidth[RG_MAX_VALS + 3], s_aoff[RG_MAX_VALS + 3], s_narr;
+  if (threadIdx.x == 0) {
+    int k = 0;
+    s_abase[k] = reinterpret_cast<const char*>(a.rows.k0); s_awidth[k] = 8; s_aoff[k] = 0; k++;
+    if (rp.has_k1) { s_abase[k] = reinterpret_cast<const char*>(a.rows.k1); s_awidth[k] = 8; s_aoff[k] = soff_k1; k++; }
+    for (int s = 0; s < rp.nvals; s++) { s_abase[k] = a.rows.v[s]; s_awidth[k] = rp.val[s].width; s_aoff[k] = soff_v[s]; k++; }
+    if (rp.use_vbits) { s_abase[k] = reinterpret_cast<const char*>(a.rows.vbits); s_awidth[k] = 4; s_aoff[k] = soff_vb; k++; }
+    s_narr = k;
+  }
+  __syncthreads();
   auto issue = [&](int64_t c, int buf) {   // one thread: TMA copies of chunk c into stage buffer buf
     const int64_t start = a0 + c * CH;
     const int64_t rows = min((int64_t)CH, a.m - start);
     char* sb = stage0 + (size_t)buf * sbytes;
-    uint32_t total = (uint32_t)((rows * 8 + 15) & ~15LL) * (rp.has_k1 ? 2 : 1);
-    for (int s = 0; s < rp.nvals; s++) total += (uint32_t)((rows * rp.val[s].width + 15) & ~15LL);
-    if (rp.use_vbits) total += (uint32_t)((rows * 4 + 15) & ~15LL);
+    const int narr = s_narr;
+    uint32_t total = 0;
+#pragma unroll 1
+    for (int k = 0; k < narr; k++) total += (uint32_t)((rows * s_awidth[k] + 15) & ~15LL);
     fence_proxy_async();
     mbar_expect_tx(&s_bar[buf], total);
-    tma_bulk_g2s(sb, a.rows.k0 + start, (uint32_t)((rows * 8 + 15) & ~15LL), &s_bar[buf]);
-    if (rp.has_k1) tma_bulk_g2s(sb + soff_k1, a.rows.k1 + start, (uint32_t)((rows * 8 + 15) & ~15LL), &s_bar[buf]);
-    for (int s = 0; s < rp.nvals; s++)
-      tma_bulk_g2s(sb + soff_v[s], a.rows.v[s] + start * rp.val[s].width, (uint32_t)((rows * rp.val[s].width + 15) & ~15LL), &s_bar[buf]);
-    if (rp.use_vbits) tma_bulk_g2s(sb + soff_vb, a.rows.vbits + start, (uint32_t)((rows * 4 + 15) & ~15LL), &s_bar[buf]);
+#pragma unroll 1
+    for (int k = 0; k < narr; k++)
+      tma_bulk_g2s(sb + s_aoff[k], s_abase[k] + start * s_awidth[k], (uint32_t)((rows * s_awidth[k] + 15) & ~15LL), &s_bar[buf]);
   };
   if (threadIdx.x == 0) {
     s_nused[0] = 0; s_nused[1] = 0;
@@ -903,36 +916,37 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
     const uint32_t* s_vb = reinterpret_cast<const uint32_t*>(sb + soff_vb);
     const int64_t cs = a0 + c * CH;
     const int64_t lo = max(cs, r_lo), hi = min(cs + CH, r_hi);
+    uint16_t claimed[4];   // slots this thread claimed in the current segment (a thread sees CH / RG_NT = 2 rows of a chunk)
+    int nclaimed = 0;
     auto aggregate_rows = [&](int64_t from, int64_t to) {
+      nclaimed = 0;
       for (int64_t r = from + threadIdx.x; r < to; r += RG_NT) {
         const int li = (int)(r - cs);
         const uint64_t k0 = s_k0[li], k1 = rp.has_k1 ? s_k1[li] : 0;
         uint32_t idx = (uint32_t)rg_hash(k0, k1) & (uint32_t)(C - 1);
         int probes = 0;
         bool found = false;
+        // A slot claimed in THIS segment carries the claiming row's stage index and is compared through the (read-only) stage
+        // buffer; its key is written to the table without any fence and only read after the barrier that ends the segment,
+        // when the claimer also sets RG_READY.  No memory fence and no volatile key read per row.
         while (!found) {
           uint32_t st = *reinterpret_cast<volatile uint32_t*>(&t_state[idx]);
           if (st == 0) {
             const uint32_t old = atomicCAS(&t_state[idx], 0u, (uint32_t)(li + 1));
-            if (old == 0) {   // mine: publish the key, then the READY bit
+            if (old == 0) {
               t_k0[idx] = k0;
               if (rp.has_k1) t_k1[idx] = k1;
-              __threadfence_block();
-              *reinterpret_cast<volatile uint32_t*>(&t_state[idx]) = (uint32_t)(li + 1) | RG_READY;
               t_used[atomicAdd(&s_nused[0], 1u)] = (uint16_t)idx;
+              if (nclaimed < 4) claimed[nclaimed] = (uint16_t)idx;
+              nclaimed++;
               found = true;
               break;
             }
             st = old;
           }
           bool same;
-          if (st & RG_READY) {
-            __threadfence_block();
-            same = *reinterpret_cast<volatile uint64_t*>(&t_k0[idx]) == k0 && (!rp.has_k1 || *reinterpret_cast<volatile uint64_t*>(&t_k1[idx]) == k1);
-          } else {   // claimed in this very segment, key not visible yet: compare with the claiming row in the stage buffer
-            const int lj = (int)(st & ~RG_READY) - 1;
-            same = s_k0[lj] == k0 && (!rp.has_k1 || s_k1[lj] == k1);
-          }
+          if (st & RG_READY) same = t_k0[idx] == k0 && (!rp.has_k1 || t_k1[idx] == k1);
+          else { const int lj = (int)st - 1; same = s_k0[lj] == k0 && (!rp.has_k1 || s_k1[lj] == k1); }
           if (same) { found = true; break; }
           idx = (idx + 1) & (uint32_t)(C - 1);
           if (++probes > C / 2) { atomicExch(a.overflow, 1); break; }
@@ -970,8 +984,9 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
       }
     }
     aggregate_rows(from, hi);
-    if (c + 1 == nchunks) flush_all();
-    __syncthreads();   // the chunk is aggregated: every key is published, the stage buffer may be refilled
+    if (c + 1 == nchunks) { flush_all(); nclaimed = 0; }
+    __syncthreads();   // the chunk is aggregated: every key is in the table, the stage buffer may be refilled
+    for (int q = 0; q < nclaimed && q < 4; q++) t_state[claimed[q]] |= RG_READY;   // from now on compared through the table
     nu = s_nused[0];
     __syncthreads();   // nobody claims a slot of the next chunk before everybody has read the count
   }
