@@ -161,7 +161,12 @@ def test_gather_nullify_oob(b2):
 # ---- a8 ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("typ", ALL_KEY_TYPES)
 @pytest.mark.parametrize("asc,nf", [(1, 1), (1, 0), (0, 0), (0, 1)])
-def test_sort_single_key(b2, typ, asc, nf):
+@pytest.mark.parametrize("path", ["one-CTA bitonic (n <= 16384)", "radix"])
+def test_sort_single_key(b2, typ, asc, nf, path, monkeypatch):
+    if path == "radix":
+        monkeypatch.setenv("B2_SORT_NO_SMALL", "1")
+    else:
+        monkeypatch.delenv("B2_SORT_NO_SMALL", raising=False)
     rng = np.random.default_rng(typ[0] * 4 + asc * 2 + nf)
     n = 3000
     k = gen(rng, typ, n, distinct=None if typ[0] in (O.BOOL8,) else 500)
@@ -189,6 +194,10 @@ def test_sort_multi_key_q3_order(b2):
     keys = [(0, 0, 0), (1, 1, 1)]
     t = G.to_b2_table(b2, cols)
     assert b2.sort_order(t, keys).to_pylist() == R.sort_order(cols, keys)
+    # the one-CTA bitonic sort of small inputs (multi-chunk keys, duplicates, non-power-of-two sizes): same stable order
+    for m in (2, 3, 1000, 8191, 8192, 8193, 16384):
+        sub = [O.OCol(c.values[:m], c.valid[:m], c.typ) for c in cols]
+        assert b2.sort_order(G.to_b2_table(b2, sub), keys).to_pylist() == R.sort_order(sub, keys)
     top = b2.top_n(t, keys, 10)
     exp = R.take(cols, R.sort_order(cols, keys)[:10])
     for i in range(3):
