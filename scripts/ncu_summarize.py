@@ -25,6 +25,9 @@ for path in args:
     data = [r for r in rows[rows.index(hdr) + 2:] if len(r) == len(hdr)]
     for r in data:
         name = r[hdr.index("Kernel Name")].split("(")[0]
+        if name.startswith("void "):
+            name = name[5:]
+        name = name.split("<")[0].split("::")[-1]   # the name bench.py's kernel timers use: no return type, namespace or template arguments
         ent = {}
         for k in WANT:
             if k in hdr:

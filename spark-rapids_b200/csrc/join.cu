@@ -412,9 +412,9 @@ int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* ou
   jt->slots = DevBuf((size_t)cap * (jt->fast ? 16 : 8));
   CUDA_CHECK(cudaMemsetAsync(jt->slots.p, 0xff, jt->slots.bytes, stream()));
   if (t->rows >= (1 << 18) && !getenv("B2_JOIN_NO_BLOOM")) {   // smaller tables are L2 resident themselves
-    // bits per key: fewer bits = more false positives (each costs one DRAM-latency slot read) but a filter that stays in
-    // L2 next to the streamed probe columns.  ncu (profiles/r2_*): a 32 MB filter was evicted by the probe stream
-    // (60 % L2 miss rate); see DESIGN.md section 9 for the sweep
+    // bits per key: fewer bits = more false positives (each costs one random HBM slot read) but a smaller filter.  Sweep on
+    // the q3 step (probe kernel, ms per step): 16 bits 5.08, 8 bits 6.07, 4 bits 7.71; pinning the filter in the persisting
+    // part of L2 (B2_JOIN_BLOOM_PERSIST) 5.31 — the false-positive rate matters more than L2 residency
     static const int bits_per_key = getenv("B2_JOIN_BLOOM_BITS") ? std::max(2, atoi(getenv("B2_JOIN_BLOOM_BITS"))) : 16;
     int64_t words = 1 << 15;
     while (words * 64 < t->rows * bits_per_key && words < (8 << 20)) words <<= 1;   // at most 64 MB
