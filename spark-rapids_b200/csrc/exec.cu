@@ -28,6 +28,7 @@ Table* scan_aggregate(const Program* prog, bool has_pred, const Table* t, const 
 Program* make_passthrough_program(const Table* t, const std::vector<int>& cols);
 Table* filter_select(const Program* prog, const Table* t, const int32_t* keep, int nkeep);
 Column* filter_row_ids(const Program* prog, const Table* t);
+bool join_probe_pred(b2_handle ht, const Table* batch, int key_col, const Program* prog, Column** out_lm, Column** out_rm, int64_t* npass_out);   // join.cu
 Table* filter_by_mask(const Table* t, Column* m);
 Column* rows_with_passing_pair(const Column* left_map, const Column* pass, int64_t stream_rows, bool invert);
 
@@ -360,20 +361,36 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
   Table* fused_next() {
     TableRef raw(fused->children[0]->next());
     if (!raw.t) return nullptr;
-    ColGuard sel(run_as(fused, [&] { return filter_row_ids(program_from(fused->program), raw.t); }));
-    fused->num_output_rows += sel.c->size; fused->num_output_batches++;
     std::vector<int> keys, left_cols;
     for (int k : stream_keys) keys.push_back(raw_col(k));
+    // simple predicate + FK -> PK inner probe: the filter is evaluated INSIDE the probe kernel (no selection vector at all)
+    struct Owned { Column* c = nullptr; ~Owned() { if (c) col_release(c); } Column* take() { Column* r = c; c = nullptr; return r; } };
+    Owned plm, prm, sel;
+    int64_t npass = 0;
+    bool in_probe = false;
+    if (kind == B2_JOIN_INNER && keys.size() == 1) {
+      try { in_probe = join_probe_pred(ht, raw.t, keys[0], program_from(fused->program), &plm.c, &prm.c, &npass); }
+      catch (const Error& e) { if (!splittable(e)) throw; in_probe = false; }   // memory pressure: the selection-vector path retries and splits
+    }
+    auto make_sel = [&] { if (!sel.c) sel.c = run_as(fused, [&] { return filter_row_ids(program_from(fused->program), raw.t); }); };
+    if (!in_probe) make_sel();
+    fused->num_output_rows += in_probe ? npass : sel.c->size; fused->num_output_batches++;
     if (pruned) for (int c : stream_out) left_cols.push_back(raw_col(c));
     else { const int n = fused->keep.empty() ? (int)raw.t->cols.size() : (int)fused->keep.size(); for (int c = 0; c < n; c++) left_cols.push_back(raw_col(c)); }
     try {
       return with_retry([&]() -> Table* {
-        TableRef sk(select(raw.t, keys));
-        b2_handle lm = 0, rm = 0;
-        int rc = b2_join_probe_sel(ht, to_handle(sk.t), to_handle(sel.c), kind, &lm, &rm);
-        if (rc != B2_OK) throw Error(rc, b2_last_error());
-        ColGuard lmap(col_from(lm));
-        ColGuard rmap(rm ? col_from(rm) : nullptr);
+        Column* lmc = nullptr; Column* rmc = nullptr;
+        if (plm.c) { lmc = plm.take(); rmc = prm.take(); }   // the maps of the fused kernel (first attempt only)
+        else {
+          make_sel();
+          TableRef sk(select(raw.t, keys));
+          b2_handle lm = 0, rm = 0;
+          int rc = b2_join_probe_sel(ht, to_handle(sk.t), to_handle(sel.c), kind, &lm, &rm);
+          if (rc != B2_OK) throw Error(rc, b2_last_error());
+          lmc = col_from(lm); rmc = rm ? col_from(rm) : nullptr;
+        }
+        ColGuard lmap(lmc);
+        ColGuard rmap(rmc);
         TableRef left(gather_table(raw.t, lmap.c->data.as<int32_t>(), lmap.c->size, false, &left_cols));
         if (!rmap.c || (pruned && build_out.empty())) return left.release();
         TableRef right(gather_table(build_table.t, rmap.c->data.as<int32_t>(), rmap.c->size, kind == B2_JOIN_LEFT_OUTER, pruned ? &build_out : nullptr));
@@ -390,6 +407,7 @@ struct GpuShuffledHashJoinExec : GpuExec {  // children[0] = stream (left), chil
       std::vector<int> fcols;
       const int n = fused->keep.empty() ? (int)raw.t->cols.size() : (int)fused->keep.size();
       for (int c = 0; c < n; c++) fcols.push_back(raw_col(c));
+      make_sel();
       TableRef ft(gather_table(raw.t, sel.c->data.as<int32_t>(), sel.c->size, false, &fcols));
       todo.emplace_back(std::move(ft), 0);
       return drain_todo();

@@ -11,6 +11,7 @@
 #include <type_traits>
 #include "prim.cuh"
 #include "rowops.cuh"
+#include "simplefilter.cuh"
 
 namespace b2 {
 
@@ -214,13 +215,32 @@ struct L2Persist {
 //      HBM accesses into the table are issued by FULL warps in one or two rounds (the generic kernel walked its 8 row
 //      slots one after the other, each round with 2-3 live lanes paying a full memory latency);
 //   3. one output reservation (atomic) per round.
+//   MODE 0: every row of the batch; 1: the rows of a selection vector (a filter below the join emitted row ids);
+//   2: the filter itself is evaluated here (a "simple" predicate, simplefilter.cuh): the predicate columns of the 256 rows are
+//      loaded first, rows that fail are dropped before their key is fetched, and no selection vector is ever written or read.
 constexpr int PQ = 8;
-template <typename K, bool SEL>
+template <typename T>
+__device__ __forceinline__ uint32_t pred_term_mask(const SimpleTerm& t, const int32_t (&r)[PQ]) {
+  T v[PQ];
+#pragma unroll
+  for (int j = 0; j < PQ; j++) v[j] = r[j] >= 0 ? reinterpret_cast<const T*>(t.col)[r[j]] : T(0);
+  const T lit = (T)t.lit;
+  uint32_t pass = 0;
+#pragma unroll
+  for (int j = 0; j < PQ; j++) {
+    const int c = v[j] < lit ? 1 : (v[j] == lit ? 2 : 4);
+    pass |= (uint32_t)((t.truth & c) != 0) << j;
+  }
+  return pass;
+}
+template <typename K, int MODE>
 __global__ void __launch_bounds__(256) join_probe_distinct1_kernel(const K* __restrict__ keys, const int32_t* __restrict__ sel, int64_t n,
                                                                    const uint64_t* __restrict__ slots, uint32_t mask,
                                                                    const unsigned long long* __restrict__ bloom, uint32_t bloom_mask,
                                                                    unsigned long long* __restrict__ total, int32_t* __restrict__ left_map,
-                                                                   int32_t* __restrict__ right_map) {
+                                                                   int32_t* __restrict__ right_map, const __grid_constant__ SimplePred sp,
+                                                                   unsigned long long* __restrict__ npass) {
+  constexpr bool SEL = MODE == 1;
   typedef typename std::make_unsigned<K>::type UK;
   __shared__ uint8_t s_q[8][32 * PQ];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -232,6 +252,23 @@ __global__ void __launch_bounds__(256) join_probe_distinct1_kernel(const K* __re
     for (int j = 0; j < PQ; j++) {
       const int64_t rr = base + j * 32 + lane;
       r[j] = rr < n ? (SEL ? sel[rr] : (int32_t)rr) : -1;
+    }
+    if (MODE == 2) {   // the filter: PQ independent loads per lane and term
+      uint32_t ok = 0xffu;
+      for (int k = 0; k < sp.n; k++) {
+        const SimpleTerm& t = sp.t[k];
+        switch (t.width) {
+          case 1: ok &= pred_term_mask<int8_t>(t, r); break;
+          case 2: ok &= pred_term_mask<int16_t>(t, r); break;
+          case 4: ok &= pred_term_mask<int32_t>(t, r); break;
+          default: ok &= pred_term_mask<int64_t>(t, r); break;
+        }
+      }
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < PQ; j++) { if (!((ok >> j) & 1u)) r[j] = -1; cnt += r[j] >= 0; }
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0 && cnt) atomicAdd(npass, (unsigned long long)cnt);
     }
     uint32_t pass = 0;
     if (bloom) {
@@ -386,6 +423,46 @@ static JoinTable* jt_from(b2_handle h) {
   return reinterpret_cast<JoinTable*>((intptr_t)h);
 }
 
+// GpuFilter directly below the stream side of an INNER FK -> PK join, fused INTO the probe when the predicate is of the simple
+// shape (simplefilter.cuh) and the probe qualifies for join_probe_distinct1_kernel: the gather maps carry ORIGINAL row ids of
+// `batch`, `npass_out` = rows that passed the filter (the filter node's numOutputRows).  false = not applicable, the caller
+// takes the selection-vector path.
+bool join_probe_pred(b2_handle ht, const Table* batch, int key_col, const Program* prog, Column** out_lm, Column** out_rm, int64_t* npass_out) {
+  if (getenv("B2_JOIN_NO_PRED_FUSION") || getenv("B2_JOIN_NO_FAST_PROBE")) return false;
+  JoinTable* jt = jt_from(ht);
+  const int64_t n = batch->rows;
+  if (!jt->distinct || !jt->fast || jt->key_idx.size() != 1 || n < (1 << 16) || n >= 0x7fffffffLL) return false;
+  const Column* pc = batch->cols[key_col];
+  const int pw = dtype_width(pc->dtype);
+  if (pc->nullable() || is_float(pc->dtype) || pc->dtype == B2_STRING || !(pw == 4 || pw == 8)) return false;
+  if (pc->dtype != jt->keys->cols[jt->key_idx[0]]->dtype) return false;
+  SimplePred sp;
+  if (!simple_pred_of(prog, batch, sp)) return false;
+  ColGuard lm(new_column(B2_INT32, 0, n, false)), rm(new_column(B2_INT32, 0, n, false));
+  DevBuf tot(16);
+  CUDA_CHECK(cudaMemsetAsync(tot.p, 0, 16, stream()));
+  {
+    KernelTimer kt("join_probe_distinct1_kernel");
+    const int grid = grid_for(n, 256);
+    const uint64_t* sl = jt->slots.as<uint64_t>(); const uint32_t msk = (uint32_t)(jt->cap - 1);
+    const unsigned long long* bl = jt->bloom.as<unsigned long long>();
+    unsigned long long* tp = tot.as<unsigned long long>();
+    if (pw == 8) join_probe_distinct1_kernel<int64_t, 2><<<grid, 256, 0, stream()>>>(pc->data.as<int64_t>(), nullptr, n, sl, msk, bl, jt->bloom_mask, tp,
+                                                                                       lm.c->data.as<int32_t>(), rm.c->data.as<int32_t>(), sp, tp + 1);
+    else join_probe_distinct1_kernel<int32_t, 2><<<grid, 256, 0, stream()>>>(pc->data.as<int32_t>(), nullptr, n, sl, msk, bl, jt->bloom_mask, tp,
+                                                                              lm.c->data.as<int32_t>(), rm.c->data.as<int32_t>(), sp, tp + 1);
+    CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  unsigned long long h[2] = {0, 0};
+  d2h(h, tot.p, 2);
+  sync();
+  lm.c->size = (int64_t)h[0]; rm.c->size = (int64_t)h[0];
+  *npass_out = (int64_t)h[1];
+  *out_lm = lm.release(); *out_rm = rm.release();
+  return true;
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -526,12 +603,13 @@ int b2_join_probe_sel(b2_handle ht, b2_handle probe_keys_table, b2_handle select
         const uint64_t* sl = jt->slots.as<uint64_t>(); const uint32_t msk = (uint32_t)(jt->cap - 1);
         const unsigned long long* bl = jt->bloom.as<unsigned long long>(); unsigned long long* tp = tot.as<unsigned long long>();
         int32_t* lp = lm.c->data.as<int32_t>(); int32_t* rp = rm.c->data.as<int32_t>();
+        SimplePred none; memset(&none, 0, sizeof(none));
         if (pw == 8) {
-          if (sel) join_probe_distinct1_kernel<int64_t, true><<<grid, 256, 0, stream()>>>(pc->data.as<int64_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp);
-          else join_probe_distinct1_kernel<int64_t, false><<<grid, 256, 0, stream()>>>(pc->data.as<int64_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp);
+          if (sel) join_probe_distinct1_kernel<int64_t, 1><<<grid, 256, 0, stream()>>>(pc->data.as<int64_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp, none, nullptr);
+          else join_probe_distinct1_kernel<int64_t, 0><<<grid, 256, 0, stream()>>>(pc->data.as<int64_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp, none, nullptr);
         } else {
-          if (sel) join_probe_distinct1_kernel<int32_t, true><<<grid, 256, 0, stream()>>>(pc->data.as<int32_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp);
-          else join_probe_distinct1_kernel<int32_t, false><<<grid, 256, 0, stream()>>>(pc->data.as<int32_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp);
+          if (sel) join_probe_distinct1_kernel<int32_t, 1><<<grid, 256, 0, stream()>>>(pc->data.as<int32_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp, none, nullptr);
+          else join_probe_distinct1_kernel<int32_t, 0><<<grid, 256, 0, stream()>>>(pc->data.as<int32_t>(), sel, n, sl, msk, bl, jt->bloom_mask, tp, lp, rp, none, nullptr);
         }
         CUDA_CHECK(cudaGetLastError());
         count_launch();

@@ -7,12 +7,11 @@
 // coalesced, through a shared-memory stage (single pass: block scan + decoupled look-back across tiles).  Anything that does not match the shape returns false and takes the VM.
 #include "prim.cuh"
 #include "vm.cuh"
+#include "simplefilter.cuh"
 
 namespace b2 {
 
-constexpr int SF_NT = 256, SF_WARPS = SF_NT / 32, SF_TILE = 32768, SF_WORDS = SF_TILE / 32, SF_WWORDS = SF_WORDS / SF_WARPS, SF_MAX_TERMS = 8;
-struct SimpleTerm { const void* col; int32_t width; int32_t truth; int64_t lit; };   // truth: bit0 '<', bit1 '==', bit2 '>'
-struct SimplePred { int32_t n; int32_t pad; SimpleTerm t[SF_MAX_TERMS]; };
+constexpr int SF_NT = 256, SF_WARPS = SF_NT / 32, SF_TILE = 32768, SF_WORDS = SF_TILE / 32, SF_WWORDS = SF_WORDS / SF_WARPS;
 struct SimpleWork { unsigned long long tile_counter, total; };
 
 constexpr uint64_t SLB_AGG = 1ull << 62, SLB_PREFIX = 2ull << 62, SLB_MASK = (1ull << 62) - 1;
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(SF_NT) simple_filter_ids_kernel(const __grid_c
 }
 
 // pattern match: output 0 = c0 AND c1 AND ... with c_i = (NOT NULL fixed-width integer column) <cmp> (non-null literal)
-static bool simple_pred_of(const Program* prog, const Table* t, SimplePred& sp) {
+bool simple_pred_of(const Program* prog, const Table* t, SimplePred& sp) {
   memset(&sp, 0, sizeof(sp));
   const int n = prog->hdr.ninstr;
   if (prog->hdr.nouts != 1 || n < 1 || n > SF_MAX_TERMS || (int)prog->code.size() != n) return false;

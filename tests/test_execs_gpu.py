@@ -195,6 +195,45 @@ def test_join_exec_output_pruning(b2):
     assert sorted(r[0] for r in only_stream.to_rows()) == sorted(r[1] for r in full.to_rows())
 
 
+@pytest.mark.parametrize("keytype", ["int64", "int32"])
+def test_filter_fused_into_probe(b2, keytype, monkeypatch):
+    """GpuFilter below the stream side of an INNER FK -> PK join: a simple predicate is evaluated inside the probe kernel
+    (no selection vector); the selection-vector path and the unfused plan give the same rows, and all equal numpy"""
+    from spark_rapids_b200 import execs as E
+    rng = np.random.default_rng(77)
+    ns, nb = 300_000, 400_000                                  # >= 2^18 build rows: the Bloom filter is on
+    kt = np.int64 if keytype == "int64" else np.int32
+    skey = rng.integers(0, 1_000_000, ns).astype(kt)           # ~40 % of the stream keys exist on the build side
+    sdate = rng.integers(8000, 11000, ns).astype(np.int32)
+    sval = rng.integers(0, 1 << 40, ns).astype(np.int64)
+    bkey = rng.permutation(1_000_000)[:nb].astype(kt)
+    bval = (bkey.astype(np.int64) * 3 + 1)
+
+    def plan():
+        st = b2.Table.from_columns([b2.Column.from_numpy(skey), b2.Column.from_numpy(sdate, dtype=b2.DATE32), b2.Column.from_numpy(sval)])
+        bt = b2.Table.from_columns([b2.Column.from_numpy(bkey), b2.Column.from_numpy(bval)])
+        half = ns // 2
+        srcs = E.GpuBatchSource([b2.slice_table(st, 0, half), b2.slice_table(st, half, ns)])
+        pred = b2.Program([(b2.col(1, b2.DATE32, nullable=False) > b2.lit(9204, b2.DATE32)) & (b2.col(2, b2.INT64, nullable=False) >= b2.lit(1 << 20, b2.INT64))])
+        flt = E.GpuFilterExec(pred, srcs)
+        return E.GpuShuffledHashJoinExec([0], [0], b2.JOIN_INNER, flt, E.GpuBatchSource([bt]), stream_out=[0, 2], build_out=[1]), flt
+
+    keep = (sdate > 9204) & (sval >= (1 << 20))
+    lut = np.full(1_000_000, -1, dtype=np.int64)
+    lut[bkey.astype(np.int64)] = bval
+    hit = keep & (lut[skey.astype(np.int64)] >= 0)
+    want = sorted(zip(skey[hit].tolist(), sval[hit].tolist(), lut[skey[hit].astype(np.int64)].tolist()))
+    for env in ({}, {"B2_JOIN_NO_PRED_FUSION": "1"}, {"B2_NO_FILTER_FUSION": "1"}):
+        for k in ("B2_JOIN_NO_PRED_FUSION", "B2_NO_FILTER_FUSION"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        j, flt = plan()
+        out = j.collect()
+        assert sorted(out.to_rows()) == want, env
+        assert flt.metrics["numOutputRows"] == int(keep.sum()), env
+
+
 @pytest.mark.parametrize("kind", [0, 1, 2, 3])
 def test_mixed_join_condition(b2, kind):
     """Table.mixed*JoinGatherMaps (GpuHashJoin.scala:335-600): equi keys + a non-equi condition over both sides
