@@ -367,6 +367,10 @@ int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, c
                          const int32_t* key_cols, int32_t nkeys, int32_t seed, b2_handle* out_table, int32_t* any_data);
 int b2_comm_fused_ready(b2_handle comm, int32_t* ok);        /* collective: peer arenas mapped on every rank? */
 int b2_comm_allmax(b2_handle comm, int32_t value, int32_t* out);   /* collective max of one int per rank */
+/* GpuShuffleExchangeExec termination without an empty last round: `more` = this rank will call the next exchange with a batch
+ * (it looked one batch ahead); after the call b2_comm_any_more tells whether any rank will.  Unset: more = "had data". */
+int b2_comm_set_more(b2_handle comm, int32_t more);
+int b2_comm_any_more(b2_handle comm, int32_t* out);
 /* out4: payload bytes sent to / received from OTHER ranks so far, exchange calls, arena bytes (0 = NCCL path) */
 int b2_comm_stats(b2_handle comm, int64_t* out4);
 /* GpuBroadcastExchangeExec data movement: root's table to every rank (ncclBroadcast); non-root pass table = 0 */

@@ -85,7 +85,7 @@ struct XHeader {
   int32_t ncols;                       // 0 = this rank has not seen a batch yet (adopts the schema of a rank that has)
   int32_t dtype[XMAX_COLS], scale[XMAX_COLS];
   uint32_t nullable_mask;              // bit c: column c carries validity bytes in my regions
-  uint32_t pad;
+  int32_t more;                        // this rank has (or may have) a batch for the NEXT call too: nobody has -> the exchange is over after this call
 };
 
 struct Comm {
@@ -93,6 +93,8 @@ struct Comm {
   int rank = 0, world = 1;
   // symmetric receive arenas (fused path)
   bool arena_tried = false, arena_ok = false;
+  int next_more = -1;      // b2_comm_set_more: the `more` flag of the next exchange call (-1 = not told: more = has_data, the old protocol)
+  int last_any_more = 1;   // max of `more` over the ranks in the last exchange call
   size_t arena_bytes = 0;
   char* arena_local[2] = {nullptr, nullptr};
   char* arena_peer[2][XMAX_W];
@@ -509,6 +511,20 @@ int b2_comm_allmax(b2_handle h, int32_t value, int32_t* out) {
   B2_CATCH
 }
 
+// Termination without an extra (empty) round: a caller that looks one batch ahead tells the next exchange call whether it
+// will come again with data; after the call b2_comm_any_more says whether ANY rank will.  Without b2_comm_set_more the flag
+// defaults to "this call carried data", i.e. the exchange ends with the first call in which nobody had a batch.
+int b2_comm_set_more(b2_handle h, int32_t more) {
+  B2_TRY
+  comm_from(h)->next_more = more ? 1 : 0;
+  B2_CATCH
+}
+int b2_comm_any_more(b2_handle h, int32_t* out) {
+  B2_TRY
+  *out = comm_from(h)->last_any_more;
+  B2_CATCH
+}
+
 int b2_comm_stats(b2_handle h, int64_t* out4) {
   B2_TRY
   Comm* c = comm_from(h);
@@ -571,6 +587,7 @@ int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, c
   if (full && nkeys > 0) keys = key_cols_of(full, key_cols, nkeys);
   XHeader hdr; memset(&hdr, 0, sizeof(hdr));
   hdr.has_data = t ? 1 : 0;
+  hdr.more = c->next_more >= 0 ? c->next_more : hdr.has_data; c->next_more = -1;
   hdr.ncols = (int)c->schema_dtype.size();
   for (int i = 0; i < hdr.ncols; i++) { hdr.dtype[i] = c->schema_dtype[i]; hdr.scale[i] = c->schema_scale[i]; }
   if (t) for (int i = 0; i < hdr.ncols; i++) if (t->cols[i]->nullable()) hdr.nullable_mask |= 1u << i;
@@ -655,6 +672,8 @@ int b2_exchange_hash_sel(b2_handle comm, b2_handle table, b2_handle selection, c
   const int parity = (int)((c->epoch - 1) & 1);
   int anyd = 0;
   for (int r = 0; r < W; r++) anyd |= all[r].has_data;
+  c->last_any_more = 0;
+  for (int r = 0; r < W; r++) c->last_any_more |= all[r].more;
   *any_data = anyd;
   c->calls++;
   if (!anyd) return B2_OK;
@@ -729,6 +748,7 @@ int b2_exchange_ex(b2_handle comm, b2_handle partitioned_table, const int32_t* o
   // round 0: who has data, and the schema for ranks that never saw a batch
   XHeader hdr; memset(&hdr, 0, sizeof(hdr));
   hdr.has_data = mine ? 1 : 0;
+  hdr.more = c->next_more >= 0 ? c->next_more : hdr.has_data; c->next_more = -1;
   hdr.ncols = (int)std::min<size_t>(c->schema_dtype.size(), XMAX_COLS);
   B2_CHECK(c->schema_dtype.size() <= (size_t)XMAX_COLS, "exchange: more than 32 columns");
   for (int i = 0; i < hdr.ncols; i++) { hdr.dtype[i] = c->schema_dtype[i]; hdr.scale[i] = c->schema_scale[i]; }
@@ -752,6 +772,8 @@ int b2_exchange_ex(b2_handle comm, b2_handle partitioned_table, const int32_t* o
   int anyd = 0, src_schema = -1;
   uint32_t any_null = 0;
   for (int r = 0; r < W; r++) { anyd |= all[r].has_data; any_null |= all[r].nullable_mask; if (src_schema < 0 && all[r].ncols > 0) src_schema = r; }
+  c->last_any_more = 0;
+  for (int r = 0; r < W; r++) c->last_any_more |= all[r].more;
   *any_data = anyd;
   c->calls++;
   if (!anyd) return B2_OK;

@@ -628,7 +628,7 @@ struct GpuShuffleExchangeExec : GpuExec {
   std::vector<int32_t> key_cols;   // empty = SinglePartition (everything to rank 0)
   b2_handle comm = 0;
   int world = 1;
-  bool child_done = false, finished = false, probed = false, fused = false;
+  bool finished = false, probed = false, fused = false;
   Table* do_next() override {
     if (finished) return nullptr;
     if (world == 1 || !comm) {
@@ -644,8 +644,15 @@ struct GpuShuffleExchangeExec : GpuExec {
     // a GpuFilterExec (with its column pruning) directly below is fused into the scatter: see GpuShuffledHashJoinExec::fused
     GpuFilterExec* ff = getenv("B2_NO_FILTER_FUSION") ? nullptr : dynamic_cast<GpuFilterExec*>(children[0]);
     GpuExec* src = ff ? ff->children[0] : children[0];
-    TableRef in;
-    if (!child_done) { in = TableRef(src->next()); if (!in.t) child_done = true; }
+    // one batch of look-ahead: the call that carries a rank's LAST batch says so (b2_comm_set_more), and when no rank has
+    // more the exchange is over without an extra, empty round (one header all-gather + D2H + sync per exchange node)
+    if (!primed) { primed = true; ahead = TableRef(src->next()); }
+    TableRef in = std::move(ahead);
+    if (in.t) ahead = TableRef(src->next());
+    {
+      int rc = b2_comm_set_more(comm, ahead.t ? 1 : 0);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+    }
     std::vector<int32_t> out_cols;     // the columns that travel (indices into the batch pulled from src)
     if (ff && in.t) {
       if (ff->keep.empty()) for (int c = 0; c < (int)in.t->cols.size(); c++) out_cols.push_back(c);
@@ -701,9 +708,17 @@ struct GpuShuffleExchangeExec : GpuExec {
       int rc = b2_exchange_ex(comm, part.t ? to_handle(part.t) : 0, part.t ? offs.data() : nullptr, &out, &any);
       if (rc != B2_OK) throw Error(rc, b2_last_error());
     }
-    if (!any) { finished = true; return nullptr; }
+    int32_t any_more = 1;
+    {
+      int rc = b2_comm_any_more(comm, &any_more);
+      if (rc != B2_OK) throw Error(rc, b2_last_error());
+    }
+    if (!any_more) finished = true;            // every rank sent its last batch (or had none): no further round
+    if (!any) { finished = true; if (out) table_release(from_handle_owned(out)); return nullptr; }
     return from_handle_owned(out);
   }
+  bool primed = false;
+  TableRef ahead;             // the batch the NEXT call will carry
   bool has_strings = false;   // the path (fused / NCCL) is a per-node property every rank agrees on at the first call
 };
 

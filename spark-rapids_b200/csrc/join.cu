@@ -428,7 +428,11 @@ static JoinTable* jt_from(b2_handle h) {
 // `batch`, `npass_out` = rows that passed the filter (the filter node's numOutputRows).  false = not applicable, the caller
 // takes the selection-vector path.
 bool join_probe_pred(b2_handle ht, const Table* batch, int key_col, const Program* prog, Column** out_lm, Column** out_rm, int64_t* npass_out) {
-  if (getenv("B2_JOIN_NO_PRED_FUSION") || getenv("B2_JOIN_NO_FAST_PROBE")) return false;
+  // OFF by default: measured on the q3 step the fused kernel is slower (probe 5.2 -> 11.2 ms, step 24.1 -> 27.5 ms).  The probe
+  // is bound by latency per row SLOT, not by bytes, and without the selection vector it walks all 600 M rows with 46 % of
+  // its lanes idle; the filter kernel's compaction is worth more than the 1.3 GB round trip of the row ids.  Kept (and
+  // tested) behind B2_JOIN_PRED_FUSION for a version that compacts the passing rows inside the warp first.
+  if (!getenv("B2_JOIN_PRED_FUSION") || getenv("B2_JOIN_NO_FAST_PROBE")) return false;
   JoinTable* jt = jt_from(ht);
   const int64_t n = batch->rows;
   if (!jt->distinct || !jt->fast || jt->key_idx.size() != 1 || n < (1 << 16) || n >= 0x7fffffffLL) return false;

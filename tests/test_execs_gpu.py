@@ -197,8 +197,9 @@ def test_join_exec_output_pruning(b2):
 
 @pytest.mark.parametrize("keytype", ["int64", "int32"])
 def test_filter_fused_into_probe(b2, keytype, monkeypatch):
-    """GpuFilter below the stream side of an INNER FK -> PK join: a simple predicate is evaluated inside the probe kernel
-    (no selection vector); the selection-vector path and the unfused plan give the same rows, and all equal numpy"""
+    """GpuFilter below the stream side of an INNER FK -> PK join: a simple predicate evaluated inside the probe kernel
+    (opt-in, B2_JOIN_PRED_FUSION: measured slower on q3), the selection-vector path (default) and the unfused plan give the
+    same rows, and all equal numpy"""
     from spark_rapids_b200 import execs as E
     rng = np.random.default_rng(77)
     ns, nb = 300_000, 400_000                                  # >= 2^18 build rows: the Bloom filter is on
@@ -223,8 +224,8 @@ def test_filter_fused_into_probe(b2, keytype, monkeypatch):
     lut[bkey.astype(np.int64)] = bval
     hit = keep & (lut[skey.astype(np.int64)] >= 0)
     want = sorted(zip(skey[hit].tolist(), sval[hit].tolist(), lut[skey[hit].astype(np.int64)].tolist()))
-    for env in ({}, {"B2_JOIN_NO_PRED_FUSION": "1"}, {"B2_NO_FILTER_FUSION": "1"}):
-        for k in ("B2_JOIN_NO_PRED_FUSION", "B2_NO_FILTER_FUSION"):
+    for env in ({"B2_JOIN_PRED_FUSION": "1"}, {}, {"B2_NO_FILTER_FUSION": "1"}):
+        for k in ("B2_JOIN_PRED_FUSION", "B2_NO_FILTER_FUSION"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
