@@ -48,10 +48,14 @@ __device__ __forceinline__ uint64_t pack_join_key(const KeyCols& ks, int64_t r) 
 }
 __device__ __forceinline__ uint32_t hash_packed(uint64_t kb) { const uint64_t h = mix64(kb ^ 0x9e3779b97f4a7c15ull); return (uint32_t)(h ^ (h >> 32)); }
 
+// bloom_mask: bits 0..27 = words - 1, bits 28..29 = extra bits set per key beyond the first two (k = 2..4)
 __device__ __forceinline__ void bloom_of(uint32_t h, uint32_t bloom_mask, uint32_t& word, unsigned long long& bits) {
   const uint64_t p = (uint64_t)h * 0x9E3779B97F4A7C15ull;
-  word = (uint32_t)(p >> 40) & bloom_mask;
+  word = (uint32_t)(p >> 40) & (bloom_mask & 0x0fffffffu);
   bits = (1ull << ((p >> 8) & 63)) | (1ull << ((p >> 14) & 63));
+  const uint32_t extra = bloom_mask >> 28;
+  if (extra >= 1) bits |= 1ull << ((p >> 20) & 63);
+  if (extra >= 2) bits |= 1ull << ((p >> 26) & 63);
 }
 __device__ __forceinline__ bool bloom_may_contain(const unsigned long long* __restrict__ bloom, uint32_t bloom_mask, uint32_t h) {
   if (!bloom) return true;
@@ -501,7 +505,8 @@ int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* ou
     while (words * 64 < t->rows * bits_per_key && words < (8 << 20)) words <<= 1;   // at most 64 MB
     if (words * 64 >= t->rows * 6) {                                // below ~6 bits per key the filter stops paying
       jt->bloom = DevBuf((size_t)words * 8);
-      jt->bloom_mask = (uint32_t)(words - 1);
+      static const int bloom_k = getenv("B2_JOIN_BLOOM_K") ? std::min(4, std::max(2, atoi(getenv("B2_JOIN_BLOOM_K")))) : 2;
+      jt->bloom_mask = (uint32_t)(words - 1) | ((uint32_t)(bloom_k - 2) << 28);
       CUDA_CHECK(cudaMemsetAsync(jt->bloom.p, 0, jt->bloom.bytes, stream()));
     }
   }
