@@ -505,7 +505,8 @@ int b2_join_build(b2_handle build_keys_table, int32_t nulls_equal, b2_handle* ou
     while (words * 64 < t->rows * bits_per_key && words < (8 << 20)) words <<= 1;   // at most 64 MB
     if (words * 64 >= t->rows * 6) {                                // below ~6 bits per key the filter stops paying
       jt->bloom = DevBuf((size_t)words * 8);
-      static const int bloom_k = getenv("B2_JOIN_BLOOM_K") ? std::min(4, std::max(2, atoi(getenv("B2_JOIN_BLOOM_K")))) : 2;
+      // bits set per key: sweep on the q3 step (probe kernel ms): 16 bits/key k=2 5.12, k=3 4.91; 8 bits/key k=3 5.58, k=4 5.43; 32 bits/key k=2 6.06
+      static const int bloom_k = getenv("B2_JOIN_BLOOM_K") ? std::min(4, std::max(2, atoi(getenv("B2_JOIN_BLOOM_K")))) : 3;
       jt->bloom_mask = (uint32_t)(words - 1) | ((uint32_t)(bloom_k - 2) << 28);
       CUDA_CHECK(cudaMemsetAsync(jt->bloom.p, 0, jt->bloom.bytes, stream()));
     }
