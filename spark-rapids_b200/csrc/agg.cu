@@ -920,7 +920,12 @@ __global__ void __launch_bounds__(RG_NT, 1) radix_agg_kernel(const __grid_consta
     int nclaimed = 0;
     auto aggregate_rows = [&](int64_t from, int64_t to) {
       nclaimed = 0;
-      for (int64_t r = from + threadIdx.x; r < to; r += RG_NT) {
+      // at most CH / RG_NT (= 2) rows per thread: fixed trip count, unrolled, so that both rows' probes overlap (with the
+      // runtime bound the compiler kept them serial in one build and interleaved them in another: 2.25 vs 2.0 ms)
+#pragma unroll
+      for (int it = 0; it < CH / RG_NT; it++) {
+        const int64_t r = from + (int64_t)it * RG_NT + threadIdx.x;
+        if (r >= to) continue;
         const int li = (int)(r - cs);
         const uint64_t k0 = s_k0[li], k1 = rp.has_k1 ? s_k1[li] : 0;
         uint32_t idx = (uint32_t)rg_hash(k0, k1) & (uint32_t)(C - 1);

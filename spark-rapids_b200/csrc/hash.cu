@@ -133,7 +133,14 @@ __device__ __forceinline__ void ps_move(const T* __restrict__ in, T* __restrict_
   // leave one by one.  (The first version stored aligned STAGE vectors and fell back to per-element loops for whole
   // misaligned runs: ncu counted 2.3x the ideal store sectors and 2x the DRAM writes.)
   constexpr int V = sizeof(T) >= 16 ? 1 : 16 / (int)sizeof(T);
-  for (int k0 = threadIdx.x * V; k0 < tile_n; k0 += PT_NT * V) {
+  // fixed trip count, fully unrolled: the iterations are independent and their shared-memory loads and global stores overlap.
+  // (With the runtime bound `k0 < tile_n` the compiler unrolled this loop in one build and not in the next — the kernel went
+  // from 1.03 to 1.63 ms per pass with an unrelated header change.)
+  constexpr int ITERS = PT_TILE / (PT_NT * V);
+#pragma unroll
+  for (int it = 0; it < ITERS; it++) {
+    const int k0 = (it * PT_NT + (int)threadIdx.x) * V;
+    if (k0 >= tile_n) continue;
     if (V == 1) { const int p = s_owner[k0]; out[(int64_t)s_gbase[p] + (k0 - s_start[p])] = stage[k0]; continue; }
     {
       const int p = s_owner[k0];
