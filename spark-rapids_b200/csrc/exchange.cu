@@ -242,7 +242,8 @@ __device__ __forceinline__ void xs_move_column(const XPlan& pl, int64_t off_byte
     const int head = min(en - st, (V - (int)((st + c) & (V - 1))) & (V - 1));
     const int vlo = st + head;
     const int nvec = (en - vlo) / V;
-    for (int v = threadIdx.x; v < nvec; v += XS_NT) {
+#pragma unroll 4
+    for (int v = threadIdx.x; v < nvec; v += XS_NT) {   // independent iterations: up to four vectors in flight per thread
       const int kk = vlo + v * V;
       *reinterpret_cast<uint4*>(out + kk) = pack16<T>(stage + kk);
     }
