@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 3 --cpu-baseline 0 --check 0 --extra-q6 0"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 501 -c 172 --csv --log-file gpurun_out/r2_launches_q3.csv $BENCH > gpurun_out/r2_launches_q3.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 390 -c 130 --csv --log-file gpurun_out/r2_launches_q3.csv $BENCH > gpurun_out/r2_launches_q3.log 2>&1
 echo "--- launches rc=$?"
 for K in join_probe_distinct1_kernel simple_filter_ids_kernel radix_agg_kernel part_scatter2_kernel gather_fixed_kernel radix_rows_kernel join_build_kernel filter_staged_kernel; do
   SRC="--import-source on"; case $K in filter_staged_kernel|radix_rows_kernel) SRC="";; esac
