@@ -2,7 +2,7 @@
 # pass S: relational / aggregation tests + q3 SF100 bench with cache-policy hints in the scatter kernel
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_relational_gpu.py tests/test_agg_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q > gpurun_out/r2s_pytest.txt 2>&1; echo "--- pytest rc=$?"; tail -3 gpurun_out/r2s_pytest.txt
+timeout 600 python -m pytest tests/test_relational_gpu.py tests/test_execs_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q > gpurun_out/r2s_pytest.txt 2>&1; echo "--- pytest rc=$?"; tail -3 gpurun_out/r2s_pytest.txt
 timeout 600 python bench.py --steps 5 --extra-q6 0 --cpu-baseline 0 --check 1 > gpurun_out/r2s_base.json 2> gpurun_out/r2s_base.err; echo "--- base rc=$?"; tail -2 gpurun_out/r2s_base.err
 python - <<'PY'
 import json
