@@ -222,14 +222,9 @@ struct L2Persist {
 //   MODE 0: every row of the batch; 1: the rows of a selection vector (a filter below the join emitted row ids);
 //   2: the filter itself is evaluated here (a "simple" predicate, simplefilter.cuh): the predicate columns of the 256 rows are
 //      loaded first, rows that fail are dropped before their key is fetched, and no selection vector is ever written or read.
+// (Tried and measured slower, 4.96 -> 5.47 ms per q3 step: evict-first loads of the selection vector and the key column plus
+// evict-last Bloom words.  Unlike part_scatter2 — hash.cu — nothing here is half-written and waiting in L2.)
 constexpr int PQ = 8;
-// a Bloom word: keep its line in L2 in preference to the streamed selection vector / key column (ld.global.L2::evict_last)
-__device__ __forceinline__ unsigned long long ld_evict_last(const unsigned long long* p) {
-  unsigned long long v, pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-  return v;
-}
 template <typename T>
 __device__ __forceinline__ uint32_t pred_term_mask(const SimpleTerm& t, const int32_t (&r)[PQ]) {
   T v[PQ];
@@ -262,7 +257,7 @@ __global__ void __launch_bounds__(256) join_probe_distinct1_kernel(const K* __re
 #pragma unroll
     for (int j = 0; j < PQ; j++) {
       const int64_t rr = base + j * 32 + lane;
-      r[j] = rr < n ? (SEL ? __ldcs(&sel[rr]) : (int32_t)rr) : -1;   // streamed once: evict-first, the Bloom words should own the L2
+      r[j] = rr < n ? (SEL ? sel[rr] : (int32_t)rr) : -1;
     }
     if (MODE == 2) {   // the filter: PQ independent loads per lane and term
       uint32_t ok = 0xffu;
@@ -286,12 +281,12 @@ __global__ void __launch_bounds__(256) join_probe_distinct1_kernel(const K* __re
       uint32_t h[PQ];
       unsigned long long wv[PQ];
 #pragma unroll
-      for (int j = 0; j < PQ; j++) h[j] = r[j] >= 0 ? hash_packed((uint64_t)(UK)__ldcs(&keys[r[j]])) : 0u;
+      for (int j = 0; j < PQ; j++) h[j] = r[j] >= 0 ? hash_packed((uint64_t)(UK)keys[r[j]]) : 0u;
 #pragma unroll
       for (int j = 0; j < PQ; j++) {
         uint32_t wi; unsigned long long bits;
         bloom_of(h[j], bloom_mask, wi, bits);
-        wv[j] = r[j] >= 0 ? ld_evict_last(&bloom[wi]) : 0ull;
+        wv[j] = r[j] >= 0 ? __ldg(&bloom[wi]) : 0ull;
       }
 #pragma unroll
       for (int j = 0; j < PQ; j++) {
