@@ -118,6 +118,42 @@ dist.destroy_process_group()
 '''
 
 
+# GpuShuffleExchangeExec's termination protocol (csrc/exec.cu: one batch of look-ahead, `more` flag in the exchange header,
+# b2_comm_set_more / b2_comm_any_more) restated over gloo: every rank keeps calling while ANY rank has more, the call that
+# carries a rank's last batch says so, and no extra empty round is spent.  Ranks with different batch counts (one with none)
+# must agree on the number of rounds and lose no rows.
+MORE_WORKER = r'''
+import os, sys
+import torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+for case, counts in enumerate([(3, 1), (0, 2), (2, 2), (0, 0), (1, 4)]):
+    batches = [[(rank, b, i) for i in range(5 + b)] for b in range(counts[rank])]       # this rank's child output
+    it = iter(batches)
+    ahead = next(it, None)                                                              # primed look-ahead
+    rounds, received, finished = 0, [], False
+    while not finished:
+        cur, ahead = ahead, (next(it, None) if ahead is not None else None)
+        hdr = {"has_data": cur is not None, "more": ahead is not None}                 # b2_comm_set_more(ahead != null)
+        hdrs = [None] * world
+        dist.all_gather_object(hdrs, hdr)                                               # the header all-gather of the call
+        rows = [None] * world
+        dist.all_gather_object(rows, cur or [])                                         # the data (every rank sees every row here)
+        rounds += 1
+        any_data, any_more = any(h["has_data"] for h in hdrs), any(h["more"] for h in hdrs)
+        if any_data:
+            received += [r for part in rows for r in part]
+        finished = not any_more                                                         # b2_comm_any_more == 0: no further round
+    expect_rounds = max(1, max(counts))                                                 # never an extra empty round
+    assert rounds == expect_rounds, (case, rank, rounds, expect_rounds)
+    want = sorted((r, b, i) for r in range(world) for b in range(counts[r]) for i in range(5 + b))
+    assert sorted(received) == want, (case, rank)
+print("MORE_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
 def _torchrun(args, script_args=(), timeout=300):
     return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                            "--master-port", "29531"] + list(args) + list(script_args), capture_output=True, text=True, timeout=timeout, cwd=ROOT)
@@ -129,6 +165,14 @@ def test_partial_exchange_final_protocol_world2(tmp_path):
     r = _torchrun([str(script)])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
+
+
+def test_exchange_lookahead_termination_protocol_world2(tmp_path):
+    script = tmp_path / "more_worker.py"
+    script.write_text(MORE_WORKER)
+    r = _torchrun([str(script)])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("MORE_OK") == 2
 
 
 def test_q3_strong_scaled_plan_protocol_world2(tmp_path):
